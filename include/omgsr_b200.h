@@ -1,0 +1,176 @@
+/*
+ * omgsr_b200 — C ABI of the B200 (sm_100a) kernels behind OMGSR's one-step SR inference path.
+ *
+ * The reference (wuer5/OMGSR) has no FFI of its own: its operator surface for this path is the Python
+ * module API of infer/omgsr_s_infer_model.py, infer/omgsr_f_infer_model.py, infer/vaehook.py and
+ * infer/wavelet_color_fix.py, underneath which diffusers/PyTorch dispatch to cuDNN, cuBLAS and SDPA.
+ * Each entry point below names the reference call site whose library kernels it replaces (paths are
+ * relative to the reference tree). omgsr_b200/capi.py is the ctypes binding; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative OMGSR_ERR_* code; the message is available from
+ *     omgsr_last_error() (thread-local). Nothing throws, nothing exits, there is no CPU fallback.
+ *   - all pointers are DEVICE pointers unless stated; the library allocates no device memory. The caller
+ *     (PyTorch's caching allocator in this repo) owns every buffer.
+ *   - every function only enqueues work on `stream` (a cudaStream_t passed as void*): no hidden
+ *     synchronisation, so call sequences are CUDA-graph capturable.
+ *   - activations are NHWC ("channels last") bf16 with an explicit channel stride `ld*` in elements so a
+ *     layer can read or write a channel slice of a wider (concatenated) buffer. Strides are multiples of 8.
+ *   - weights are bf16 [Cout, R*S*Cin] with k = (r*S + s)*Cin + cin; biases / norm affine vectors are fp32.
+ */
+#ifndef OMGSR_B200_H
+#define OMGSR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMGSR_OK 0
+#define OMGSR_ERR_SHAPE (-1)
+#define OMGSR_ERR_ALIGN (-2)
+#define OMGSR_ERR_ARCH (-3)
+#define OMGSR_ERR_CUDA (-4)
+
+/* epilogue activations of omgsr_gemm_bf16 / omgsr_conv2d_nhwc_bf16 */
+#define OMGSR_ACT_NONE 0
+#define OMGSR_ACT_SILU 1
+#define OMGSR_ACT_GELU_ERF 2
+#define OMGSR_ACT_GELU_TANH 3
+#define OMGSR_ACT_GEGLU 4 /* out[:, j] = v[:, j] * gelu_erf(g[:, j]); weight rows interleaved per tile by the packer */
+
+/* flags */
+#define OMGSR_OUT_F32 1      /* store fp32 instead of bf16 */
+#define OMGSR_B_MN_MAJOR 2   /* batched GEMM: B operand given as [K, N] (row-major V), not [N, K] */
+
+int omgsr_version(void);
+const char* omgsr_last_error(void);
+/* frees per-process caches (function attributes are process-wide; nothing device-side is owned). */
+int omgsr_destroy(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+long long omgsr_launch_count(void);
+
+/* ---- contractions (tcgen05 + TMEM + TMA) ------------------------------------------------------ */
+
+/* D[M,N] = epi(A[M,K] * Wt[N,K]^T). Replaces torch.nn.Linear under the UNet transformer blocks and
+ * the FLUX DiT (reference call sites infer/omgsr_s_infer_model.py:75-79, infer/omgsr_f_infer_model.py:191-200).
+ * epi: +bias[N] -> act -> *gate[m / gate_rows, N] -> +res[M,N].  K % 64 == 0. */
+int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias, const void* res, const float* gate, void* D,
+                    long long M, int N, int K, long long lda, long long ldd, long long ldr, int act, int gate_rows,
+                    int flags, int force_bn, void* stream);
+
+/* Batched attention-style GEMM over (batch b, head h):
+ *   D[b,h,m,n] = alpha-free sum_k A[b,m,h,k] * Bm[b,n,h,k]          (flags & OMGSR_B_MN_MAJOR == 0; Q K^T)
+ *   D[b,m,h,n] =            sum_k A[b,h,m,k] * Bm[b,k,h,n]          (flags & OMGSR_B_MN_MAJOR;      P V)
+ * Used for the materialised-score attention path (VAE mid-block attention d=512,
+ * infer/vaehook.py:137-171, and as the bring-up path for UNet/DiT attention).
+ * strides are in elements: a_* for A (row, head, batch), b_* for Bm, d_* for D. */
+int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batch, int heads, int M, int N, int K,
+                     long long a_row, long long a_head, long long a_batch, long long b_row, long long b_head,
+                     long long b_batch, long long d_row, long long d_head, long long d_batch, int flags,
+                     int force_bn, void* stream);
+
+/* Fused flash attention (TMA + tcgen05, online softmax, scores never leave the SM):
+ *   out[b,m,h,:] = softmax_n(scale * q[b,m,h,:] . k[b,n,h,:]) v[b,n,h,:],  D in {64, 128}.
+ * Replaces F.scaled_dot_product_attention under the UNet self/cross attention (d=64) and the FLUX joint
+ * attention (d=128) (infer/omgsr_s_infer_model.py:75-79, infer/omgsr_f_infer_model.py:191-200).
+ * Strides in elements (row = token, head, batch); D is contiguous. */
+int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N, int D,
+                          long long q_row, long long q_head, long long q_batch, long long k_row, long long k_head,
+                          long long k_batch, long long v_row, long long v_head, long long v_batch, long long o_row,
+                          long long o_head, long long o_batch, float scale, void* stream);
+
+/* NHWC implicit-GEMM convolution, ksize in {1,3}, stride in {1,2}; `upsample2x` fuses a nearest 2x
+ * upsample in front of a 3x3/p1 conv (weights must be packed by pack_upsample_weight: 4 x [Cout, 4*Cin]).
+ * Replaces cuDNN under diffusers ResnetBlock2D/Downsample2D/Upsample2D in the VAE and UNet
+ * (infer/omgsr_s_infer_model.py:84,173; infer/vaehook.py:248-329 lists the same layers). Cin % 64 == 0.
+ * epi: +bias -> act -> +res. */
+int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H,
+                           int W, int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b,
+                           int pad_r, int upsample2x, int act, long long ldx, long long ldy, long long ldr,
+                           int flags, int force_bn, void* stream);
+
+/* ---- thin convolutions (CUDA cores; too few channels for the tensor pipe) --------------------- */
+
+/* conv_in: x NCHW (bf16 if !x_f32 else fp32) [B,Cin,H,W], Cin <= 16, ksize 1|3 'same' -> y NHWC bf16 [B,H,W,Cout].
+ * w: fp32 [ksize*ksize*Cin, Cout]. (VAE encoder.conv_in, decoder.conv_in, unet.conv_in) */
+int omgsr_conv_in_nchw(const void* x, int x_f32, const float* w, const float* bias, void* y, int B, int Cin, int H,
+                       int W, int Cout, int ksize, long long ldy, void* stream);
+/* conv_out: x NHWC bf16 [B,H,W,Cin] -> y NCHW [B,Cout,H,W] (bf16 or fp32), Cout <= 4, 3x3 p1, optional clamp
+ * to [-1,1] (infer/omgsr_s_infer_model.py:85). w: bf16 [Cout, 9*Cin]. (VAE decoder.conv_out) */
+int omgsr_conv_out_nchw(const void* x, const void* w, const float* bias, void* y, int y_f32, int B, int H, int W,
+                        int Cin, int Cout, int clamp, long long ldx, void* stream);
+
+/* ---- normalisation / glue (HBM-bound) --------------------------------------------------------- */
+
+/* GroupNorm statistics: stats[B, G, 2] = (sum, sum of squares) over (HW, C/G). Zeroes stats first. */
+int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats, int B, long long HW, int C, int G,
+                          void* stream);
+/* y = (x - mean) * rstd * gamma + beta, optional SiLU. (diffusers GroupNorm+SiLU pairs: VAE eps 1e-6,
+ * UNet eps 1e-5; infer/vaehook.py:384-413 restates the same op as custom_group_norm.) */
+int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,
+                          const float* gamma, const float* beta, int B, long long HW, int C, int G, float eps,
+                          int silu, void* stream);
+/* LayerNorm over the last dim with y = xhat * g + b where g/b are fp32 vectors of length C taken from
+ * gamma + (row / rows_per_batch) * gb_stride (gb_stride = 0: shared affine; >0: per-image AdaLN modulation,
+ * caller passes g = 1 + scale, b = shift). gamma/beta may be null (no affine). */
+int omgsr_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,
+                    long long rows_per_batch, long long gb_stride, void* stream);
+/* softmax over rows of fp32 scores: P[r, j] = softmax_j(scale * S[r, j]) for j < n, P[r, j] = 0 for
+ * n <= j < n_pad. */
+int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int n_pad,
+                       float scale, void* stream);
+/* FLUX q/k RMSNorm (per head, d = 128, learned weight) + rotary embedding, in place on [rows, heads, 128]
+ * bf16 with row stride ld. cos/sin: fp32 [rows_per_batch, 128] (interleaved-pair layout). */
+int omgsr_rmsnorm_rope(void* x, long long ld, const float* weight, const float* cos_t, const float* sin_t,
+                       long long rows, int heads, long long rows_per_batch, float eps, void* stream);
+
+/* ---- latent-sized elementwise steps ------------------------------------------------------------ */
+
+/* VAE posterior sample: moments NHWC fp32 [B,h,w,ldm] (first 2*Cz channels = mean | logvar),
+ * eps NCHW fp32 [B,Cz,h,w] -> z NCHW (bf16/fp32) = ((mean + exp(0.5*clamp(logvar,-30,20))*eps) - shift) * scale.
+ * (infer/omgsr_s_infer_model.py:173, infer/omgsr_f_infer_model.py:15-18) */
+int omgsr_posterior_sample(const float* moments, long long ldm, const float* eps, void* z, int z_f32, int B, int Cz,
+                           int h, int w, float shift, float scale, void* stream);
+/* generic latent axpby: out = a*x + b*y + c (x, y, out same dtype: bf16 or fp32), n elements.
+ * DDPM x0 step (infer/omgsr_s_infer_model.py:80-82), Euler step (infer/omgsr_f_infer_model.py:202),
+ * un-scale (infer/omgsr_f_infer_model.py:210) and the training-time mid-timestep mix
+ * z_t = (1-sigma) z + sigma eps (train/train_omgsr_f.py:537-538) are all this op. */
+int omgsr_latent_axpby(const void* x, const void* y, void* out, int is_f32, long long n, float a, float b, float c,
+                       void* stream);
+/* x0 prediction fused with un-scale and SD post_quant_conv (1x1, CzxCz):
+ *   z0 = (z - s1*eps_hat)/s2 / scale + shift ; out[b,:,y,x] = Wpq * z0[b,:,y,x] + bpq   (Wpq null -> identity)
+ * z NCHW (bf16/fp32), eps_hat NHWC fp32 (ld = lde), out NCHW bf16. */
+int omgsr_x0_unscale(const void* z, int z_f32, const float* eps_hat, long long lde, void* out, const float* Wpq,
+                     const float* bpq, int B, int Cz, int h, int w, float s1, float s2, float scale, float shift,
+                     void* stream);
+/* FLUX 2x2 pack / unpack between NCHW latents [B,C,h,w] and token rows [B,(h/2)(w/2),4C] (bf16).
+ * (infer/omgsr_f_infer_model.py:21-41) */
+int omgsr_pack_latents(const void* z, void* tokens, int B, int C, int h, int w, long long ld_tok, void* stream);
+int omgsr_unpack_latents(const void* tokens, void* z, int B, int C, int h, int w, long long ld_tok, void* stream);
+/* Gaussian-weighted blend of per-tile denoiser outputs into the full latent
+ * (infer/omgsr_s_infer_model.py:137-161). tiles: NCHW fp32/bf16 [ntiles,B,C,T,T]; ofs_xy: DEVICE int
+ * [ntiles,2] = (x, y) offsets; weights fp32 [T,T]; out fp32 NCHW [B,C,h,w] = sum w*tile / sum w. */
+int omgsr_tile_blend(const void* tiles, int tiles_f32, const float* weights, const int* ofs_xy, int ntiles,
+                     float* out, int B, int C, int h, int w, int T, void* stream);
+
+/* ---- colour fix (infer/wavelet_color_fix.py) ---------------------------------------------------- */
+
+/* out = content + LP5(style - content), LP5 = 5-stage a-trous [1,2,1]x[1,2,1]/16 cascade with replicate
+ * padding (identical to wavelet_reconstruction, infer/wavelet_color_fix.py:77-125). fp32 NCHW [B,3,H,W];
+ * tmp0/tmp1 are caller-provided scratch of the same size. */
+int omgsr_wavelet_fix(const float* content, const float* style, float* out, float* tmp0, float* tmp1, int B, int C,
+                      int H, int W, void* stream);
+/* AdaIN: out = (content - mean_c)/std_c * std_s + mean_s per (b,c), unbiased var + 1e-5
+ * (infer/wavelet_color_fix.py:44-74). scratch: B*C*4 doubles (32*B*C bytes). */
+int omgsr_adain_fix(const float* content, const float* style, float* out, void* scratch, int B, int C, int H, int W,
+                    void* stream);
+
+/* ---- layout ---------------------------------------------------------------------------------------- */
+int omgsr_nchw_to_nhwc(const void* x, int x_f32, void* y, int B, int C, int H, int W, long long ldy, void* stream);
+int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f32, int B, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMGSR_B200_H */

@@ -1,0 +1,395 @@
+"""ctypes binding of libomgsr_b200.so (the C ABI declared in include/omgsr_b200.h).
+
+PyTorch is plumbing only: tensors provide device memory (`data_ptr()`), the current CUDA stream and
+shapes. Every wrapper raises RuntimeError with the library's message on a non-zero return code; there is
+no CPU fallback — if the shared library is missing, import of this module fails loudly.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libomgsr_b200.so")
+
+ACT_NONE, ACT_SILU, ACT_GELU_ERF, ACT_GELU_TANH, ACT_GEGLU = 0, 1, 2, 3, 4
+OUT_F32, B_MN_MAJOR = 1, 2
+
+# every symbol include/omgsr_b200.h declares (tests/test_abi.py checks the two lists agree)
+SYMBOLS = [
+    "omgsr_version", "omgsr_last_error", "omgsr_destroy", "omgsr_launch_count",
+    "omgsr_gemm_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
+    "omgsr_conv_in_nchw", "omgsr_conv_out_nchw",
+    "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_layernorm", "omgsr_softmax_rows",
+    "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
+    "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
+    "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
+    "omgsr_flash_attn_bf16",
+]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m omgsr_b200.build` (or __graft_entry__.build()). "
+            "omgsr_b200 has no CPU / PyTorch fallback for the hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.omgsr_last_error.restype = ctypes.c_char_p
+    lib.omgsr_launch_count.restype = ctypes.c_longlong
+    return lib
+
+
+_lib = _load()
+
+_vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+
+def lib():
+    return _lib
+
+
+def _ptr(t):
+    if t is None:
+        return _vp(0)
+    return _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {_lib.omgsr_last_error().decode()}")
+
+
+def version():
+    return _lib.omgsr_version()
+
+
+def launch_count():
+    return int(_lib.omgsr_launch_count())
+
+
+def _cuda_bf16(t, name):
+    if not (t.is_cuda and t.dtype == torch.bfloat16):
+        raise TypeError(f"{name} must be a CUDA bf16 tensor (got {t.device}, {t.dtype})")
+
+
+def _cuda_f32(t, name):
+    if t is not None and not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{name} must be a CUDA fp32 tensor (got {t.device}, {t.dtype})")
+
+
+# ------------------------------------------------------------------------------------------------
+# contractions
+# ------------------------------------------------------------------------------------------------
+def gemm(a, w, bias=None, res=None, gate=None, act=ACT_NONE, gate_rows=0, out=None, out_f32=False, force_bn=0,
+         n_out=None):
+    """out[M, N] = epi(a[M, K] @ w[N, K]^T). a may be a row-strided 2-D view (last dim contiguous)."""
+    _cuda_bf16(a, "a"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias"); _cuda_f32(gate, "gate")
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    n_cols = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        ld = (n_cols + 7) // 8 * 8
+        out = torch.empty((M, ld), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+        if ld != n_cols:
+            out = out[:, :n_cols]
+    assert out.stride(1) == 1
+    ldr = res.stride(0) if res is not None else 0
+    rc = _lib.omgsr_gemm_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(res), _ptr(gate), _ptr(out), _ll(M), _i(N), _i(K),
+                              _ll(a.stride(0)), _ll(out.stride(0)), _ll(ldr), _i(act), _i(gate_rows),
+                              _i(OUT_F32 if out.dtype == torch.float32 else 0), _i(force_bn), _stream())
+    _check(rc, "omgsr_gemm_bf16")
+    return out
+
+
+def bgemm_qk(q, k, out=None, force_bn=0):
+    """scores[b,h,m,n] = sum_d q[b,m,h,d] k[b,n,h,d] (fp32). q/k: [B, T, H, D] views with D contiguous."""
+    _cuda_bf16(q, "q"); _cuda_bf16(k, "k")
+    B, M, H, D = q.shape
+    N = k.shape[1]
+    n_pad = (N + 63) // 64 * 64
+    if out is None:
+        out = torch.empty((B, H, M, n_pad), device=q.device, dtype=torch.float32)
+    rc = _lib.omgsr_bgemm_bf16(_ptr(q), _ptr(k), _ptr(out), _i(B), _i(H), _i(M), _i(N), _i(D),
+                               _ll(q.stride(1)), _ll(q.stride(2)), _ll(q.stride(0)),
+                               _ll(k.stride(1)), _ll(k.stride(2)), _ll(k.stride(0)),
+                               _ll(out.stride(2)), _ll(out.stride(1)), _ll(out.stride(0)),
+                               _i(OUT_F32), _i(force_bn), _stream())
+    _check(rc, "omgsr_bgemm_bf16(qk)")
+    return out
+
+
+def bgemm_pv(p, v, out=None, n_kv=None, force_bn=0):
+    """out[b,m,h,d] = sum_n p[b,h,m,n] v[b,n,h,d]. p: [B,H,M,Npad] bf16 (zero beyond n_kv); v: [B,N,H,D]."""
+    _cuda_bf16(p, "p"); _cuda_bf16(v, "v")
+    B, H, M, Np = p.shape
+    D = v.shape[3]
+    if out is None:
+        out = torch.empty((B, M, H, D), device=p.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_bgemm_bf16(_ptr(p), _ptr(v), _ptr(out), _i(B), _i(H), _i(M), _i(D), _i(Np),
+                               _ll(p.stride(2)), _ll(p.stride(1)), _ll(p.stride(0)),
+                               _ll(v.stride(1)), _ll(v.stride(2)), _ll(v.stride(0)),
+                               _ll(out.stride(1)), _ll(out.stride(2)), _ll(out.stride(0)),
+                               _i(B_MN_MAJOR), _i(force_bn), _stream())
+    _check(rc, "omgsr_bgemm_bf16(pv)")
+    return out
+
+
+def conv2d(x, w, bias=None, res=None, ksize=3, stride=1, pad=(1, 1, 1, 1), upsample2x=False, act=ACT_NONE, out=None,
+           out_f32=False, cout=None, force_bn=0):
+    """NHWC conv. x: [B,H,W,Cin] bf16 view (channel-contiguous, dense in B/H/W with a channel stride);
+    w: packed [Cout, k*k*Cin] (or [4, Cout, 4*Cin] for upsample2x). pad = (top, left, bottom, right)."""
+    _cuda_bf16(x, "x"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias")
+    B, H, W, Cin = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
+    Cout = cout if cout is not None else (w.shape[1] if upsample2x else w.shape[0])
+    if upsample2x:
+        OH, OW = 2 * H, 2 * W
+    else:
+        OH = (H + pad[0] + pad[2] - ksize) // stride + 1
+        OW = (W + pad[1] + pad[3] - ksize) // stride + 1
+    if out is None:
+        ld = (Cout + 7) // 8 * 8
+        out = torch.empty((B, OH, OW, ld), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+        if ld != Cout:
+            out = out[..., :Cout]
+    assert out.shape[:3] == (B, OH, OW) and out.stride(3) == 1
+    assert out.stride(1) == OW * out.stride(2) and out.stride(0) == OH * out.stride(1)
+    ldr = 0
+    if res is not None:
+        _cuda_bf16(res, "res")
+        assert res.shape[:3] == (B, OH, OW) and res.stride(3) == 1
+        ldr = res.stride(2)
+    rc = _lib.omgsr_conv2d_nhwc_bf16(_ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), _i(B), _i(H), _i(W),
+                                     _i(Cin), _i(Cout), _i(ksize), _i(stride), _i(pad[0]), _i(pad[1]), _i(pad[2]),
+                                     _i(pad[3]), _i(1 if upsample2x else 0), _i(act), _ll(x.stride(2)),
+                                     _ll(out.stride(2)), _ll(ldr),
+                                     _i(OUT_F32 if out.dtype == torch.float32 else 0), _i(force_bn), _stream())
+    _check(rc, "omgsr_conv2d_nhwc_bf16")
+    return out
+
+
+def conv_in_nchw(x, w, bias, cout, ksize=3, out=None):
+    """x NCHW (bf16|fp32) -> NHWC bf16. w fp32 [k*k*Cin, Cout]."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32)
+    _cuda_f32(w, "w"); _cuda_f32(bias, "bias")
+    B, Cin, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, cout), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_conv_in_nchw(_ptr(x), _i(int(x.dtype == torch.float32)), _ptr(w), _ptr(bias), _ptr(out), _i(B),
+                                 _i(Cin), _i(H), _i(W), _i(cout), _i(ksize), _ll(out.stride(2)), _stream())
+    _check(rc, "omgsr_conv_in_nchw")
+    return out
+
+
+def conv_out_nchw(x, w, bias, cout, clamp=False, out_dtype=torch.bfloat16):
+    """x NHWC bf16 -> NCHW (bf16|fp32), 3x3 p1, Cout in {3,4}. w bf16 [Cout, 9*Cin]."""
+    _cuda_bf16(x, "x"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias")
+    B, H, W, Cin = x.shape
+    out = torch.empty((B, cout, H, W), device=x.device, dtype=out_dtype)
+    rc = _lib.omgsr_conv_out_nchw(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), _i(int(out_dtype == torch.float32)), _i(B),
+                                  _i(H), _i(W), _i(Cin), _i(cout), _i(int(clamp)), _ll(x.stride(2)), _stream())
+    _check(rc, "omgsr_conv_out_nchw")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# glue
+# ------------------------------------------------------------------------------------------------
+def groupnorm(x, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, stats=None):
+    """x: [B, ..., C] NHWC bf16 (channel stride = x.stride(-2)). Two launches: stats, apply(+SiLU)."""
+    _cuda_bf16(x, "x"); _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta")
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    ldx = x.stride(-2)
+    if stats is None:
+        stats = torch.empty((B, groups, 2), device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_groupnorm_stats(_ptr(x), _ll(ldx), _ptr(stats), _i(B), _ll(HW), _i(C), _i(groups), _stream())
+    _check(rc, "omgsr_groupnorm_stats")
+    rc = _lib.omgsr_groupnorm_apply(_ptr(x), _ll(ldx), _ptr(out), _ll(out.stride(-2)), _ptr(stats), _ptr(gamma),
+                                    _ptr(beta), _i(B), _ll(HW), _i(C), _i(groups), _f(eps), _i(int(silu)), _stream())
+    _check(rc, "omgsr_groupnorm_apply")
+    return out
+
+
+def layernorm(x, gamma=None, beta=None, eps=1e-5, rows_per_batch=0, gb_stride=0, out=None):
+    _cuda_bf16(x, "x"); _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.omgsr_layernorm(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ll(rows), _i(C), _f(eps),
+                              _ll(rows_per_batch), _ll(gb_stride), _stream())
+    _check(rc, "omgsr_layernorm")
+    return out
+
+
+def softmax_rows(s, n, scale, out=None):
+    """s: fp32 [..., n_pad]; returns bf16 probabilities with columns >= n zeroed."""
+    _cuda_f32(s, "s")
+    n_pad = s.shape[-1]
+    rows = s.numel() // n_pad
+    assert s.is_contiguous()
+    if out is None:
+        out = torch.empty(s.shape, device=s.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_softmax_rows(_ptr(s), _ll(n_pad), _ptr(out), _ll(n_pad), _ll(rows), _i(n), _i(n_pad), _f(scale),
+                                 _stream())
+    _check(rc, "omgsr_softmax_rows")
+    return out
+
+
+def rmsnorm_rope_(x, weight, cos_t, sin_t, heads, rows_per_batch, eps=1e-6):
+    """in place on x: [rows, >= heads*128] bf16 view (row stride x.stride(0))."""
+    _cuda_bf16(x, "x"); _cuda_f32(weight, "weight"); _cuda_f32(cos_t, "cos"); _cuda_f32(sin_t, "sin")
+    rows = x.shape[0]
+    rc = _lib.omgsr_rmsnorm_rope(_ptr(x), _ll(x.stride(0)), _ptr(weight), _ptr(cos_t), _ptr(sin_t), _ll(rows),
+                                 _i(heads), _ll(rows_per_batch), _f(eps), _stream())
+    _check(rc, "omgsr_rmsnorm_rope")
+    return x
+
+
+def posterior_sample(moments, eps, cz, shift, scale, out_dtype=torch.bfloat16):
+    """moments: NHWC fp32 [B,h,w,ld>=2cz]; eps: NCHW fp32 [B,cz,h,w] -> z NCHW."""
+    _cuda_f32(moments, "moments"); _cuda_f32(eps, "eps")
+    B, h, w, _ = moments.shape
+    z = torch.empty((B, cz, h, w), device=moments.device, dtype=out_dtype)
+    rc = _lib.omgsr_posterior_sample(_ptr(moments), _ll(moments.stride(2)), _ptr(eps.contiguous()), _ptr(z),
+                                     _i(int(out_dtype == torch.float32)), _i(B), _i(cz), _i(h), _i(w), _f(shift),
+                                     _f(scale), _stream())
+    _check(rc, "omgsr_posterior_sample")
+    return z
+
+
+def latent_axpby(x, y, a, b, c=0.0, out=None):
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32)
+    if y is not None:
+        assert y.dtype == x.dtype and y.is_contiguous() and y.numel() == x.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.omgsr_latent_axpby(_ptr(x), _ptr(y), _ptr(out), _i(int(x.dtype == torch.float32)), _ll(x.numel()),
+                                 _f(a), _f(b), _f(c), _stream())
+    _check(rc, "omgsr_latent_axpby")
+    return out
+
+
+def x0_unscale(z, eps_hat, s1, s2, scale, shift=0.0, wpq=None, bpq=None):
+    """z NCHW (bf16|fp32), eps_hat NHWC fp32 [B,h,w,ld] -> NCHW bf16."""
+    _cuda_f32(eps_hat, "eps_hat"); _cuda_f32(wpq, "wpq"); _cuda_f32(bpq, "bpq")
+    assert z.is_contiguous()
+    B, cz, h, w = z.shape
+    out = torch.empty((B, cz, h, w), device=z.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_x0_unscale(_ptr(z), _i(int(z.dtype == torch.float32)), _ptr(eps_hat), _ll(eps_hat.stride(2)),
+                               _ptr(out), _ptr(wpq), _ptr(bpq), _i(B), _i(cz), _i(h), _i(w), _f(s1), _f(s2), _f(scale),
+                               _f(shift), _stream())
+    _check(rc, "omgsr_x0_unscale")
+    return out
+
+
+def pack_latents(z, out=None):
+    _cuda_bf16(z, "z")
+    B, C, h, w = z.shape
+    if out is None:
+        out = torch.empty((B, (h // 2) * (w // 2), 4 * C), device=z.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_pack_latents(_ptr(z.contiguous()), _ptr(out), _i(B), _i(C), _i(h), _i(w), _ll(out.stride(1)),
+                                 _stream())
+    _check(rc, "omgsr_pack_latents")
+    return out
+
+
+def unpack_latents(tokens, C, h, w):
+    _cuda_bf16(tokens, "tokens")
+    B = tokens.shape[0]
+    z = torch.empty((B, C, h, w), device=tokens.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_unpack_latents(_ptr(tokens), _ptr(z), _i(B), _i(C), _i(h), _i(w), _ll(tokens.stride(1)), _stream())
+    _check(rc, "omgsr_unpack_latents")
+    return z
+
+
+def tile_blend(tiles, weights, ofs_xy, h, w):
+    """tiles [ntiles,B,C,T,T] (bf16|fp32), weights fp32 [T,T], ofs_xy int32 device [ntiles,2] -> fp32 [B,C,h,w]."""
+    _cuda_f32(weights, "weights")
+    nt, B, C, T, _ = tiles.shape
+    assert ofs_xy.is_cuda and ofs_xy.dtype == torch.int32 and tiles.is_contiguous()
+    out = torch.empty((B, C, h, w), device=tiles.device, dtype=torch.float32)
+    rc = _lib.omgsr_tile_blend(_ptr(tiles), _i(int(tiles.dtype == torch.float32)), _ptr(weights), _ptr(ofs_xy),
+                               _i(nt), _ptr(out), _i(B), _i(C), _i(h), _i(w), _i(T), _stream())
+    _check(rc, "omgsr_tile_blend")
+    return out
+
+
+def wavelet_fix(content, style):
+    _cuda_f32(content, "content"); _cuda_f32(style, "style")
+    assert content.shape == style.shape and content.is_contiguous() and style.is_contiguous()
+    B, C, H, W = content.shape
+    out = torch.empty_like(content)
+    t0 = torch.empty_like(content)
+    t1 = torch.empty_like(content)
+    rc = _lib.omgsr_wavelet_fix(_ptr(content), _ptr(style), _ptr(out), _ptr(t0), _ptr(t1), _i(B), _i(C), _i(H), _i(W),
+                                _stream())
+    _check(rc, "omgsr_wavelet_fix")
+    return out
+
+
+def adain_fix(content, style):
+    _cuda_f32(content, "content"); _cuda_f32(style, "style")
+    assert content.shape == style.shape and content.is_contiguous() and style.is_contiguous()
+    B, C, H, W = content.shape
+    out = torch.empty_like(content)
+    scratch = torch.empty((B * C * 4,), device=content.device, dtype=torch.float64)
+    rc = _lib.omgsr_adain_fix(_ptr(content), _ptr(style), _ptr(out), _ptr(scratch), _i(B), _i(C), _i(H), _i(W),
+                              _stream())
+    _check(rc, "omgsr_adain_fix")
+    return out
+
+
+def nchw_to_nhwc(x, out=None):
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32)
+    B, C, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, (C + 7) // 8 * 8), device=x.device, dtype=torch.bfloat16)[..., :C]
+    rc = _lib.omgsr_nchw_to_nhwc(_ptr(x), _i(int(x.dtype == torch.float32)), _ptr(out), _i(B), _i(C), _i(H), _i(W),
+                                 _ll(out.stride(2)), _stream())
+    _check(rc, "omgsr_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, out_dtype=torch.bfloat16):
+    _cuda_bf16(x, "x")
+    B, H, W, C = x.shape
+    out = torch.empty((B, C, H, W), device=x.device, dtype=out_dtype)
+    rc = _lib.omgsr_nhwc_to_nchw(_ptr(x), _ll(x.stride(2)), _ptr(out), _i(int(out_dtype == torch.float32)), _i(B),
+                                 _i(C), _i(H), _i(W), _stream())
+    _check(rc, "omgsr_nhwc_to_nchw")
+    return out
+
+
+def flash_attn(q, k, v, scale, out=None):
+    """out[b,m,h,:] = softmax(scale * q[b,m,h,:] . k[b,:,h,:]) v[b,:,h,:]. q/k/v: [B,T,H,D] bf16 views."""
+    _cuda_bf16(q, "q"); _cuda_bf16(k, "k"); _cuda_bf16(v, "v")
+    B, M, H, D = q.shape
+    N = k.shape[1]
+    if out is None:
+        out = torch.empty((B, M, H, D), device=q.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_flash_attn_bf16(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _i(B), _i(H), _i(M), _i(N), _i(D),
+                                    _ll(q.stride(1)), _ll(q.stride(2)), _ll(q.stride(0)),
+                                    _ll(k.stride(1)), _ll(k.stride(2)), _ll(k.stride(0)),
+                                    _ll(v.stride(1)), _ll(v.stride(2)), _ll(v.stride(0)),
+                                    _ll(out.stride(1)), _ll(out.stride(2)), _ll(out.stride(0)), _f(scale), _stream())
+    _check(rc, "omgsr_flash_attn_bf16")
+    return out
+
+
+def attention_materialised(q, k, v, scale):
+    """softmax(scale q k^T) v through the batched tcgen05 GEMMs + row softmax (fp32 scores in HBM)."""
+    n = k.shape[1]
+    s = bgemm_qk(q, k)
+    p = softmax_rows(s, n, scale)
+    return bgemm_pv(p, v)

@@ -1,0 +1,326 @@
+// Fused flash attention on tcgen05: out = softmax(scale * Q K^T) V for one (batch, head) per CTA row-tile.
+//
+//   * Q/K/V are [B, T, H, D] bf16 views (D contiguous, arbitrary row/head/batch strides), D in {64, 128}.
+//   * CTA = 128 query rows. warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = softmax/accumulate
+//     (one query row per thread, so row max / row sum need no shuffles).
+//   * per KV block: S = Q K^T into TMEM (tcgen05.mma, K-major operands) -> threads read S with tcgen05.ld,
+//     online softmax in fp32 (exp2 with the scale folded in), P written to shared memory as bf16 in the
+//     128B-swizzled K-major layout -> O_blk = P V into TMEM (V consumed in place as an MN-major operand)
+//     -> threads fold O_blk into register accumulators with the running rescale.
+//   * TMEM: S (BLK_N columns) + O_blk (D columns) <= 256 columns and <= 112 KB of shared memory, so two
+//     CTAs are co-resident per SM: while one CTA runs its softmax the other one owns the tensor pipe.
+//
+// Replaces F.scaled_dot_product_attention under diffusers' Attention processors for the UNet self/cross
+// attention (d=64) and the FLUX joint attention (d=128) that the reference reaches from
+// infer/omgsr_s_infer_model.py:75-79 and infer/omgsr_f_infer_model.py:191-200.
+#include "common.cuh"
+#include "../../include/omgsr_b200.h"
+
+namespace omgsr {
+
+template <int D>
+struct AttnCfg {
+  static constexpr int kBM = 128;
+  static constexpr int kBN = (D == 64) ? 128 : 64;
+  static constexpr int kStages = 2;
+  static constexpr int kQBytes = kBM * D * 2;
+  static constexpr int kKBytes = kBN * D * 2;
+  static constexpr int kVBytes = kBN * D * 2;
+  static constexpr int kPBytes = kBM * kBN * 2;
+  static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 1024 + 256;
+  static constexpr int kTmemCols = 256;
+  static constexpr int kSCol = 0;
+  static constexpr int kOCol = 128;
+};
+
+struct AttnParams {
+  int M, N, H, B;
+  long long o_row, o_head, o_batch;
+  bf16* out;
+  float scale_log2;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = AttnCfg<D>;
+  constexpr int BN = C::kBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + C::kQBytes;  // [stage][K | V]
+  uint8_t* sP = sKV + C::kStages * (C::kKBytes + C::kVBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::kPBytes);
+  uint64_t* q_full = bars;                      // 1
+  uint64_t* k_full = bars + 1;                  // [kStages]
+  uint64_t* v_full = bars + 1 + C::kStages;     // [kStages]
+  uint64_t* kv_empty = bars + 1 + 2 * C::kStages;  // [kStages]
+  uint64_t* s_full = bars + 1 + 3 * C::kStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * C::kBM, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: Q once, then K_j / V_j through a kStages ring ----
+      mbar_expect_tx(q_full, C::kQBytes);
+#pragma unroll
+      for (int pnl = 0; pnl < D / 64; ++pnl) tma_load_4d(sQ + pnl * (C::kBM * 128), &tmQ, q_full, pnl * 64, m0, h, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sK = sKV + stage * (C::kKBytes + C::kVBytes);
+        uint8_t* sV = sK + C::kKBytes;
+        mbar_expect_tx(&k_full[stage], C::kKBytes);
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sK + pnl * (BN * 128), &tmK, &k_full[stage], pnl * 64, j * BN, h, b);
+        mbar_expect_tx(&v_full[stage], C::kVBytes);
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sV + pnl * (BN * 128), &tmV, &v_full[stage], pnl * 64, j * BN, h, b);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);  // S = Q K^T : both K-major
+      const uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);   // O = P V   : V is MN-major ([kv, d])
+      const uint32_t tS = tmem_base + C::kSCol, tO = tmem_base + C::kOCol;
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      auto issue_s = [&](int stage) {
+        const uint32_t aK = smem_u32(sKV + stage * (C::kKBytes + C::kVBytes));
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (C::kBM * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
+          tc_mma_ss(tS, da, db, idesc_s, kk != 0);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      tc_commit(s_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(p_full, j & 1);  // softmax consumed S_j and wrote P_j
+        mbar_wait(&v_full[stage], phase);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + stage * (C::kKBytes + C::kVBytes) + C::kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aP + (kk >> 2) * (C::kBM * 128) + (kk & 3) * 32, 16, 1024);
+          // MN-major V: 64-wide d atoms are BN*128 bytes apart (LBO), 8-row kv groups 1024 B apart (SBO)
+          const uint64_t db = umma_desc_sw128(aV + kk * 2048, BN * 128, 1024);
+          tc_mma_ss(tO, da, db, idesc_o, kk != 0);
+        }
+        tc_commit(o_full);
+        const int nstage = (stage + 1 == C::kStages) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == C::kStages) ? (phase ^ 1) : phase;
+        if (j + 1 < nblk) {
+          mbar_wait(&k_full[nstage], nphase);
+          tc_fence_after();
+          issue_s(nstage);
+          tc_commit(s_full);
+        }
+        tc_commit(&kv_empty[stage]);  // K_j and V_j are free once everything issued so far retires
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ---- softmax + accumulate: one query row per thread ----
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + C::kSCol + lane_off, tO = tmem_base + C::kOCol + lane_off;
+    float o_acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* p_row = sP + row * 128;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int n_valid = min(BN, p.N - j * BN);
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+      const float mb = m_new * p.scale_log2;
+      // pass 2: probabilities -> bf16 P tile (128B-swizzled K-major, 64-column panels)
+      float lsum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + c0, v);
+        tmem_wait_ld();
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(__uint_as_float(v[i]) * p.scale_log2 - mb);
+          pr[i] = (c0 + i < n_valid) ? e : 0.f;
+          lsum += pr[i];
+        }
+        uint8_t* panel = p_row + (c0 >> 6) * (C::kBM * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c0 & 63) >> 3) + q;  // 16-byte chunk inside the 128-byte row
+          uint4 u;
+          u.x = pack_bf16x2(pr[q * 8 + 0], pr[q * 8 + 1]);
+          u.y = pack_bf16x2(pr[q * 8 + 2], pr[q * 8 + 3]);
+          u.z = pack_bf16x2(pr[q * 8 + 4], pr[q * 8 + 5]);
+          u.w = pack_bf16x2(pr[q * 8 + 6], pr[q * 8 + 7]);
+          *reinterpret_cast<uint4*>(panel + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      tc_fence_before();
+      fence_proxy_async_smem();  // make the generic-proxy P writes visible to the tensor core
+      mbar_arrive(p_full);
+      // fold O_blk = P_j V_j into the running accumulator
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tO + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    const int m = m0 + row;
+    if (m < p.M) {
+      const float inv = 1.0f / l_run;
+      bf16* o = p.out + static_cast<long long>(b) * p.o_batch + static_cast<long long>(m) * p.o_row +
+                static_cast<long long>(h) * p.o_head;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(o_acc[c + 0] * inv, o_acc[c + 1] * inv);
+        u.y = pack_bf16x2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+        u.z = pack_bf16x2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
+        u.w = pack_bf16x2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(o + c) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int D>
+static int launch_attn(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
+                       const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
+                       cudaStream_t st) {
+  using C = AttnCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(flash_attn<%d>): %s", D, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t eb = 2;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(M), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t str[3] = {qs[0] * eb, qs[1] * eb, qs[2] * eb};
+    uint32_t box[4] = {64, static_cast<uint32_t>(C::kBM), 1, 1};
+    int rc = make_tmap_bf16(&tmQ, q, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint32_t box[4] = {64, static_cast<uint32_t>(C::kBN), 1, 1};
+    uint64_t strk[3] = {ks[0] * eb, ks[1] * eb, ks[2] * eb};
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, strk, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    uint64_t strv[3] = {vs[0] * eb, vs[1] * eb, vs[2] * eb};
+    rc = make_tmap_bf16(&tmV, v, 4, dims, strv, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.M = M; p.N = N; p.H = H; p.B = B;
+  p.o_row = os[0]; p.o_head = os[1]; p.o_batch = os[2];
+  p.out = static_cast<bf16*>(out);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((M + C::kBM - 1) / C::kBM, H, B);
+  flash_attn_kernel<D><<<grid, 192, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  return check_launch("flash_attn_kernel");
+}
+
+}  // namespace omgsr
+
+using namespace omgsr;
+
+extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int M,
+                                     int N, int D, long long q_row, long long q_head, long long q_batch,
+                                     long long k_row, long long k_head, long long k_batch, long long v_row,
+                                     long long v_head, long long v_batch, long long o_row, long long o_head,
+                                     long long o_batch, float scale, void* stream) {
+  if (B <= 0 || H <= 0 || M <= 0 || N <= 0) return set_error(OMGSR_ERR_SHAPE, "flash_attn: empty problem");
+  if (H > 65535 || B > 65535) return set_error(OMGSR_ERR_SHAPE, "flash_attn: H/B exceed grid limits");
+  const long long all = q_row | q_head | q_batch | k_row | k_head | k_batch | v_row | v_head | v_batch | o_row |
+                        o_head | o_batch;
+  if (all & 7) return set_error(OMGSR_ERR_ALIGN, "flash_attn: strides must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return set_error(OMGSR_ERR_ALIGN, "flash_attn: pointers must be 16-byte aligned");
+  const long long qs[3] = {q_row, q_head, q_batch}, ks[3] = {k_row, k_head, k_batch}, vs[3] = {v_row, v_head, v_batch},
+                  os[3] = {o_row, o_head, o_batch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 64) return launch_attn<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+  if (D == 128) return launch_attn<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+  return set_error(OMGSR_ERR_SHAPE, "flash_attn: head dim %d unsupported (64 or 128)", D);
+}

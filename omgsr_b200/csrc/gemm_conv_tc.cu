@@ -1,0 +1,568 @@
+// Implicit-GEMM convolution / linear layer / batched attention GEMM on the 5th-gen tensor cores
+// (tcgen05 + TMEM), fed by TMA.
+//
+//   D[pixel, cout] = epilogue( sum_{tap, cin} A[pixel + tap, cin] * Wt[cout, tap*Cin + cin] )
+//
+// * Activations are NHWC bf16. The A operand of a 128-pixel tile for one (tap, 64-channel slice) is ONE
+//   TMA box {64 ch, tw, th, tb} of the input tensor shifted by the tap offset; TMA's out-of-bounds zero
+//   fill implements the convolution padding, so no im2col buffer is ever materialised. The box lands in
+//   shared memory as 128 rows x 128 B with the 128-byte swizzle, which is exactly the K-major UMMA
+//   operand layout. Stride-2 convolutions use a 5-D space-to-depth view of the same tensor
+//   {2C, W/2, 2, H/2, B}; nearest-2x-upsample + 3x3 is algebraically collapsed on the host into four
+//   2x2 convolutions (one per output parity) and uses the stride-1 path with strided output addressing.
+// * Weights are [Cout, R*S*Cin] bf16 (K-major), one TMA box {64, BN} per k-block. For the batched
+//   attention GEMMs the B operand is a per-(batch, head) matrix, either K-major (Q K^T) or MN-major
+//   (P V, V read in place as [kv, d]).
+// * Warp-specialised persistent kernel, one CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer
+//   (single elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=16), warps 2..5 = epilogue
+//   (tcgen05.ld -> bias/activation/gate/residual -> bf16|f32 -> global). smem ring of kStages, two TMEM
+//   accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Replaces the cuDNN / cuBLAS calls underneath diffusers' Conv2d / Linear modules that the reference
+// reaches from infer/omgsr_s_infer_model.py:75-84,173 and infer/omgsr_f_infer_model.py:16,191-211.
+#include "common.cuh"
+#include "../../include/omgsr_b200.h"
+
+namespace omgsr {
+
+struct ConvGemmParams {
+  int tiles_x, tiles_y, tiles_b;  // tile grid over (W, H, B) of the GEMM-side pixel space
+  int log_tw, log_th;             // tile extents are powers of two, tw*th*tb == 128
+  int W, H, B;                    // GEMM-side pixel extents
+  int n_tiles, Cout;
+  int kc_per_tap, R, S, pad_t, pad_l;
+  int stride2, Cin;
+  int b_batched;                  // B operand has (head, batch) coordinates taken from the tile (y, b)
+  int b_mn_major;                 // B operand is [K, N] row-major (attention P*V)
+  long long o_sx, o_sy, o_sb;     // output element strides per GEMM-side x / y / b
+  long long r_sx, r_sy, r_sb;     // residual strides
+  void* out;
+  const float* bias;   // [Cout] or null
+  const bf16* res;     // or null
+  const float* gate;   // [B or M/gate_rows, Cout_out] or null
+  int gate_rows;       // linear mode: rows per gate vector (tokens per image)
+  int act;             // OMGSR_ACT_*
+  int out_f32;
+  int a_bytes;         // bytes one A box delivers (tb may be clamped to B)
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kThreads = 192;
+constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
+
+template <int BN>
+struct Cfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case OMGSR_ACT_SILU: return silu_f(v);
+    case OMGSR_ACT_GELU_ERF: return gelu_erf_f(v);
+    case OMGSR_ACT_GELU_TANH: return gelu_tanh_f(v);
+    default: return v;
+  }
+}
+
+struct TileCoord {
+  int n_tile, tx, ty, tbi;
+};
+__device__ __forceinline__ TileCoord decode_tile(int tile, const ConvGemmParams& p) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  const int m = tile / p.n_tiles;
+  t.tx = m % p.tiles_x;
+  t.ty = (m / p.tiles_x) % p.tiles_y;
+  t.tbi = m / (p.tiles_x * p.tiles_y);
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const ConvGemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;                        // [kStages]
+  uint64_t* empty_bar = bars + C::kStages;          // [kStages]
+  uint64_t* acc_full = bars + 2 * C::kStages;       // [2]
+  uint64_t* acc_empty = bars + 2 * C::kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+  const int num_kb = p.R * p.S * p.kc_per_tap;
+  const int tw = 1 << p.log_tw, th = 1 << p.log_th;
+  const int tb = kBM >> (p.log_tw + p.log_th);
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(tile, p);
+        const int x0 = t.tx * tw, y0 = t.ty * th, b0 = t.tbi * tb;
+        const int bh = p.b_batched ? t.ty : 0, bb = p.b_batched ? t.tbi : 0;
+        int kb = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            int c1, c2, c3, c4, cbase;
+            if (!p.stride2) {
+              cbase = 0;
+              c1 = x0 + s - p.pad_l;
+              c2 = y0 + r - p.pad_t;
+              c3 = b0;
+              c4 = 0;
+            } else {
+              // input (iy, ix) = (2*oy + r - pad_t, 2*ox + s - pad_l) in the {2C, W/2, 2, H/2, B} view
+              const int dy = r - p.pad_t, dx = s - p.pad_l;
+              const int py = dy & 1, px = dx & 1;
+              cbase = px * p.Cin;
+              c1 = x0 + ((dx - px) >> 1);
+              c2 = py;
+              c3 = y0 + ((dy - py) >> 1);
+              c4 = b0;
+            }
+            for (int kc = 0; kc < p.kc_per_tap; ++kc, ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * C::kStageBytes;
+              uint8_t* sb = sa + C::kABytes;
+              mbar_expect_tx(&full_bar[stage], p.a_bytes + C::kBBytes);
+              tma_load_5d(sa, &tmA, &full_bar[stage], cbase + kc * kBK, c1, c2, c3, c4);
+              if (!p.b_mn_major) {
+                tma_load_4d(sb, &tmB, &full_bar[stage], kb * kBK, t.n_tile * BN, bh, bb);
+              } else {
+                // [K, N] row-major operand: one {64 n, 64 k} box per 64-wide N atom
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_4d(sb + j * (64 * kBK * 2), &tmB, &full_bar[stage], t.n_tile * BN + j * 64, kb * kBK, bh,
+                              bb);
+              }
+              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, p.b_mn_major);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+          if (!p.b_mn_major) {
+            const uint64_t db = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              tc_mma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+          } else {
+            // MN-major SW128: atoms of {64 n x 8 k}; LBO = next 64-wide N atom, SBO = next 8 k-rows
+            const uint64_t db = umma_desc_sw128(sb, 64 * kBK * 2, 1024);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // 16 k-rows = two 1024-byte row groups: +128 in the (addr >> 4) field
+              tc_mma_ss(d_tmem, da + 2 * k, db + 128 * k, idesc, (kb | k) != 0);
+            }
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&acc_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;  // accumulator row == pixel index inside the tile
+    const int xl = row & (tw - 1);
+    const int yl = (row >> p.log_tw) & (th - 1);
+    const int bl = row >> (p.log_tw + p.log_th);
+    const bool geglu = (p.act == OMGSR_ACT_GEGLU);
+    const int out_bn = geglu ? BN / 2 : BN;
+    const int cout_out = geglu ? p.Cout / 2 : p.Cout;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(tile, p);
+      const int x = t.tx * tw + xl, y = t.ty * th + yl, b = t.tbi * tb + bl;
+      const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
+      const long long o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+      const bf16* res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+      const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : b) : 0;
+      const float* gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * cout_out : nullptr;
+
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < out_bn; c0 += 32) {
+        uint32_t v[32];
+        float f[32];
+        tmem_ld32(t_row + c0, v);
+        if (geglu) {
+          uint32_t g[32];
+          tmem_ld32(t_row + BN / 2 + c0, g);
+          tmem_wait_ld();
+          const int cv = t.n_tile * BN + c0;           // value column in the (row-permuted) weight
+          const int cg = t.n_tile * BN + BN / 2 + c0;  // gate column
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + cv + j) : 0.f);
+            float gg = __uint_as_float(g[j]) + (p.bias ? __ldg(p.bias + cg + j) : 0.f);
+            f[j] = a * gelu_erf_f(gg);
+          }
+        } else {
+          tmem_wait_ld();
+          const int cv = t.n_tile * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(v[j]);
+            if (p.bias) a += __ldg(p.bias + min(cv + j, p.Cout - 1));
+            f[j] = apply_act(a, p.act);
+          }
+        }
+        const int oc0 = t.n_tile * out_bn + c0;  // first output channel of this chunk
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {  // 4 x 8 channels
+            const int oc = oc0 + q * 8;
+            if (oc < cout_out) {
+              float* ff = f + q * 8;
+              if (gate_row) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ff[j] *= __ldg(gate_row + oc + j);
+              }
+              if (res_row) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res_row + oc);
+                const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                             r3 = unpack_bf16x2(rr.w);
+                ff[0] += r0.x; ff[1] += r0.y; ff[2] += r1.x; ff[3] += r1.y;
+                ff[4] += r2.x; ff[5] += r2.y; ff[6] += r3.x; ff[7] += r3.y;
+              }
+              if (p.out_f32) {
+                float* o = static_cast<float*>(p.out) + o_off + oc;
+                *reinterpret_cast<float4*>(o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(ff[4], ff[5], ff[6], ff[7]);
+              } else {
+                uint4 o;
+                o.x = pack_bf16x2(ff[0], ff[1]);
+                o.y = pack_bf16x2(ff[2], ff[3]);
+                o.z = pack_bf16x2(ff[4], ff[5]);
+                o.w = pack_bf16x2(ff[6], ff[7]);
+                *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_off + oc) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+template <int BN>
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  conv_gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmB, p);
+  return check_launch("conv_gemm_tc_kernel");
+}
+
+static int pick_bn(int Cout, long long m_tiles, int forced, bool geglu, bool mn_major) {
+  if (forced > 0) return forced;
+  if (mn_major) return (Cout % 128 == 0) ? 128 : 64;
+  const int cands[4] = {256, 160, 128, 64};
+  // widest tile that divides Cout and still gives every SM a tile; otherwise the narrowest divisor
+  int narrowest = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (Cout % bn) continue;
+    if (geglu && (bn % 64)) continue;
+    narrowest = bn;
+    if (m_tiles * (Cout / bn) >= sm_count()) return bn;
+  }
+  if (narrowest) return narrowest;
+  return 64;  // ragged Cout: 64-wide tiles, last one masked
+}
+
+struct ConvDesc {
+  const void* x; const void* w; const float* bias; const void* res; const float* gate; void* y;
+  int B, H, W;   // GEMM-side pixel space (== output pixels enumerated by the kernel)
+  int IH, IW;    // input tensor spatial extents
+  int Cin, Cout, R, S, stride2, pad_t, pad_l;
+  long long x_sx, x_sy, x_sb;  // input element strides per x / y / b (stride-1 path)
+  long long o_sx, o_sy, o_sb, r_sx, r_sy, r_sb;
+  int act, gate_rows, force_bn, out_f32;
+  long long w_ld;  // elements per weight row (R*S*Cin)
+  // batched B operand (attention)
+  int b_batched, b_mn_major, flat;
+  long long b_row, b_head, b_batch;
+  int b_rows;  // rows of the B matrix (N for K-major, K for MN-major)
+};
+
+static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
+  if (d.Cin % kBK) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: K/Cin=%d must be a multiple of %d", d.Cin, kBK);
+  if ((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.w) | reinterpret_cast<uintptr_t>(d.y) |
+       reinterpret_cast<uintptr_t>(d.res)) & 15)
+    return set_error(OMGSR_ERR_ALIGN, "conv_gemm: pointers must be 16-byte aligned");
+  if ((d.x_sx | d.x_sy | d.x_sb | d.o_sx | d.o_sy | d.o_sb | d.r_sx | d.r_sy | d.r_sb | d.w_ld) & 7)
+    return set_error(OMGSR_ERR_ALIGN, "conv_gemm: strides must be multiples of 8 elements");
+  const bool geglu = d.act == OMGSR_ACT_GEGLU;
+
+  // tile shape {tw, th, tb} (powers of two, product 128): minimise the padded pixel count, prefer wide rows
+  int tw = 128, th = 1, tb = 1;
+  if (!d.flat) {
+    long long best = -1;
+    for (int c = 128; c >= 1; c >>= 1) {
+      if (c > d.W && c > 1) continue;
+      int h = 128 / c;
+      while (h > 1 && h > d.H) h >>= 1;
+      const int nb = 128 / (c * h);
+      const long long cost = static_cast<long long>((d.W + c - 1) / c) * c * ((d.H + h - 1) / h) * h *
+                             ((d.B + nb - 1) / nb) * nb;
+      if (best < 0 || cost < best) { best = cost; tw = c; th = h; tb = nb; }
+    }
+  }
+  // never ask TMA for a box larger than the tensor along the batch axis; the unused accumulator rows
+  // are masked in the epilogue
+  const int tb_box = tb > d.B ? d.B : tb;
+
+  ConvGemmParams p;
+  p.log_tw = ilog2(tw); p.log_th = ilog2(th);
+  p.tiles_x = (d.W + tw - 1) / tw; p.tiles_y = (d.H + th - 1) / th; p.tiles_b = (d.B + tb - 1) / tb;
+  p.W = d.W; p.H = d.H; p.B = d.B;
+  p.Cout = d.Cout; p.kc_per_tap = d.Cin / kBK; p.R = d.R; p.S = d.S; p.pad_t = d.pad_t; p.pad_l = d.pad_l;
+  p.stride2 = d.stride2; p.Cin = d.Cin;
+  p.b_batched = d.b_batched; p.b_mn_major = d.b_mn_major;
+  p.o_sx = d.o_sx; p.o_sy = d.o_sy; p.o_sb = d.o_sb; p.r_sx = d.r_sx; p.r_sy = d.r_sy; p.r_sb = d.r_sb;
+  p.out = d.y; p.bias = d.bias; p.res = static_cast<const bf16*>(d.res);
+  p.gate = d.gate; p.gate_rows = d.gate_rows; p.act = d.act; p.out_f32 = d.out_f32;
+  p.a_bytes = kBK * 2 * tw * th * tb_box;
+
+  const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_b;
+  const int bn = pick_bn(d.Cout, m_tiles, d.force_bn, geglu, d.b_mn_major);
+  if (bn != 256 && bn != 160 && bn != 128 && bn != 64) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: BN=%d", bn);
+  if (geglu && ((bn % 64) || (d.Cout % bn)))
+    return set_error(OMGSR_ERR_SHAPE, "conv_gemm: GEGLU needs Cout %% BN == 0 and BN %% 64 == 0");
+  if (d.b_mn_major && bn != 64 && bn != 128)
+    return set_error(OMGSR_ERR_SHAPE, "conv_gemm: MN-major B needs BN in {64,128}");
+  if ((d.Cout % 8) && d.o_sx < ((d.Cout + 7) & ~7))
+    // ragged Cout: the 8-channel store granule writes up to the next multiple of 8
+    return set_error(OMGSR_ERR_SHAPE, "conv_gemm: Cout=%d needs an output row stride >= %d", d.Cout,
+                     (d.Cout + 7) & ~7);
+  p.n_tiles = (d.Cout + bn - 1) / bn;
+  if (m_tiles * p.n_tiles > 0x7fffffffLL) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: too many tiles");
+
+  // ---- tensor maps ----
+  CUtensorMap tmA, tmB;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  const uint64_t eb = 2;
+  if (!d.stride2) {
+    dims[0] = d.Cin; dims[1] = d.IW; dims[2] = d.IH; dims[3] = d.B; dims[4] = 1;
+    strides[0] = d.x_sx * eb; strides[1] = d.x_sy * eb; strides[2] = d.x_sb * eb;
+    strides[3] = strides[2] * d.B;
+    box[0] = kBK; box[1] = tw; box[2] = th; box[3] = tb_box; box[4] = 1;
+  } else {
+    if ((d.IW & 1) || (d.IH & 1)) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: stride-2 needs even input extents");
+    if (d.x_sx != d.Cin || d.x_sy != d.x_sx * d.IW || d.x_sb != d.x_sy * d.IH)
+      return set_error(OMGSR_ERR_SHAPE, "conv_gemm: stride-2 needs a dense NHWC input");
+    dims[0] = 2 * d.Cin; dims[1] = d.IW / 2; dims[2] = 2; dims[3] = d.IH / 2; dims[4] = d.B;
+    strides[0] = 2 * d.Cin * eb;                            // next even x
+    strides[1] = static_cast<uint64_t>(d.IW) * d.Cin * eb;  // next row parity
+    strides[2] = 2 * strides[1];                            // next even y
+    strides[3] = strides[1] * d.IH;                         // next image
+    box[0] = kBK; box[1] = tw; box[2] = 1; box[3] = th; box[4] = tb_box;
+  }
+  int rc = make_tmap_bf16(&tmA, d.x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  uint64_t wd[4], ws[3];
+  uint32_t wb[4];
+  if (!d.b_batched) {
+    wd[0] = d.w_ld; wd[1] = d.Cout; wd[2] = 1; wd[3] = 1;
+    ws[0] = d.w_ld * eb; ws[1] = ws[0] * d.Cout; ws[2] = ws[1];
+    wb[0] = kBK; wb[1] = bn; wb[2] = 1; wb[3] = 1;
+  } else if (!d.b_mn_major) {
+    wd[0] = d.Cin; wd[1] = d.b_rows; wd[2] = d.H; wd[3] = d.B;
+    ws[0] = d.b_row * eb; ws[1] = d.b_head * eb; ws[2] = d.b_batch * eb;
+    wb[0] = kBK; wb[1] = bn; wb[2] = 1; wb[3] = 1;
+  } else {
+    wd[0] = d.Cout; wd[1] = d.b_rows; wd[2] = d.H; wd[3] = d.B;
+    ws[0] = d.b_row * eb; ws[1] = d.b_head * eb; ws[2] = d.b_batch * eb;
+    wb[0] = 64; wb[1] = kBK; wb[2] = 1; wb[3] = 1;
+  }
+  rc = make_tmap_bf16(&tmB, d.w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+
+  switch (bn) {
+    case 256: return launch_cfg<256>(tmA, tmB, p, st);
+    case 160: return launch_cfg<160>(tmA, tmB, p, st);
+    case 128: return launch_cfg<128>(tmA, tmB, p, st);
+    default: return launch_cfg<64>(tmA, tmB, p, st);
+  }
+}
+
+}  // namespace omgsr
+
+using namespace omgsr;
+
+extern "C" int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias, const void* res, const float* gate,
+                               void* D, long long M, int N, int K, long long lda, long long ldd, long long ldr,
+                               int act, int gate_rows, int flags, int force_bn, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(OMGSR_ERR_SHAPE, "gemm: empty problem");
+  if (M > 0x7fffffffLL) return set_error(OMGSR_ERR_SHAPE, "gemm: M too large");
+  if (gate && gate_rows <= 0) return set_error(OMGSR_ERR_SHAPE, "gemm: gate needs gate_rows > 0");
+  ConvDesc d{};
+  d.x = A; d.w = Wt; d.bias = bias; d.res = res; d.gate = gate; d.y = D;
+  d.B = 1; d.H = 1; d.W = static_cast<int>(M); d.IH = 1; d.IW = static_cast<int>(M);
+  d.Cin = K; d.Cout = N; d.R = 1; d.S = 1;
+  d.x_sx = lda; d.x_sy = lda * M; d.x_sb = lda * M;
+  d.o_sx = ldd; d.o_sy = 0; d.o_sb = 0; d.r_sx = ldr; d.r_sy = 0; d.r_sb = 0;
+  d.act = act; d.gate_rows = gate ? gate_rows : 0; d.force_bn = force_bn; d.w_ld = K;
+  d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
+  d.flat = 1;
+  return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batch, int heads, int M, int N, int K,
+                                long long a_row, long long a_head, long long a_batch, long long b_row,
+                                long long b_head, long long b_batch, long long d_row, long long d_head,
+                                long long d_batch, int flags, int force_bn, void* stream) {
+  if (batch <= 0 || heads <= 0 || M <= 0 || N <= 0 || K <= 0)
+    return set_error(OMGSR_ERR_SHAPE, "bgemm: empty problem");
+  if ((b_row | b_head | b_batch) & 7) return set_error(OMGSR_ERR_ALIGN, "bgemm: B strides must be multiples of 8");
+  ConvDesc d{};
+  d.x = A; d.w = Bm; d.y = D;
+  d.B = batch; d.H = heads; d.W = M; d.IH = heads; d.IW = M;
+  d.Cin = K; d.Cout = N; d.R = 1; d.S = 1;
+  d.x_sx = a_row; d.x_sy = a_head; d.x_sb = a_batch;
+  d.o_sx = d_row; d.o_sy = d_head; d.o_sb = d_batch;
+  d.force_bn = force_bn; d.w_ld = 8;
+  d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
+  d.flat = 1; d.b_batched = 1; d.b_mn_major = (flags & OMGSR_B_MN_MAJOR) ? 1 : 0;
+  d.b_row = b_row; d.b_head = b_head; d.b_batch = b_batch;
+  d.b_rows = d.b_mn_major ? K : N;
+  return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* res, void* y,
+                                      int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad_t,
+                                      int pad_l, int pad_b, int pad_r, int upsample2x, int act, long long ldx,
+                                      long long ldy, long long ldr, int flags, int force_bn, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: empty problem");
+  if (ksize != 1 && ksize != 3) return set_error(OMGSR_ERR_SHAPE, "conv2d: ksize must be 1 or 3");
+  if (stride != 1 && stride != 2) return set_error(OMGSR_ERR_SHAPE, "conv2d: stride must be 1 or 2");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvDesc d{};
+  d.x = x; d.bias = bias; d.res = res; d.y = y;
+  d.B = B; d.IH = H; d.IW = W; d.Cin = Cin; d.Cout = Cout;
+  d.x_sx = ldx; d.x_sy = ldx * W; d.x_sb = ldx * W * H;
+  d.act = act; d.force_bn = force_bn; d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
+  if (upsample2x) {
+    // nearest-2x + 3x3/p1 == four 2x2 convolutions on the un-upsampled input (weights pre-collapsed
+    // per output parity by the packer): out(2i+py, 2j+px).
+    if (ksize != 3 || stride != 1 || pad_t != 1 || pad_l != 1)
+      return set_error(OMGSR_ERR_SHAPE, "conv2d: upsample2x fusion needs 3x3 stride 1 pad 1");
+    d.H = H; d.W = W; d.R = 2; d.S = 2; d.w_ld = 4LL * Cin;
+    const long long OW = 2LL * W, OH = 2LL * H;
+    d.o_sx = 2 * ldy; d.o_sy = 2 * OW * ldy; d.o_sb = OH * OW * ldy;
+    d.r_sx = 2 * ldr; d.r_sy = 2 * OW * ldr; d.r_sb = OH * OW * ldr;
+    const size_t esz = d.out_f32 ? 4 : 2;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        d.w = static_cast<const bf16*>(w) + static_cast<long long>(py * 2 + px) * Cout * d.w_ld;
+        d.pad_t = 1 - py; d.pad_l = 1 - px;
+        const long long shift = py * OW + px;
+        d.y = static_cast<char*>(y) + shift * ldy * esz;
+        d.res = res ? static_cast<const bf16*>(res) + shift * ldr : nullptr;
+        int rc = run_conv_gemm(d, st);
+        if (rc) return rc;
+      }
+    return OMGSR_OK;
+  }
+  const int OHh = (H + pad_t + pad_b - ksize) / stride + 1;
+  const int OWw = (W + pad_l + pad_r - ksize) / stride + 1;
+  if (OHh <= 0 || OWw <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: empty output");
+  d.w = w; d.H = OHh; d.W = OWw; d.R = ksize; d.S = ksize; d.stride2 = (stride == 2);
+  d.pad_t = pad_t; d.pad_l = pad_l;
+  d.o_sx = ldy; d.o_sy = ldy * OWw; d.o_sb = ldy * OWw * OHh;
+  d.r_sx = ldr; d.r_sy = ldr * OWw; d.r_sb = ldr * OWw * OHh;
+  d.w_ld = static_cast<long long>(ksize) * ksize * Cin;
+  return run_conv_gemm(d, st);
+}

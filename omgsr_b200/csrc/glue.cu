@@ -1,0 +1,660 @@
+// HBM-bound glue kernels of the OMGSR inference path: GroupNorm(+SiLU), LayerNorm(+AdaLN modulation),
+// row softmax, FLUX RMSNorm+RoPE, thin convolutions at the NCHW module boundary, latent-sized
+// elementwise steps, 2x2 pack/unpack, Gaussian tile blend, layout changes.
+// All of them are vectorised (16-byte accesses), warp-reduced and sized in multiples of the SM count.
+#include "common.cuh"
+#include "../../include/omgsr_b200.h"
+
+namespace omgsr {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[b, g] = (sum, sumsq). Thread owns one 8-channel vector column and walks
+// pixels; per-channel partials are folded into per-group shared bins, then one global atomic per bin.
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ stats, long long HW,
+                                int C, int G, int vpr, int rows_per_iter, int blocks_per_img) {
+  extern __shared__ float bins[];  // [G*2]
+  const int b = blockIdx.x / blocks_per_img;
+  const int blk = blockIdx.x % blocks_per_img;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) bins[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (threadIdx.x < vpr * rows_per_iter) {
+    const bf16* base = x + static_cast<long long>(b) * HW * ldx + v * 8;
+    for (long long r = static_cast<long long>(blk) * rows_per_iter + r0; r < HW;
+         r += static_cast<long long>(blocks_per_img) * rows_per_iter) {
+      float f[8];
+      unpack8(ld_stream(base + r * ldx), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    }
+    const int cpg = C / G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cpg;
+      atomicAdd(&bins[2 * g], s[j]);
+      atomicAdd(&bins[2 * g + 1], q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[static_cast<long long>(b) * 2 * G + i], bins[i]);
+}
+
+// y = (x - mean) * rstd * gamma + beta (+SiLU). One thread = one 8-channel vector of one pixel.
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, long long HW, int C, int G, float eps, int silu,
+                                int vpr, long long total_vec) {
+  const int cpg = C / G;
+  const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpr);
+    const long long pix = i / vpr;       // b*HW + p
+    const int b = static_cast<int>(pix / HW);
+    float f[8];
+    unpack8(ld_stream(x + pix * ldx + v * 8), f);
+    const float* st = stats + static_cast<long long>(b) * 2 * G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const int g = c / cpg;
+      const float mean = st[2 * g] * inv_n;
+      const float var = fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float o = (f[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      f[j] = silu ? silu_f(o) : o;
+    }
+    *reinterpret_cast<uint4*>(y + pix * ldy + v * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row; the row is cached in registers (C <= 4096).
+// ------------------------------------------------------------------------------------------------
+template <int VPL>  // 8-element vectors per lane
+__global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, long long rows, int C, float eps,
+                                 long long rows_per_batch, long long gb_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = C / 8;
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    float f[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        unpack8(ld_stream(x + row * C + v * 8), f[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[i][j];
+      }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    const long long gb = (rows_per_batch > 0 ? (row / rows_per_batch) : 0) * gb_stride;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float o = (f[i][j] - mean) * rstd;
+          if (gamma) o *= __ldg(gamma + gb + v * 8 + j);
+          if (beta) o += __ldg(beta + gb + v * 8 + j);
+          f[i][j] = o;
+        }
+        *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(f[i]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax of fp32 scores -> bf16 probabilities (one block per row, scores re-read from L2).
+// ------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s, bf16* __restrict__ P, long long ld_p,
+                                    int n, int n_pad, float scale_log2e) {
+  __shared__ float red[32];
+  const float* s = S + blockIdx.x * ld_s;
+  bf16* p = P + blockIdx.x * ld_p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, s[j]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = (lane < nw) ? red[lane] : -INFINITY;
+  m = warp_max(m);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sum += exp2f((s[j] - m) * scale_log2e);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = (lane < nw) ? red[lane] : 0.f;
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int j = threadIdx.x; j < n_pad; j += blockDim.x)
+    p[j] = __float2bfloat16(j < n ? exp2f((s[j] - m) * scale_log2e) * inv : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FLUX: per-head RMSNorm (d = 128) + rotary embedding on q or k, in place. One warp per (row, head):
+// lane owns 4 consecutive channels = 2 rotation pairs.
+// ------------------------------------------------------------------------------------------------
+__global__ void rmsnorm_rope_kernel(bf16* __restrict__ x, long long ld, const float* __restrict__ weight,
+                                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                    long long rows, int heads, long long rows_per_batch, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long it = wg; it < rows * heads; it += nw) {
+    const long long row = it / heads;
+    const int h = static_cast<int>(it % heads);
+    bf16* px = x + row * ld + h * 128 + lane * 4;
+    const uint2 u = *reinterpret_cast<const uint2*>(px);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    float ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss * (1.0f / 128.f) + eps);
+    const float4 w = *reinterpret_cast<const float4*>(weight + lane * 4);
+    const float v0 = a.x * r * w.x, v1 = a.y * r * w.y, v2 = b.x * r * w.z, v3 = b.y * r * w.w;
+    const long long pos = row % rows_per_batch;
+    const float4 c = *reinterpret_cast<const float4*>(cos_t + pos * 128 + lane * 4);
+    const float4 s = *reinterpret_cast<const float4*>(sin_t + pos * 128 + lane * 4);
+    uint2 o;
+    o.x = pack_bf16x2(v0 * c.x - v1 * s.x, v1 * c.y + v0 * s.y);
+    o.y = pack_bf16x2(v2 * c.z - v3 * s.z, v3 * c.w + v2 * s.w);
+    *reinterpret_cast<uint2*>(px) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_in: NCHW (bf16|f32) -> NHWC bf16, Cin <= 16, 1x1 or 3x3 'same'. Thread = (pixel, 8 out channels).
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void conv_in_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               bf16* __restrict__ y, int B, int Cin, int H, int W, int Cout, int ks, long long ldy,
+                               int cg, long long total) {
+  const int pad = ks / 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    const long long pix = i / cg;
+    const int xx = static_cast<int>(pix % W);
+    const int yy = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? __ldg(bias + g * 8 + j) : 0.f;
+    for (int r = 0; r < ks; ++r) {
+      const int iy = yy + r - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < ks; ++s) {
+        const int ix = xx + s - pad;
+        if (ix < 0 || ix >= W) continue;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = static_cast<float>(x[((static_cast<long long>(b) * Cin + ci) * H + iy) * W + ix]);
+          const float* wp = w + (static_cast<long long>((r * ks + s) * Cin + ci)) * Cout + g * 8;
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+          acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
+          acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(y + pix * ldy + g * 8) = pack8(acc);
+  }
+}
+
+// conv_out: NHWC bf16 -> NCHW, Cout <= 4, 3x3 p1. Weights (bf16 [Cout, 9*Cin]) staged in smem as fp32.
+template <int COUT, typename TOut>
+__global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
+                                TOut* __restrict__ y, int B, int H, int W, int Cin, int clamp, long long ldx,
+                                long long total) {
+  extern __shared__ float ws[];  // [COUT][9*Cin]
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) ws[i] = __bfloat162float(w[i]);
+  __syncthreads();
+  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(pix % W);
+    const int yy = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = bias ? __ldg(bias + co) : 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const int iy = yy + r - 1;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int ix = xx + s - 1;
+        if (ix < 0 || ix >= W) continue;
+        const bf16* px = x + ((static_cast<long long>(b) * H + iy) * W + ix) * ldx;
+        const float* wk = ws + (r * 3 + s) * Cin;
+        for (int c = 0; c < Cin; c += 8) {
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(px + c)), f);
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wk + co * K + c);
+            const float4 w1 = *reinterpret_cast<const float4*>(wk + co * K + c + 4);
+            acc[co] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                       f[6] * w1.z + f[7] * w1.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      float v = acc[co];
+      if (clamp) v = fminf(fmaxf(v, -1.f), 1.f);
+      y[((static_cast<long long>(b) * COUT + co) * H + yy) * W + xx] = static_cast<TOut>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// latent-sized elementwise steps
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void posterior_kernel(const float* __restrict__ mom, long long ldm, const float* __restrict__ eps,
+                                 TOut* __restrict__ z, int Cz, long long hw, long long total, float shift,
+                                 float scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i % hw;
+    const int c = static_cast<int>((i / hw) % Cz);
+    const long long b = i / (hw * Cz);
+    const float* m = mom + (b * hw + p) * ldm;
+    const float mean = m[c];
+    const float logvar = fminf(fmaxf(m[Cz + c], -30.f), 20.f);
+    const float v = mean + __expf(0.5f * logvar) * eps[i];
+    z[i] = static_cast<TOut>((v - shift) * scale);
+  }
+}
+
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, long long n,
+                             float a, float b, float c) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = a * static_cast<float>(x[i]) + c;
+    if (y) v += b * static_cast<float>(y[i]);
+    out[i] = static_cast<T>(v);
+  }
+}
+
+template <typename TZ>
+__global__ void x0_unscale_kernel(const TZ* __restrict__ z, const float* __restrict__ eh, long long lde,
+                                  bf16* __restrict__ out, const float* __restrict__ Wpq, const float* __restrict__ bpq,
+                                  int Cz, long long hw, long long total_pix, float s1, float inv_s2, float inv_scale,
+                                  float shift) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_pix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / hw, p = i % hw;
+    float z0[16];
+    for (int c = 0; c < Cz; ++c) {
+      const float zz = static_cast<float>(z[(b * Cz + c) * hw + p]);
+      z0[c] = (zz - s1 * eh[i * lde + c]) * inv_s2 * inv_scale + shift;
+    }
+    for (int co = 0; co < Cz; ++co) {
+      float v;
+      if (Wpq) {
+        v = bpq ? bpq[co] : 0.f;
+        for (int c = 0; c < Cz; ++c) v += Wpq[co * Cz + c] * z0[c];
+      } else {
+        v = z0[co];
+      }
+      out[(b * Cz + co) * hw + p] = __float2bfloat16(v);
+    }
+  }
+}
+
+// FLUX 2x2 pack: tokens[b, (y/2)(w/2) + x/2, c*4 + dy*2 + dx] = z[b, c, y, x]
+__global__ void pack_kernel(const bf16* __restrict__ z, bf16* __restrict__ tok, int C, int h, int w, long long ld,
+                            long long total, int unpack) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    const int y = static_cast<int>((i / w) % h);
+    const int c = static_cast<int>((i / (static_cast<long long>(w) * h)) % C);
+    const long long b = i / (static_cast<long long>(w) * h * C);
+    const long long t = b * (h / 2) * (w / 2) + static_cast<long long>(y / 2) * (w / 2) + x / 2;
+    bf16* tp = tok + t * ld + c * 4 + (y & 1) * 2 + (x & 1);
+    if (unpack) const_cast<bf16*>(z)[i] = *tp; else *tp = z[i];
+  }
+}
+
+// out[b,c,y,x] = sum_t w[y-oy_t, x-ox_t] * tile_t[b,c,y-oy_t,x-ox_t] / sum_t w[...]
+template <typename T>
+__global__ void tile_blend_kernel(const T* __restrict__ tiles, const float* __restrict__ wts,
+                                  const int* __restrict__ ofs, int ntiles, float* __restrict__ out, int B, int C, int h,
+                                  int w, int T_, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    const int y = static_cast<int>((i / w) % h);
+    const int c = static_cast<int>((i / (static_cast<long long>(w) * h)) % C);
+    const int b = static_cast<int>(i / (static_cast<long long>(w) * h * C));
+    float num = 0.f, den = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+      const int tx = x - ofs[2 * t], ty = y - ofs[2 * t + 1];
+      if (tx < 0 || ty < 0 || tx >= T_ || ty >= T_) continue;
+      const float wv = wts[ty * T_ + tx];
+      num += wv * static_cast<float>(tiles[(((static_cast<long long>(t) * B + b) * C + c) * T_ + ty) * T_ + tx]);
+      den += wv;
+    }
+    out[i] = num / den;
+  }
+}
+
+// layout changes through a 32x32 smem tile
+template <typename TIn>
+__global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, int C, long long HW, long long ldy) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = blockIdx.x * 32LL;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? static_cast<float>(x[(b * C + c) * HW + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int c = c0 + threadIdx.x;
+    if (c < C && p < HW) y[(b * HW + p) * ldy + c] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+template <typename TOut>
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, long long ldx, TOut* __restrict__ y, int C,
+                                    long long HW) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = blockIdx.x * 32LL;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(x[(b * HW + p) * ldx + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    if (c < C && p < HW) y[(b * C + c) * HW + p] = static_cast<TOut>(tile[threadIdx.x][j]);
+  }
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace omgsr
+
+using namespace omgsr;
+
+extern "C" int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats, int B, long long HW, int C, int G,
+                                     void* stream) {
+  if (C % 8 || C % G || G > 512 || C / 8 > 1024) return set_error(OMGSR_ERR_SHAPE, "groupnorm_stats: C=%d G=%d", C, G);
+  if (ldx % 8) return set_error(OMGSR_ERR_ALIGN, "groupnorm_stats: ldx %% 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * B, st);
+  if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "groupnorm_stats memset: %s", cudaGetErrorString(e));
+  const int vpr = C / 8;
+  int rows_per_iter = 256 / vpr;
+  if (rows_per_iter < 1) rows_per_iter = 1;
+  const int threads = ((vpr * rows_per_iter + 31) / 32) * 32;
+  long long bpi = (static_cast<long long>(sm_count()) * 8 + B - 1) / B;
+  const long long max_bpi = (HW + rows_per_iter - 1) / rows_per_iter;
+  if (bpi > max_bpi) bpi = max_bpi;
+  if (bpi < 1) bpi = 1;
+  gn_stats_kernel<<<static_cast<unsigned>(bpi * B), threads, 2 * G * sizeof(float), st>>>(
+      static_cast<const bf16*>(x), ldx, stats, HW, C, G, vpr, rows_per_iter, static_cast<int>(bpi));
+  return check_launch("gn_stats_kernel");
+}
+
+extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,
+                                     const float* gamma, const float* beta, int B, long long HW, int C, int G,
+                                     float eps, int silu, void* stream) {
+  if (C % 8 || C % G) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: C=%d G=%d", C, G);
+  if ((ldx | ldy) % 8) return set_error(OMGSR_ERR_ALIGN, "groupnorm_apply: ld %% 8");
+  const int vpr = C / 8;
+  const long long total = static_cast<long long>(B) * HW * vpr;
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, stats, gamma, beta, HW, C, G, eps, silu, vpr, total);
+  return check_launch("gn_apply_kernel");
+}
+
+extern "C" int omgsr_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C,
+                               float eps, long long rows_per_batch, long long gb_stride, void* stream) {
+  if (C % 8 || C > 4096) return set_error(OMGSR_ERR_SHAPE, "layernorm: C=%d", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const int grid = grid_for(rows * 32, threads);
+  const int vpl = (C / 8 + 31) / 32;
+  const bf16* xi = static_cast<const bf16*>(x);
+  bf16* yo = static_cast<bf16*>(y);
+#define LN_CASE(V)                                                                                               \
+  layernorm_kernel<V><<<grid, threads, 0, st>>>(xi, yo, gamma, beta, rows, C, eps, rows_per_batch, gb_stride)
+  if (vpl <= 1) LN_CASE(1);
+  else if (vpl <= 2) LN_CASE(2);
+  else if (vpl <= 4) LN_CASE(4);
+  else if (vpl <= 5) LN_CASE(5);
+  else if (vpl <= 8) LN_CASE(8);
+  else if (vpl <= 12) LN_CASE(12);
+  else LN_CASE(16);
+#undef LN_CASE
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n,
+                                  int n_pad, float scale, void* stream) {
+  if (rows <= 0 || n <= 0 || n_pad < n) return set_error(OMGSR_ERR_SHAPE, "softmax_rows: rows=%lld n=%d", rows, n);
+  if (rows > 0x7fffffffLL) return set_error(OMGSR_ERR_SHAPE, "softmax_rows: too many rows");
+  const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f);
+  return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int omgsr_rmsnorm_rope(void* x, long long ld, const float* weight, const float* cos_t, const float* sin_t,
+                                  long long rows, int heads, long long rows_per_batch, float eps, void* stream) {
+  if (ld % 4) return set_error(OMGSR_ERR_ALIGN, "rmsnorm_rope: ld %% 4");
+  rmsnorm_rope_kernel<<<grid_for(rows * heads * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(x), ld, weight, cos_t, sin_t, rows, heads, rows_per_batch, eps);
+  return check_launch("rmsnorm_rope_kernel");
+}
+
+extern "C" int omgsr_conv_in_nchw(const void* x, int x_f32, const float* w, const float* bias, void* y, int B, int Cin,
+                                  int H, int W, int Cout, int ksize, long long ldy, void* stream) {
+  if (Cout % 8 || (ksize != 1 && ksize != 3) || Cin > 64) return set_error(OMGSR_ERR_SHAPE, "conv_in: Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
+  if (ldy % 8) return set_error(OMGSR_ERR_ALIGN, "conv_in: ldy %% 8");
+  const int cg = Cout / 8;
+  const long long total = static_cast<long long>(B) * H * W * cg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_f32)
+    conv_in_kernel<float><<<grid_for(total, 256) * 4, 256, 0, st>>>(static_cast<const float*>(x), w, bias,
+                                                                   static_cast<bf16*>(y), B, Cin, H, W, Cout, ksize,
+                                                                   ldy, cg, total);
+  else
+    conv_in_kernel<bf16><<<grid_for(total, 256) * 4, 256, 0, st>>>(static_cast<const bf16*>(x), w, bias,
+                                                                  static_cast<bf16*>(y), B, Cin, H, W, Cout, ksize,
+                                                                  ldy, cg, total);
+  return check_launch("conv_in_kernel");
+}
+
+template <int COUT, typename TOut>
+static int launch_conv_out(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int Cin,
+                           int clamp, long long ldx, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(COUT) * 9 * Cin * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel<COUT, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "conv_out smem: %s", cudaGetErrorString(e));
+  }
+  const long long total = static_cast<long long>(B) * H * W;
+  conv_out_kernel<COUT, TOut><<<grid_for(total, 128), 128, smem, st>>>(
+      static_cast<const bf16*>(x), static_cast<const bf16*>(w), bias, static_cast<TOut*>(y), B, H, W, Cin, clamp, ldx,
+      total);
+  return check_launch("conv_out_kernel");
+}
+
+extern "C" int omgsr_conv_out_nchw(const void* x, const void* w, const float* bias, void* y, int y_f32, int B, int H,
+                                   int W, int Cin, int Cout, int clamp, long long ldx, void* stream) {
+  if (Cin % 8 || ldx % 8) return set_error(OMGSR_ERR_SHAPE, "conv_out: Cin=%d ldx=%lld", Cin, ldx);
+  if (static_cast<size_t>(Cout) * 9 * Cin * 4 > 200 * 1024) return set_error(OMGSR_ERR_SHAPE, "conv_out: weights exceed smem");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cout == 3)
+    return y_f32 ? launch_conv_out<3, float>(x, w, bias, y, B, H, W, Cin, clamp, ldx, st)
+                 : launch_conv_out<3, bf16>(x, w, bias, y, B, H, W, Cin, clamp, ldx, st);
+  if (Cout == 4)
+    return y_f32 ? launch_conv_out<4, float>(x, w, bias, y, B, H, W, Cin, clamp, ldx, st)
+                 : launch_conv_out<4, bf16>(x, w, bias, y, B, H, W, Cin, clamp, ldx, st);
+  return set_error(OMGSR_ERR_SHAPE, "conv_out: Cout=%d unsupported (3 or 4)", Cout);
+}
+
+extern "C" int omgsr_posterior_sample(const float* moments, long long ldm, const float* eps, void* z, int z_f32, int B,
+                                      int Cz, int h, int w, float shift, float scale, void* stream) {
+  const long long hw = static_cast<long long>(h) * w, total = hw * Cz * B;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (z_f32)
+    posterior_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(moments, ldm, eps, static_cast<float*>(z), Cz, hw,
+                                                                  total, shift, scale);
+  else
+    posterior_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(moments, ldm, eps, static_cast<bf16*>(z), Cz, hw,
+                                                                 total, shift, scale);
+  return check_launch("posterior_kernel");
+}
+
+extern "C" int omgsr_latent_axpby(const void* x, const void* y, void* out, int is_f32, long long n, float a, float b,
+                                  float c, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    axpby_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(y),
+                                                          static_cast<float*>(out), n, a, b, c);
+  else
+    axpby_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(y),
+                                                         static_cast<bf16*>(out), n, a, b, c);
+  return check_launch("axpby_kernel");
+}
+
+extern "C" int omgsr_x0_unscale(const void* z, int z_f32, const float* eps_hat, long long lde, void* out,
+                                const float* Wpq, const float* bpq, int B, int Cz, int h, int w, float s1, float s2,
+                                float scale, float shift, void* stream) {
+  if (Cz > 16) return set_error(OMGSR_ERR_SHAPE, "x0_unscale: Cz=%d > 16", Cz);
+  const long long hw = static_cast<long long>(h) * w, total = hw * B;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (z_f32)
+    x0_unscale_kernel<float><<<grid_for(total, 128), 128, 0, st>>>(static_cast<const float*>(z), eps_hat, lde,
+                                                                   static_cast<bf16*>(out), Wpq, bpq, Cz, hw, total, s1,
+                                                                   1.0f / s2, 1.0f / scale, shift);
+  else
+    x0_unscale_kernel<bf16><<<grid_for(total, 128), 128, 0, st>>>(static_cast<const bf16*>(z), eps_hat, lde,
+                                                                  static_cast<bf16*>(out), Wpq, bpq, Cz, hw, total, s1,
+                                                                  1.0f / s2, 1.0f / scale, shift);
+  return check_launch("x0_unscale_kernel");
+}
+
+extern "C" int omgsr_pack_latents(const void* z, void* tokens, int B, int C, int h, int w, long long ld_tok,
+                                  void* stream) {
+  if ((h | w) & 1) return set_error(OMGSR_ERR_SHAPE, "pack_latents: odd latent size");
+  const long long total = static_cast<long long>(B) * C * h * w;
+  pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(z), static_cast<bf16*>(tokens), C, h, w, ld_tok, total, 0);
+  return check_launch("pack_kernel");
+}
+extern "C" int omgsr_unpack_latents(const void* tokens, void* z, int B, int C, int h, int w, long long ld_tok,
+                                    void* stream) {
+  if ((h | w) & 1) return set_error(OMGSR_ERR_SHAPE, "unpack_latents: odd latent size");
+  const long long total = static_cast<long long>(B) * C * h * w;
+  pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(z), const_cast<bf16*>(static_cast<const bf16*>(tokens)), C, h, w, ld_tok, total, 1);
+  return check_launch("pack_kernel");
+}
+
+extern "C" int omgsr_tile_blend(const void* tiles, int tiles_f32, const float* weights, const int* ofs_xy_dev,
+                                int ntiles, float* out, int B, int C, int h, int w, int T, void* stream) {
+  const long long total = static_cast<long long>(B) * C * h * w;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tiles_f32)
+    tile_blend_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(tiles), weights,
+                                                                   ofs_xy_dev, ntiles, out, B, C, h, w, T, total);
+  else
+    tile_blend_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const bf16*>(tiles), weights, ofs_xy_dev,
+                                                                  ntiles, out, B, C, h, w, T, total);
+  return check_launch("tile_blend_kernel");
+}
+
+extern "C" int omgsr_nchw_to_nhwc(const void* x, int x_f32, void* y, int B, int C, int H, int W, long long ldy,
+                                  void* stream) {
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_f32)
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x), static_cast<bf16*>(y), C, HW, ldy);
+  else
+    nchw_to_nhwc_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), C, HW, ldy);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+extern "C" int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f32, int B, int C, int H, int W,
+                                  void* stream) {
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (y_f32)
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<float*>(y), C, HW);
+  else
+    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), C, HW);
+  return check_launch("nhwc_to_nchw_kernel");
+}

@@ -1,0 +1,337 @@
+"""GPU parity tests of the individual sm_100a kernels against the operator-level oracle (oracle/ops.py),
+called through the C ABI (omgsr_b200.capi -> libomgsr_b200.so). Tolerances: bf16 storage with fp32
+accumulation, max-abs error <= 1e-2 of the reference magnitude (north_star: latent rel-err <= 2e-2)."""
+import math
+
+import pytest
+import torch
+
+from tests.util import bf16r, report
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from omgsr_b200 import capi as c
+    return c
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 64, 64, 64), (128, 64, 256, 64), (256, 128, 128, 128), (384, 256, 192, 256), (1000, 320, 320, 160),
+    (4096, 1280, 1280, 0), (77, 640, 1024, 0), (300, 2560, 320, 0), (128, 72, 64, 0),
+])
+def test_gemm(capi, M, N, K, bn):
+    from oracle import ops
+    g = _g(M + N + K)
+    a = bf16r(torch.randn(M, K, generator=g))
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g)
+    ref = ops.linear(a, w, b)
+    out = capi.gemm(a.cuda().bfloat16(), w.cuda().bfloat16(), b.cuda(), force_bn=bn)
+    torch.cuda.synchronize()
+    ok, _ = report(f"gemm {M}x{N}x{K} bn={bn}", out, ref)
+    assert ok
+
+
+def test_gemm_epilogues(capi):
+    from oracle import ops
+    g = _g(7)
+    M, N, K = 512, 640, 320
+    a = bf16r(torch.randn(M, K, generator=g))
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g)
+    res = bf16r(torch.randn(M, N, generator=g))
+    gate = torch.randn(2, N, generator=g)
+    lin = ops.linear(a, w, b)
+    ac, wc, bc = a.cuda().bfloat16(), w.cuda().bfloat16(), b.cuda()
+    for act, fn in [(capi.ACT_SILU, torch.nn.functional.silu), (capi.ACT_GELU_ERF, torch.nn.functional.gelu),
+                    (capi.ACT_GELU_TANH, lambda t: torch.nn.functional.gelu(t, approximate="tanh"))]:
+        out = capi.gemm(ac, wc, bc, act=act)
+        assert report(f"gemm act={act}", out, fn(lin))[0]
+    out = capi.gemm(ac, wc, bc, res=res.cuda().bfloat16(), gate=gate.cuda(), gate_rows=256)
+    ref = res + gate.repeat_interleave(256, 0) * lin
+    assert report("gemm gate+res", out, ref)[0]
+    out = capi.gemm(ac, wc, bc, out_f32=True)
+    assert out.dtype == torch.float32
+    assert report("gemm f32 out", out, lin, tol=2e-3)[0]
+    # strided A (column slice of a wider buffer) and strided output
+    wide = torch.zeros(M, K + 64, device="cuda", dtype=torch.bfloat16)
+    wide[:, 64:] = ac
+    dst = torch.zeros(M, N + 128, device="cuda", dtype=torch.bfloat16)
+    capi.gemm(wide[:, 64:], wc, bc, out=dst[:, 128:])
+    assert report("gemm strided", dst[:, 128:], lin)[0]
+    assert float(dst[:, :128].abs().max()) == 0.0
+
+
+def test_gemm_geglu(capi):
+    from oracle import ops
+    from omgsr_b200.pack import pack_geglu_weight
+    g = _g(11)
+    M, K, F_ = 256, 320, 1280
+    a = bf16r(torch.randn(M, K, generator=g))
+    w = bf16r(torch.randn(2 * F_, K, generator=g) / math.sqrt(K))
+    b = torch.randn(2 * F_, generator=g)
+    ref = ops.geglu(a, w, b)
+    for bn in (256, 128):
+        wi, bi = pack_geglu_weight(w, b, bn)
+        out = capi.gemm(a.cuda().bfloat16(), wi.cuda().bfloat16(), bi.cuda(), act=capi.ACT_GEGLU, force_bn=bn)
+        assert out.shape == (M, F_)
+        assert report(f"geglu bn={bn}", out, ref)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad(t,l,b,r), upsample
+    (1, 16, 16, 64, 64, 3, 1, (1, 1, 1, 1), False),
+    (2, 32, 32, 128, 128, 3, 1, (1, 1, 1, 1), False),
+    (1, 128, 128, 128, 256, 3, 1, (1, 1, 1, 1), False),
+    (2, 8, 8, 320, 320, 3, 1, (1, 1, 1, 1), False),
+    (1, 8, 8, 128, 128, 3, 1, (1, 1, 1, 1), False),
+    (3, 20, 24, 64, 128, 3, 1, (1, 1, 1, 1), False),     # ragged tiles
+    (1, 150, 150, 64, 64, 3, 1, (1, 1, 1, 1), False),    # vaehook-style odd tile
+    (2, 32, 32, 256, 128, 1, 1, (0, 0, 0, 0), False),    # conv_shortcut
+    (2, 32, 32, 128, 128, 3, 2, (0, 0, 1, 1), False),    # VAE downsample (asymmetric pad)
+    (2, 16, 16, 320, 320, 3, 2, (1, 1, 1, 1), False),    # UNet downsample
+    (1, 64, 64, 64, 64, 3, 2, (0, 0, 1, 1), False),
+    (2, 16, 16, 128, 128, 3, 1, (1, 1, 1, 1), True),     # nearest-2x + conv, collapsed to 4 x (2x2)
+    (1, 8, 8, 320, 320, 3, 1, (1, 1, 1, 1), True),
+    (1, 64, 64, 256, 256, 3, 1, (1, 1, 1, 1), True),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,pad,up", CONV_CASES)
+def test_conv(capi, B, H, W, Cin, Cout, k, stride, pad, up):
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight, pack_upsample_weight
+    g = _g(B * 1000 + H + Cin + Cout + k + stride)
+    x = bf16r(torch.randn(B, H, W, Cin, generator=g))
+    w = bf16r(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k))
+    b = torch.randn(Cout, generator=g)
+    ref = ops.conv2d_nhwc(x, w, b, stride=stride, pad=pad, upsample2x=up)
+    pw = pack_upsample_weight(w) if up else pack_conv_weight(w)
+    out = capi.conv2d(x.cuda().bfloat16(), pw.cuda(), b.cuda(), ksize=k, stride=stride, pad=pad, upsample2x=up)
+    torch.cuda.synchronize()
+    tol = 2e-2 if up else 1e-2   # collapsed taps are re-rounded to bf16 once
+    assert report(f"conv {B}x{H}x{W} {Cin}->{Cout} k{k} s{stride} up={up}", out, ref, tol)[0]
+
+
+def test_conv_residual_silu_concat(capi):
+    """residual epilogue + reading a channel slice of a concat buffer + writing into a slice."""
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight
+    g = _g(21)
+    B, H, W, C1, C2, Cout = 2, 16, 16, 128, 192, 128
+    x = bf16r(torch.randn(B, H, W, C1 + C2, generator=g))
+    w = bf16r(torch.randn(Cout, C1 + C2, 3, 3, generator=g) / math.sqrt(9 * (C1 + C2)))
+    b = torch.randn(Cout, generator=g)
+    res = bf16r(torch.randn(B, H, W, Cout, generator=g))
+    ref = ops.conv2d_nhwc(x, w, b) + res
+    dst = torch.zeros(B, H, W, Cout + 64, device="cuda", dtype=torch.bfloat16)
+    capi.conv2d(x.cuda().bfloat16(), pack_conv_weight(w).cuda(), b.cuda(), res=res.cuda().bfloat16(),
+                out=dst[..., 64:])
+    assert report("conv res+slice", dst[..., 64:], ref)[0]
+    assert float(dst[..., :64].abs().max()) == 0.0
+    out = capi.conv2d(x.cuda().bfloat16(), pack_conv_weight(w).cuda(), b.cuda(), act=capi.ACT_SILU)
+    assert report("conv silu", out, torch.nn.functional.silu(ops.conv2d_nhwc(x, w, b)))[0]
+    # thin Cout through the tensor-core path with fp32 output (encoder conv_out / unet conv_out)
+    w8 = bf16r(torch.randn(8, C1 + C2, 3, 3, generator=g) / math.sqrt(9 * (C1 + C2)))
+    b8 = torch.randn(8, generator=g)
+    out = capi.conv2d(x.cuda().bfloat16(), pack_conv_weight(w8).cuda(), b8.cuda(), out_f32=True)
+    assert report("conv Cout=8 f32", out, ops.conv2d_nhwc(x, w8, b8), 2e-3)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Hh,M,N,D", [(1, 1, 128, 128, 64), (2, 5, 256, 256, 64), (2, 5, 1024, 77, 64),
+                                         (1, 2, 200, 300, 64), (1, 1, 256, 256, 512), (1, 3, 256, 320, 128)])
+def test_attention_materialised(capi, B, Hh, M, N, D):
+    from oracle import ops
+    g = _g(B + Hh + M + N + D)
+    q = bf16r(torch.randn(B, M, Hh, D, generator=g))
+    k = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    v = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    scale = 1.0 / math.sqrt(D)
+    s = capi.bgemm_qk(q.cuda().bfloat16(), k.cuda().bfloat16())
+    sref = torch.einsum("bmhd,bnhd->bhmn", q, k)
+    assert report(f"bgemm qk {B},{Hh},{M},{N},{D}", s[..., :N], sref, 2e-3)[0]
+    p = capi.softmax_rows(s, N, scale)
+    pref = (sref * scale).softmax(-1)
+    assert report("softmax", p[..., :N], pref)[0]
+    assert float(p[..., N:].abs().max()) == 0.0 if p.shape[-1] > N else True
+    o = capi.bgemm_pv(p, v.cuda().bfloat16())
+    assert report(f"bgemm pv (MN-major V) {B},{Hh},{M},{N},{D}", o, ops.attention(q, k, v, scale), 2e-2)[0]
+
+
+@pytest.mark.parametrize("B,Hh,M,N,D", [(1, 1, 128, 128, 64), (2, 5, 256, 384, 64), (2, 5, 1024, 77, 64),
+                                         (1, 2, 200, 300, 64), (1, 10, 64, 64, 64), (1, 2, 4096, 4096, 64),
+                                         (1, 1, 128, 64, 128), (1, 3, 256, 320, 128), (1, 2, 4608, 4608, 128)])
+def test_flash_attention(capi, B, Hh, M, N, D):
+    from oracle import ops
+    g = _g(B + Hh + M + N + D + 1)
+    q = bf16r(torch.randn(B, M, Hh, D, generator=g))
+    k = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    v = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    scale = 1.0 / math.sqrt(D)
+    o = capi.flash_attn(q.cuda().bfloat16(), k.cuda().bfloat16(), v.cuda().bfloat16(), scale)
+    torch.cuda.synchronize()
+    assert report(f"flash {B},{Hh},{M},{N},{D}", o, ops.attention(q, k, v, scale), 2e-2)[0]
+
+
+def test_flash_attention_fused_qkv_layout(capi):
+    """q/k/v as column slices of one fused [B, T, 3*H*D] projection output (strided views)."""
+    from oracle import ops
+    g = _g(99)
+    B, T, Hh, D = 2, 256, 5, 64
+    qkv = bf16r(torch.randn(B, T, 3 * Hh * D, generator=g))
+    q, k, v = [qkv[..., i * Hh * D:(i + 1) * Hh * D].reshape(B, T, Hh, D) for i in range(3)]
+    qc = qkv.cuda().bfloat16()
+    qv, kv, vv = [qc[..., i * Hh * D:(i + 1) * Hh * D].unflatten(-1, (Hh, D)) for i in range(3)]
+    o = capi.flash_attn(qv, kv, vv, 0.125)
+    assert report("flash fused-qkv", o, ops.attention(q, k, v, 0.125), 2e-2)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,HW,C,eps,silu", [(2, 64 * 64, 128, 1e-6, True), (1, 32 * 32, 512, 1e-6, False),
+                                              (3, 16 * 16, 320, 1e-5, True), (2, 8 * 8, 2560, 1e-5, True),
+                                              (1, 150 * 150, 256, 1e-6, True), (2, 64, 960, 1e-5, True)])
+def test_groupnorm(capi, B, HW, C, eps, silu):
+    from oracle import ops
+    g = _g(B + HW + C)
+    x = bf16r(torch.randn(B, HW, C, generator=g) * 2 + 0.5)
+    gamma = torch.randn(C, generator=g)
+    beta = torch.randn(C, generator=g)
+    ref = ops.groupnorm_nhwc(x, gamma, beta, 32, eps, silu)
+    out = capi.groupnorm(x.cuda().bfloat16(), gamma.cuda(), beta.cuda(), 32, eps, silu)
+    assert report(f"groupnorm {B},{HW},{C}", out, ref)[0]
+
+
+@pytest.mark.parametrize("rows,C", [(512, 320), (100, 640), (64, 1280), (4608, 3072)])
+def test_layernorm(capi, rows, C):
+    from oracle import ops
+    g = _g(rows + C)
+    x = bf16r(torch.randn(rows, C, generator=g) * 3 + 1)
+    gamma = torch.randn(C, generator=g)
+    beta = torch.randn(C, generator=g)
+    out = capi.layernorm(x.cuda().bfloat16(), gamma.cuda(), beta.cuda(), 1e-5)
+    assert report(f"layernorm {rows}x{C}", out, ops.layernorm(x, gamma, beta, 1e-5))[0]
+    # AdaLN modulation: per-image (1+scale, shift), no learned affine
+    nb = 2
+    sc = torch.randn(nb, C, generator=g)
+    sh = torch.randn(nb, C, generator=g)
+    rpb = rows // nb
+    ref = ops.layernorm(x, None, None, 1e-6).reshape(nb, rpb, C) * (1 + sc[:, None]) + sh[:, None]
+    out = capi.layernorm(x.cuda().bfloat16(), (1 + sc).cuda().contiguous(), sh.cuda(), 1e-6, rows_per_batch=rpb,
+                         gb_stride=C)
+    assert report("layernorm modulate", out, ref.reshape(rows, C))[0]
+
+
+def test_thin_convs_and_layout(capi):
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_in_weight, pack_conv_weight
+    g = _g(5)
+    for (B, Cin, H, W, Cout, k) in [(2, 3, 40, 48, 128, 3), (1, 4, 16, 16, 320, 3), (2, 16, 8, 8, 512, 3),
+                                     (1, 4, 16, 16, 8, 1)]:
+        x = bf16r(torch.randn(B, Cin, H, W, generator=g))
+        w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+        b = torch.randn(Cout, generator=g)
+        ref = torch.nn.functional.conv2d(x, w, b, padding=k // 2).permute(0, 2, 3, 1)
+        for dt in (torch.bfloat16, torch.float32):
+            out = capi.conv_in_nchw(x.cuda().to(dt), pack_conv_in_weight(w).cuda(), b.cuda(), Cout, k)
+            assert report(f"conv_in {Cin}->{Cout} {dt}", out, ref)[0]
+    for (B, H, W, Cin, Cout) in [(2, 24, 40, 128, 3), (1, 16, 16, 320, 4)]:
+        x = bf16r(torch.randn(B, H, W, Cin, generator=g))
+        w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+        b = torch.randn(Cout, generator=g)
+        ref = ops.conv2d_nhwc(x, w, b).permute(0, 3, 1, 2)
+        out = capi.conv_out_nchw(x.cuda().bfloat16(), pack_conv_weight(w).cuda(), b.cuda(), Cout, clamp=False,
+                                 out_dtype=torch.float32)
+        assert report(f"conv_out {Cin}->{Cout}", out, ref, 2e-3)[0]
+        out = capi.conv_out_nchw(x.cuda().bfloat16(), pack_conv_weight(w).cuda(), b.cuda(), Cout, clamp=True)
+        assert report("conv_out clamp", out, ref.clamp(-1, 1))[0]
+    x = bf16r(torch.randn(2, 20, 9, 11, generator=g))
+    nhwc = capi.nchw_to_nhwc(x.cuda().bfloat16())
+    assert report("nchw->nhwc", nhwc, x.permute(0, 2, 3, 1), 1e-6)[0]
+    back = capi.nhwc_to_nchw(nhwc, torch.float32)
+    assert report("nhwc->nchw", back, x, 1e-6)[0]
+
+
+def test_latent_steps(capi):
+    g = _g(31)
+    B, Cz, h, w = 2, 4, 16, 24
+    mom = torch.randn(B, h, w, 8, generator=g)
+    eps = torch.randn(B, Cz, h, w, generator=g)
+    mean = mom[..., :Cz].permute(0, 3, 1, 2)
+    logvar = mom[..., Cz:].permute(0, 3, 1, 2).clamp(-30, 20)
+    ref = ((mean + torch.exp(0.5 * logvar) * eps) - 0.1159) * 0.3611
+    z = capi.posterior_sample(mom.cuda(), eps.cuda(), Cz, 0.1159, 0.3611, torch.float32)
+    assert report("posterior", z, ref, 1e-5)[0]
+    x = torch.randn(1000, generator=g)
+    y = torch.randn(1000, generator=g)
+    out = capi.latent_axpby(x.cuda(), y.cuda(), 0.495, 0.505, 0.0)   # z_t = (1-sigma) z + sigma eps
+    assert report("axpby f32", out, 0.495 * x + 0.505 * y, 1e-6)[0]
+    out = capi.latent_axpby(x.cuda().bfloat16(), y.cuda().bfloat16(), 1.0, -0.505112)
+    assert report("axpby bf16", out, bf16r(x) - 0.505112 * bf16r(y))[0]
+    # x0 prediction + post_quant_conv
+    zz = torch.randn(B, Cz, h, w, generator=g)
+    eh = torch.randn(B, h, w, 8, generator=g)
+    Wpq = torch.randn(Cz, Cz, generator=g)
+    bpq = torch.randn(Cz, generator=g)
+    a = 0.6357423
+    z0 = (zz - math.sqrt(1 - a) * eh[..., :Cz].permute(0, 3, 1, 2)) / math.sqrt(a) / 0.18215
+    ref = torch.einsum("oc,bchw->bohw", Wpq, z0) + bpq[None, :, None, None]
+    out = capi.x0_unscale(zz.cuda(), eh.cuda(), math.sqrt(1 - a), math.sqrt(a), 0.18215, 0.0, Wpq.cuda(), bpq.cuda())
+    assert report("x0+postquant", out, ref)[0]
+    # pack / unpack (infer/omgsr_f_infer_model.py:21-41)
+    lat = bf16r(torch.randn(2, 16, 8, 12, generator=g))
+    ref = lat.view(2, 16, 4, 2, 6, 2).permute(0, 2, 4, 1, 3, 5).reshape(2, 24, 64)
+    tok = capi.pack_latents(lat.cuda().bfloat16())
+    assert report("pack", tok, ref, 1e-6)[0]
+    assert report("unpack", capi.unpack_latents(tok, 16, 8, 12), lat, 1e-6)[0]
+
+
+def test_rmsnorm_rope(capi):
+    g = _g(41)
+    rows_pb, nb, Hh = 96, 2, 3
+    x = bf16r(torch.randn(nb * rows_pb, Hh * 128, generator=g))
+    wt = torch.rand(128, generator=g) + 0.5
+    ang = torch.randn(rows_pb, 64, generator=g)
+    cos = torch.cos(ang).repeat_interleave(2, -1)
+    sin = torch.sin(ang).repeat_interleave(2, -1)
+    xr = x.view(nb, rows_pb, Hh, 128)
+    n = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * wt
+    n2 = n.reshape(nb, rows_pb, Hh, 64, 2)
+    rot = torch.stack([-n2[..., 1], n2[..., 0]], -1).reshape(nb, rows_pb, Hh, 128)
+    ref = n * cos[None, :, None] + rot * sin[None, :, None]
+    xc = x.cuda().bfloat16().contiguous()
+    capi.rmsnorm_rope_(xc, wt.cuda(), cos.cuda().contiguous(), sin.cuda().contiguous(), Hh, rows_pb)
+    assert report("rmsnorm+rope", xc, ref.reshape(nb * rows_pb, Hh * 128))[0]
+
+
+def test_tile_blend(capi):
+    g = _g(51)
+    B, C, h, w, T = 1, 4, 24, 24, 16
+    offs = [(0, 0), (8, 0), (0, 8), (8, 8)]
+    tiles = torch.randn(len(offs), B, C, T, T, generator=g)
+    wts = torch.rand(T, T, generator=g) + 0.1
+    num = torch.zeros(B, C, h, w)
+    den = torch.zeros(B, C, h, w)
+    for t, (ox, oy) in enumerate(offs):
+        num[:, :, oy:oy + T, ox:ox + T] += tiles[t] * wts
+        den[:, :, oy:oy + T, ox:ox + T] += wts
+    out = capi.tile_blend(tiles.cuda(), wts.cuda(), torch.tensor(offs, dtype=torch.int32).cuda(), h, w)
+    assert report("tile blend", out, num / den, 1e-5)[0]
+
+
+def test_colorfix(capi):
+    g = _g(61)
+    c = torch.rand(2, 3, 70, 90, generator=g)
+    s = torch.rand(2, 3, 70, 90, generator=g)
+    # oracle restatement lives in oracle/colorfix.py (pinned to the reference's own functions on CPU)
+    from oracle import colorfix
+    assert report("wavelet", capi.wavelet_fix(c.cuda(), s.cuda()), colorfix.wavelet_reconstruction(c, s), 1e-5)[0]
+    assert report("adain", capi.adain_fix(c.cuda(), s.cuda()), colorfix.adaptive_instance_normalization(c, s), 1e-4)[0]
