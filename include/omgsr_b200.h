@@ -107,10 +107,17 @@ int omgsr_conv_out_nchw(const void* x, const void* w, const float* bias, void* y
 int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats, int B, long long HW, int C, int G,
                           void* stream);
 /* y = (x - mean) * rstd * gamma + beta, optional SiLU. (diffusers GroupNorm+SiLU pairs: VAE eps 1e-6,
- * UNet eps 1e-5; infer/vaehook.py:384-413 restates the same op as custom_group_norm.) */
+ * UNet eps 1e-5; infer/vaehook.py:384-413 restates the same op as custom_group_norm.)
+ * stats_mode 0: stats[B,G,2] = (sum, sumsq) from omgsr_groupnorm_stats on this tensor.
+ * stats_mode 1: stats[stats_mod,G,2] = (mean, var) from omgsr_groupnorm_combine, row = batch index % stats_mod. */
 int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,
                           const float* gamma, const float* beta, int B, long long HW, int C, int G, float eps,
-                          int silu, void* stream);
+                          int silu, int stats_mode, int stats_mod, void* stream);
+/* Cross-tile GroupNorm statistics of the tiled VAE (GroupNormParam.summary, infer/vaehook.py:489-508).
+ * sums[entries,G,2] = per-(tile,image) (sum, sumsq) with image = entry % n_img; pixels[entries] = pixels of
+ * that tile (fp32, device). out[n_img,G,2] = pixel-weighted mean of the per-tile (mean, biased var). */
+int omgsr_groupnorm_combine(const float* sums, const float* pixels, int entries, int n_img, int C, int G, float* out,
+                            void* stream);
 /* LayerNorm over the last dim with y = xhat * g + b where g/b are fp32 vectors of length C taken from
  * gamma + (row / rows_per_batch) * gb_stride (gb_stride = 0: shared affine; >0: per-image AdaLN modulation,
  * caller passes g = 1 + scale, b = shift). gamma/beta may be null (no affine). */
@@ -149,10 +156,13 @@ int omgsr_x0_unscale(const void* z, int z_f32, const float* eps_hat, long long l
 int omgsr_pack_latents(const void* z, void* tokens, int B, int C, int h, int w, long long ld_tok, void* stream);
 int omgsr_unpack_latents(const void* tokens, void* z, int B, int C, int h, int w, long long ld_tok, void* stream);
 /* Gaussian-weighted blend of per-tile denoiser outputs into the full latent
- * (infer/omgsr_s_infer_model.py:137-161). tiles: NCHW fp32/bf16 [ntiles,B,C,T,T]; ofs_xy: DEVICE int
- * [ntiles,2] = (x, y) offsets; weights fp32 [T,T]; out fp32 NCHW [B,C,h,w] = sum w*tile / sum w. */
+ * (infer/omgsr_s_infer_model.py:137-161, infer/omgsr_f_infer_model.py:283-314): out = sum_t w*tile_t / sum_t w.
+ * tiles: fp32|bf16, logical [ntiles,B,C,T,T] addressed through tile_strides (HOST array of 5 element
+ * strides: tile, batch, channel, y, x); out: fp32 logical [B,C,h,w] through out_strides (HOST array of 4);
+ * ofs_xy: DEVICE int [ntiles,2] = (x, y) tile offsets; weights: fp32 [T,T]. */
 int omgsr_tile_blend(const void* tiles, int tiles_f32, const float* weights, const int* ofs_xy, int ntiles,
-                     float* out, int B, int C, int h, int w, int T, void* stream);
+                     float* out, int B, int C, int h, int w, int T, const long long* tile_strides,
+                     const long long* out_strides, void* stream);
 
 /* ---- colour fix (infer/wavelet_color_fix.py) ---------------------------------------------------- */
 

@@ -1,0 +1,112 @@
+"""Tiled VAE — B200-native drop-in for the reference's infer/vaehook.py (`VAEHook`).
+
+Same constructor / call contract: `VAEHook(net, tile_size, is_decoder, fast_decoder, fast_encoder, color_fix,
+to_gpu)(x)` replaces `vae.encoder.forward` / `vae.decoder.forward`; inputs whose larger side fits in
+`2*pad + tile_size` go to `net.original_forward` (reference :554-556), everything else is split into padded
+tiles (`split_tiles`, reference :577-634), every tile runs the whole net, GroupNorm statistics are shared
+across tiles as the pixel-weighted mean of the per-tile mean and variance (`GroupNormParam.summary`,
+reference :489-508), the mid-block attention is evaluated per tile (:243-246), and the valid region of each
+tile is cropped and stitched into an fp32 result (:800-806).
+
+What is different is the schedule: the reference keeps ONE tile on the GPU and bounces every tile through
+host memory at each of the 22/30 GroupNorm sites (:705,764,782,814). Here all tiles stay in HBM (180 GB),
+tiles of equal shape are stacked on the batch axis and advanced layer-synchronously as coroutines that
+yield at every GroupNorm; the cross-tile statistics are combined on the device
+(omgsr_groupnorm_combine) and the normalise+SiLU is applied to every tile group before the coroutines
+resume. No device<->host traffic happens inside the call.
+"""
+import math
+
+import torch
+
+from omgsr_b200 import capi
+
+
+class VAEHook:
+    def __init__(self, net, tile_size, is_decoder, fast_decoder, fast_encoder, color_fix, to_gpu=False):
+        self.net = net  # encoder | decoder
+        self.tile_size = tile_size
+        self.is_decoder = is_decoder
+        self.fast_mode = (fast_encoder and not is_decoder) or (fast_decoder and is_decoder)
+        self.color_fix = color_fix and not is_decoder
+        self.to_gpu = to_gpu
+        self.pad = 11 if is_decoder else 32
+
+    def __call__(self, x):
+        B, C, H, W = x.shape
+        if max(H, W) <= self.pad * 2 + self.tile_size:
+            print("[Tiled VAE]: the input size is tiny and unnecessary to tile.")
+            return self.net.original_forward(x)
+        return self.vae_tile_forward(x)
+
+    def get_best_tile_size(self, lowerbound, upperbound):
+        """smallest size >= lowerbound that is a multiple of 32 (else 16, 8, 4, 2) and <= upperbound."""
+        divider = 32
+        while divider >= 2:
+            rem = lowerbound % divider
+            if rem == 0:
+                return lowerbound
+            cand = lowerbound - rem + divider
+            if cand <= upperbound:
+                return cand
+            divider //= 2
+        return lowerbound
+
+    def split_tiles(self, h, w):
+        """-> (input bboxes grown by `pad`, output bboxes scaled x8 | //8); bbox = [x1, x2, y1, y2]."""
+        pad, tile = self.pad, self.tile_size
+        n_h = max(math.ceil((h - 2 * pad) / tile), 1)
+        n_w = max(math.ceil((w - 2 * pad) / tile), 1)
+        real_h = self.get_best_tile_size(math.ceil((h - 2 * pad) / n_h), tile)
+        real_w = self.get_best_tile_size(math.ceil((w - 2 * pad) / n_w), tile)
+        print(f'[Tiled VAE]: split to {n_h}x{n_w} = {n_h * n_w} tiles. '
+              f'Optimal tile size {real_w}x{real_h}, original tile size {tile}x{tile}')
+        in_boxes, out_boxes = [], []
+        for i in range(n_h):
+            for j in range(n_w):
+                core = [pad + j * real_w, min(pad + (j + 1) * real_w, w),
+                        pad + i * real_h, min(pad + (i + 1) * real_h, h)]
+                # cores touching the border own the border strip as well
+                out = [core[0] if core[0] > pad else 0, core[1] if core[1] < w - pad else w,
+                       core[2] if core[2] > pad else 0, core[3] if core[3] < h - pad else h]
+                out_boxes.append([v * 8 if self.is_decoder else v // 8 for v in out])
+                in_boxes.append([max(0, core[0] - pad), min(w, core[1] + pad),
+                                 max(0, core[2] - pad), min(h, core[3] + pad)])
+        return in_boxes, out_boxes
+
+    @staticmethod
+    def crop_margins(in_box, out_box, is_decoder):
+        """margins of the valid region inside a processed tile (crop_valid_region, reference :416-427)."""
+        scaled = [v * 8 if is_decoder else v // 8 for v in in_box]
+        return [out_box[k] - scaled[k] for k in range(4)]
+
+    @torch.no_grad()
+    def vae_tile_forward(self, z):
+        net = self.net
+        N, _, height, width = z.shape
+        print(f'[Tiled VAE]: input_size: {z.shape}, tile_size: {self.tile_size}, padding: {self.pad}')
+        if self.fast_mode:
+            raise NotImplementedError("VAEHook fast mode (GroupNorm estimation on a downsampled copy) is not built; "
+                                      "the reference default and OMGSR's settings use fast_*=False")
+        in_boxes, out_boxes = self.split_tiles(height, width)
+        # group tiles of equal padded shape: each group is one batched tensor [n_tiles*N, C, th, tw]
+        groups = {}
+        for idx, bx in enumerate(in_boxes):
+            groups.setdefault((bx[3] - bx[2], bx[1] - bx[0]), []).append(idx)
+        gens, members, pixels = [], [], []
+        for (th, tw), ids in groups.items():
+            stack = torch.cat([z[:, :, in_boxes[i][2]:in_boxes[i][3], in_boxes[i][0]:in_boxes[i][1]] for i in ids], 0)
+            gens.append(net.forward_gen(stack.contiguous()))
+            members.append(ids)
+            pixels.append((th, tw))
+        outs = net.run_tiled(gens, [len(m) for m in members], N)
+        scale = 8 if self.is_decoder else 1
+        oh, ow = (height * 8, width * 8) if self.is_decoder else (height // 8, width // 8)
+        result = torch.zeros((N, outs[0].shape[1], oh, ow), device=z.device, dtype=torch.float32)
+        for out, ids in zip(outs, members):
+            for k, i in enumerate(ids):
+                tile = out[k * N:(k + 1) * N]
+                m = self.crop_margins(in_boxes[i], out_boxes[i], self.is_decoder)
+                ob = out_boxes[i]
+                result[:, :, ob[2]:ob[3], ob[0]:ob[1]] = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]]
+        return result

@@ -20,7 +20,7 @@ SYMBOLS = [
     "omgsr_version", "omgsr_last_error", "omgsr_destroy", "omgsr_launch_count",
     "omgsr_gemm_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
     "omgsr_conv_in_nchw", "omgsr_conv_out_nchw",
-    "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_layernorm", "omgsr_softmax_rows",
+    "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_groupnorm_combine", "omgsr_layernorm", "omgsr_softmax_rows",
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
@@ -201,21 +201,47 @@ def conv_out_nchw(x, w, bias, cout, clamp=False, out_dtype=torch.bfloat16):
 # ------------------------------------------------------------------------------------------------
 # glue
 # ------------------------------------------------------------------------------------------------
-def groupnorm(x, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, stats=None):
-    """x: [B, ..., C] NHWC bf16 (channel stride = x.stride(-2)). Two launches: stats, apply(+SiLU)."""
-    _cuda_bf16(x, "x"); _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta")
+def groupnorm_stats(x, groups=32, stats=None):
+    """(sum, sumsq) per (batch entry, group) of an NHWC bf16 view -> fp32 [B, groups, 2]."""
+    _cuda_bf16(x, "x")
     B, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * C)
-    ldx = x.stride(-2)
     if stats is None:
         stats = torch.empty((B, groups, 2), device=x.device, dtype=torch.float32)
+    rc = _lib.omgsr_groupnorm_stats(_ptr(x), _ll(x.stride(-2)), _ptr(stats), _i(B), _ll(HW), _i(C), _i(groups),
+                                    _stream())
+    _check(rc, "omgsr_groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply(x, stats, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, shared_mod=0):
+    """normalise with given statistics. shared_mod > 0: stats are (mean, var) rows shared by batch % shared_mod."""
+    _cuda_bf16(x, "x"); _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta"); _cuda_f32(stats, "stats")
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    rc = _lib.omgsr_groupnorm_stats(_ptr(x), _ll(ldx), _ptr(stats), _i(B), _ll(HW), _i(C), _i(groups), _stream())
-    _check(rc, "omgsr_groupnorm_stats")
-    rc = _lib.omgsr_groupnorm_apply(_ptr(x), _ll(ldx), _ptr(out), _ll(out.stride(-2)), _ptr(stats), _ptr(gamma),
-                                    _ptr(beta), _i(B), _ll(HW), _i(C), _i(groups), _f(eps), _i(int(silu)), _stream())
+    rc = _lib.omgsr_groupnorm_apply(_ptr(x), _ll(x.stride(-2)), _ptr(out), _ll(out.stride(-2)), _ptr(stats),
+                                    _ptr(gamma), _ptr(beta), _i(B), _ll(HW), _i(C), _i(groups), _f(eps),
+                                    _i(int(silu)), _i(1 if shared_mod > 0 else 0), _i(shared_mod), _stream())
     _check(rc, "omgsr_groupnorm_apply")
+    return out
+
+
+def groupnorm(x, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, stats=None):
+    """x: [B, ..., C] NHWC bf16 (channel stride = x.stride(-2)). Two launches: stats, apply(+SiLU)."""
+    stats = groupnorm_stats(x, groups, stats)
+    return groupnorm_apply(x, stats, gamma, beta, groups, eps, silu, out)
+
+
+def groupnorm_combine(sums, pixels, n_img, C, groups=32):
+    """sums fp32 [entries, groups, 2], pixels fp32 [entries] -> (mean, var) fp32 [n_img, groups, 2]."""
+    _cuda_f32(sums, "sums"); _cuda_f32(pixels, "pixels")
+    entries = sums.shape[0]
+    out = torch.empty((n_img, groups, 2), device=sums.device, dtype=torch.float32)
+    rc = _lib.omgsr_groupnorm_combine(_ptr(sums.contiguous()), _ptr(pixels), _i(entries), _i(n_img), _i(C),
+                                      _i(groups), _ptr(out), _stream())
+    _check(rc, "omgsr_groupnorm_combine")
     return out
 
 
@@ -313,14 +339,17 @@ def unpack_latents(tokens, C, h, w):
     return z
 
 
-def tile_blend(tiles, weights, ofs_xy, h, w):
-    """tiles [ntiles,B,C,T,T] (bf16|fp32), weights fp32 [T,T], ofs_xy int32 device [ntiles,2] -> fp32 [B,C,h,w]."""
-    _cuda_f32(weights, "weights")
-    nt, B, C, T, _ = tiles.shape
-    assert ofs_xy.is_cuda and ofs_xy.dtype == torch.int32 and tiles.is_contiguous()
-    out = torch.empty((B, C, h, w), device=tiles.device, dtype=torch.float32)
+def tile_blend(tiles, weights, ofs_xy, out, T):
+    """tiles: logical [ntiles,B,C,T,T] view (any strides, bf16|fp32); out: fp32 logical [B,C,h,w] view (any strides);
+    weights fp32 [T,T]; ofs_xy int32 device [ntiles,2]."""
+    _cuda_f32(weights, "weights"); _cuda_f32(out, "out")
+    nt, B, C = tiles.shape[:3]
+    h, w = out.shape[2], out.shape[3]
+    assert ofs_xy.is_cuda and ofs_xy.dtype == torch.int32 and tiles.dtype in (torch.float32, torch.bfloat16)
+    ts = (ctypes.c_longlong * 5)(*tiles.stride())
+    os_ = (ctypes.c_longlong * 4)(*out.stride())
     rc = _lib.omgsr_tile_blend(_ptr(tiles), _i(int(tiles.dtype == torch.float32)), _ptr(weights), _ptr(ofs_xy),
-                               _i(nt), _ptr(out), _i(B), _i(C), _i(h), _i(w), _i(T), _stream())
+                               _i(nt), _ptr(out), _i(B), _i(C), _i(h), _i(w), _i(T), ts, os_, _stream())
     _check(rc, "omgsr_tile_blend")
     return out
 

@@ -8,7 +8,7 @@
 //   fill implements the convolution padding, so no im2col buffer is ever materialised. The box lands in
 //   shared memory as 128 rows x 128 B with the 128-byte swizzle, which is exactly the K-major UMMA
 //   operand layout. Stride-2 convolutions use a 5-D space-to-depth view of the same tensor
-//   {2C, W/2, 2, H/2, B}; nearest-2x-upsample + 3x3 is algebraically collapsed on the host into four
+//   {pixel pair, W/2, row parity, H/2, B}; nearest-2x-upsample + 3x3 is algebraically collapsed on the host into four
 //   2x2 convolutions (one per output parity) and uses the stride-1 path with strided output addressing.
 // * Weights are [Cout, R*S*Cin] bf16 (K-major), one TMA box {64, BN} per k-block. For the batched
 //   attention GEMMs the B operand is a per-(batch, head) matrix, either K-major (Q K^T) or MN-major
@@ -31,7 +31,7 @@ struct ConvGemmParams {
   int W, H, B;                    // GEMM-side pixel extents
   int n_tiles, Cout;
   int kc_per_tap, R, S, pad_t, pad_l;
-  int stride2, Cin;
+  int stride2, pair_off;          // stride-2 view: channel offset of the odd pixel of a pair (= input ld)
   int b_batched;                  // B operand has (head, batch) coordinates taken from the tile (y, b)
   int b_mn_major;                 // B operand is [K, N] row-major (attention P*V)
   long long o_sx, o_sy, o_sb;     // output element strides per GEMM-side x / y / b
@@ -150,7 +150,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               // input (iy, ix) = (2*oy + r - pad_t, 2*ox + s - pad_l) in the {2C, W/2, 2, H/2, B} view
               const int dy = r - p.pad_t, dx = s - p.pad_l;
               const int py = dy & 1, px = dx & 1;
-              cbase = px * p.Cin;
+              cbase = px * p.pair_off;
               c1 = x0 + ((dx - px) >> 1);
               c2 = py;
               c3 = y0 + ((dy - py) >> 1);
@@ -408,7 +408,7 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
   p.tiles_x = (d.W + tw - 1) / tw; p.tiles_y = (d.H + th - 1) / th; p.tiles_b = (d.B + tb - 1) / tb;
   p.W = d.W; p.H = d.H; p.B = d.B;
   p.Cout = d.Cout; p.kc_per_tap = d.Cin / kBK; p.R = d.R; p.S = d.S; p.pad_t = d.pad_t; p.pad_l = d.pad_l;
-  p.stride2 = d.stride2; p.Cin = d.Cin;
+  p.stride2 = d.stride2; p.pair_off = static_cast<int>(d.x_sx);
   p.b_batched = d.b_batched; p.b_mn_major = d.b_mn_major;
   p.o_sx = d.o_sx; p.o_sy = d.o_sy; p.o_sb = d.o_sb; p.r_sx = d.r_sx; p.r_sy = d.r_sy; p.r_sb = d.r_sb;
   p.out = d.y; p.bias = d.bias; p.res = static_cast<const bf16*>(d.res);
@@ -441,13 +441,14 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
     box[0] = kBK; box[1] = tw; box[2] = th; box[3] = tb_box; box[4] = 1;
   } else {
     if ((d.IW & 1) || (d.IH & 1)) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: stride-2 needs even input extents");
-    if (d.x_sx != d.Cin || d.x_sy != d.x_sx * d.IW || d.x_sb != d.x_sy * d.IH)
-      return set_error(OMGSR_ERR_SHAPE, "conv_gemm: stride-2 needs a dense NHWC input");
-    dims[0] = 2 * d.Cin; dims[1] = d.IW / 2; dims[2] = 2; dims[3] = d.IH / 2; dims[4] = d.B;
-    strides[0] = 2 * d.Cin * eb;                            // next even x
-    strides[1] = static_cast<uint64_t>(d.IW) * d.Cin * eb;  // next row parity
-    strides[2] = 2 * strides[1];                            // next even y
-    strides[3] = strides[1] * d.IH;                         // next image
+    if (d.x_sy != d.x_sx * d.IW || d.x_sb != d.x_sy * d.IH)
+      return set_error(OMGSR_ERR_SHAPE, "conv_gemm: stride-2 needs an input dense in x/y/b (channel stride allowed)");
+    // {pixel pair (ld + Cin channels: even pixel at 0, odd pixel at ld), W/2, row parity, H/2, B}
+    dims[0] = d.x_sx + d.Cin; dims[1] = d.IW / 2; dims[2] = 2; dims[3] = d.IH / 2; dims[4] = d.B;
+    strides[0] = 2 * d.x_sx * eb;                            // next even x
+    strides[1] = static_cast<uint64_t>(d.IW) * d.x_sx * eb;  // next row parity
+    strides[2] = 2 * strides[1];                             // next even y
+    strides[3] = strides[1] * d.IH;                          // next image
     box[0] = kBK; box[1] = tw; box[2] = 1; box[3] = th; box[4] = tb_box;
   }
   int rc = make_tmap_bf16(&tmA, d.x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);

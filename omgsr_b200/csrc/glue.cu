@@ -76,7 +76,9 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                 const float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, long long HW, int C, int G, float eps, int silu,
-                                int vpr, long long total_vec) {
+                                int vpr, long long total_vec, int stats_mode, int stats_mod) {
+  // stats_mode 0: stats[b] = (sum, sumsq) of this very tensor; 1: stats[b % stats_mod] = (mean, var) shared
+  // by several tiles of the same image (cross-tile GroupNorm of the tiled VAE)
   const int cpg = C / G;
   const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vec;
@@ -86,19 +88,40 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
     const int b = static_cast<int>(pix / HW);
     float f[8];
     unpack8(ld_stream(x + pix * ldx + v * 8), f);
-    const float* st = stats + static_cast<long long>(b) * 2 * G;
+    const float* st = stats + static_cast<long long>(stats_mode ? b % stats_mod : b) * 2 * G;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = v * 8 + j;
       const int g = c / cpg;
-      const float mean = st[2 * g] * inv_n;
-      const float var = fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.f);
+      const float mean = stats_mode ? st[2 * g] : st[2 * g] * inv_n;
+      const float var = stats_mode ? st[2 * g + 1] : fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.f);
       const float rstd = rsqrtf(var + eps);
       float o = (f[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
       f[j] = silu ? silu_f(o) : o;
     }
     *reinterpret_cast<uint4*>(y + pix * ldy + v * 8) = pack8(f);
   }
+}
+
+// cross-tile GroupNorm statistics of the tiled VAE (GroupNormParam.summary, infer/vaehook.py:489-508):
+// per entry e = (tile, image b = e % n_img): mean_e, biased var_e; result[b] = sum_e w_e * (mean_e, var_e)
+// with w_e = pixels_e / sum of pixels over the tiles of image b.
+__global__ void gn_combine_kernel(const float* __restrict__ sums, const float* __restrict__ pixels, int entries,
+                                  int n_img, int G, int cpg, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * G) return;
+  const int b = i / G, g = i % G;
+  float wsum = 0.f, m = 0.f, v = 0.f;
+  for (int e = b; e < entries; e += n_img) {
+    const float n = pixels[e] * cpg;
+    const float mean = sums[(static_cast<long long>(e) * G + g) * 2] / n;
+    const float var = fmaxf(sums[(static_cast<long long>(e) * G + g) * 2 + 1] / n - mean * mean, 0.f);
+    wsum += pixels[e];
+    m += pixels[e] * mean;
+    v += pixels[e] * var;
+  }
+  out[2 * i] = m / wsum;
+  out[2 * i + 1] = v / wsum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -370,26 +393,30 @@ __global__ void pack_kernel(const bf16* __restrict__ z, bf16* __restrict__ tok, 
   }
 }
 
-// out[b,c,y,x] = sum_t w[y-oy_t, x-ox_t] * tile_t[b,c,y-oy_t,x-ox_t] / sum_t w[...]
+// out[b,c,y,x] = sum_t w[y-oy_t, x-ox_t] * tile_t[b,c,y-oy_t,x-ox_t] / sum_t w[...]   (generic strides)
+struct BlendStrides {
+  long long t_t, t_b, t_c, t_y, t_x;  // tile tensor strides (elements)
+  long long o_b, o_c, o_y, o_x;       // output strides
+};
 template <typename T>
 __global__ void tile_blend_kernel(const T* __restrict__ tiles, const float* __restrict__ wts,
                                   const int* __restrict__ ofs, int ntiles, float* __restrict__ out, int B, int C, int h,
-                                  int w, int T_, long long total) {
+                                  int w, int T_, long long total, BlendStrides st) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(i % w);
-    const int y = static_cast<int>((i / w) % h);
-    const int c = static_cast<int>((i / (static_cast<long long>(w) * h)) % C);
-    const int b = static_cast<int>(i / (static_cast<long long>(w) * h * C));
+    const int c = static_cast<int>(i % C);
+    const int x = static_cast<int>((i / C) % w);
+    const int y = static_cast<int>((i / (static_cast<long long>(C) * w)) % h);
+    const int b = static_cast<int>(i / (static_cast<long long>(C) * w * h));
     float num = 0.f, den = 0.f;
     for (int t = 0; t < ntiles; ++t) {
       const int tx = x - ofs[2 * t], ty = y - ofs[2 * t + 1];
       if (tx < 0 || ty < 0 || tx >= T_ || ty >= T_) continue;
       const float wv = wts[ty * T_ + tx];
-      num += wv * static_cast<float>(tiles[(((static_cast<long long>(t) * B + b) * C + c) * T_ + ty) * T_ + tx]);
+      num += wv * static_cast<float>(tiles[t * st.t_t + b * st.t_b + c * st.t_c + ty * st.t_y + tx * st.t_x]);
       den += wv;
     }
-    out[i] = num / den;
+    out[b * st.o_b + c * st.o_c + y * st.o_y + x * st.o_x] = num / den;
   }
 }
 
@@ -466,14 +493,26 @@ extern "C" int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats,
 
 extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,
                                      const float* gamma, const float* beta, int B, long long HW, int C, int G,
-                                     float eps, int silu, void* stream) {
+                                     float eps, int silu, int stats_mode, int stats_mod, void* stream) {
+  if (stats_mode && stats_mod <= 0) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: stats_mod must be > 0");
   if (C % 8 || C % G) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: C=%d G=%d", C, G);
   if ((ldx | ldy) % 8) return set_error(OMGSR_ERR_ALIGN, "groupnorm_apply: ld %% 8");
   const int vpr = C / 8;
   const long long total = static_cast<long long>(B) * HW * vpr;
   gn_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, stats, gamma, beta, HW, C, G, eps, silu, vpr, total);
+      static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, stats, gamma, beta, HW, C, G, eps, silu, vpr, total,
+      stats_mode, stats_mod);
   return check_launch("gn_apply_kernel");
+}
+
+extern "C" int omgsr_groupnorm_combine(const float* sums, const float* pixels, int entries, int n_img, int C, int G,
+                                       float* out, void* stream) {
+  if (entries <= 0 || n_img <= 0 || entries % n_img || C % G)
+    return set_error(OMGSR_ERR_SHAPE, "groupnorm_combine: entries=%d n_img=%d", entries, n_img);
+  const int n = n_img * G;
+  gn_combine_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, pixels, entries, n_img, G,
+                                                                                 C / G, out);
+  return check_launch("gn_combine_kernel");
 }
 
 extern "C" int omgsr_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C,
@@ -624,15 +663,20 @@ extern "C" int omgsr_unpack_latents(const void* tokens, void* z, int B, int C, i
 }
 
 extern "C" int omgsr_tile_blend(const void* tiles, int tiles_f32, const float* weights, const int* ofs_xy_dev,
-                                int ntiles, float* out, int B, int C, int h, int w, int T, void* stream) {
+                                int ntiles, float* out, int B, int C, int h, int w, int T, const long long* tile_strides,
+                                const long long* out_strides, void* stream) {
   const long long total = static_cast<long long>(B) * C * h * w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BlendStrides bs;
+  bs.t_t = tile_strides[0]; bs.t_b = tile_strides[1]; bs.t_c = tile_strides[2]; bs.t_y = tile_strides[3];
+  bs.t_x = tile_strides[4];
+  bs.o_b = out_strides[0]; bs.o_c = out_strides[1]; bs.o_y = out_strides[2]; bs.o_x = out_strides[3];
   if (tiles_f32)
     tile_blend_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(tiles), weights,
-                                                                   ofs_xy_dev, ntiles, out, B, C, h, w, T, total);
+                                                                   ofs_xy_dev, ntiles, out, B, C, h, w, T, total, bs);
   else
     tile_blend_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const bf16*>(tiles), weights, ofs_xy_dev,
-                                                                  ntiles, out, B, C, h, w, T, total);
+                                                                  ntiles, out, B, C, h, w, T, total, bs);
   return check_launch("tile_blend_kernel");
 }
 

@@ -1,0 +1,251 @@
+"""UNet2DConditionModel (SD-2.1-base shape) driven through the sm_100a kernels.
+
+Replaces `self.unet(z, mid_timestep, encoder_hidden_states=prompt_embeds).sample`
+(infer/omgsr_s_infer_model.py:75-79,132). Architecture per SURVEY.md Appendix C (diffusers 0.34.0).
+
+B200-first choices
+  * NHWC bf16 residual stream; every skip tensor is produced directly into the channel slice of the
+    concat buffer its up-block consumer reads (torch.cat never runs, no copy).
+  * the timestep is a constructor constant (273), so the whole time-embedding MLP and each ResBlock's
+    time_emb_proj are folded into the conv1 bias at load time.
+  * q/k/v of self-attention are one fused [3C, C] GEMM whose output the flash-attention kernel reads in
+    place through strided TMA views; cross-attention K/V depend only on the prompt and are cached.
+  * GEGLU is fused into the ff.net.0 GEMM epilogue; bias/residual adds into the producing GEMM/conv.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+
+from . import capi
+from .engine_vae import _Res, _dev
+from .pack import pack_conv_in_weight, pack_conv_weight, pack_geglu_weight, pack_upsample_weight
+
+
+def _timestep_embedding(t, dim):
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    args = float(t) * freqs
+    return torch.cat([torch.cos(args), torch.sin(args)])[None]  # flip_sin_to_cos=True, freq_shift=0
+
+
+class _T2D:
+    """Transformer2DModel with one BasicTransformerBlock (self-attn, cross-attn, GEGLU ff)."""
+
+    def __init__(self, sd, name, heads, device):
+        f32, bf = torch.float32, torch.bfloat16
+        tb = name + ".transformer_blocks.0"
+        g = lambda k, dt=f32: _dev(sd[k], device, dt)
+        self.heads = heads
+        self.gn_g, self.gn_b = g(name + ".norm.weight"), g(name + ".norm.bias")
+        self.pin_w, self.pin_b = g(name + ".proj_in.weight", bf), g(name + ".proj_in.bias")
+        self.pout_w, self.pout_b = g(name + ".proj_out.weight", bf), g(name + ".proj_out.bias")
+        self.ln = [(g(f"{tb}.norm{i}.weight"), g(f"{tb}.norm{i}.bias")) for i in (1, 2, 3)]
+        self.wqkv = _dev(torch.cat([sd[f"{tb}.attn1.{p}.weight"] for p in ("to_q", "to_k", "to_v")], 0), device, bf)
+        self.wo1, self.bo1 = g(tb + ".attn1.to_out.0.weight", bf), g(tb + ".attn1.to_out.0.bias")
+        self.wq2 = g(tb + ".attn2.to_q.weight", bf)
+        self.wkv2 = _dev(torch.cat([sd[f"{tb}.attn2.{p}.weight"] for p in ("to_k", "to_v")], 0), device, bf)
+        self.wo2, self.bo2 = g(tb + ".attn2.to_out.0.weight", bf), g(tb + ".attn2.to_out.0.bias")
+        c = sd[name + ".proj_in.weight"].shape[0]
+        bn = 256 if (4 * c) % 128 == 0 else 128
+        wi, bi = pack_geglu_weight(sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"], bn)
+        self.ff_bn = bn
+        self.wff1, self.bff1 = _dev(wi, device, bf), _dev(bi, device, f32)
+        self.wff2, self.bff2 = g(tb + ".ff.net.2.weight", bf), g(tb + ".ff.net.2.bias")
+        self.c = c
+        self.kv_cache = None  # (key, kv [B,77,2C])
+
+    def cross_kv(self, ctx, ctx_key, B):
+        if self.kv_cache is None or self.kv_cache[0] != (ctx_key, B):
+            T = ctx.shape[1]
+            ctx2 = ctx.reshape(-1, ctx.shape[-1])
+            if ctx2.shape[1] % 64:
+                raise RuntimeError("cross_attention_dim must be a multiple of 64")
+            kv = capi.gemm(ctx2, self.wkv2).view(ctx.shape[0], T, 2 * self.c)
+            if ctx.shape[0] != B:  # batch-1 text broadcast over the image batch
+                kv = kv.expand(B, T, 2 * self.c).contiguous()
+            self.kv_cache = ((ctx_key, B), kv)
+        return self.kv_cache[1]
+
+    def forward(self, x, ctx, ctx_key, out):
+        B, H, W, C = x.shape
+        T, hd = H * W, self.heads
+        scale = 1.0 / 8.0  # head dim 64
+        h = capi.groupnorm(x, self.gn_g, self.gn_b, 32, 1e-6, silu=False).view(B * T, C)
+        h = capi.gemm(h, self.pin_w, self.pin_b)
+        # self-attention
+        n = capi.layernorm(h, *self.ln[0], eps=1e-5)
+        qkv = capi.gemm(n, self.wqkv).view(B, T, 3 * C)
+        q, k, v = (qkv[..., i * C:(i + 1) * C].unflatten(-1, (hd, 64)) for i in range(3))
+        a = capi.flash_attn(q, k, v, scale).view(B * T, C)
+        h = capi.gemm(a, self.wo1, self.bo1, res=h)
+        # cross-attention against the (cached) prompt projections
+        n = capi.layernorm(h, *self.ln[1], eps=1e-5)
+        q = capi.gemm(n, self.wq2).view(B, T, hd, 64)
+        kv = self.cross_kv(ctx, ctx_key, B)
+        k2, v2 = (kv[..., i * C:(i + 1) * C].unflatten(-1, (hd, 64)) for i in range(2))
+        a = capi.flash_attn(q, k2, v2, scale).view(B * T, C)
+        h = capi.gemm(a, self.wo2, self.bo2, res=h)
+        # GEGLU feed-forward (gate fused into the first GEMM's epilogue)
+        n = capi.layernorm(h, *self.ln[2], eps=1e-5)
+        f = capi.gemm(n, self.wff1, self.bff1, act=capi.ACT_GEGLU, force_bn=self.ff_bn)
+        h = capi.gemm(f, self.wff2, self.bff2, res=h)
+        # proj_out + outer residual, written straight into the consumer's buffer slice
+        o2 = torch.as_strided(out, (B * T, C), (out.stride(2), 1), out.storage_offset())
+        r2 = torch.as_strided(x, (B * T, C), (x.stride(2), 1), x.storage_offset())
+        capi.gemm(h, self.pout_w, self.pout_b, res=r2, out=o2)
+        return out
+
+
+class B200UNet(torch.nn.Module):
+    def __init__(self, sd, cfg, mid_timestep, device="cuda", dtype=torch.bfloat16):
+        super().__init__()
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("B200UNet: boundary dtype must be bf16 or fp32")
+        self.cfg, self.dev, self._dtype = cfg, device, dtype
+        self.config = SimpleNamespace(in_channels=cfg.in_channels, out_channels=cfg.out_channels)
+        f32 = torch.float32
+        ch = cfg.block_out_channels
+        # ---- constant time embedding (timestep is fixed for the lifetime of the module) ----
+        temb = _timestep_embedding(mid_timestep, ch[0])
+        temb = torch.nn.functional.linear(temb, sd["time_embedding.linear_1.weight"].float(), sd["time_embedding.linear_1.bias"].float())
+        temb = torch.nn.functional.linear(torch.nn.functional.silu(temb), sd["time_embedding.linear_2.weight"].float(),
+                                          sd["time_embedding.linear_2.bias"].float())
+        st = torch.nn.functional.silu(temb)[0]
+
+        def res(name):
+            tb = sd[name + ".time_emb_proj.weight"].float() @ st + sd[name + ".time_emb_proj.bias"].float()
+            return _Res(sd, name, device, extra_bias1=tb)
+
+        self.conv_in_w = _dev(pack_conv_in_weight(sd["conv_in.weight"]), device)
+        self.conv_in_b = _dev(sd["conv_in.bias"], device, f32)
+        n = len(ch)
+        self.down = []
+        for i in range(n):
+            layers = []
+            for j in range(cfg.layers_per_block):
+                r = res(f"down_blocks.{i}.resnets.{j}")
+                t = _T2D(sd, f"down_blocks.{i}.attentions.{j}", cfg.num_heads[i], device) if cfg.down_has_attn[i] else None
+                layers.append((r, t))
+            ds = None
+            if i < n - 1:
+                nm = f"down_blocks.{i}.downsamplers.0.conv"
+                ds = (_dev(pack_conv_weight(sd[nm + ".weight"]), device), _dev(sd[nm + ".bias"], device, f32))
+            self.down.append((layers, ds))
+        self.mid = (res("mid_block.resnets.0"), _T2D(sd, "mid_block.attentions.0", cfg.num_heads[-1], device),
+                    res("mid_block.resnets.1"))
+        rev_attn = list(reversed(cfg.down_has_attn))
+        rev_heads = list(reversed(cfg.num_heads))
+        self.up = []
+        for i in range(n):
+            layers = []
+            for j in range(cfg.layers_per_block + 1):
+                r = res(f"up_blocks.{i}.resnets.{j}")
+                t = _T2D(sd, f"up_blocks.{i}.attentions.{j}", rev_heads[i], device) if rev_attn[i] else None
+                layers.append((r, t))
+            us = None
+            if i < n - 1:
+                nm = f"up_blocks.{i}.upsamplers.0.conv"
+                us = (_dev(pack_upsample_weight(sd[nm + ".weight"]), device), _dev(sd[nm + ".bias"], device, f32))
+            self.up.append((layers, us))
+        self.gno, self.bno = _dev(sd["conv_norm_out.weight"], device, f32), _dev(sd["conv_norm_out.bias"], device, f32)
+        self.conv_out_w = _dev(pack_conv_weight(sd["conv_out.weight"]), device)
+        self.conv_out_b = _dev(sd["conv_out.bias"], device, f32)
+        self._p = torch.nn.Parameter(torch.zeros(1, device=device, dtype=dtype), requires_grad=False)
+        # ---- skip plan: (channels, resolution level) of every pushed tensor, and who consumes it ----
+        self._skip_meta = [(ch[0], 0)]
+        for i in range(n):
+            for _ in range(cfg.layers_per_block):
+                self._skip_meta.append((ch[i], i))
+            if i < n - 1:
+                self._skip_meta.append((ch[i], i + 1))
+        # consumer k (in up order) pops skip index len-1-k; its own width comes from the up path
+        self._up_in = []  # per up resnet: channels arriving from the up path
+        cin = ch[-1]
+        rev = list(reversed(ch))
+        for i in range(n):
+            for j in range(cfg.layers_per_block + 1):
+                self._up_in.append(cin)
+                cin = rev[i]
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    def eps_hat_nhwc(self, z, ctx):
+        """z NCHW latent [B,4,h,w] (bf16|fp32), ctx [1|B,77,D] -> fp32 NHWC [B,h,w,8] (first 4 channels valid)."""
+        cfg = self.cfg
+        ch = cfg.block_out_channels
+        eps = cfg.norm_eps
+        B, _, H0, W0 = z.shape
+        n = len(ch)
+        ctx = ctx.to(device=z.device, dtype=torch.bfloat16).contiguous()
+        ctx_key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
+        res_hw = [(H0 >> l, W0 >> l) for l in range(n)]
+        # concat buffers, one per up resnet; skip s lives in the right slice of its consumer's buffer
+        nsk = len(self._skip_meta)
+        cat = []
+        for k, c_up in enumerate(self._up_in):
+            c_sk, lvl = self._skip_meta[nsk - 1 - k]
+            hh, ww = res_hw[lvl]
+            cat.append(torch.empty((B, hh, ww, c_up + c_sk), device=z.device, dtype=torch.bfloat16))
+
+        def skip_home(s):
+            k = nsk - 1 - s
+            return cat[k][..., self._up_in[k]:]
+
+        # ---- down path ----
+        s = 0
+        h = capi.conv_in_nchw(z.contiguous(), self.conv_in_w, self.conv_in_b, ch[0], out=skip_home(s))
+        s += 1
+        for i, (layers, ds) in enumerate(self.down):
+            for r, t in layers:
+                if t is None:
+                    h = self._res(r, h, eps, out=skip_home(s))
+                else:
+                    hm = self._res(r, h, eps)
+                    h = t.forward(hm, ctx, ctx_key, out=skip_home(s))
+                s += 1
+            if ds is not None:
+                h = capi.conv2d(h, ds[0], ds[1], stride=2, pad=(1, 1, 1, 1), out=skip_home(s))
+                s += 1
+        # ---- mid ----
+        h = self._res(self.mid[0], h, eps)
+        hm = torch.empty_like(h)
+        h = self.mid[1].forward(h, ctx, ctx_key, out=hm)
+        k = 0
+        h = self._res(self.mid[2], h, eps, out=cat[k][..., :self._up_in[k]])
+        # ---- up path ----
+        for i, (layers, us) in enumerate(self.up):
+            for j, (r, t) in enumerate(layers):
+                x = cat[k]
+                k += 1
+                last_of_level = (j == len(layers) - 1)
+                # destination of this layer's result: left slice of the next concat buffer, unless an
+                # upsampler (different resolution) or the output head follows
+                if k < len(cat) and not (last_of_level and us is not None):
+                    dst = cat[k][..., :self._up_in[k]]
+                else:
+                    dst = None
+                if t is None:
+                    h = self._res(r, x, eps, out=dst)
+                else:
+                    hm = self._res(r, x, eps)
+                    if dst is None:
+                        dst = torch.empty_like(hm)
+                    h = t.forward(hm, ctx, ctx_key, out=dst)
+            if us is not None:
+                h = capi.conv2d(h, us[0], us[1], upsample2x=True, out=cat[k][..., :self._up_in[k]])
+        h = capi.groupnorm(h, self.gno, self.bno, 32, eps, silu=True)
+        return capi.conv2d(h, self.conv_out_w, self.conv_out_b, out_f32=True, cout=cfg.out_channels)
+
+    @staticmethod
+    def _res(r, x, eps, out=None):
+        from .engine_vae import resnet_forward
+        return resnet_forward(r, x, eps, out=out)
+
+    def forward(self, sample, timestep=None, encoder_hidden_states=None, **kw):
+        """diffusers-style call: returns an object with `.sample` (NCHW, boundary dtype)."""
+        e = self.eps_hat_nhwc(sample, encoder_hidden_states)
+        out = e[..., :self.cfg.out_channels].permute(0, 3, 1, 2).contiguous().to(self._dtype)
+        return SimpleNamespace(sample=out)

@@ -323,8 +323,15 @@ def test_tile_blend(capi):
     for t, (ox, oy) in enumerate(offs):
         num[:, :, oy:oy + T, ox:ox + T] += tiles[t] * wts
         den[:, :, oy:oy + T, ox:ox + T] += wts
-    out = capi.tile_blend(tiles.cuda(), wts.cuda(), torch.tensor(offs, dtype=torch.int32).cuda(), h, w)
+    out = torch.empty(B, C, h, w, device="cuda")
+    capi.tile_blend(tiles.cuda(), wts.cuda(), torch.tensor(offs, dtype=torch.int32).cuda(), out, T)
     assert report("tile blend", out, num / den, 1e-5)[0]
+    # NHWC-strided tiles and output (the layout the UNet path produces)
+    tn = tiles.permute(0, 1, 3, 4, 2).contiguous().cuda()           # [nt,B,T,T,C]
+    on = torch.empty(B, h, w, 8, device="cuda")
+    capi.tile_blend(tn.permute(0, 1, 4, 2, 3), wts.cuda(), torch.tensor(offs, dtype=torch.int32).cuda(),
+                    on[..., :C].permute(0, 3, 1, 2), T)
+    assert report("tile blend nhwc", on[..., :C].permute(0, 3, 1, 2), num / den, 1e-5)[0]
 
 
 def test_colorfix(capi):
