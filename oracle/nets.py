@@ -21,7 +21,12 @@ def _lin(sd, name, x):
     return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
 
 
+GN_HOOK = None  # set by oracle/vaehook.py to share GroupNorm statistics across tiles
+
+
 def _gn(sd, name, x, eps, groups=32):
+    if GN_HOOK is not None:
+        return GN_HOOK(x, groups, sd[name + ".weight"], sd[name + ".bias"], eps)
     return F.group_norm(x, groups, sd[name + ".weight"], sd[name + ".bias"], eps)
 
 
@@ -45,7 +50,7 @@ def vae_attention(sd, name, x, eps):
     b, c, hh, ww = x.shape
     h = _gn(sd, name + ".group_norm", x, eps).reshape(b, c, hh * ww).transpose(1, 2)
     q, k, v = _lin(sd, name + ".to_q", h), _lin(sd, name + ".to_k", h), _lin(sd, name + ".to_v", h)
-    a = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+    a = torch.softmax(q @ k.transpose(1, 2) * (c ** -0.5), dim=-1) @ v  # materialised, as infer/vaehook.py:160-161
     a = _lin(sd, name + ".to_out.0", a)
     return x + a.transpose(1, 2).reshape(b, c, hh, ww)
 

@@ -29,9 +29,13 @@ def _slice_exec(path, start, end, extra_globals=None):
 
 
 def main():
-    sys.path.insert(0, REF)
-    from infer import wavelet_color_fix as wcf
-    from infer import vaehook
+    # bind `infer` to the reference directory (it is a namespace package there; this repo's own `infer`
+    # package would otherwise shadow it)
+    pkg = types.ModuleType("infer")
+    pkg.__path__ = [os.path.join(REF, "infer")]
+    sys.modules["infer"] = pkg
+    import infer.wavelet_color_fix as wcf
+    import infer.vaehook as vaehook
 
     torch.manual_seed(1234)
     gold = {}

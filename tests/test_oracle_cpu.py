@@ -1,0 +1,163 @@
+"""CPU tests that PIN the oracle against fixtures produced by the reference's own code
+(tests/golden/make_golden.py, make_golden_vaehook.py), plus the host-side logic of the drop-in modules."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(GOLD, "reference_fixtures.pt"), weights_only=False)
+
+
+def test_colorfix_oracle_matches_reference(gold):
+    from oracle import colorfix
+    g = gold["colorfix"]
+    c, s = g["content"], g["style"]
+    assert torch.allclose(colorfix.wavelet_reconstruction(c, s), g["wavelet"], atol=1e-6)
+    assert torch.allclose(colorfix.adaptive_instance_normalization(c, s), g["adain"], atol=1e-6)
+    assert torch.allclose(colorfix.atrous_blur(c, 4), g["blur_r4"], atol=1e-7)
+    # the telescoping identity the CUDA kernel uses: out = content + LP5(style - content)
+    _, low = colorfix.wavelet_decomposition(s - c)
+    assert torch.allclose(c + low, g["wavelet"], atol=2e-6)
+
+
+def test_colorfix_pil_wrappers_match_reference(gold):
+    from PIL import Image
+    from oracle import colorfix
+    g = gold["colorfix_pil"]
+    tgt = Image.fromarray(g["target"].numpy(), "RGB")
+    src = Image.fromarray(g["source"].numpy(), "RGB")
+    assert np.array_equal(np.asarray(colorfix.wavelet_color_fix(tgt, src)), g["wavelet"].numpy())
+    assert np.array_equal(np.asarray(colorfix.adain_color_fix(tgt, src)), g["adain"].numpy())
+
+
+def test_tile_planner_matches_reference(gold):
+    from infer.vaehook import VAEHook
+    from oracle import vaehook as ov
+    for (is_dec, tile, h, w), (ib, ob) in gold["split_tiles"].items():
+        hk = VAEHook(None, tile, is_dec, False, False, False)
+        with contextlib.redirect_stdout(io.StringIO()):
+            a, b = hk.split_tiles(h, w)
+        assert a == ib and b == ob, (is_dec, tile, h, w)
+        assert ov.split_tiles(h, w, tile, is_dec) == (ib, ob)
+    hk = VAEHook(None, 256, False, False, False, False)
+    for (lo, hi), v in gold["best_tile"].items():
+        assert hk.get_best_tile_size(lo, hi) == v
+        assert ov.get_best_tile_size(lo, hi) == v
+
+
+def test_crop_margins_match_reference(gold):
+    from infer.vaehook import VAEHook
+    g = gold["crop"]
+    x = g["x"]
+    m = VAEHook.crop_margins([0, 6, 0, 5], [0, 37, 0, 29], True)
+    assert torch.equal(x[:, :, m[2]:x.size(2) + m[3], m[0]:x.size(3) + m[1]], g["dec"])
+    m = VAEHook.crop_margins([64, 448, 0, 320], [12, 52, 0, 36], False)
+    assert torch.equal(x[:, :, m[2]:x.size(2) + m[3], m[0]:x.size(3) + m[1]], g["enc"])
+
+
+def test_groupnorm_helpers_match_reference(gold):
+    from oracle import ops
+    g = gold["groupnorm"]
+    x = g["x"]
+    xr = x.reshape(2, 32, -1)
+    var, mean = torch.var_mean(xr, dim=2, unbiased=False)
+    assert torch.allclose(var.flatten(), g["var"], atol=1e-6) and torch.allclose(mean.flatten(), g["mean"], atol=1e-6)
+    ref = ops.groupnorm_nhwc(x.permute(0, 2, 3, 1), g["w"], g["b"], 32, 1e-6).permute(0, 3, 1, 2)
+    assert torch.allclose(ref, g["out"], atol=1e-5)
+
+
+def test_flux_helpers_match_reference(gold):
+    from infer import omgsr_f_infer_model as fm
+    g = gold["flux"]
+    sched = fm.get_flux_setting_timesteps()
+    assert len(sched) == 1000
+    assert torch.allclose(torch.tensor(sched, dtype=torch.float64), g["schedule"], atol=0, rtol=0)
+    assert sched[-(244 + 1)] == g["t_curr_244"]
+    lat = g["lat"]
+    packed = fm._pack_latents(lat, 2, 16, 8, 12)
+    assert torch.equal(packed, g["packed"])
+    assert torch.equal(fm._unpack_latents(packed, 64, 96, 8), g["unpacked"])
+    from infer.infer_omgsr_f import _prepare_latent_image_ids
+    assert torch.equal(_prepare_latent_image_ids(6, 4, "cpu", torch.float32), g["img_ids"])
+
+
+def test_gaussian_weights_match_reference(gold):
+    from oracle import omgsr_s
+    for (tw, th), ref in gold["gauss"].items():
+        mine = omgsr_s.gaussian_weights(tw, th)
+        assert mine.dtype == torch.float64
+        assert torch.allclose(mine, ref[0, 0], rtol=1e-14, atol=0)
+        assert ref.shape == (1, 4, th, tw)
+
+
+def test_tile_offsets_cover_reference_cases():
+    from oracle import omgsr_s
+    # latent 128 / tile 64 / overlap 32 -> offsets {0,32,64}; 256/128/64 -> {0,64,128}
+    offs = omgsr_s.tile_offsets(128, 128, 64, 32)
+    assert sorted(set(o[0] for o in offs)) == [0, 32, 64] and len(offs) == 9
+    offs = omgsr_s.tile_offsets(256, 256, 128, 64)
+    assert sorted(set(o[1] for o in offs)) == [0, 64, 128]
+    # non-square, last tile forced to dim - T
+    offs = omgsr_s.tile_offsets(80, 100, 64, 32)
+    assert offs[-1] == (100 - 64, 80 - 64)
+
+
+def test_vaehook_oracle_matches_reference_vaehook():
+    """oracle/vaehook.py (+ oracle/nets.py) against the reference's own VAEHook run on a stub net (CPU)."""
+    from omgsr_b200 import weights as W
+    from oracle import nets
+    from oracle import vaehook as ov
+    g = torch.load(os.path.join(GOLD, "vaehook_fixtures.pt"), weights_only=False)
+    cfg = W.VAEConfig(block_out_channels=W.TINY_VAE.block_out_channels, use_quant_conv=False)
+    sd = W.random_state_dict(W.vae_shapes(W.TINY_VAE), 0)
+    gen = torch.Generator().manual_seed(4321)
+    x = torch.rand(1, 3, 192, 160, generator=gen) * 2 - 1
+    z = torch.randn(1, 4, 40, 48, generator=gen)
+    assert x.double().sum() == g["enc_in_sum"] and z.double().sum() == g["dec_in_sum"]
+    with torch.no_grad():
+        assert torch.allclose(nets.vae_encode_moments(sd, cfg, x), g["enc_untiled_oracle"], atol=1e-5)
+        enc = ov.tiled_forward(lambda t: nets.vae_encode_moments(sd, cfg, t), x, 64, False)
+        dec = ov.tiled_forward(lambda t: nets.vae_decode(sd, cfg, t), z, 16, True)
+    assert enc.shape == g["enc_tiled"].shape and dec.shape == g["dec_tiled"].shape
+    assert (enc - g["enc_tiled"]).abs().max() < 2e-4, (enc - g["enc_tiled"]).abs().max()
+    assert (dec - g["dec_tiled"]).abs().max() < 2e-4, (dec - g["dec_tiled"]).abs().max()
+
+
+def test_weight_tables_reproduce_public_parameter_counts():
+    from omgsr_b200 import weights as W
+    n = lambda shapes: sum(int(np.prod(s)) for s in shapes.values())
+    assert n(W.vae_shapes(W.SD21_VAE)) == 83_653_863
+    assert n(W.unet_shapes(W.SD21_UNET)) == 865_910_724
+    assert abs(n(W.flux_shapes(W.FLUX_DEV)) - 11.90e9) < 0.01e9
+
+
+def test_lora_merge_matches_definition():
+    from omgsr_b200 import weights as W
+    shapes = W.vae_shapes(W.TINY_VAE)
+    sd = W.random_state_dict(shapes, 0)
+    ad = W.random_lora(shapes, W.LORA_TARGETS_SD, 4, 1, prefix="encoder.")
+    assert all(k.startswith("encoder.") for k in ad)
+    assert "encoder.conv_in" in ad and "encoder.down_blocks.0.downsamplers.0.conv" in ad
+    assert "encoder.mid_block.attentions.0.to_out.0" in ad and "decoder.conv_in" not in ad
+    merged = W.merge_lora(sd, ad)
+    a, b = ad["encoder.down_blocks.1.resnets.0.conv1"]
+    x = torch.randn(1, a.shape[1], 9, 9)
+    base = torch.nn.functional.conv2d(x, sd["encoder.down_blocks.1.resnets.0.conv1.weight"], padding=1)
+    lora = torch.nn.functional.conv2d(torch.nn.functional.conv2d(x, a, padding=1), b)  # PEFT Conv2d LoRA: B(A(x))
+    full = torch.nn.functional.conv2d(x, merged["encoder.down_blocks.1.resnets.0.conv1.weight"], padding=1)
+    assert torch.allclose(full, base + lora, atol=1e-5)
+    assert torch.equal(merged["decoder.conv_in.weight"], sd["decoder.conv_in.weight"])
+
+
+def test_ddpm_alpha_matches_survey_constant():
+    from omgsr_b200 import weights as W
+    a = W.ddpm_alphas_cumprod()[273].item()
+    assert abs(a - 0.6357423) < 1e-6
