@@ -59,6 +59,16 @@ int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias, const void
                     long long M, int N, int K, long long lda, long long ldd, long long ldr, int act, int gate_rows,
                     int flags, int force_bn, void* stream);
 
+/* Row-batched linear layer: D[b, m, :] = epi(A[b, m, :] * Wt^T) for b < batch, with independent batch strides
+ * for A / D / res (tokens of one image may live inside a longer joint [text; image] sequence), a per-batch
+ * gate vector gate[b * gate_ld + n], and the activation restricted to output columns [act_c0, act_c1)
+ * (act_c1 <= act_c0: all columns). Used by the FLUX DiT blocks (fused q|mlp|k|v projection of the single
+ * blocks, gated residual projections). */
+int omgsr_gemm_batched_bf16(const void* A, const void* Wt, const float* bias, const void* res, const float* gate,
+                            void* D, int batch, int M, int N, int K, long long lda, long long a_batch, long long ldd,
+                            long long d_batch, long long ldr, long long r_batch, long long gate_ld, int act,
+                            int act_c0, int act_c1, int flags, int force_bn, void* stream);
+
 /* Batched attention-style GEMM over (batch b, head h):
  *   D[b,h,m,n] = alpha-free sum_k A[b,m,h,k] * Bm[b,n,h,k]          (flags & OMGSR_B_MN_MAJOR == 0; Q K^T)
  *   D[b,m,h,n] =            sum_k A[b,h,m,k] * Bm[b,k,h,n]          (flags & OMGSR_B_MN_MAJOR;      P V)
@@ -120,17 +130,25 @@ int omgsr_groupnorm_combine(const float* sums, const float* pixels, int entries,
                             void* stream);
 /* LayerNorm over the last dim with y = xhat * g + b where g/b are fp32 vectors of length C taken from
  * gamma + (row / rows_per_batch) * gb_stride (gb_stride = 0: shared affine; >0: per-image AdaLN modulation,
- * caller passes g = 1 + scale, b = shift). gamma/beta may be null (no affine). */
+ * caller passes g = 1 + scale, b = shift). gamma/beta may be null (no affine). Input row r lives at
+ * x + r*ldx, or at x + (r / rows_per_batch)*x_batch_stride + (r % rows_per_batch)*ldx when x_batch_stride > 0
+ * (a token range of a longer joint sequence); the output is dense [rows, C]. ldx = 0 means C.
+ * (UNet BasicTransformerBlock norms, eps 1e-5; FLUX AdaLayerNormZero / Continuous, eps 1e-6) */
 int omgsr_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,
-                    long long rows_per_batch, long long gb_stride, void* stream);
+                    long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch_stride,
+                    void* stream);
 /* softmax over rows of fp32 scores: P[r, j] = softmax_j(scale * S[r, j]) for j < n, P[r, j] = 0 for
  * n <= j < n_pad. */
 int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int n_pad,
                        float scale, void* stream);
-/* FLUX q/k RMSNorm (per head, d = 128, learned weight) + rotary embedding, in place on [rows, heads, 128]
- * bf16 with row stride ld. cos/sin: fp32 [rows_per_batch, 128] (interleaved-pair layout). */
-int omgsr_rmsnorm_rope(void* x, long long ld, const float* weight, const float* cos_t, const float* sin_t,
-                       long long rows, int heads, long long rows_per_batch, float eps, void* stream);
+/* FLUX q/k RMSNorm (per head, d = 128, learned weight, fp32 statistics) + rotary embedding, in place on
+ * x[b, r, h, 128] = x + b*batch_stride + r*ld + h*128 (bf16). Heads [0, heads_per_weight) use weight[0],
+ * the next heads_per_weight use weight[1], ... so q and k of a fused qkv row take one launch.
+ * cos/sin: fp32 [positions, 128] (repeat-interleaved pairs); row r uses position pos_offset + r.
+ * (diffusers FluxAttnProcessor2_0 under infer/omgsr_f_infer_model.py:191-200) */
+int omgsr_rmsnorm_rope(void* x, long long ld, long long batch_stride, const float* weight, const float* cos_t,
+                       const float* sin_t, long long rows_per_batch, int batch, int heads, int heads_per_weight,
+                       int pos_offset, float eps, void* stream);
 
 /* ---- latent-sized elementwise steps ------------------------------------------------------------ */
 

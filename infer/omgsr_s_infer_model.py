@@ -88,7 +88,7 @@ class OMGSR_S_Infer(torch.nn.Module):
         self._s2 = float(self.alpha_t.sqrt())
         self._wts = {}
         pq = self.vae.post_quant_conv
-        self._pq = (pq.wf, pq.b) if pq is not None else (None, None)
+        self._pq = (pq.wf, pq.bf) if pq is not None else (None, None)
         # self._init_tiled_vae(encoder_tile_size=1024, decoder_tile_size=224)   (off by default, as in the reference :32)
 
     def _init_tiled_vae(
@@ -180,6 +180,8 @@ class OMGSR_S_Infer(torch.nn.Module):
         # stacked on the batch axis and run as ONE UNet forward of batch nt*B.
         tiles = torch.stack([lq_latent[:, :, oy:oy + tile_size, ox:ox + tile_size] for ox, oy in offs], 0)
         tiles = tiles.reshape(nt * B, C, tile_size, tile_size).contiguous()
+        if prompt_embeds.shape[0] not in (1, nt * B):  # per-image prompts: repeat for every tile of that image
+            prompt_embeds = prompt_embeds.repeat(nt, 1, 1)
         eps_t = self.unet.eps_hat_nhwc(tiles, prompt_embeds)  # fp32 NHWC view [nt*B,T,T,C] (ld 8)
         ld = eps_t.stride(2)
         et = torch.as_strided(eps_t, (nt, B, C, tile_size, tile_size),

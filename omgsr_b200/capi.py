@@ -18,7 +18,7 @@ OUT_F32, B_MN_MAJOR = 1, 2
 # every symbol include/omgsr_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
     "omgsr_version", "omgsr_last_error", "omgsr_destroy", "omgsr_launch_count",
-    "omgsr_gemm_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
+    "omgsr_gemm_bf16", "omgsr_gemm_batched_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
     "omgsr_conv_in_nchw", "omgsr_conv_out_nchw",
     "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_groupnorm_combine", "omgsr_layernorm", "omgsr_softmax_rows",
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
@@ -175,14 +175,18 @@ def conv2d(x, w, bias=None, res=None, ksize=3, stride=1, pad=(1, 1, 1, 1), upsam
 
 
 def conv_in_nchw(x, w, bias, cout, ksize=3, out=None):
-    """x NCHW (bf16|fp32) -> NHWC bf16. w fp32 [k*k*Cin, Cout]."""
+    """x NCHW (bf16|fp32) -> NHWC bf16 [B,H,W,cout]. w fp32 [k*k*Cin, cout8], bias fp32 [cout8] (zero-padded to a
+    multiple of 8, omgsr_b200.pack.pack_conv_in_weight / pad8)."""
     assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32)
     _cuda_f32(w, "w"); _cuda_f32(bias, "bias")
     B, Cin, H, W = x.shape
+    cout8 = w.shape[1]
+    assert cout8 % 8 == 0 and cout8 >= cout and bias.numel() == cout8
     if out is None:
-        out = torch.empty((B, H, W, cout), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((B, H, W, cout8), device=x.device, dtype=torch.bfloat16)[..., :cout]
+    assert out.stride(2) >= cout8 or cout8 == cout
     rc = _lib.omgsr_conv_in_nchw(_ptr(x), _i(int(x.dtype == torch.float32)), _ptr(w), _ptr(bias), _ptr(out), _i(B),
-                                 _i(Cin), _i(H), _i(W), _i(cout), _i(ksize), _ll(out.stride(2)), _stream())
+                                 _i(Cin), _i(H), _i(W), _i(cout8), _i(ksize), _ll(out.stride(2)), _stream())
     _check(rc, "omgsr_conv_in_nchw")
     return out
 
@@ -246,14 +250,21 @@ def groupnorm_combine(sums, pixels, n_img, C, groups=32):
 
 
 def layernorm(x, gamma=None, beta=None, eps=1e-5, rows_per_batch=0, gb_stride=0, out=None):
+    """x: dense [..., C] or a 3-D view [B, rows, C] with free row / batch strides; output dense."""
     _cuda_bf16(x, "x"); _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta")
-    assert x.is_contiguous()
     C = x.shape[-1]
     rows = x.numel() // C
+    ldx, xbs = C, 0
+    if not x.is_contiguous():
+        assert x.dim() == 3 and x.stride(2) == 1, "layernorm: strided input must be a [B, rows, C] view"
+        ldx, xbs = x.stride(1), x.stride(0)
+        if rows_per_batch == 0:
+            rows_per_batch = x.shape[1]
+        assert rows_per_batch == x.shape[1]
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     rc = _lib.omgsr_layernorm(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ll(rows), _i(C), _f(eps),
-                              _ll(rows_per_batch), _ll(gb_stride), _stream())
+                              _ll(rows_per_batch), _ll(gb_stride), _ll(ldx), _ll(xbs), _stream())
     _check(rc, "omgsr_layernorm")
     return out
 
@@ -272,14 +283,45 @@ def softmax_rows(s, n, scale, out=None):
     return out
 
 
-def rmsnorm_rope_(x, weight, cos_t, sin_t, heads, rows_per_batch, eps=1e-6):
-    """in place on x: [rows, >= heads*128] bf16 view (row stride x.stride(0))."""
+def rmsnorm_rope_(x, weight, cos_t, sin_t, heads, heads_per_weight, pos_offset=0, eps=1e-6):
+    """in place on x: [B, rows, >= heads*128] bf16 view (last dim contiguous). weight fp32 [heads/heads_per_weight, 128]."""
     _cuda_bf16(x, "x"); _cuda_f32(weight, "weight"); _cuda_f32(cos_t, "cos"); _cuda_f32(sin_t, "sin")
-    rows = x.shape[0]
-    rc = _lib.omgsr_rmsnorm_rope(_ptr(x), _ll(x.stride(0)), _ptr(weight), _ptr(cos_t), _ptr(sin_t), _ll(rows),
-                                 _i(heads), _ll(rows_per_batch), _f(eps), _stream())
+    B, rows = x.shape[0], x.shape[1]
+    assert x.stride(2) == 1 and cos_t.is_contiguous() and sin_t.is_contiguous() and weight.is_contiguous()
+    assert cos_t.shape[0] >= pos_offset + rows
+    rc = _lib.omgsr_rmsnorm_rope(_ptr(x), _ll(x.stride(1)), _ll(x.stride(0)), _ptr(weight), _ptr(cos_t), _ptr(sin_t),
+                                 _ll(rows), _i(B), _i(heads), _i(heads_per_weight), _i(pos_offset), _f(eps), _stream())
     _check(rc, "omgsr_rmsnorm_rope")
     return x
+
+
+def gemm_batched(a, w, bias=None, res=None, gate=None, act=ACT_NONE, act_cols=None, out=None, out_f32=False,
+                 force_bn=0):
+    """out[b, m, :] = epi(a[b, m, :] @ w^T). a/out/res: 3-D views [B, M, *] with the last dim contiguous and
+    arbitrary row / batch strides; gate: fp32 2-D view [B, N] (row stride free)."""
+    _cuda_bf16(a, "a"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias"); _cuda_f32(gate, "gate")
+    B, M, K = a.shape
+    N = w.shape[0]
+    assert a.stride(2) == 1 and w.is_contiguous() and w.shape[1] == K
+    if out is None:
+        out = torch.empty((B, M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    assert out.stride(2) == 1 and out.shape[:2] == (B, M)
+    ldr = rb = 0
+    if res is not None:
+        _cuda_bf16(res, "res")
+        assert res.stride(2) == 1
+        ldr, rb = res.stride(1), res.stride(0)
+    gld = 0
+    if gate is not None:
+        assert gate.stride(1) == 1 and gate.shape[0] == B
+        gld = gate.stride(0)
+    c0, c1 = act_cols if act_cols is not None else (0, 0)
+    rc = _lib.omgsr_gemm_batched_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(res), _ptr(gate), _ptr(out), _i(B), _i(M),
+                                      _i(N), _i(K), _ll(a.stride(1)), _ll(a.stride(0)), _ll(out.stride(1)),
+                                      _ll(out.stride(0)), _ll(ldr), _ll(rb), _ll(gld), _i(act), _i(c0), _i(c1),
+                                      _i(OUT_F32 if out.dtype == torch.float32 else 0), _i(force_bn), _stream())
+    _check(rc, "omgsr_gemm_batched_bf16")
+    return out
 
 
 def posterior_sample(moments, eps, cz, shift, scale, out_dtype=torch.bfloat16):

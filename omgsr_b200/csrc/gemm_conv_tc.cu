@@ -41,6 +41,8 @@ struct ConvGemmParams {
   const bf16* res;     // or null
   const float* gate;   // [B or M/gate_rows, Cout_out] or null
   int gate_rows;       // linear mode: rows per gate vector (tokens per image)
+  long long gate_ld;   // elements between consecutive gate vectors
+  int act_c0, act_c1;  // the activation is applied to output columns in [act_c0, act_c1) only
   int act;             // OMGSR_ACT_*
   int out_f32;
   int a_bytes;         // bytes one A box delivers (tb may be clamped to B)
@@ -237,7 +239,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
       const bf16* res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
       const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : b) : 0;
-      const float* gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * cout_out : nullptr;
+      const float* gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
@@ -266,7 +268,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) {
             float a = __uint_as_float(v[j]);
             if (p.bias) a += __ldg(p.bias + min(cv + j, p.Cout - 1));
-            f[j] = apply_act(a, p.act);
+            f[j] = (cv + j >= p.act_c0 && cv + j < p.act_c1) ? apply_act(a, p.act) : a;
           }
         }
         const int oc0 = t.n_tile * out_bn + c0;  // first output channel of this chunk
@@ -369,6 +371,7 @@ struct ConvDesc {
   long long x_sx, x_sy, x_sb;  // input element strides per x / y / b (stride-1 path)
   long long o_sx, o_sy, o_sb, r_sx, r_sy, r_sb;
   int act, gate_rows, force_bn, out_f32;
+  long long gate_ld; int act_c0, act_c1;
   long long w_ld;  // elements per weight row (R*S*Cin)
   // batched B operand (attention)
   int b_batched, b_mn_major, flat;
@@ -413,6 +416,8 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
   p.o_sx = d.o_sx; p.o_sy = d.o_sy; p.o_sb = d.o_sb; p.r_sx = d.r_sx; p.r_sy = d.r_sy; p.r_sb = d.r_sb;
   p.out = d.y; p.bias = d.bias; p.res = static_cast<const bf16*>(d.res);
   p.gate = d.gate; p.gate_rows = d.gate_rows; p.act = d.act; p.out_f32 = d.out_f32;
+  p.gate_ld = d.gate_ld > 0 ? d.gate_ld : (geglu ? d.Cout / 2 : d.Cout);
+  p.act_c0 = d.act_c1 > d.act_c0 ? d.act_c0 : 0; p.act_c1 = d.act_c1 > d.act_c0 ? d.act_c1 : 0x7fffffff;
   p.a_bytes = kBK * 2 * tw * th * tb_box;
 
   const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_b;
@@ -498,6 +503,25 @@ extern "C" int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias,
   d.act = act; d.gate_rows = gate ? gate_rows : 0; d.force_bn = force_bn; d.w_ld = K;
   d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
   d.flat = 1;
+  return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int omgsr_gemm_batched_bf16(const void* A, const void* Wt, const float* bias, const void* res,
+                                       const float* gate, void* D, int batch, int M, int N, int K, long long lda,
+                                       long long a_batch, long long ldd, long long d_batch, long long ldr,
+                                       long long r_batch, long long gate_ld, int act, int act_c0, int act_c1,
+                                       int flags, int force_bn, void* stream) {
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) return set_error(OMGSR_ERR_SHAPE, "gemm_batched: empty problem");
+  ConvDesc d{};
+  d.x = A; d.w = Wt; d.bias = bias; d.res = res; d.gate = gate; d.y = D;
+  d.B = batch; d.H = 1; d.W = M; d.IH = 1; d.IW = M;
+  d.Cin = K; d.Cout = N; d.R = 1; d.S = 1;
+  d.x_sx = lda; d.x_sy = lda * M; d.x_sb = a_batch;
+  d.o_sx = ldd; d.o_sy = 0; d.o_sb = d_batch; d.r_sx = ldr; d.r_sy = 0; d.r_sb = r_batch;
+  d.act = act; d.gate_rows = 0; d.force_bn = force_bn; d.w_ld = K; d.gate_ld = gate_ld;
+  d.act_c0 = act_c0; d.act_c1 = act_c1;
+  d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
+  d.flat = 1;  // 128-row tiles never straddle two batch entries
   return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
 }
 

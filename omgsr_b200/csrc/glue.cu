@@ -130,19 +130,23 @@ __global__ void gn_combine_kernel(const float* __restrict__ sums, const float* _
 template <int VPL>  // 8-element vectors per lane
 __global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, long long rows, int C, float eps,
-                                 long long rows_per_batch, long long gb_stride) {
+                                 long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int nvec = C / 8;
   for (long long row = warp_global; row < rows; row += nwarps) {
+    // input rows may be batch-strided (a token range inside a longer joint sequence); output is dense
+    const bf16* xr = (rows_per_batch > 0 && x_batch > 0)
+                         ? x + (row / rows_per_batch) * x_batch + (row % rows_per_batch) * ldx
+                         : x + row * ldx;
     float f[VPL][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        unpack8(ld_stream(x + row * C + v * 8), f[i]);
+        unpack8(ld_stream(xr + v * 8), f[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += f[i][j];
       }
@@ -206,27 +210,31 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s,
 }
 
 // ------------------------------------------------------------------------------------------------
-// FLUX: per-head RMSNorm (d = 128) + rotary embedding on q or k, in place. One warp per (row, head):
-// lane owns 4 consecutive channels = 2 rotation pairs.
+// FLUX: per-head RMSNorm (d = 128) + rotary embedding on q and k, in place. One warp per (row, head):
+// lane owns 4 consecutive channels = 2 rotation pairs. Heads [0, heads_per_w) use weight[0] (q),
+// the next heads_per_w use weight[1] (k), so q and k of a fused qkv row are handled by one launch.
 // ------------------------------------------------------------------------------------------------
-__global__ void rmsnorm_rope_kernel(bf16* __restrict__ x, long long ld, const float* __restrict__ weight,
-                                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
-                                    long long rows, int heads, long long rows_per_batch, float eps) {
+__global__ void rmsnorm_rope_kernel(bf16* __restrict__ x, long long ld, long long batch_stride,
+                                    const float* __restrict__ weight, const float* __restrict__ cos_t,
+                                    const float* __restrict__ sin_t, long long rows_per_batch, int batch, int heads,
+                                    int heads_per_w, int pos_offset, float eps) {
   const int lane = threadIdx.x & 31;
   const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long it = wg; it < rows * heads; it += nw) {
-    const long long row = it / heads;
+  const long long total = rows_per_batch * batch * heads;
+  for (long long it = wg; it < total; it += nw) {
     const int h = static_cast<int>(it % heads);
-    bf16* px = x + row * ld + h * 128 + lane * 4;
+    const long long br = it / heads;
+    const long long r = br % rows_per_batch, b = br / rows_per_batch;
+    bf16* px = x + b * batch_stride + r * ld + h * 128 + lane * 4;
     const uint2 u = *reinterpret_cast<const uint2*>(px);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    float ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    const float2 a = unpack_bf16x2(u.x), c2 = unpack_bf16x2(u.y);
+    float ss = a.x * a.x + a.y * a.y + c2.x * c2.x + c2.y * c2.y;
     ss = warp_sum(ss);
-    const float r = rsqrtf(ss * (1.0f / 128.f) + eps);
-    const float4 w = *reinterpret_cast<const float4*>(weight + lane * 4);
-    const float v0 = a.x * r * w.x, v1 = a.y * r * w.y, v2 = b.x * r * w.z, v3 = b.y * r * w.w;
-    const long long pos = row % rows_per_batch;
+    const float rs = rsqrtf(ss * (1.0f / 128.f) + eps);
+    const float4 w = *reinterpret_cast<const float4*>(weight + (h / heads_per_w) * 128 + lane * 4);
+    const float v0 = a.x * rs * w.x, v1 = a.y * rs * w.y, v2 = c2.x * rs * w.z, v3 = c2.y * rs * w.w;
+    const long long pos = pos_offset + r;
     const float4 c = *reinterpret_cast<const float4*>(cos_t + pos * 128 + lane * 4);
     const float4 s = *reinterpret_cast<const float4*>(sin_t + pos * 128 + lane * 4);
     uint2 o;
@@ -516,8 +524,11 @@ extern "C" int omgsr_groupnorm_combine(const float* sums, const float* pixels, i
 }
 
 extern "C" int omgsr_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C,
-                               float eps, long long rows_per_batch, long long gb_stride, void* stream) {
+                               float eps, long long rows_per_batch, long long gb_stride, long long ldx,
+                               long long x_batch_stride, void* stream) {
   if (C % 8 || C > 4096) return set_error(OMGSR_ERR_SHAPE, "layernorm: C=%d", C);
+  if (ldx <= 0) ldx = C;
+  if ((ldx | x_batch_stride) % 8) return set_error(OMGSR_ERR_ALIGN, "layernorm: strides %% 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
@@ -525,7 +536,8 @@ extern "C" int omgsr_layernorm(const void* x, void* y, const float* gamma, const
   const bf16* xi = static_cast<const bf16*>(x);
   bf16* yo = static_cast<bf16*>(y);
 #define LN_CASE(V)                                                                                               \
-  layernorm_kernel<V><<<grid, threads, 0, st>>>(xi, yo, gamma, beta, rows, C, eps, rows_per_batch, gb_stride)
+  layernorm_kernel<V><<<grid, threads, 0, st>>>(xi, yo, gamma, beta, rows, C, eps, rows_per_batch, gb_stride, ldx,   \
+                                                x_batch_stride)
   if (vpl <= 1) LN_CASE(1);
   else if (vpl <= 2) LN_CASE(2);
   else if (vpl <= 4) LN_CASE(4);
@@ -547,11 +559,14 @@ extern "C" int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long 
   return check_launch("softmax_rows_kernel");
 }
 
-extern "C" int omgsr_rmsnorm_rope(void* x, long long ld, const float* weight, const float* cos_t, const float* sin_t,
-                                  long long rows, int heads, long long rows_per_batch, float eps, void* stream) {
-  if (ld % 4) return set_error(OMGSR_ERR_ALIGN, "rmsnorm_rope: ld %% 4");
-  rmsnorm_rope_kernel<<<grid_for(rows * heads * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<bf16*>(x), ld, weight, cos_t, sin_t, rows, heads, rows_per_batch, eps);
+extern "C" int omgsr_rmsnorm_rope(void* x, long long ld, long long batch_stride, const float* weight,
+                                  const float* cos_t, const float* sin_t, long long rows_per_batch, int batch,
+                                  int heads, int heads_per_weight, int pos_offset, float eps, void* stream) {
+  if ((ld | batch_stride) % 4) return set_error(OMGSR_ERR_ALIGN, "rmsnorm_rope: strides %% 4");
+  if (heads <= 0 || heads_per_weight <= 0) return set_error(OMGSR_ERR_SHAPE, "rmsnorm_rope: heads");
+  rmsnorm_rope_kernel<<<grid_for(rows_per_batch * batch * heads * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(x), ld, batch_stride, weight, cos_t, sin_t, rows_per_batch, batch, heads, heads_per_weight,
+      pos_offset, eps);
   return check_launch("rmsnorm_rope_kernel");
 }
 

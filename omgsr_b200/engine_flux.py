@@ -1,0 +1,224 @@
+"""FluxTransformer2DModel (FLUX.1-dev shape) driven through the sm_100a kernels.
+
+Replaces `self.flux_transformer(hidden_states=..., timestep=..., guidance=..., pooled_projections=...,
+encoder_hidden_states=..., txt_ids=..., img_ids=..., return_dict=False)[0]`
+(infer/omgsr_f_infer_model.py:191-200,271-280). Architecture per SURVEY.md Appendix C (diffusers 0.34.0).
+
+B200-first choices
+  * ONE GEMM produces every AdaLN modulation vector of the whole network (57 blocks + output norm: the
+    1.06 M x 3072 stacked weight is streamed once, 6.5 GB at HBM rate) — they all depend only on
+    silu(temb). The "+1" of (1 + scale) is folded into that GEMM's bias.
+  * text and image tokens live in one joint [B, 512+T, *] buffer from the first block on, so the joint
+    attention reads q/k/v in place (strided TMA views) and the double->single block transition needs no
+    concat; q|k|v (double blocks) and q|mlp|k|v (single blocks) are single fused GEMMs, the attention
+    output overwrites the dead q slot so proj_out of the single blocks reads [attn | gelu(mlp)] contiguously.
+  * per-head RMSNorm + RoPE run in place on the fused projection (one launch for q and k).
+  * gate * (.) + residual and GELU-tanh are GEMM epilogues; LayerNorm + modulation is one kernel.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+
+from . import capi
+from .engine_vae import _dev
+
+
+def _sincos256(v):
+    half = 128
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    args = v.float()[:, None] * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def flux_rope_tables(ids, axes_dims, theta=10000.0):
+    """cos/sin [S, sum(axes_dims)] fp32, each frequency repeated twice (FluxPosEmbed)."""
+    cos_out, sin_out = [], []
+    pos = ids.double().cpu()
+    for i, d in enumerate(axes_dims):
+        freqs = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64) / d))
+        ang = pos[:, i:i + 1] * freqs[None]
+        cos_out.append(ang.cos().repeat_interleave(2, dim=1).float())
+        sin_out.append(ang.sin().repeat_interleave(2, dim=1).float())
+    return torch.cat(cos_out, dim=-1).contiguous(), torch.cat(sin_out, dim=-1).contiguous()
+
+
+class B200FluxTransformer(torch.nn.Module):
+    def __init__(self, sd, cfg, device="cuda", dtype=torch.bfloat16):
+        super().__init__()
+        if cfg.head_dim != 128:
+            raise ValueError("B200FluxTransformer: head_dim must be 128")
+        self.cfg, self.dev, self._dtype = cfg, device, dtype
+        self.config = SimpleNamespace(in_channels=cfg.in_channels, guidance_embeds=cfg.guidance_embeds)
+        bf, f32 = torch.bfloat16, torch.float32
+        d = cfg.dim
+        g = lambda k, dt: _dev(sd[k], device, dt)
+        self.x_emb = (g("x_embedder.weight", bf), g("x_embedder.bias", f32))
+        self.c_emb = (g("context_embedder.weight", bf), g("context_embedder.bias", f32))
+        self.emb = {}
+        for e in ("timestep_embedder", "guidance_embedder", "text_embedder"):
+            if f"time_text_embed.{e}.linear_1.weight" in sd:
+                self.emb[e] = tuple(g(f"time_text_embed.{e}.linear_{i}.{p}", bf if p == "weight" else f32)
+                                    for i in (1, 2) for p in ("weight", "bias"))
+        # ---- one stacked modulation projection for the whole network ----
+        mods_w, mods_b, self.mod_off = [], [], {}
+        off = 0
+
+        def add_mod(key, name, chunks, scale_chunks):
+            nonlocal off
+            w = sd[name + ".weight"]
+            b = sd[name + ".bias"].float().clone()
+            for c in scale_chunks:  # (1 + scale): fold the 1 into the bias
+                b[c * d:(c + 1) * d] += 1.0
+            mods_w.append(w)
+            mods_b.append(b)
+            self.mod_off[key] = off
+            off += chunks * d
+
+        for i in range(cfg.num_layers):
+            add_mod(("d", i, "x"), f"transformer_blocks.{i}.norm1.linear", 6, (1, 4))
+            add_mod(("d", i, "c"), f"transformer_blocks.{i}.norm1_context.linear", 6, (1, 4))
+        for i in range(cfg.num_single_layers):
+            add_mod(("s", i), f"single_transformer_blocks.{i}.norm.linear", 3, (1,))
+        add_mod(("out",), "norm_out.linear", 2, (0,))  # AdaLayerNormContinuous: (scale, shift)
+        self.mod_w = _dev(torch.cat(mods_w, 0), device, bf)
+        self.mod_b = _dev(torch.cat(mods_b, 0), device, f32)
+        self.mod_total = off
+        # ---- blocks ----
+        self.double = []
+        for i in range(cfg.num_layers):
+            b = f"transformer_blocks.{i}"
+            blk = SimpleNamespace()
+            blk.wqkv = _dev(torch.cat([sd[f"{b}.attn.{p}.weight"] for p in ("to_q", "to_k", "to_v")], 0), device, bf)
+            blk.bqkv = _dev(torch.cat([sd[f"{b}.attn.{p}.bias"] for p in ("to_q", "to_k", "to_v")], 0), device, f32)
+            blk.cwqkv = _dev(torch.cat([sd[f"{b}.attn.{p}.weight"] for p in ("add_q_proj", "add_k_proj", "add_v_proj")], 0), device, bf)
+            blk.cbqkv = _dev(torch.cat([sd[f"{b}.attn.{p}.bias"] for p in ("add_q_proj", "add_k_proj", "add_v_proj")], 0), device, f32)
+            blk.nqk = _dev(torch.stack([sd[f"{b}.attn.norm_q.weight"], sd[f"{b}.attn.norm_k.weight"]], 0), device, f32)
+            blk.cnqk = _dev(torch.stack([sd[f"{b}.attn.norm_added_q.weight"], sd[f"{b}.attn.norm_added_k.weight"]], 0), device, f32)
+            blk.wo, blk.bo = g(f"{b}.attn.to_out.0.weight", bf), g(f"{b}.attn.to_out.0.bias", f32)
+            blk.cwo, blk.cbo = g(f"{b}.attn.to_add_out.weight", bf), g(f"{b}.attn.to_add_out.bias", f32)
+            blk.ff1, blk.ff1b = g(f"{b}.ff.net.0.proj.weight", bf), g(f"{b}.ff.net.0.proj.bias", f32)
+            blk.ff2, blk.ff2b = g(f"{b}.ff.net.2.weight", bf), g(f"{b}.ff.net.2.bias", f32)
+            blk.cff1, blk.cff1b = g(f"{b}.ff_context.net.0.proj.weight", bf), g(f"{b}.ff_context.net.0.proj.bias", f32)
+            blk.cff2, blk.cff2b = g(f"{b}.ff_context.net.2.weight", bf), g(f"{b}.ff_context.net.2.bias", f32)
+            self.double.append(blk)
+        self.single = []
+        for i in range(cfg.num_single_layers):
+            b = f"single_transformer_blocks.{i}"
+            blk = SimpleNamespace()
+            # fused projection, columns [q | mlp | k | v]
+            order = (f"{b}.attn.to_q", f"{b}.proj_mlp", f"{b}.attn.to_k", f"{b}.attn.to_v")
+            blk.w1 = _dev(torch.cat([sd[n + ".weight"] for n in order], 0), device, bf)
+            blk.b1 = _dev(torch.cat([sd[n + ".bias"] for n in order], 0), device, f32)
+            blk.nq = g(f"{b}.attn.norm_q.weight", f32).reshape(1, 128).contiguous()
+            blk.nk = g(f"{b}.attn.norm_k.weight", f32).reshape(1, 128).contiguous()
+            blk.w2, blk.b2 = g(f"{b}.proj_out.weight", bf), g(f"{b}.proj_out.bias", f32)
+            self.single.append(blk)
+        self.proj_out = (g("proj_out.weight", bf), g("proj_out.bias", f32))
+        self._rope_cache = None
+        self._p = torch.nn.Parameter(torch.zeros(1, device=device, dtype=dtype), requires_grad=False)
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    def _mlp(self, key, x):
+        w1, b1, w2, b2 = self.emb[key]
+        return capi.gemm(capi.gemm(x, w1, b1, act=capi.ACT_SILU), w2, b2, out_f32=True)
+
+    def _rope(self, txt_ids, img_ids):
+        key = (txt_ids.data_ptr(), img_ids.data_ptr(), tuple(txt_ids.shape), tuple(img_ids.shape), img_ids._version)
+        if self._rope_cache is None or self._rope_cache[0] != key:
+            ids = torch.cat([txt_ids.float().cpu(), img_ids.float().cpu()], 0)
+            cos, sin = flux_rope_tables(ids, self.cfg.axes_dims_rope)
+            self._rope_cache = (key, cos.to(self.dev), sin.to(self.dev))
+        return self._rope_cache[1], self._rope_cache[2]
+
+    def forward(self, hidden_states, timestep, guidance, pooled_projections, encoder_hidden_states, txt_ids, img_ids,
+                return_dict=False, **kw):
+        cfg = self.cfg
+        d, H = cfg.dim, cfg.num_heads
+        dev = hidden_states.device
+        bf = torch.bfloat16
+        x_in = hidden_states.to(bf).contiguous()
+        B, T, _ = x_in.shape
+        ctx = encoder_hidden_states.to(device=dev, dtype=bf)
+        if ctx.shape[0] != B:
+            ctx = ctx.expand(B, -1, -1)
+        ctx = ctx.contiguous()
+        Tt = ctx.shape[1]
+        S = Tt + T
+        cos, sin = self._rope(txt_ids, img_ids)
+        if cos.shape[0] != S:
+            raise RuntimeError(f"RoPE table has {cos.shape[0]} positions but the joint sequence has {S} tokens "
+                               "(latent_image_ids must match the packed latent grid)")
+        # ---- conditioning vector (fp32 sinusoid of 1000*t, as the fp32 reference) ----
+        t = timestep.float().reshape(-1).cpu().expand(B) * 1000.0
+        temb = self._mlp("timestep_embedder", _sincos256(t).to(dev, bf))
+        if "guidance_embedder" in self.emb:
+            gd = guidance.float().reshape(-1).cpu().expand(B) * 1000.0
+            temb = temb + self._mlp("guidance_embedder", _sincos256(gd).to(dev, bf))
+        pooled = pooled_projections.to(device=dev, dtype=bf)
+        if pooled.shape[0] != B:
+            pooled = pooled.expand(B, -1)
+        temb = temb + self._mlp("text_embedder", pooled.contiguous())
+        st = torch.nn.functional.silu(temb).to(bf).contiguous()  # [B, d]: the only torch math on the path (B x 3072)
+        mod = capi.gemm(st, self.mod_w, self.mod_b, out_f32=True)  # [B, mod_total] fp32
+
+        def mvec(key, chunk):
+            o = self.mod_off[key] + chunk * d
+            return mod[:, o:o + d]
+
+        def ln_mod(x3, key, c_scale, c_shift):
+            """LayerNorm(no affine, 1e-6) * (1 + scale) + shift on a [B, rows, d] view -> dense [B, rows, d]."""
+            gsc, gsh = mvec(key, c_scale), mvec(key, c_shift)
+            return capi.layernorm(x3, gsc, gsh, eps=1e-6, rows_per_batch=x3.shape[1], gb_stride=mod.stride(0))
+
+        # joint residual stream [B, S, d]: text rows first
+        h = torch.empty((B, S, d), device=dev, dtype=bf)
+        capi.gemm_batched(ctx, self.c_emb[0], self.c_emb[1], out=h[:, :Tt])
+        capi.gemm_batched(x_in, self.x_emb[0], self.x_emb[1], out=h[:, Tt:])
+        scale = 1.0 / math.sqrt(cfg.head_dim)
+        qkv = torch.empty((B, S, 3 * d), device=dev, dtype=bf)
+        att = torch.empty((B, S, d), device=dev, dtype=bf)
+        hx, hc = h[:, Tt:], h[:, :Tt]
+        for i, blk in enumerate(self.double):
+            kx, kc = ("d", i, "x"), ("d", i, "c")
+            # chunks: 0 shift_msa, 1 scale_msa, 2 gate_msa, 3 shift_mlp, 4 scale_mlp, 5 gate_mlp
+            xn = ln_mod(hx, kx, 1, 0)
+            cn = ln_mod(hc, kc, 1, 0)
+            capi.gemm_batched(cn, blk.cwqkv, blk.cbqkv, out=qkv[:, :Tt])
+            capi.gemm_batched(xn, blk.wqkv, blk.bqkv, out=qkv[:, Tt:])
+            capi.rmsnorm_rope_(qkv[:, :Tt], blk.cnqk, cos, sin, 2 * H, H, pos_offset=0)
+            capi.rmsnorm_rope_(qkv[:, Tt:], blk.nqk, cos, sin, 2 * H, H, pos_offset=Tt)
+            q, k, v = (qkv[..., j * d:(j + 1) * d].unflatten(-1, (H, 128)) for j in range(3))
+            capi.flash_attn(q, k, v, scale, out=att.unflatten(-1, (H, 128)))
+            capi.gemm_batched(att[:, Tt:], blk.wo, blk.bo, res=hx, gate=mvec(kx, 2), out=hx)
+            capi.gemm_batched(att[:, :Tt], blk.cwo, blk.cbo, res=hc, gate=mvec(kc, 2), out=hc)
+            xn = ln_mod(hx, kx, 4, 3)
+            f = capi.gemm_batched(xn, blk.ff1, blk.ff1b, act=capi.ACT_GELU_TANH)
+            capi.gemm_batched(f, blk.ff2, blk.ff2b, res=hx, gate=mvec(kx, 5), out=hx)
+            cn = ln_mod(hc, kc, 4, 3)
+            f = capi.gemm_batched(cn, blk.cff1, blk.cff1b, act=capi.ACT_GELU_TANH)
+            capi.gemm_batched(f, blk.cff2, blk.cff2b, res=hc, gate=mvec(kc, 5), out=hc)
+        # ---- single blocks on the joint stream ----
+        dm = cfg.mlp_ratio * d
+        wide = torch.empty((B, S, 3 * d + dm), device=dev, dtype=bf) if self.single else None
+        for i, blk in enumerate(self.single):
+            ks = ("s", i)
+            hn = ln_mod(h, ks, 1, 0)
+            # columns [q | gelu(mlp) | k | v]
+            capi.gemm_batched(hn, blk.w1, blk.b1, act=capi.ACT_GELU_TANH, act_cols=(d, d + dm), out=wide)
+            capi.rmsnorm_rope_(wide[..., :d], blk.nq, cos, sin, H, H, pos_offset=0)
+            capi.rmsnorm_rope_(wide[..., d + dm:2 * d + dm], blk.nk, cos, sin, H, H, pos_offset=0)
+            q = wide[..., :d].unflatten(-1, (H, 128))
+            k = wide[..., d + dm:2 * d + dm].unflatten(-1, (H, 128))
+            v = wide[..., 2 * d + dm:].unflatten(-1, (H, 128))
+            capi.flash_attn(q, k, v, scale, out=q)  # attention output overwrites the dead q slot
+            capi.gemm_batched(wide[..., :d + dm], blk.w2, blk.b2, res=h, gate=mvec(ks, 2), out=h)
+        xo = capi.layernorm(h[:, Tt:], mvec(("out",), 0), mvec(("out",), 1), eps=1e-6,
+                            rows_per_batch=T, gb_stride=mod.stride(0))
+        out = capi.gemm_batched(xo, self.proj_out[0], self.proj_out[1]).to(self._dtype)
+        if return_dict:
+            return SimpleNamespace(sample=out)
+        return (out,)

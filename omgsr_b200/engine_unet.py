@@ -19,7 +19,7 @@ import torch
 
 from . import capi
 from .engine_vae import _Res, _dev
-from .pack import pack_conv_in_weight, pack_conv_weight, pack_geglu_weight, pack_upsample_weight
+from .pack import pack_conv_in_weight, pack_conv_weight, pack_geglu_weight, pack_upsample_weight, pad8
 
 
 def _timestep_embedding(t, dim):
@@ -118,7 +118,7 @@ class B200UNet(torch.nn.Module):
             return _Res(sd, name, device, extra_bias1=tb)
 
         self.conv_in_w = _dev(pack_conv_in_weight(sd["conv_in.weight"]), device)
-        self.conv_in_b = _dev(sd["conv_in.bias"], device, f32)
+        self.conv_in_b = _dev(pad8(sd["conv_in.bias"]), device, f32)
         n = len(ch)
         self.down = []
         for i in range(n):

@@ -15,7 +15,7 @@ from types import SimpleNamespace
 import torch
 
 from . import capi
-from .pack import pack_conv_in_weight, pack_conv_weight, pack_upsample_weight
+from .pack import pack_conv_in_weight, pack_conv_weight, pack_upsample_weight, pad8
 
 
 def _dev(t, device, dtype=None):
@@ -139,7 +139,7 @@ class B200Encoder(torch.nn.Module):
         f32 = torch.float32
         ch = cfg.block_out_channels
         self.conv_in_w = _dev(pack_conv_in_weight(sd["encoder.conv_in.weight"]), device)
-        self.conv_in_b = _dev(sd["encoder.conv_in.bias"], device, f32)
+        self.conv_in_b = _dev(pad8(sd["encoder.conv_in.bias"]), device, f32)
         self.levels = []
         for i in range(len(ch)):
             res = [_Res(sd, f"encoder.down_blocks.{i}.resnets.{j}", device) for j in range(cfg.layers_per_block)]
@@ -204,7 +204,7 @@ class B200Decoder(torch.nn.Module):
         f32 = torch.float32
         ch = list(reversed(cfg.block_out_channels))
         self.conv_in_w = _dev(pack_conv_in_weight(sd["decoder.conv_in.weight"]), device)
-        self.conv_in_b = _dev(sd["decoder.conv_in.bias"], device, f32)
+        self.conv_in_b = _dev(pad8(sd["decoder.conv_in.bias"]), device, f32)
         self.mid0 = _Res(sd, "decoder.mid_block.resnets.0", device)
         self.attn = _MidAttn(sd, "decoder.mid_block.attentions.0", device)
         self.mid1 = _Res(sd, "decoder.mid_block.resnets.1", device)
@@ -257,7 +257,8 @@ class _Conv1x1(torch.nn.Module):
     def __init__(self, w, b, device, dtype):
         super().__init__()
         self.w = _dev(pack_conv_in_weight(w), device)
-        self.b = _dev(b, device, torch.float32)
+        self.b = _dev(pad8(b), device, torch.float32)
+        self.bf = _dev(b, device, torch.float32)
         self.wf = _dev(w.reshape(w.shape[0], w.shape[1]), device, torch.float32)
         self.cout, self.out_dtype = w.shape[0], dtype
 

@@ -58,6 +58,18 @@ def pack_geglu_weight(w, b, bn=256):
 
 
 def pack_conv_in_weight(w):
-    """OIHW [Cout, Cin, R, S] -> fp32 [R*S*Cin, Cout] for the thin conv_in kernel."""
+    """OIHW [Cout, Cin, R, S] -> fp32 [R*S*Cin, Cout8] for the thin conv_in kernel (Cout zero-padded to a
+    multiple of 8: the kernel computes 8 output channels per thread)."""
     co, ci, r, s = w.shape
-    return w.permute(2, 3, 1, 0).reshape(r * s * ci, co).contiguous().float()
+    co8 = (co + 7) // 8 * 8
+    out = torch.zeros(r * s * ci, co8, dtype=torch.float32)
+    out[:, :co] = w.permute(2, 3, 1, 0).reshape(r * s * ci, co).float()
+    return out.contiguous()
+
+
+def pad8(v):
+    """zero-pad a 1-D fp32 vector to a multiple of 8 entries."""
+    n8 = (v.numel() + 7) // 8 * 8
+    out = torch.zeros(n8, dtype=torch.float32)
+    out[: v.numel()] = v.float()
+    return out

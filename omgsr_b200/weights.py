@@ -249,23 +249,25 @@ def flux_shapes(cfg: FluxConfig) -> Dict[str, tuple]:
 # ------------------------------------------------------------------------------------------------
 # random init (synthetic weights: there is no network access for checkpoints)
 # ------------------------------------------------------------------------------------------------
-def random_state_dict(shapes: Dict[str, tuple], seed: int, dtype=torch.float32, out_gain: Dict[str, float] = None):
+def random_state_dict(shapes: Dict[str, tuple], seed: int, dtype=torch.float32, out_gain: Dict[str, float] = None,
+                      device="cpu"):
     """Variance-preserving init: conv/linear weights ~ N(0, 1/fan_in), biases ~ N(0, 0.02^2), norm affine
     ~ (1 + N(0, 0.1^2), N(0, 0.1^2)). `out_gain` rescales selected layers (substring match) so that the
     end-to-end outputs have O(1) range and the PSNR / relative-error bars are meaningful."""
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device).manual_seed(seed)
+    rn = lambda shp: torch.randn(shp, generator=g, device=device)
     sd = {}
     for name, shp in shapes.items():
         if name.endswith(".weight") and len(shp) >= 2:
             fan_in = 1
             for s in shp[1:]:
                 fan_in *= s
-            t = torch.randn(shp, generator=g) / math.sqrt(fan_in)
+            t = rn(shp) / math.sqrt(fan_in)
         elif name.endswith(".weight"):
-            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+            t = 1.0 + 0.1 * rn(shp)
         else:
             is_norm = name.replace(".bias", ".weight") in shapes and len(shapes[name.replace(".bias", ".weight")]) == 1
-            t = (0.1 if is_norm else 0.02) * torch.randn(shp, generator=g)
+            t = (0.1 if is_norm else 0.02) * rn(shp)
         if out_gain:
             for key, gain in out_gain.items():
                 if key in name and name.endswith(".weight") and len(shp) >= 2:
@@ -292,20 +294,21 @@ def lora_target_names(shapes: Dict[str, tuple], targets, prefix=""):
     return out
 
 
-def random_lora(shapes, targets, rank, seed, prefix="", b_std=0.02):
+def random_lora(shapes, targets, rank, seed, prefix="", b_std=0.02, device="cpu"):
     """PEFT-format adapter tensors {module: (A, B)}: Linear A [r,in], B [out,r]; Conv2d A [r,Cin,k,k]
     (same kernel as the base conv), B [Cout,r,1,1]. A ~ N(0, 1/r) ('gaussian' init, train_omgsr_s.py:78);
     PEFT zero-inits B, here B ~ N(0, b_std^2) so that the merge is actually exercised."""
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device).manual_seed(seed)
+    rn = lambda shp: torch.randn(shp, generator=g, device=device)
     ad = {}
     for mod in lora_target_names(shapes, targets, prefix):
         shp = shapes[mod + ".weight"]
         if len(shp) == 4:
-            a = torch.randn((rank, shp[1], shp[2], shp[3]), generator=g) / rank
-            b = torch.randn((shp[0], rank, 1, 1), generator=g) * b_std
+            a = rn((rank, shp[1], shp[2], shp[3])) / rank
+            b = rn((shp[0], rank, 1, 1)) * b_std
         else:
-            a = torch.randn((rank, shp[1]), generator=g) / rank
-            b = torch.randn((shp[0], rank), generator=g) * b_std
+            a = rn((rank, shp[1])) / rank
+            b = rn((shp[0], rank)) * b_std
         ad[mod] = (a, b)
     return ad
 

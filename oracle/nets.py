@@ -175,3 +175,111 @@ def unet_forward(sd, cfg, x, timestep, ctx):
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
             h = _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", h)
     return _conv(sd, "conv_out", F.silu(_gn(sd, "conv_norm_out", h, eps)))
+
+
+# ------------------------------------------------------------------------------------------------
+# FluxTransformer2DModel (FLUX.1-dev shape) — diffusers 0.34.0 semantics, SURVEY.md Appendix C.
+# Cross-checked against torchtitan's BFL FLUX (experiments/flux/model/{layers,math}.py) for the block math;
+# parameter names are diffusers' (train/train_omgsr_f.py:155-169 lists the same module names).
+# ------------------------------------------------------------------------------------------------
+def flux_rope(ids, axes_dims, theta=10000.0):
+    """FluxPosEmbed: per axis cos/sin of pos * theta^(-2i/d), each repeated twice -> [S, sum(axes_dims)]."""
+    cos_out, sin_out = [], []
+    pos = ids.double()
+    for i, d in enumerate(axes_dims):
+        freqs = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64) / d))
+        ang = pos[:, i:i + 1] * freqs[None]
+        cos_out.append(ang.cos().repeat_interleave(2, dim=1).float())
+        sin_out.append(ang.sin().repeat_interleave(2, dim=1).float())
+    return torch.cat(cos_out, dim=-1), torch.cat(sin_out, dim=-1)
+
+
+def apply_rope(x, cos, sin):
+    """x [B,H,S,D]; pairs (x0,x1) -> (x0 cos - x1 sin, x1 cos + x0 sin), computed in fp32 and cast back."""
+    xf = x.float()
+    x2 = xf.reshape(*xf.shape[:-1], -1, 2)
+    rot = torch.stack([-x2[..., 1], x2[..., 0]], dim=-1).flatten(3)
+    return (xf * cos[None, None] + rot * sin[None, None]).to(x.dtype)
+
+
+def _rms(x, w, eps=1e-6):
+    xf = x.float()
+    return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype) * w
+
+
+def _sincos256(v):
+    half = 128
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    args = v.float()[:, None] * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)  # flip_sin_to_cos=True
+
+
+def _mlp_embed(sd, name, x):
+    return _lin(sd, name + ".linear_2", F.silu(_lin(sd, name + ".linear_1", x)))
+
+
+def _ln_plain(x, eps=1e-6):
+    return F.layer_norm(x, (x.shape[-1],), None, None, eps)
+
+
+def _heads(x, h):
+    b, s, c = x.shape
+    return x.reshape(b, s, h, c // h).transpose(1, 2)  # [B,H,S,D]
+
+
+def flux_forward(sd, cfg, hidden_states, timestep, guidance, pooled, encoder_hidden_states, txt_ids, img_ids):
+    """hidden_states [B,T,64] packed latents; timestep [1] or [B] in sigma units (0..1); guidance [B];
+    pooled [B,768]; encoder_hidden_states [B,512,4096]; txt_ids [512,3]; img_ids [T,3] -> [B,T,64]."""
+    H = cfg.num_heads
+    dt = hidden_states.dtype
+    B = hidden_states.shape[0]
+    x = _lin(sd, "x_embedder", hidden_states)
+    t = timestep.to(dt).expand(B) * 1000
+    temb = _mlp_embed(sd, "time_text_embed.timestep_embedder", _sincos256(t).to(dt))
+    if cfg.guidance_embeds:
+        g = guidance.to(dt) * 1000
+        temb = temb + _mlp_embed(sd, "time_text_embed.guidance_embedder", _sincos256(g).to(dt))
+    temb = temb + _mlp_embed(sd, "time_text_embed.text_embedder", pooled)
+    c = _lin(sd, "context_embedder", encoder_hidden_states)
+    cos, sin = flux_rope(torch.cat([txt_ids, img_ids], dim=0).float(), cfg.axes_dims_rope)
+    st = F.silu(temb)
+    n_txt = c.shape[1]
+    for i in range(cfg.num_layers):
+        b = f"transformer_blocks.{i}"
+        sh1, sc1, g1, sh2, sc2, g2 = _lin(sd, b + ".norm1.linear", st).chunk(6, dim=1)
+        csh1, csc1, cg1, csh2, csc2, cg2 = _lin(sd, b + ".norm1_context.linear", st).chunk(6, dim=1)
+        xn = _ln_plain(x) * (1 + sc1[:, None]) + sh1[:, None]
+        cn = _ln_plain(c) * (1 + csc1[:, None]) + csh1[:, None]
+        q = _rms(_heads(_lin(sd, b + ".attn.to_q", xn), H), sd[b + ".attn.norm_q.weight"])
+        k = _rms(_heads(_lin(sd, b + ".attn.to_k", xn), H), sd[b + ".attn.norm_k.weight"])
+        v = _heads(_lin(sd, b + ".attn.to_v", xn), H)
+        cq = _rms(_heads(_lin(sd, b + ".attn.add_q_proj", cn), H), sd[b + ".attn.norm_added_q.weight"])
+        ck = _rms(_heads(_lin(sd, b + ".attn.add_k_proj", cn), H), sd[b + ".attn.norm_added_k.weight"])
+        cv = _heads(_lin(sd, b + ".attn.add_v_proj", cn), H)
+        q, k, v = torch.cat([cq, q], 2), torch.cat([ck, k], 2), torch.cat([cv, v], 2)  # [text ; image]
+        a = F.scaled_dot_product_attention(apply_rope(q, cos, sin), apply_rope(k, cos, sin), v)
+        a = a.transpose(1, 2).reshape(B, -1, H * cfg.head_dim)
+        ca, xa = a[:, :n_txt], a[:, n_txt:]
+        x = x + g1[:, None] * _lin(sd, b + ".attn.to_out.0", xa)
+        xn = _ln_plain(x) * (1 + sc2[:, None]) + sh2[:, None]
+        x = x + g2[:, None] * _lin(sd, b + ".ff.net.2", F.gelu(_lin(sd, b + ".ff.net.0.proj", xn), approximate="tanh"))
+        c = c + cg1[:, None] * _lin(sd, b + ".attn.to_add_out", ca)
+        cn = _ln_plain(c) * (1 + csc2[:, None]) + csh2[:, None]
+        c = c + cg2[:, None] * _lin(sd, b + ".ff_context.net.2",
+                                    F.gelu(_lin(sd, b + ".ff_context.net.0.proj", cn), approximate="tanh"))
+    h = torch.cat([c, x], dim=1)
+    for i in range(cfg.num_single_layers):
+        b = f"single_transformer_blocks.{i}"
+        sh, sc, gt = _lin(sd, b + ".norm.linear", st).chunk(3, dim=1)
+        hn = _ln_plain(h) * (1 + sc[:, None]) + sh[:, None]
+        m = F.gelu(_lin(sd, b + ".proj_mlp", hn), approximate="tanh")
+        q = _rms(_heads(_lin(sd, b + ".attn.to_q", hn), H), sd[b + ".attn.norm_q.weight"])
+        k = _rms(_heads(_lin(sd, b + ".attn.to_k", hn), H), sd[b + ".attn.norm_k.weight"])
+        v = _heads(_lin(sd, b + ".attn.to_v", hn), H)
+        a = F.scaled_dot_product_attention(apply_rope(q, cos, sin), apply_rope(k, cos, sin), v)
+        a = a.transpose(1, 2).reshape(B, -1, H * cfg.head_dim)
+        h = h + gt[:, None] * _lin(sd, b + ".proj_out", torch.cat([a, m], dim=2))
+    x = h[:, n_txt:]
+    scale, shift = _lin(sd, "norm_out.linear", st).chunk(2, dim=1)  # diffusers AdaLayerNormContinuous: scale first
+    x = _ln_plain(x) * (1 + scale[:, None]) + shift[:, None]
+    return _lin(sd, "proj_out", x)

@@ -228,20 +228,25 @@ def test_layernorm(capi, rows, C):
     out = capi.layernorm(x.cuda().bfloat16(), (1 + sc).cuda().contiguous(), sh.cuda(), 1e-6, rows_per_batch=rpb,
                          gb_stride=C)
     assert report("layernorm modulate", out, ref.reshape(rows, C))[0]
+    # batch-strided input view (image tokens inside a joint [text; image] sequence)
+    joint = torch.zeros(nb, rpb + 16, C, device="cuda", dtype=torch.bfloat16)
+    joint[:, 16:] = x.cuda().bfloat16().view(nb, rpb, C)
+    out = capi.layernorm(joint[:, 16:], (1 + sc).cuda().contiguous(), sh.cuda(), 1e-6, gb_stride=C)
+    assert report("layernorm strided view", out.reshape(rows, C), ref.reshape(rows, C))[0]
 
 
 def test_thin_convs_and_layout(capi):
     from oracle import ops
-    from omgsr_b200.pack import pack_conv_in_weight, pack_conv_weight
+    from omgsr_b200.pack import pack_conv_in_weight, pack_conv_weight, pad8
     g = _g(5)
     for (B, Cin, H, W, Cout, k) in [(2, 3, 40, 48, 128, 3), (1, 4, 16, 16, 320, 3), (2, 16, 8, 8, 512, 3),
-                                     (1, 4, 16, 16, 8, 1)]:
+                                     (1, 4, 16, 16, 8, 1), (2, 4, 12, 20, 4, 1)]:
         x = bf16r(torch.randn(B, Cin, H, W, generator=g))
         w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
         b = torch.randn(Cout, generator=g)
         ref = torch.nn.functional.conv2d(x, w, b, padding=k // 2).permute(0, 2, 3, 1)
         for dt in (torch.bfloat16, torch.float32):
-            out = capi.conv_in_nchw(x.cuda().to(dt), pack_conv_in_weight(w).cuda(), b.cuda(), Cout, k)
+            out = capi.conv_in_nchw(x.cuda().to(dt), pack_conv_in_weight(w).cuda(), pad8(b).cuda(), Cout, k)
             assert report(f"conv_in {Cin}->{Cout} {dt}", out, ref)[0]
     for (B, H, W, Cin, Cout) in [(2, 24, 40, 128, 3), (1, 16, 16, 320, 4)]:
         x = bf16r(torch.randn(B, H, W, Cin, generator=g))
@@ -296,20 +301,49 @@ def test_latent_steps(capi):
 
 def test_rmsnorm_rope(capi):
     g = _g(41)
-    rows_pb, nb, Hh = 96, 2, 3
-    x = bf16r(torch.randn(nb * rows_pb, Hh * 128, generator=g))
-    wt = torch.rand(128, generator=g) + 0.5
-    ang = torch.randn(rows_pb, 64, generator=g)
+    rows, nb, Hh, off = 96, 2, 3, 16
+    # fused [q | k | v] rows: q and k normalised with their own weights in one launch, v untouched
+    x = bf16r(torch.randn(nb, rows, 3 * Hh * 128, generator=g))
+    wt = torch.rand(2, 128, generator=g) + 0.5
+    ang = torch.randn(off + rows, 64, generator=g)
     cos = torch.cos(ang).repeat_interleave(2, -1)
     sin = torch.sin(ang).repeat_interleave(2, -1)
-    xr = x.view(nb, rows_pb, Hh, 128)
-    n = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * wt
-    n2 = n.reshape(nb, rows_pb, Hh, 64, 2)
-    rot = torch.stack([-n2[..., 1], n2[..., 0]], -1).reshape(nb, rows_pb, Hh, 128)
-    ref = n * cos[None, :, None] + rot * sin[None, :, None]
+    qk = x[..., :2 * Hh * 128].reshape(nb, rows, 2, Hh, 128)
+    n = qk * torch.rsqrt(qk.pow(2).mean(-1, keepdim=True) + 1e-6) * wt[None, None, :, None, :]
+    n2 = n.reshape(nb, rows, 2, Hh, 64, 2)
+    rot = torch.stack([-n2[..., 1], n2[..., 0]], -1).reshape(nb, rows, 2, Hh, 128)
+    c, s_ = cos[off:][None, :, None, None], sin[off:][None, :, None, None]
+    ref = x.clone()
+    ref[..., :2 * Hh * 128] = (n * c + rot * s_).reshape(nb, rows, 2 * Hh * 128)
     xc = x.cuda().bfloat16().contiguous()
-    capi.rmsnorm_rope_(xc, wt.cuda(), cos.cuda().contiguous(), sin.cuda().contiguous(), Hh, rows_pb)
-    assert report("rmsnorm+rope", xc, ref.reshape(nb * rows_pb, Hh * 128))[0]
+    capi.rmsnorm_rope_(xc, wt.cuda(), cos.cuda().contiguous(), sin.cuda().contiguous(), 2 * Hh, Hh, pos_offset=off)
+    assert report("rmsnorm+rope", xc, ref)[0]
+
+
+def test_gemm_batched(capi):
+    from oracle import ops
+    g = _g(43)
+    B, S, T0, M, K, N = 2, 384, 128, 256, 128, 320
+    joint = bf16r(torch.randn(B, S, K, generator=g))          # [text(128) ; image(256)] rows
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g)
+    gate = torch.randn(B, 3 * N, generator=g)
+    res = bf16r(torch.randn(B, M, N, generator=g))
+    a = joint[:, T0:T0 + M]
+    lin = ops.linear(a, w, b)
+    ref = res + gate[:, N:2 * N, None].transpose(1, 2) * lin
+    jc = joint.cuda().bfloat16()
+    out = capi.gemm_batched(jc[:, T0:T0 + M], w.cuda().bfloat16(), b.cuda(), res=res.cuda().bfloat16(),
+                            gate=gate.cuda()[:, N:2 * N])
+    assert report("gemm_batched gate+res", out, ref)[0]
+    # activation on a column range only, written into a slice of a wider joint buffer
+    dst = torch.zeros(B, S, N + 64, device="cuda", dtype=torch.bfloat16)
+    capi.gemm_batched(jc[:, T0:T0 + M], w.cuda().bfloat16(), b.cuda(), act=capi.ACT_GELU_TANH, act_cols=(64, 192),
+                      out=dst[:, T0:T0 + M, 64:])
+    ref2 = lin.clone()
+    ref2[..., 64:192] = torch.nn.functional.gelu(lin[..., 64:192], approximate="tanh")
+    assert report("gemm_batched act range", dst[:, T0:T0 + M, 64:], ref2)[0]
+    assert float(dst[:, :T0].abs().max()) == 0.0 and float(dst[..., :64].abs().max()) == 0.0
 
 
 def test_tile_blend(capi):

@@ -147,7 +147,8 @@ def test_tiled_vae_matches_reference_vaehook():
     with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
         a = VAEHook(vae.encoder, 64, False, False, False, False)(xs.cuda().bfloat16())
         b = vae.encoder.original_forward(xs.cuda().bfloat16())
-    assert torch.equal(a, b)
+    # GroupNorm sums use fp32 atomics, so two runs agree to rounding, not bit for bit
+    assert torch.allclose(a.float(), b.float(), atol=2e-2, rtol=2e-2)
 
 
 def test_s_1024_tiled_config3():
@@ -188,4 +189,76 @@ def test_s_1024_tiled_config3():
             out, _ = model(lq.cuda().bfloat16(), ctx.cuda().bfloat16(), T, ov_)
     p = psnr(out, ref)
     print(f"config-3 style (tiled VAE + 9 latent tiles) e2e psnr {p:.2f} dB")
+    assert p >= 40.0
+
+
+# ----------------------------------------------------------------------------------------------------
+# OMGSR-F
+# ----------------------------------------------------------------------------------------------------
+def _build_f(spec="random://tiny?seed=0", lora="random://lora?seed=1&rank=8"):
+    from infer.omgsr_f_infer_model import OMGSR_F_Infer, build_f_state
+    from oracle.omgsr_f import OracleF
+    vae_sd, flux_sd, vae_cfg, flux_cfg = build_f_state(spec, lora, torch.float32)
+    state = {"vae": vae_sd, "flux": flux_sd, "vae_cfg": vae_cfg, "flux_cfg": flux_cfg}
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = OMGSR_F_Infer(state, None, "cuda", torch.bfloat16)
+    return model, OracleF(vae_sd, flux_sd, vae_cfg, flux_cfg)
+
+
+def _inputs_f(B, H, W, cfg, seed=4321):
+    from infer.infer_omgsr_f import _prepare_latent_image_ids
+    g = torch.Generator().manual_seed(seed)
+    lq = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    pe = torch.randn(1, 32, cfg.joint_attention_dim, generator=g)
+    pp = torch.randn(1, cfg.pooled_projection_dim, generator=g)
+    eps = torch.randn(B, 16, H // 8, W // 8, generator=g)
+    return lq, pe, pp, torch.zeros(32, 3), eps, _prepare_latent_image_ids
+
+
+def test_f_tiny_stages():
+    from oracle import nets
+    from oracle.omgsr_f import pack_latents
+    model, oracle = _build_f()
+    cfg = oracle.flux_cfg
+    lq, pe, pp, tid, eps, mk_ids = _inputs_f(2, 128, 128, cfg)
+    ids = mk_ids(8, 8, "cpu", torch.float32)
+    with torch.no_grad():
+        model.vae.posterior_eps = eps
+        z_ref = oracle.encode(lq, eps)
+        from infer.omgsr_f_infer_model import encode_images
+        z = encode_images(lq.cuda().bfloat16(), model.vae, torch.bfloat16)
+        e_lat = relerr(z, z_ref)
+        print(f"F latent relerr {e_lat:.4f}")
+        assert e_lat <= 2e-2
+        # DiT on the same packed latent
+        zq = z.float().cpu()
+        packed = pack_latents(zq)
+        v_ref = oracle.dit(packed, pe, pp, tid, ids)
+        v = model._dit(pack_latents(z), pe.cuda().bfloat16(), pp.cuda().bfloat16(), tid.cuda(), ids.cuda())
+        fb = {k: t.bfloat16() for k, t in oracle.flux_sd.items()}
+        v_bf = nets.flux_forward(fb, cfg, packed.bfloat16(), torch.tensor([oracle.t_curr]), torch.full((2,), 1.0),
+                                 pp.bfloat16().expand(2, -1), pe.bfloat16().expand(2, -1, -1), tid, ids).float()
+        e_dit, floor = relerr(v, v_ref), relerr(v_bf, v_ref)
+        print(f"DiT relerr {e_dit:.4f} (bf16-oracle noise floor {floor:.4f})")
+        assert e_dit <= max(2e-2, 1.5 * floor)
+        with contextlib.redirect_stdout(io.StringIO()):
+            out, t = model(lq.cuda().bfloat16(), pe.cuda().bfloat16(), pp.cuda().bfloat16(), tid.cuda(), ids.cuda(), 16, 8)
+        ref = oracle.forward(lq, pe, pp, tid, ids, 16, 8, eps)
+    p = psnr(out, ref)
+    print(f"F e2e psnr {p:.2f} dB (ref std {ref.std():.3f})")
+    assert out.shape == ref.shape and p >= 40.0
+
+
+def test_f_tiny_latent_tiling():
+    model, oracle = _build_f("random://tiny?seed=2", "random://lora?seed=3&rank=8")
+    cfg = oracle.flux_cfg
+    lq, pe, pp, tid, eps, mk_ids = _inputs_f(1, 128, 128, cfg, seed=55)
+    ids = mk_ids(4, 4, "cpu", torch.float32)   # tile 8 -> 4x4 packed grid, reused for every tile (:278)
+    with torch.no_grad():
+        model.vae.posterior_eps = eps
+        with contextlib.redirect_stdout(io.StringIO()):
+            out, _ = model(lq.cuda().bfloat16(), pe.cuda().bfloat16(), pp.cuda().bfloat16(), tid.cuda(), ids.cuda(), 8, 4)
+        ref = oracle.forward(lq, pe, pp, tid, ids, 8, 4, eps)
+    p = psnr(out, ref)
+    print(f"F tiled e2e psnr {p:.2f} dB")
     assert p >= 40.0
