@@ -42,6 +42,8 @@ extern "C" {
 /* flags */
 #define OMGSR_OUT_F32 1      /* store fp32 instead of bf16 */
 #define OMGSR_B_MN_MAJOR 2   /* batched GEMM: B operand given as [K, N] (row-major V), not [N, K] */
+#define OMGSR_CONV_NO_HALO 4     /* conv2d: force the generic implicit-GEMM kernel (testing / A-B timing) */
+#define OMGSR_CONV_HALO_DESC1 8  /* conv2d: halo kernel with the descriptor base-offset field set (bring-up probe) */
 
 int omgsr_version(void);
 const char* omgsr_last_error(void);
@@ -74,11 +76,13 @@ int omgsr_gemm_batched_bf16(const void* A, const void* Wt, const float* bias, co
  *   D[b,m,h,n] =            sum_k A[b,h,m,k] * Bm[b,k,h,n]          (flags & OMGSR_B_MN_MAJOR;      P V)
  * Used for the materialised-score attention path (VAE mid-block attention d=512,
  * infer/vaehook.py:137-171, and as the bring-up path for UNet/DiT attention).
- * strides are in elements: a_* for A (row, head, batch), b_* for Bm, d_* for D. */
+ * strides are in elements: a_* for A (row, head, batch), b_* for Bm, d_* for D. b_valid_rows = number of rows of
+ * Bm that exist per (b,h) (N for Q K^T; the un-padded kv length for P V, where K is the padded width of P):
+ * rows beyond it are read as zero. */
 int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batch, int heads, int M, int N, int K,
                      long long a_row, long long a_head, long long a_batch, long long b_row, long long b_head,
-                     long long b_batch, long long d_row, long long d_head, long long d_batch, int flags,
-                     int force_bn, void* stream);
+                     long long b_batch, long long d_row, long long d_head, long long d_batch, int b_valid_rows,
+                     int flags, int force_bn, void* stream);
 
 /* Fused flash attention (TMA + tcgen05, online softmax, scores never leave the SM):
  *   out[b,m,h,:] = softmax_n(scale * q[b,m,h,:] . k[b,n,h,:]) v[b,n,h,:],  D in {64, 128}.
@@ -189,6 +193,9 @@ int omgsr_tile_blend(const void* tiles, int tiles_f32, const float* weights, con
  * tmp0/tmp1 are caller-provided scratch of the same size. */
 int omgsr_wavelet_fix(const float* content, const float* style, float* out, float* tmp0, float* tmp1, int B, int C,
                       int H, int W, void* stream);
+/* one a-trous stage (wavelet_blur, infer/wavelet_color_fix.py:77-96): 3x3 binomial kernel at dilation `radius`,
+ * replicate padding, depthwise. fp32 NCHW. */
+int omgsr_atrous_blur(const float* in, float* out, int B, int C, int H, int W, int radius, void* stream);
 /* AdaIN: out = (content - mean_c)/std_c * std_s + mean_s per (b,c), unbiased var + 1e-5
  * (infer/wavelet_color_fix.py:44-74). scratch: B*C*4 doubles (32*B*C bytes). */
 int omgsr_adain_fix(const float* content, const float* style, float* out, void* scratch, int B, int C, int H, int W,

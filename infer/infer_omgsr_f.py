@@ -1,5 +1,15 @@
-"""CLI driver for OMGSR-F (mirror of the reference's infer/infer_omgsr_f.py; completed in the next step)."""
+"""OMGSR-F inference driver — same flags as the reference's infer/infer_omgsr_f.py, plus `--synthetic N` and
+`--prompt_embeds file.pt` (a dict with prompt_embeds / pooled_prompt_embeds / text_ids) for boxes without the
+FLUX text encoders."""
+import argparse
+import os
+import sys
+
 import torch
+
+SCRIPT_DIR = os.path.dirname(os.path.realpath(__file__))
+sys.path.append(os.path.dirname(SCRIPT_DIR))
+from infer import _driver_common as dc  # noqa: E402
 
 
 def _prepare_latent_image_ids(height, width, device, dtype):
@@ -8,3 +18,70 @@ def _prepare_latent_image_ids(height, width, device, dtype):
     ids[..., 1] += torch.arange(height)[:, None]
     ids[..., 2] += torch.arange(width)[None, :]
     return ids.reshape(height * width, 3).to(device=device, dtype=dtype)
+
+
+def main(args):
+    from infer.omgsr_f_infer_model import OMGSR_F_Infer
+    omgsr = OMGSR_F_Infer(args.flux_path, args.lora_path, device=args.device, guidance_scale=args.guidance_scale,
+                          mid_timestep=args.mid_timestep)
+    if args.prompt_embeds:
+        pe = torch.load(args.prompt_embeds)
+        prompt_embeds, pooled, text_ids = pe["prompt_embeds"], pe["pooled_prompt_embeds"], pe["text_ids"]
+    elif args.flux_path.startswith("random://"):
+        g = torch.Generator().manual_seed(1235)
+        full = "flux_dev" in args.flux_path
+        prompt_embeds = torch.randn(1, 512 if full else 32, 4096 if full else 256, generator=g)
+        pooled = torch.randn(1, 768 if full else 64, generator=g)
+        text_ids = torch.zeros(prompt_embeds.shape[1], 3)
+    else:
+        from diffusers import FluxPipeline  # needs the real checkpoint + diffusers (reference :36-48)
+        pipe = FluxPipeline.from_pretrained(args.flux_path, transformer=None, vae=None, torch_dtype=args.weight_dtype).to("cuda")
+        with torch.no_grad():
+            prompt_embeds, pooled, text_ids = pipe.encode_prompt(args.prompt, prompt_2=None)
+        del pipe
+        torch.cuda.empty_cache()
+    to = dict(device=args.device, dtype=args.weight_dtype)
+    prompt_embeds, pooled, text_ids = prompt_embeds.to(**to), pooled.to(**to), text_ids.to(**to)
+    grid = (args.process_size // 8) // 2
+    latent_image_ids = _prepare_latent_image_ids(grid, grid, args.device, args.weight_dtype)
+    if args.synthetic:
+        items = dc.synthetic_images(args.synthetic, args.process_size // args.upscale)
+    else:
+        from PIL import Image
+        items = [(os.path.basename(p).split('.')[0] + ".png", Image.open(p).convert('RGB'))
+                 for p in dc.list_inputs(args.input_image)]
+    os.makedirs(args.output_dir, exist_ok=True)
+    print(f"There are {len(items)} images.")
+    total_time = 0
+    for bname, img in items:
+        lq, resize_flag, orig = dc.preprocess(img, args.process_size, args.upscale)
+        tile_size = args.process_size // 8
+        tile_overlap = tile_size // 2
+        with torch.no_grad():
+            lq_img = dc.pil_to_model_input(lq, args.device, args.weight_dtype)
+            output_image, t = omgsr(lq_img, prompt_embeds, pooled, text_ids, latent_image_ids, tile_size, tile_overlap)
+            total_time += t
+        dc.finish(output_image, lq, args.align_method, resize_flag, orig, args.upscale,
+                  os.path.join(args.output_dir, bname))
+    print(f"Average inference time: {total_time / max(len(items), 1)}s")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser(description="OMGSR-F Inference Script")
+    ap.add_argument("--input_image", type=str, default="")
+    ap.add_argument("--output_dir", type=str, required=True)
+    ap.add_argument("--flux_path", type=str, required=True)
+    ap.add_argument("--lora_path", type=str, required=True)
+    ap.add_argument("--device", type=str, default="cuda:0")
+    ap.add_argument("--process_size", type=int, default=1024)
+    ap.add_argument("--upscale", type=int, default=4)
+    ap.add_argument("--align_method", type=str, default="adain", choices=["wavelet", "adain", "nofix"])
+    ap.add_argument("--weight_dtype", type=str, default="bf16", choices=["bf16"])
+    ap.add_argument("--prompt", type=str, default="")
+    ap.add_argument("--mid_timestep", type=int, default=244)
+    ap.add_argument("--guidance_scale", type=float, default=1.0)
+    ap.add_argument("--synthetic", type=int, default=0)
+    ap.add_argument("--prompt_embeds", type=str, default="")
+    a = ap.parse_args()
+    a.weight_dtype = torch.bfloat16
+    main(a)

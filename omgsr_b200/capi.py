@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libomgsr_b200.so")
 
 ACT_NONE, ACT_SILU, ACT_GELU_ERF, ACT_GELU_TANH, ACT_GEGLU = 0, 1, 2, 3, 4
-OUT_F32, B_MN_MAJOR = 1, 2
+OUT_F32, B_MN_MAJOR, CONV_NO_HALO, CONV_HALO_DESC1 = 1, 2, 4, 8
 
 # every symbol include/omgsr_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
@@ -23,7 +23,7 @@ SYMBOLS = [
     "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_groupnorm_combine", "omgsr_layernorm", "omgsr_softmax_rows",
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
-    "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
+    "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
     "omgsr_flash_attn_bf16",
 ]
 
@@ -118,7 +118,7 @@ def bgemm_qk(q, k, out=None, force_bn=0):
     rc = _lib.omgsr_bgemm_bf16(_ptr(q), _ptr(k), _ptr(out), _i(B), _i(H), _i(M), _i(N), _i(D),
                                _ll(q.stride(1)), _ll(q.stride(2)), _ll(q.stride(0)),
                                _ll(k.stride(1)), _ll(k.stride(2)), _ll(k.stride(0)),
-                               _ll(out.stride(2)), _ll(out.stride(1)), _ll(out.stride(0)),
+                               _ll(out.stride(2)), _ll(out.stride(1)), _ll(out.stride(0)), _i(N),
                                _i(OUT_F32), _i(force_bn), _stream())
     _check(rc, "omgsr_bgemm_bf16(qk)")
     return out
@@ -134,14 +134,14 @@ def bgemm_pv(p, v, out=None, n_kv=None, force_bn=0):
     rc = _lib.omgsr_bgemm_bf16(_ptr(p), _ptr(v), _ptr(out), _i(B), _i(H), _i(M), _i(D), _i(Np),
                                _ll(p.stride(2)), _ll(p.stride(1)), _ll(p.stride(0)),
                                _ll(v.stride(1)), _ll(v.stride(2)), _ll(v.stride(0)),
-                               _ll(out.stride(1)), _ll(out.stride(2)), _ll(out.stride(0)),
+                               _ll(out.stride(1)), _ll(out.stride(2)), _ll(out.stride(0)), _i(v.shape[1]),
                                _i(B_MN_MAJOR), _i(force_bn), _stream())
     _check(rc, "omgsr_bgemm_bf16(pv)")
     return out
 
 
 def conv2d(x, w, bias=None, res=None, ksize=3, stride=1, pad=(1, 1, 1, 1), upsample2x=False, act=ACT_NONE, out=None,
-           out_f32=False, cout=None, force_bn=0):
+           out_f32=False, cout=None, force_bn=0, flags=0):
     """NHWC conv. x: [B,H,W,Cin] bf16 view (channel-contiguous, dense in B/H/W with a channel stride);
     w: packed [Cout, k*k*Cin] (or [4, Cout, 4*Cin] for upsample2x). pad = (top, left, bottom, right)."""
     _cuda_bf16(x, "x"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias")
@@ -169,7 +169,8 @@ def conv2d(x, w, bias=None, res=None, ksize=3, stride=1, pad=(1, 1, 1, 1), upsam
                                      _i(Cin), _i(Cout), _i(ksize), _i(stride), _i(pad[0]), _i(pad[1]), _i(pad[2]),
                                      _i(pad[3]), _i(1 if upsample2x else 0), _i(act), _ll(x.stride(2)),
                                      _ll(out.stride(2)), _ll(ldr),
-                                     _i(OUT_F32 if out.dtype == torch.float32 else 0), _i(force_bn), _stream())
+                                     _i((OUT_F32 if out.dtype == torch.float32 else 0) | flags), _i(force_bn),
+                                     _stream())
     _check(rc, "omgsr_conv2d_nhwc_bf16")
     return out
 
@@ -406,6 +407,16 @@ def wavelet_fix(content, style):
     rc = _lib.omgsr_wavelet_fix(_ptr(content), _ptr(style), _ptr(out), _ptr(t0), _ptr(t1), _i(B), _i(C), _i(H), _i(W),
                                 _stream())
     _check(rc, "omgsr_wavelet_fix")
+    return out
+
+
+def atrous_blur(x, radius):
+    _cuda_f32(x, "x")
+    assert x.is_contiguous() and x.dim() == 4
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    rc = _lib.omgsr_atrous_blur(_ptr(x), _ptr(out), _i(B), _i(C), _i(H), _i(W), _i(int(radius)), _stream())
+    _check(rc, "omgsr_atrous_blur")
     return out
 
 

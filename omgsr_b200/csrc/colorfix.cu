@@ -114,6 +114,14 @@ extern "C" int omgsr_wavelet_fix(const float* content, const float* style, float
   return OMGSR_OK;
 }
 
+extern "C" int omgsr_atrous_blur(const float* in, float* out, int B, int C, int H, int W, int radius, void* stream) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || radius <= 0) return set_error(OMGSR_ERR_SHAPE, "atrous_blur: bad shape");
+  const long long total = static_cast<long long>(B) * C * H * W;
+  atrous_kernel<<<grid_cf(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, nullptr, nullptr, out, H, W,
+                                                                                  radius, total);
+  return check_launch("atrous_kernel");
+}
+
 extern "C" int omgsr_adain_fix(const float* content, const float* style, float* out, void* scratch, int B, int C, int H,
                                int W, void* stream) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(OMGSR_ERR_SHAPE, "adain_fix: empty");

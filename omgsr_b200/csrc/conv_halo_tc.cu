@@ -1,0 +1,291 @@
+// 3x3 / 2x2 stride-1 convolution on tcgen05 with input-halo reuse ("halo kernel").
+//
+// The generic implicit-GEMM kernel (gemm_conv_tc.cu) re-fetches the input tile once per filter tap: for the wide,
+// thin-channel VAE levels (C = 128/256 at 256^2..1024^2) that makes the L2->SMEM stream, not the tensor pipe, the
+// limit (ncu: 19 % of peak on the 128->128 @512^2 layer). This kernel instead loads, per 64-channel slice, ONE
+// halo tile {64 ch, 128+S-1 pixels, TM+R-1 rows} and forms the A operand of every (tap, output row) directly
+// from it: in the 128B-swizzled K-major layout a shift by one pixel is a shift of the descriptor start address by
+// one 128-byte row, so all R*S*TM operand views alias the same shared-memory tile. One CTA computes TM output
+// rows x 128 pixels (TM accumulators in TMEM) so each weight k-block is also reused TM times.
+//   traffic per 2x128 output pixels, C=128: 4 rows x 130 px x 256 B + 295 KB weights = 428 KB
+//   (generic kernel: 2 x 18 k-blocks x 32 KB = 1152 KB).
+// Warp roles as in gemm_conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+#include "common.cuh"
+#include "../../include/omgsr_b200.h"
+
+namespace omgsr {
+
+struct HaloParams {
+  int tiles_x, tiles_y, B;    // tiles_y counts groups of TM rows
+  int W, H;                   // output extents
+  int n_tiles, Cout;
+  int chunks;                 // Cin / 64
+  int R, S, pad_t, pad_l, Cin;
+  int pw;                     // halo pitch in pixels = 128 + S - 1
+  int a_bytes;                // bytes of one halo load
+  int desc_mode;              // 1: put (addr >> 7) & 7 into the descriptor base-offset field
+  long long o_sx, o_sy, o_sb, r_sx, r_sy, r_sb;
+  void* out;
+  const float* bias;
+  const bf16* res;
+  int act, out_f32;
+};
+
+template <int BN, int TM>
+struct HaloCfg {
+  static constexpr int kABytes = (((TM + 2) * 130 * 128) + 1023) / 1024 * 1024;
+  static constexpr int kAStages = 2;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBStages = (BN == 128) ? 5 : 2;
+  static constexpr int kAccSets = (BN * TM * 2 <= 512) ? 2 : 1;
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint64_t halo_desc(uint32_t addr, int mode) {
+  uint64_t d = umma_desc_sw128(addr, 16, 1024);
+  if (mode) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
+  return d;
+}
+
+__device__ __forceinline__ float halo_act(float v, int act) {
+  switch (act) {
+    case OMGSR_ACT_SILU: return silu_f(v);
+    case OMGSR_ACT_GELU_ERF: return gelu_erf_f(v);
+    case OMGSR_ACT_GELU_TANH: return gelu_tanh_f(v);
+    default: return v;
+  }
+}
+
+template <int BN, int TM>
+__global__ void __launch_bounds__(192, 1)
+conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const HaloParams p) {
+  using C = HaloCfg<BN, TM>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::kAStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::kBStages * C::kBBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + C::kAStages;
+  uint64_t* b_full = a_empty + C::kAStages;
+  uint64_t* b_empty = b_full + C::kBStages;
+  uint64_t* acc_full = b_empty + C::kBStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::kAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.tiles_x * p.tiles_y * p.B * p.n_tiles;
+  const int taps = p.R * p.S;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m = tile / p.n_tiles;
+        const int tx = m % p.tiles_x; m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int b = m / p.tiles_y;
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          mbar_expect_tx(&a_full[as], p.a_bytes);
+          tma_load_5d(sA + as * C::kABytes, &tmA, &a_full[as], c * 64, tx * 128 - p.pad_l, ty * TM - p.pad_t, b, 0);
+          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            mbar_expect_tx(&b_full[bs], C::kBBytes);
+            tma_load_4d(sB + bs * C::kBBytes, &tmB, &b_full[bs], tap * p.Cin + c * 64, n_tile * BN, 0, 0);
+            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int as = 0, bs = 0, set = 0;
+      uint32_t aph = 0, bph = 0, sph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[set], sph ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + set * (TM * BN);
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + as * C::kABytes);
+          int tap = 0;
+          for (int r = 0; r < p.R; ++r) {
+            for (int s = 0; s < p.S; ++s, ++tap) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(sB + bs * C::kBBytes);
+#pragma unroll
+              for (int t = 0; t < TM; ++t) {
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_ss(acc0 + t * BN, halo_desc(a_addr + k * 32, p.desc_mode),
+                            umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (c | tap | k) != 0);
+              }
+              tc_commit(&b_empty[bs]);
+              if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+            }
+          }
+          tc_commit(&a_empty[as]);
+          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+        }
+        tc_commit(&acc_full[set]);
+        if (C::kAccSets == 2) { if (++set == 2) { set = 0; sph ^= 1; } }
+        else { sph ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int set = 0;
+    uint32_t sph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      const int tx = m % p.tiles_x; m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int b = m / p.tiles_y;
+      const int x = tx * 128 + row;
+      mbar_wait(&acc_full[set], sph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < TM; ++t) {
+        const int y = ty * TM + t;
+        const bool valid = (x < p.W) && (y < p.H);
+        const long long o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+        const bf16* res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+        const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          float f[32];
+          tmem_ld32(t_row + c0, v);
+          tmem_wait_ld();
+          const int cv = n_tile * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(v[j]);
+            if (p.bias) a += __ldg(p.bias + cv + j);
+            f[j] = halo_act(a, p.act);
+          }
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int oc = cv + q * 8;
+              float* ff = f + q * 8;
+              if (res_row) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res_row + oc);
+                const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                             r3 = unpack_bf16x2(rr.w);
+                ff[0] += r0.x; ff[1] += r0.y; ff[2] += r1.x; ff[3] += r1.y;
+                ff[4] += r2.x; ff[5] += r2.y; ff[6] += r3.x; ff[7] += r3.y;
+              }
+              if (p.out_f32) {
+                float* o = static_cast<float*>(p.out) + o_off + oc;
+                *reinterpret_cast<float4*>(o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(ff[4], ff[5], ff[6], ff[7]);
+              } else {
+                uint4 o;
+                o.x = pack_bf16x2(ff[0], ff[1]); o.y = pack_bf16x2(ff[2], ff[3]);
+                o.z = pack_bf16x2(ff[4], ff[5]); o.w = pack_bf16x2(ff[6], ff[7]);
+                *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_off + oc) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
+      if (C::kAccSets == 2) { if (++set == 2) { set = 0; sph ^= 1; } }
+      else { sph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BN, int TM>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
+  using C = HaloCfg<BN, TM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_tc_kernel<BN, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_halo<%d,%d>): %s", BN, TM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long total = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles;
+  const int grid = total < sm_count() ? static_cast<int>(total) : sm_count();
+  conv_halo_tc_kernel<BN, TM><<<grid, 192, C::kSmemBytes, st>>>(tmA, tmB, p);
+  return check_launch("conv_halo_tc_kernel");
+}
+
+// Returns 1 if this problem is not eligible (caller falls through to the generic kernel), 0 on success, <0 on error.
+int try_conv_halo(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int IH, int IW,
+                  int OH, int OW, int Cin, int Cout, int R, int S, int pad_t, int pad_l, long long x_sx, long long x_sy,
+                  long long x_sb, long long o_sx, long long o_sy, long long o_sb, long long r_sx, long long r_sy,
+                  long long r_sb, long long w_ld, int act, int out_f32, int desc_mode, cudaStream_t st) {
+  if (R * S < 4 || R > 3 || S > 3) return 1;
+  if (OW < 96) return 1;                        // a 128-pixel row tile would be mostly padding
+  if (Cin % 64 || (Cout % 128)) return 1;
+  if (act == OMGSR_ACT_GEGLU) return 1;
+  const int bn = (Cout % 256 == 0) ? 256 : 128;
+  constexpr int TM = 2;
+  HaloParams p;
+  p.tiles_x = (OW + 127) / 128; p.tiles_y = (OH + TM - 1) / TM; p.B = B; p.W = OW; p.H = OH;
+  p.n_tiles = Cout / bn; p.Cout = Cout; p.chunks = Cin / 64; p.R = R; p.S = S; p.pad_t = pad_t; p.pad_l = pad_l;
+  p.Cin = Cin; p.pw = 128 + S - 1;
+  p.a_bytes = 128 * p.pw * (TM + R - 1);
+  p.desc_mode = desc_mode;
+  p.o_sx = o_sx; p.o_sy = o_sy; p.o_sb = o_sb; p.r_sx = r_sx; p.r_sy = r_sy; p.r_sb = r_sb;
+  p.out = y; p.bias = bias; p.res = static_cast<const bf16*>(res); p.act = act; p.out_f32 = out_f32;
+  if (static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles > 0x7fffffffLL) return 1;
+  CUtensorMap tmA, tmB;
+  const uint64_t eb = 2;
+  uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(IW), static_cast<uint64_t>(IH),
+                      static_cast<uint64_t>(B), 1};
+  uint64_t strides[4] = {x_sx * eb, x_sy * eb, x_sb * eb, x_sb * eb * B};
+  uint32_t box[5] = {64, static_cast<uint32_t>(p.pw), static_cast<uint32_t>(TM + R - 1), 1, 1};
+  int rc = make_tmap_bf16(&tmA, x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  uint64_t wd[4] = {static_cast<uint64_t>(w_ld), static_cast<uint64_t>(Cout), 1, 1};
+  uint64_t ws[3] = {w_ld * eb, w_ld * eb * Cout, w_ld * eb * Cout};
+  uint32_t wb[4] = {64, static_cast<uint32_t>(bn), 1, 1};
+  rc = make_tmap_bf16(&tmB, w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  if (bn == 256) return launch_halo<256, TM>(tmA, tmB, p, st);
+  return launch_halo<128, TM>(tmA, tmB, p, st);
+}
+
+}  // namespace omgsr

@@ -375,9 +375,15 @@ struct ConvDesc {
   long long w_ld;  // elements per weight row (R*S*Cin)
   // batched B operand (attention)
   int b_batched, b_mn_major, flat;
+  int halo_mode;  // 0: generic kernel only; 1|2: try the halo kernel (descriptor base-offset mode 0|1)
   long long b_row, b_head, b_batch;
   int b_rows;  // rows of the B matrix (N for K-major, K for MN-major)
 };
+
+int try_conv_halo(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int IH, int IW,
+                  int OH, int OW, int Cin, int Cout, int R, int S, int pad_t, int pad_l, long long x_sx, long long x_sy,
+                  long long x_sb, long long o_sx, long long o_sy, long long o_sb, long long r_sx, long long r_sy,
+                  long long r_sb, long long w_ld, int act, int out_f32, int desc_mode, cudaStream_t st);
 
 static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
   if (d.Cin % kBK) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: K/Cin=%d must be a multiple of %d", d.Cin, kBK);
@@ -387,6 +393,13 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
   if ((d.x_sx | d.x_sy | d.x_sb | d.o_sx | d.o_sy | d.o_sb | d.r_sx | d.r_sy | d.r_sb | d.w_ld) & 7)
     return set_error(OMGSR_ERR_ALIGN, "conv_gemm: strides must be multiples of 8 elements");
   const bool geglu = d.act == OMGSR_ACT_GEGLU;
+  if (d.halo_mode && !d.stride2 && !d.b_batched && !d.flat && !d.gate && (d.force_bn == 0)) {
+    // wide stride-1 3x3 / 2x2 layers: input-halo kernel (conv_halo_tc.cu); returns 1 when not eligible
+    const int rc = try_conv_halo(d.x, d.w, d.bias, d.res, d.y, d.B, d.IH, d.IW, d.H, d.W, d.Cin, d.Cout, d.R, d.S,
+                                 d.pad_t, d.pad_l, d.x_sx, d.x_sy, d.x_sb, d.o_sx, d.o_sy, d.o_sb, d.r_sx, d.r_sy,
+                                 d.r_sb, d.w_ld, d.act, d.out_f32, d.halo_mode - 1, st);
+    if (rc != 1) return rc;
+  }
 
   // tile shape {tw, th, tb} (powers of two, product 128): minimise the padded pixel count, prefer wide rows
   int tw = 128, th = 1, tb = 1;
@@ -528,7 +541,7 @@ extern "C" int omgsr_gemm_batched_bf16(const void* A, const void* Wt, const floa
 extern "C" int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batch, int heads, int M, int N, int K,
                                 long long a_row, long long a_head, long long a_batch, long long b_row,
                                 long long b_head, long long b_batch, long long d_row, long long d_head,
-                                long long d_batch, int flags, int force_bn, void* stream) {
+                                long long d_batch, int b_valid_rows, int flags, int force_bn, void* stream) {
   if (batch <= 0 || heads <= 0 || M <= 0 || N <= 0 || K <= 0)
     return set_error(OMGSR_ERR_SHAPE, "bgemm: empty problem");
   if ((b_row | b_head | b_batch) & 7) return set_error(OMGSR_ERR_ALIGN, "bgemm: B strides must be multiples of 8");
@@ -542,7 +555,8 @@ extern "C" int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batc
   d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
   d.flat = 1; d.b_batched = 1; d.b_mn_major = (flags & OMGSR_B_MN_MAJOR) ? 1 : 0;
   d.b_row = b_row; d.b_head = b_head; d.b_batch = b_batch;
-  d.b_rows = d.b_mn_major ? K : N;
+  // rows of Bm that really exist (K may be padded up to the operand granule; the rest must read as zero)
+  d.b_rows = b_valid_rows > 0 ? b_valid_rows : (d.b_mn_major ? K : N);
   return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
 }
 
@@ -559,6 +573,7 @@ extern "C" int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float*
   d.B = B; d.IH = H; d.IW = W; d.Cin = Cin; d.Cout = Cout;
   d.x_sx = ldx; d.x_sy = ldx * W; d.x_sb = ldx * W * H;
   d.act = act; d.force_bn = force_bn; d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
+  d.halo_mode = (flags & OMGSR_CONV_NO_HALO) ? 0 : ((flags & OMGSR_CONV_HALO_DESC1) ? 2 : 1);
   if (upsample2x) {
     // nearest-2x + 3x3/p1 == four 2x2 convolutions on the un-upsampled input (weights pre-collapsed
     // per output parity by the packer): out(2i+py, 2j+px).

@@ -121,6 +121,40 @@ def test_conv(capi, B, H, W, Cin, Cout, k, stride, pad, up):
     assert report(f"conv {B}x{H}x{W} {Cin}->{Cout} k{k} s{stride} up={up}", out, ref, tol)[0]
 
 
+HALO_CASES = [
+    # B, H, W, Cin, Cout, upsample   (W >= 96 and Cout % 128 == 0 -> input-halo kernel)
+    (1, 8, 128, 64, 128, False),
+    (2, 40, 256, 128, 128, False),
+    (1, 33, 200, 128, 256, False),      # ragged in x (masked tail) and odd row count
+    (1, 64, 128, 256, 512, False),      # two n-tiles of 256
+    (1, 130, 128, 64, 128, False),
+    (1, 32, 128, 128, 128, True),       # nearest-2x + conv: four 2x2 parity convs through the halo kernel
+    (2, 64, 96, 64, 256, True),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,up", HALO_CASES)
+@pytest.mark.parametrize("mode", ["halo", "halo_desc1"])
+def test_conv_halo(capi, B, H, W, Cin, Cout, up, mode):
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight, pack_upsample_weight
+    g = _g(B * 7 + H + W + Cin + Cout)
+    x = bf16r(torch.randn(B, H, W, Cin, generator=g))
+    w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+    b = torch.randn(Cout, generator=g)
+    res = bf16r(torch.randn(B, H * (2 if up else 1), W * (2 if up else 1), Cout, generator=g))
+    ref = ops.conv2d_nhwc(x, w, b, upsample2x=up) + res
+    pw = pack_upsample_weight(w) if up else pack_conv_weight(w)
+    flags = capi.CONV_HALO_DESC1 if mode == "halo_desc1" else 0
+    xc, wc, bc, rc = x.cuda().bfloat16(), pw.cuda(), b.cuda(), res.cuda().bfloat16()
+    out = capi.conv2d(xc, wc, bc, res=rc, upsample2x=up, flags=flags)
+    torch.cuda.synchronize()
+    ok, _ = report(f"conv-halo[{mode}] {B}x{H}x{W} {Cin}->{Cout} up={up}", out, ref, 2e-2 if up else 1e-2)
+    gen = capi.conv2d(xc, wc, bc, res=rc, upsample2x=up, flags=capi.CONV_NO_HALO)
+    assert report("generic kernel, same problem", gen, ref, 2e-2 if up else 1e-2)[0]
+    assert ok
+
+
 def test_conv_residual_silu_concat(capi):
     """residual epilogue + reading a channel slice of a concat buffer + writing into a slice."""
     from oracle import ops
