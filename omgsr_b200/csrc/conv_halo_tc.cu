@@ -11,6 +11,7 @@
 //   (generic kernel: 2 x 18 k-blocks x 32 KB = 1152 KB).
 // Warp roles as in gemm_conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "../../include/omgsr_b200.h"
 
 namespace omgsr {
@@ -42,9 +43,11 @@ struct HaloCfg {
 };
 
 __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, int mode) {
-  uint64_t d = umma_desc_sw128(addr, 16, 1024);
-  if (mode) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
-  return d;
+  // The 128B swizzle is a function of the absolute shared-memory address bits [4:6] ^ [7:9], so an operand view that
+  // starts at any 128-byte row of a 1024-byte aligned, TMA-written tile needs NO base-offset correction
+  // (verified on B200: setting the base-offset field to (addr >> 7) & 7 gives wrong results).
+  (void)mode;
+  return umma_desc_sw128(addr, 16, 1024);
 }
 
 __device__ __forceinline__ float halo_act(float v, int act) {
@@ -176,8 +179,12 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = 0; t < TM; ++t) {
         const int y = ty * TM + t;
         const bool valid = (x < p.W) && (y < p.H);
-        const long long o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
-        const bf16* res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+        EpiArgs e;
+        e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
+        e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+        e.res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+        e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
+        e.out_f32 = p.out_f32;
         const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -185,37 +192,11 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float f[32];
           tmem_ld32(t_row + c0, v);
           tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           const int cv = n_tile * BN + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]);
-            if (p.bias) a += __ldg(p.bias + cv + j);
-            f[j] = halo_act(a, p.act);
-          }
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int oc = cv + q * 8;
-              float* ff = f + q * 8;
-              if (res_row) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_row + oc);
-                const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                             r3 = unpack_bf16x2(rr.w);
-                ff[0] += r0.x; ff[1] += r0.y; ff[2] += r1.x; ff[3] += r1.y;
-                ff[4] += r2.x; ff[5] += r2.y; ff[6] += r3.x; ff[7] += r3.y;
-              }
-              if (p.out_f32) {
-                float* o = static_cast<float*>(p.out) + o_off + oc;
-                *reinterpret_cast<float4*>(o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(ff[4], ff[5], ff[6], ff[7]);
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(ff[0], ff[1]); o.y = pack_bf16x2(ff[2], ff[3]);
-                o.z = pack_bf16x2(ff[4], ff[5]); o.w = pack_bf16x2(ff[6], ff[7]);
-                *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_off + oc) = o;
-              }
-            }
-          }
+          if (p.bias) add_bias32(f, p.bias, cv, p.Cout);
+          epilogue_store32(f, cv, cv, valid, e);
         }
       }
       tc_fence_before();

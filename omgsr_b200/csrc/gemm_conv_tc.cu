@@ -21,6 +21,7 @@
 // Replaces the cuDNN / cuBLAS calls underneath diffusers' Conv2d / Linear modules that the reference
 // reaches from infer/omgsr_s_infer_model.py:75-84,173 and infer/omgsr_f_infer_model.py:16,191-211.
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "../../include/omgsr_b200.h"
 
 namespace omgsr {
@@ -236,10 +237,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord t = decode_tile(tile, p);
       const int x = t.tx * tw + xl, y = t.ty * th + yl, b = t.tbi * tb + bl;
       const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
-      const long long o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
-      const bf16* res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+      EpiArgs e;
+      e.bias = p.bias;
+      e.out = p.out;
+      e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+      e.res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
       const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : b) : 0;
-      const float* gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
+      e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
+      e.Cout = p.Cout; e.cout_out = cout_out; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
+      e.out_f32 = p.out_f32;
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
@@ -251,59 +257,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld32(t_row + c0, v);
         if (geglu) {
           uint32_t g[32];
+          float gf[32];
           tmem_ld32(t_row + BN / 2 + c0, g);
           tmem_wait_ld();
-          const int cv = t.n_tile * BN + c0;           // value column in the (row-permuted) weight
-          const int cg = t.n_tile * BN + BN / 2 + c0;  // gate column
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + cv + j) : 0.f);
-            float gg = __uint_as_float(g[j]) + (p.bias ? __ldg(p.bias + cg + j) : 0.f);
-            f[j] = a * gelu_erf_f(gg);
+          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gf[j] = __uint_as_float(g[j]); }
+          if (p.bias) {
+            add_bias32(f, p.bias, t.n_tile * BN + c0, p.Cout);            // value columns (row-permuted weight)
+            add_bias32(gf, p.bias, t.n_tile * BN + BN / 2 + c0, p.Cout);  // gate columns
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_f(gf[j]);
         } else {
           tmem_wait_ld();
-          const int cv = t.n_tile * BN + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]);
-            if (p.bias) a += __ldg(p.bias + min(cv + j, p.Cout - 1));
-            f[j] = (cv + j >= p.act_c0 && cv + j < p.act_c1) ? apply_act(a, p.act) : a;
-          }
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) add_bias32(f, p.bias, t.n_tile * BN + c0, p.Cout);
         }
-        const int oc0 = t.n_tile * out_bn + c0;  // first output channel of this chunk
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {  // 4 x 8 channels
-            const int oc = oc0 + q * 8;
-            if (oc < cout_out) {
-              float* ff = f + q * 8;
-              if (gate_row) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) ff[j] *= __ldg(gate_row + oc + j);
-              }
-              if (res_row) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_row + oc);
-                const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                             r3 = unpack_bf16x2(rr.w);
-                ff[0] += r0.x; ff[1] += r0.y; ff[2] += r1.x; ff[3] += r1.y;
-                ff[4] += r2.x; ff[5] += r2.y; ff[6] += r3.x; ff[7] += r3.y;
-              }
-              if (p.out_f32) {
-                float* o = static_cast<float*>(p.out) + o_off + oc;
-                *reinterpret_cast<float4*>(o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(ff[4], ff[5], ff[6], ff[7]);
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(ff[0], ff[1]);
-                o.y = pack_bf16x2(ff[2], ff[3]);
-                o.z = pack_bf16x2(ff[4], ff[5]);
-                o.w = pack_bf16x2(ff[6], ff[7]);
-                *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_off + oc) = o;
-              }
-            }
-          }
-        }
+        epilogue_store32(f, t.n_tile * BN + c0, t.n_tile * out_bn + c0, valid, e);
       }
       tc_fence_before();
       __syncwarp();

@@ -134,7 +134,7 @@ HALO_CASES = [
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,up", HALO_CASES)
-@pytest.mark.parametrize("mode", ["halo", "halo_desc1"])
+@pytest.mark.parametrize("mode", ["halo"])
 def test_conv_halo(capi, B, H, W, Cin, Cout, up, mode):
     from oracle import ops
     from omgsr_b200.pack import pack_conv_weight, pack_upsample_weight
