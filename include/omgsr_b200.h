@@ -123,10 +123,11 @@ int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats, int B, lon
 /* y = (x - mean) * rstd * gamma + beta, optional SiLU. (diffusers GroupNorm+SiLU pairs: VAE eps 1e-6,
  * UNet eps 1e-5; infer/vaehook.py:384-413 restates the same op as custom_group_norm.)
  * stats_mode 0: stats[B,G,2] = (sum, sumsq) from omgsr_groupnorm_stats on this tensor.
- * stats_mode 1: stats[stats_mod,G,2] = (mean, var) from omgsr_groupnorm_combine, row = batch index % stats_mod. */
+ * stats_mode 1: stats[stats_mod,G,2] = (mean, var) from omgsr_groupnorm_combine, row = batch index % stats_mod.
+ * coef_scratch: caller-provided B*C float2 (8*B*C bytes) for the per-(image, channel) affine coefficients. */
 int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,
-                          const float* gamma, const float* beta, int B, long long HW, int C, int G, float eps,
-                          int silu, int stats_mode, int stats_mod, void* stream);
+                          const float* gamma, const float* beta, void* coef_scratch, int B, long long HW, int C,
+                          int G, float eps, int silu, int stats_mode, int stats_mod, void* stream);
 /* Cross-tile GroupNorm statistics of the tiled VAE (GroupNormParam.summary, infer/vaehook.py:489-508).
  * sums[entries,G,2] = per-(tile,image) (sum, sumsq) with image = entry % n_img; pixels[entries] = pixels of
  * that tile (fp32, device). out[n_img,G,2] = pixel-weighted mean of the per-tile (mean, biased var). */
@@ -203,7 +204,9 @@ int omgsr_adain_fix(const float* content, const float* style, float* out, void* 
 
 /* ---- layout ---------------------------------------------------------------------------------------- */
 int omgsr_nchw_to_nhwc(const void* x, int x_f32, void* y, int B, int C, int H, int W, long long ldy, void* stream);
-int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f32, int B, int C, int H, int W, void* stream);
+/* clamp != 0: clamp to [-1, 1] on the way out (infer/omgsr_s_infer_model.py:85) */
+int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f32, int B, int C, int H, int W, int clamp,
+                       void* stream);
 
 #ifdef __cplusplus
 }

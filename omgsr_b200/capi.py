@@ -226,8 +226,9 @@ def groupnorm_apply(x, stats, gamma, beta, groups=32, eps=1e-6, silu=False, out=
     HW = x.numel() // (B * C)
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    coef = torch.empty((B, C, 2), device=x.device, dtype=torch.float32)
     rc = _lib.omgsr_groupnorm_apply(_ptr(x), _ll(x.stride(-2)), _ptr(out), _ll(out.stride(-2)), _ptr(stats),
-                                    _ptr(gamma), _ptr(beta), _i(B), _ll(HW), _i(C), _i(groups), _f(eps),
+                                    _ptr(gamma), _ptr(beta), _ptr(coef), _i(B), _ll(HW), _i(C), _i(groups), _f(eps),
                                     _i(int(silu)), _i(1 if shared_mod > 0 else 0), _i(shared_mod), _stream())
     _check(rc, "omgsr_groupnorm_apply")
     return out
@@ -443,12 +444,12 @@ def nchw_to_nhwc(x, out=None):
     return out
 
 
-def nhwc_to_nchw(x, out_dtype=torch.bfloat16):
+def nhwc_to_nchw(x, out_dtype=torch.bfloat16, clamp=False):
     _cuda_bf16(x, "x")
     B, H, W, C = x.shape
     out = torch.empty((B, C, H, W), device=x.device, dtype=out_dtype)
     rc = _lib.omgsr_nhwc_to_nchw(_ptr(x), _ll(x.stride(2)), _ptr(out), _i(int(out_dtype == torch.float32)), _i(B),
-                                 _i(C), _i(H), _i(W), _stream())
+                                 _i(C), _i(H), _i(W), _i(int(clamp)), _stream())
     _check(rc, "omgsr_nhwc_to_nchw")
     return out
 

@@ -241,7 +241,12 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   if (OW < 96) return 1;                        // a 128-pixel row tile would be mostly padding
   if (Cin % 64 || (Cout % 128)) return 1;
   if (act == OMGSR_ACT_GEGLU) return 1;
-  const int bn = (Cout % 256 == 0) ? 256 : 128;
+  // measured on B200 (profiles/r01/conv_gemm_timing_v2.txt): the halo kernel wins where the generic kernel is
+  // bound by its L2->SMEM operand stream, i.e. Cout = 128 (128-wide tiles re-read A per 128 output channels):
+  // 1150 vs 918 TFLOP/s at 128->128 @512^2. With 256-wide tiles (no room for a second TMEM accumulator set at
+  // TM=2) the generic kernel is faster (1333 vs 1209 at 256->256 @256^2), so those stay on the generic path.
+  if (Cout % 256 == 0) return 1;
+  const int bn = 128;
   constexpr int TM = 2;
   HaloParams p;
   p.tiles_x = (OW + 127) / 128; p.tiles_y = (OH + TM - 1) / TM; p.B = B; p.W = OW; p.H = OH;

@@ -53,8 +53,20 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (threadIdx.x < vpr * rows_per_iter) {
     const bf16* base = x + static_cast<long long>(b) * HW * ldx + v * 8;
-    for (long long r = static_cast<long long>(blk) * rows_per_iter + r0; r < HW;
-         r += static_cast<long long>(blocks_per_img) * rows_per_iter) {
+    const long long step = static_cast<long long>(blocks_per_img) * rows_per_iter;
+    long long r = static_cast<long long>(blk) * rows_per_iter + r0;
+    for (; r + 3 * step < HW; r += 4 * step) {  // four independent 16-byte loads in flight per thread
+      float f0[8], f1[8], f2[8], f3[8];
+      const uint4 u0 = ld_stream(base + r * ldx), u1 = ld_stream(base + (r + step) * ldx),
+                  u2 = ld_stream(base + (r + 2 * step) * ldx), u3 = ld_stream(base + (r + 3 * step) * ldx);
+      unpack8(u0, f0); unpack8(u1, f1); unpack8(u2, f2); unpack8(u3, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        q[j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
+      }
+    }
+    for (; r < HW; r += step) {
       float f[8];
       unpack8(ld_stream(base + r * ldx), f);
 #pragma unroll
@@ -72,34 +84,75 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[static_cast<long long>(b) * 2 * G + i], bins[i]);
 }
 
-// y = (x - mean) * rstd * gamma + beta (+SiLU). One thread = one 8-channel vector of one pixel.
+// GroupNorm apply, stage 1: per-(image, channel) affine coefficients  y = x * a + b  with
+//   a = rstd_g * gamma_c,  b = beta_c - mean_g * a       (tiny: B*C entries)
+// stats_mode 0: stats[b] = (sum, sumsq) of this very tensor; 1: stats[b % stats_mod] = (mean, var) shared by the
+// tiles of one image (cross-tile GroupNorm of the tiled VAE).
+__global__ void gn_coef_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float2* __restrict__ coef, int B, long long HW, int C,
+                               int G, float eps, int stats_mode, int stats_mod) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const int cpg = C / G, g = c / cpg;
+  const float* st = stats + static_cast<long long>(stats_mode ? b % stats_mod : b) * 2 * G;
+  float mean, var;
+  if (stats_mode) {
+    mean = st[2 * g];
+    var = st[2 * g + 1];
+  } else {
+    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+    mean = st[2 * g] * inv_n;
+    var = fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.f);
+  }
+  const float a = rsqrtf(var + eps) * gamma[c];
+  coef[i] = make_float2(a, beta[c] - mean * a);
+}
+
+// stage 2: streaming y = silu?(x * a + b). A thread owns one 8-channel column for its whole pixel range, so its
+// 16 coefficients are loaded once; per element the loop is one FMA (+ SiLU).
+template <bool SILU>
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
-                                const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, long long HW, int C, int G, float eps, int silu,
-                                int vpr, long long total_vec, int stats_mode, int stats_mod) {
-  // stats_mode 0: stats[b] = (sum, sumsq) of this very tensor; 1: stats[b % stats_mod] = (mean, var) shared
-  // by several tiles of the same image (cross-tile GroupNorm of the tiled VAE)
-  const int cpg = C / G;
-  const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % vpr);
-    const long long pix = i / vpr;       // b*HW + p
-    const int b = static_cast<int>(pix / HW);
-    float f[8];
-    unpack8(ld_stream(x + pix * ldx + v * 8), f);
-    const float* st = stats + static_cast<long long>(stats_mode ? b % stats_mod : b) * 2 * G;
+                                const float2* __restrict__ coef, long long HW, int C, int vpr, int rows_per_iter,
+                                int blocks_per_img) {
+  const int b = blockIdx.x / blocks_per_img;
+  const int blk = blockIdx.x % blocks_per_img;
+  if (threadIdx.x >= vpr * rows_per_iter) return;
+  const int v = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  float ca[8], cb[8];
+  const float2* cf = coef + static_cast<long long>(b) * C + v * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float2 t = __ldg(cf + j); ca[j] = t.x; cb[j] = t.y; }
+  const bf16* xb = x + static_cast<long long>(b) * HW * ldx + v * 8;
+  bf16* yb = y + static_cast<long long>(b) * HW * ldy + v * 8;
+  const long long step = static_cast<long long>(blocks_per_img) * rows_per_iter;
+  long long r = static_cast<long long>(blk) * rows_per_iter + r0;
+  // two pixels in flight per thread
+  for (; r + step < HW; r += 2 * step) {
+    float f0[8], f1[8];
+    const uint4 u0 = ld_stream(xb + r * ldx);
+    const uint4 u1 = ld_stream(xb + (r + step) * ldx);
+    unpack8(u0, f0);
+    unpack8(u1, f1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cpg;
-      const float mean = stats_mode ? st[2 * g] : st[2 * g] * inv_n;
-      const float var = stats_mode ? st[2 * g + 1] : fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
-      float o = (f[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-      f[j] = silu ? silu_f(o) : o;
+      float o0 = fmaf(f0[j], ca[j], cb[j]), o1 = fmaf(f1[j], ca[j], cb[j]);
+      f0[j] = SILU ? silu_f(o0) : o0;
+      f1[j] = SILU ? silu_f(o1) : o1;
     }
-    *reinterpret_cast<uint4*>(y + pix * ldy + v * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(yb + r * ldy) = pack8(f0);
+    *reinterpret_cast<uint4*>(yb + (r + step) * ldy) = pack8(f1);
+  }
+  for (; r < HW; r += step) {
+    float f0[8];
+    unpack8(ld_stream(xb + r * ldx), f0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float o0 = fmaf(f0[j], ca[j], cb[j]);
+      f0[j] = SILU ? silu_f(o0) : o0;
+    }
+    *reinterpret_cast<uint4*>(yb + r * ldy) = pack8(f0);
   }
 }
 
@@ -449,7 +502,7 @@ __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, bf16* __restrict_
 }
 template <typename TOut>
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, long long ldx, TOut* __restrict__ y, int C,
-                                    long long HW) {
+                                    long long HW, int clamp) {
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const long long p0 = blockIdx.x * 32LL;
@@ -463,7 +516,11 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, long long ldx, T
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j;
     const long long p = p0 + threadIdx.x;
-    if (c < C && p < HW) y[(b * C + c) * HW + p] = static_cast<TOut>(tile[threadIdx.x][j]);
+    if (c < C && p < HW) {
+      float v = tile[threadIdx.x][j];
+      if (clamp) v = fminf(fmaxf(v, -1.f), 1.f);
+      y[(b * C + c) * HW + p] = static_cast<TOut>(v);
+    }
   }
 }
 
@@ -500,16 +557,32 @@ extern "C" int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats,
 }
 
 extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,
-                                     const float* gamma, const float* beta, int B, long long HW, int C, int G,
-                                     float eps, int silu, int stats_mode, int stats_mod, void* stream) {
-  if (stats_mode && stats_mod <= 0) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: stats_mod must be > 0");
-  if (C % 8 || C % G) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: C=%d G=%d", C, G);
+                                     const float* gamma, const float* beta, void* coef_scratch, int B, long long HW,
+                                     int C, int G, float eps, int silu, int stats_mode, int stats_mod, void* stream) {
+  if (C % 8 || C % G || C / 8 > 1024) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: C=%d G=%d", C, G);
   if ((ldx | ldy) % 8) return set_error(OMGSR_ERR_ALIGN, "groupnorm_apply: ld %% 8");
+  if (stats_mode && stats_mod <= 0) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: stats_mod must be > 0");
+  if (!coef_scratch) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: coef_scratch (B*C float2) is required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* coef = static_cast<float2*>(coef_scratch);
+  gn_coef_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(stats, gamma, beta, coef, B, HW, C, G, eps, stats_mode, stats_mod);
+  int rc = check_launch("gn_coef_kernel");
+  if (rc) return rc;
   const int vpr = C / 8;
-  const long long total = static_cast<long long>(B) * HW * vpr;
-  gn_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, stats, gamma, beta, HW, C, G, eps, silu, vpr, total,
-      stats_mode, stats_mod);
+  int rows_per_iter = 256 / vpr;
+  if (rows_per_iter < 1) rows_per_iter = 1;
+  const int threads = ((vpr * rows_per_iter + 31) / 32) * 32;
+  long long bpi = (static_cast<long long>(sm_count()) * 16 + B - 1) / B;
+  const long long max_bpi = (HW + 2LL * rows_per_iter - 1) / (2LL * rows_per_iter);
+  if (bpi > max_bpi) bpi = max_bpi;
+  if (bpi < 1) bpi = 1;
+  const unsigned grid = static_cast<unsigned>(bpi * B);
+  if (silu)
+    gn_apply_kernel<true><<<grid, threads, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, coef,
+                                                    HW, C, vpr, rows_per_iter, static_cast<int>(bpi));
+  else
+    gn_apply_kernel<false><<<grid, threads, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, coef,
+                                                     HW, C, vpr, rows_per_iter, static_cast<int>(bpi));
   return check_launch("gn_apply_kernel");
 }
 
@@ -707,13 +780,15 @@ extern "C" int omgsr_nchw_to_nhwc(const void* x, int x_f32, void* y, int B, int 
   return check_launch("nchw_to_nhwc_kernel");
 }
 extern "C" int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f32, int B, int C, int H, int W,
-                                  void* stream) {
+                                  int clamp, void* stream) {
   const long long HW = static_cast<long long>(H) * W;
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (y_f32)
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<float*>(y), C, HW);
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<float*>(y), C, HW,
+                                                       clamp);
   else
-    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), C, HW);
+    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), C, HW,
+                                                      clamp);
   return check_launch("nhwc_to_nchw_kernel");
 }
