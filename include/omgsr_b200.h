@@ -43,7 +43,6 @@ extern "C" {
 #define OMGSR_OUT_F32 1      /* store fp32 instead of bf16 */
 #define OMGSR_B_MN_MAJOR 2   /* batched GEMM: B operand given as [K, N] (row-major V), not [N, K] */
 #define OMGSR_CONV_NO_HALO 4     /* conv2d: force the generic implicit-GEMM kernel (testing / A-B timing) */
-#define OMGSR_CONV_HALO_DESC1 8  /* conv2d: halo kernel with the descriptor base-offset field set (bring-up probe) */
 
 int omgsr_version(void);
 const char* omgsr_last_error(void);
@@ -98,11 +97,14 @@ int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out
  * upsample in front of a 3x3/p1 conv (weights must be packed by pack_upsample_weight: 4 x [Cout, 4*Cin]).
  * Replaces cuDNN under diffusers ResnetBlock2D/Downsample2D/Upsample2D in the VAE and UNet
  * (infer/omgsr_s_infer_model.py:84,173; infer/vaehook.py:248-329 lists the same layers). Cin % 64 == 0.
- * epi: +bias -> act -> +res. */
+ * epi: +bias -> act -> +res. gn_sums (nullable): fp32 [B, gn_groups, 2]; the call zeroes it and the epilogue
+ * accumulates (sum, sum of squares) of the STORED bf16 output per (image, group), i.e. the statistics pass of the
+ * GroupNorm that follows the conv costs no extra trip over HBM (needs >= 128 output pixels per image and
+ * Cout/gn_groups in {4, 8, 16, ...}; otherwise OMGSR_ERR_SHAPE). */
 int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H,
                            int W, int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b,
                            int pad_r, int upsample2x, int act, long long ldx, long long ldy, long long ldr,
-                           int flags, int force_bn, void* stream);
+                           float* gn_sums, int gn_groups, int flags, int force_bn, void* stream);
 
 /* ---- thin convolutions (CUDA cores; too few channels for the tensor pipe) --------------------- */
 

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libomgsr_b200.so")
 
 ACT_NONE, ACT_SILU, ACT_GELU_ERF, ACT_GELU_TANH, ACT_GEGLU = 0, 1, 2, 3, 4
-OUT_F32, B_MN_MAJOR, CONV_NO_HALO, CONV_HALO_DESC1 = 1, 2, 4, 8
+OUT_F32, B_MN_MAJOR, CONV_NO_HALO = 1, 2, 4
 
 # every symbol include/omgsr_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
@@ -141,7 +141,7 @@ def bgemm_pv(p, v, out=None, n_kv=None, force_bn=0):
 
 
 def conv2d(x, w, bias=None, res=None, ksize=3, stride=1, pad=(1, 1, 1, 1), upsample2x=False, act=ACT_NONE, out=None,
-           out_f32=False, cout=None, force_bn=0, flags=0):
+           out_f32=False, cout=None, force_bn=0, flags=0, gn_stats=None, gn_groups=32):
     """NHWC conv. x: [B,H,W,Cin] bf16 view (channel-contiguous, dense in B/H/W with a channel stride);
     w: packed [Cout, k*k*Cin] (or [4, Cout, 4*Cin] for upsample2x). pad = (top, left, bottom, right)."""
     _cuda_bf16(x, "x"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias")
@@ -168,7 +168,8 @@ def conv2d(x, w, bias=None, res=None, ksize=3, stride=1, pad=(1, 1, 1, 1), upsam
     rc = _lib.omgsr_conv2d_nhwc_bf16(_ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), _i(B), _i(H), _i(W),
                                      _i(Cin), _i(Cout), _i(ksize), _i(stride), _i(pad[0]), _i(pad[1]), _i(pad[2]),
                                      _i(pad[3]), _i(1 if upsample2x else 0), _i(act), _ll(x.stride(2)),
-                                     _ll(out.stride(2)), _ll(ldr),
+                                     _ll(out.stride(2)), _ll(ldr), _ptr(gn_stats),
+                                     _i(gn_groups if gn_stats is not None else 0),
                                      _i((OUT_F32 if out.dtype == torch.float32 else 0) | flags), _i(force_bn),
                                      _stream())
     _check(rc, "omgsr_conv2d_nhwc_bf16")
@@ -206,6 +207,12 @@ def conv_out_nchw(x, w, bias, cout, clamp=False, out_dtype=torch.bfloat16):
 # ------------------------------------------------------------------------------------------------
 # glue
 # ------------------------------------------------------------------------------------------------
+def gn_fusable(B, H, W, C, groups=32):
+    """can the conv producing an NHWC [B,H,W,C] tensor also produce its GroupNorm statistics (conv2d gn_stats=)?"""
+    cpg = C // groups
+    return C % groups == 0 and H * W >= 128 and (cpg == 4 or (cpg >= 8 and cpg % 8 == 0))
+
+
 def groupnorm_stats(x, groups=32, stats=None):
     """(sum, sumsq) per (batch entry, group) of an NHWC bf16 view -> fp32 [B, groups, 2]."""
     _cuda_bf16(x, "x")

@@ -30,6 +30,8 @@ struct HaloParams {
   const float* bias;
   const bf16* res;
   int act, out_f32;
+  float* gn_sums;
+  int gn_cpg, gn_groups;
 };
 
 template <int BN, int TM>
@@ -185,6 +187,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         e.res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
         e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
         e.out_f32 = p.out_f32;
+        e.gn_sums = p.gn_sums ? p.gn_sums + static_cast<long long>(b) * p.gn_groups * 2 : nullptr;
+        e.gn_cpg = p.gn_cpg;
         const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -236,7 +240,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
 int try_conv_halo(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int IH, int IW,
                   int OH, int OW, int Cin, int Cout, int R, int S, int pad_t, int pad_l, long long x_sx, long long x_sy,
                   long long x_sb, long long o_sx, long long o_sy, long long o_sb, long long r_sx, long long r_sy,
-                  long long r_sb, long long w_ld, int act, int out_f32, int desc_mode, cudaStream_t st) {
+                  long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, cudaStream_t st) {
   if (R * S < 4 || R > 3 || S > 3) return 1;
   if (OW < 96) return 1;                        // a 128-pixel row tile would be mostly padding
   if (Cin % 64 || (Cout % 128)) return 1;
@@ -253,7 +257,13 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   p.n_tiles = Cout / bn; p.Cout = Cout; p.chunks = Cin / 64; p.R = R; p.S = S; p.pad_t = pad_t; p.pad_l = pad_l;
   p.Cin = Cin; p.pw = 128 + S - 1;
   p.a_bytes = 128 * p.pw * (TM + R - 1);
-  p.desc_mode = desc_mode;
+  p.desc_mode = 0;
+  p.gn_sums = nullptr; p.gn_cpg = 0; p.gn_groups = 0;
+  if (gn_sums) {
+    const int cpg = gn_groups > 0 ? Cout / gn_groups : 0;
+    if (out_f32 || gn_groups <= 0 || Cout % gn_groups || !(cpg == 4 || (cpg >= 8 && cpg % 8 == 0))) return 1;
+    p.gn_sums = gn_sums; p.gn_cpg = cpg; p.gn_groups = gn_groups;
+  }
   p.o_sx = o_sx; p.o_sy = o_sy; p.o_sb = o_sb; p.r_sx = r_sx; p.r_sy = r_sy; p.r_sb = r_sb;
   p.out = y; p.bias = bias; p.res = static_cast<const bf16*>(res); p.act = act; p.out_f32 = out_f32;
   if (static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles > 0x7fffffffLL) return 1;

@@ -19,7 +19,15 @@ struct EpiArgs {
   int cout_out;           // output channels (Cout, or Cout/2 for GEGLU)
   int act, act_c0, act_c1;
   int out_f32;
+  float* gn_sums;  // optional [groups][2] (sum, sumsq) accumulator of THIS row's image: GroupNorm statistics of
+  int gn_cpg;      // the stored tensor are produced here instead of by a separate pass over HBM
 };
+
+__device__ __forceinline__ float warp_sum_all(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 template <int ACT>
 __device__ __forceinline__ void act32(float (&f)[32]) {
@@ -54,11 +62,12 @@ __device__ __forceinline__ void epilogue_store32(float (&f)[32], int cv, int oc0
       default: act32<OMGSR_ACT_GELU_TANH>(f); break;
     }
   }
-  if (!valid) return;
+  // NOTE: every lane of the warp runs this loop (the GroupNorm reduction below is warp-collective);
+  // rows outside the tensor only skip their loads / stores and contribute zeros.
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int oc = oc0 + q * 8;
-    if (oc >= e.cout_out) break;
+    if (oc >= e.cout_out) break;  // warp-uniform
     float* ff = f + q * 8;
     if (e.gate_row) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.gate_row + oc));
@@ -66,7 +75,7 @@ __device__ __forceinline__ void epilogue_store32(float (&f)[32], int cv, int oc0
       ff[0] *= g0.x; ff[1] *= g0.y; ff[2] *= g0.z; ff[3] *= g0.w;
       ff[4] *= g1.x; ff[5] *= g1.y; ff[6] *= g1.z; ff[7] *= g1.w;
     }
-    if (e.res_row) {
+    if (e.res_row && valid) {
       const uint4 rr = *reinterpret_cast<const uint4*>(e.res_row + oc);
       const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
                    r3 = unpack_bf16x2(rr.w);
@@ -74,14 +83,37 @@ __device__ __forceinline__ void epilogue_store32(float (&f)[32], int cv, int oc0
       ff[4] += r2.x; ff[5] += r2.y; ff[6] += r3.x; ff[7] += r3.y;
     }
     if (e.out_f32) {
-      float* o = static_cast<float*>(e.out) + e.o_off + oc;
-      *reinterpret_cast<float4*>(o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(ff[4], ff[5], ff[6], ff[7]);
+      if (valid) {
+        float* o = static_cast<float*>(e.out) + e.o_off + oc;
+        *reinterpret_cast<float4*>(o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(ff[4], ff[5], ff[6], ff[7]);
+      }
     } else {
       uint4 o;
       o.x = pack_bf16x2(ff[0], ff[1]); o.y = pack_bf16x2(ff[2], ff[3]);
       o.z = pack_bf16x2(ff[4], ff[5]); o.w = pack_bf16x2(ff[6], ff[7]);
-      *reinterpret_cast<uint4*>(static_cast<bf16*>(e.out) + e.o_off + oc) = o;
+      if (valid) *reinterpret_cast<uint4*>(static_cast<bf16*>(e.out) + e.o_off + oc) = o;
+      if (e.gn_sums) {
+        // statistics of the values as stored (bf16-rounded), 8 channels = one or two groups (cpg 4 | >= 8)
+        const float2 v0 = unpack_bf16x2(o.x), v1 = unpack_bf16x2(o.y), v2 = unpack_bf16x2(o.z), v3 = unpack_bf16x2(o.w);
+        float s0 = valid ? (v0.x + v0.y) + (v1.x + v1.y) : 0.f;
+        float q0 = valid ? (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) : 0.f;
+        float s1 = valid ? (v2.x + v2.y) + (v3.x + v3.y) : 0.f;
+        float q1 = valid ? (v2.x * v2.x + v2.y * v2.y) + (v3.x * v3.x + v3.y * v3.y) : 0.f;
+        if (e.gn_cpg == 4) {
+          s0 = warp_sum_all(s0); q0 = warp_sum_all(q0); s1 = warp_sum_all(s1); q1 = warp_sum_all(q1);
+          if ((threadIdx.x & 31) == 0) {
+            float* g = e.gn_sums + (oc >> 2) * 2;
+            atomicAdd(g, s0); atomicAdd(g + 1, q0); atomicAdd(g + 2, s1); atomicAdd(g + 3, q1);
+          }
+        } else {
+          s0 = warp_sum_all(s0 + s1); q0 = warp_sum_all(q0 + q1);
+          if ((threadIdx.x & 31) == 0) {
+            float* g = e.gn_sums + (oc / e.gn_cpg) * 2;
+            atomicAdd(g, s0); atomicAdd(g + 1, q0);
+          }
+        }
+      }
     }
   }
 }

@@ -47,6 +47,8 @@ struct ConvGemmParams {
   int act;             // OMGSR_ACT_*
   int out_f32;
   int a_bytes;         // bytes one A box delivers (tb may be clamped to B)
+  float* gn_sums;      // optional fused GroupNorm statistics of the output: [B][groups][2]
+  int gn_cpg, gn_groups;
 };
 
 constexpr int kBM = 128;
@@ -246,6 +248,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
       e.Cout = p.Cout; e.cout_out = cout_out; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
       e.out_f32 = p.out_f32;
+      e.gn_sums = p.gn_sums ? p.gn_sums + static_cast<long long>(min(b, p.B - 1)) * p.gn_groups * 2 : nullptr;
+      e.gn_cpg = p.gn_cpg;
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
@@ -343,6 +347,7 @@ struct ConvDesc {
   long long o_sx, o_sy, o_sb, r_sx, r_sy, r_sb;
   int act, gate_rows, force_bn, out_f32;
   long long gate_ld; int act_c0, act_c1;
+  float* gn_sums; int gn_groups;
   long long w_ld;  // elements per weight row (R*S*Cin)
   // batched B operand (attention)
   int b_batched, b_mn_major, flat;
@@ -354,7 +359,7 @@ struct ConvDesc {
 int try_conv_halo(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int IH, int IW,
                   int OH, int OW, int Cin, int Cout, int R, int S, int pad_t, int pad_l, long long x_sx, long long x_sy,
                   long long x_sb, long long o_sx, long long o_sy, long long o_sb, long long r_sx, long long r_sy,
-                  long long r_sb, long long w_ld, int act, int out_f32, int desc_mode, cudaStream_t st);
+                  long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, cudaStream_t st);
 
 static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
   if (d.Cin % kBK) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: K/Cin=%d must be a multiple of %d", d.Cin, kBK);
@@ -368,7 +373,7 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
     // wide stride-1 3x3 / 2x2 layers: input-halo kernel (conv_halo_tc.cu); returns 1 when not eligible
     const int rc = try_conv_halo(d.x, d.w, d.bias, d.res, d.y, d.B, d.IH, d.IW, d.H, d.W, d.Cin, d.Cout, d.R, d.S,
                                  d.pad_t, d.pad_l, d.x_sx, d.x_sy, d.x_sb, d.o_sx, d.o_sy, d.o_sb, d.r_sx, d.r_sy,
-                                 d.r_sb, d.w_ld, d.act, d.out_f32, d.halo_mode - 1, st);
+                                 d.r_sb, d.w_ld, d.act, d.out_f32, d.gn_sums, d.gn_groups, st);
     if (rc != 1) return rc;
   }
 
@@ -381,6 +386,7 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
       int h = 128 / c;
       while (h > 1 && h > d.H) h >>= 1;
       const int nb = 128 / (c * h);
+      if (d.gn_sums && nb != 1) continue;  // fused GroupNorm statistics: a tile must not straddle two images
       const long long cost = static_cast<long long>((d.W + c - 1) / c) * c * ((d.H + h - 1) / h) * h *
                              ((d.B + nb - 1) / nb) * nb;
       if (best < 0 || cost < best) { best = cost; tw = c; th = h; tb = nb; }
@@ -403,6 +409,15 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
   p.gate_ld = d.gate_ld > 0 ? d.gate_ld : (geglu ? d.Cout / 2 : d.Cout);
   p.act_c0 = d.act_c1 > d.act_c0 ? d.act_c0 : 0; p.act_c1 = d.act_c1 > d.act_c0 ? d.act_c1 : 0x7fffffff;
   p.a_bytes = kBK * 2 * tw * th * tb_box;
+  p.gn_sums = nullptr; p.gn_cpg = 0; p.gn_groups = 0;
+  if (d.gn_sums) {
+    // fused statistics need: bf16 output, one image per tile, 8-channel store granules that map to whole groups
+    const int cpg = d.gn_groups > 0 ? d.Cout / d.gn_groups : 0;
+    if (d.out_f32 || geglu || tb != 1 || d.gn_groups <= 0 || d.Cout % d.gn_groups || !(cpg == 4 || (cpg >= 8 && cpg % 8 == 0)))
+      return set_error(OMGSR_ERR_SHAPE, "conv_gemm: fused GroupNorm statistics unsupported for this shape (Cout=%d groups=%d tb=%d)",
+                       d.Cout, d.gn_groups, tb);
+    p.gn_sums = d.gn_sums; p.gn_cpg = cpg; p.gn_groups = d.gn_groups;
+  }
 
   const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_b;
   const int bn = pick_bn(d.Cout, m_tiles, d.force_bn, geglu, d.b_mn_major);
@@ -534,7 +549,8 @@ extern "C" int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batc
 extern "C" int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* res, void* y,
                                       int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad_t,
                                       int pad_l, int pad_b, int pad_r, int upsample2x, int act, long long ldx,
-                                      long long ldy, long long ldr, int flags, int force_bn, void* stream) {
+                                      long long ldy, long long ldr, float* gn_sums, int gn_groups, int flags,
+                                      int force_bn, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: empty problem");
   if (ksize != 1 && ksize != 3) return set_error(OMGSR_ERR_SHAPE, "conv2d: ksize must be 1 or 3");
   if (stride != 1 && stride != 2) return set_error(OMGSR_ERR_SHAPE, "conv2d: stride must be 1 or 2");
@@ -544,7 +560,13 @@ extern "C" int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float*
   d.B = B; d.IH = H; d.IW = W; d.Cin = Cin; d.Cout = Cout;
   d.x_sx = ldx; d.x_sy = ldx * W; d.x_sb = ldx * W * H;
   d.act = act; d.force_bn = force_bn; d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
-  d.halo_mode = (flags & OMGSR_CONV_NO_HALO) ? 0 : ((flags & OMGSR_CONV_HALO_DESC1) ? 2 : 1);
+  d.halo_mode = (flags & OMGSR_CONV_NO_HALO) ? 0 : 1;
+  d.gn_sums = gn_sums; d.gn_groups = gn_groups;
+  if (gn_sums) {
+    if (gn_groups <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: gn_groups must be > 0 with gn_sums");
+    cudaError_t e = cudaMemsetAsync(gn_sums, 0, sizeof(float) * 2 * gn_groups * B, st);
+    if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "conv2d gn memset: %s", cudaGetErrorString(e));
+  }
   if (upsample2x) {
     // nearest-2x + 3x3/p1 == four 2x2 convolutions on the un-upsampled input (weights pre-collapsed
     // per output parity by the packer): out(2i+py, 2j+px).

@@ -44,17 +44,37 @@ class _Res:
             self.sb = _dev(sd[name + ".conv_shortcut.bias"], device, f32)
 
 
-def resnet_gen(r, x, out=None):
-    """ResnetBlock2D as a coroutine: yields (x, gamma, beta, silu) at each GroupNorm and receives the
-    normalised tensor, so a driver can share statistics across tiles (infer/vaehook.py task queue)."""
-    h = yield (x, r.g1, r.b1, True)
-    h = capi.conv2d(h, r.w1, r.c1b)
-    h = yield (h, r.g2, r.b2, True)
+def _stats_buf(x_like_B, device):
+    return torch.empty((x_like_B, 32, 2), device=device, dtype=torch.float32)
+
+
+def conv_with_stats(x, w, bias, want_stats, **kw):
+    """conv2d that also returns the GroupNorm (sum, sumsq) statistics of its output when the shape allows the fused
+    epilogue path (None otherwise: the consumer then runs the separate statistics kernel)."""
+    B, H, W = x.shape[0], x.shape[1], x.shape[2]
+    if kw.get("upsample2x"):
+        H, W = 2 * H, 2 * W
+    elif kw.get("stride", 1) == 2:
+        H, W = H // 2, W // 2
+    cout = w.shape[1] if kw.get("upsample2x") else w.shape[0]
+    if want_stats and capi.gn_fusable(B, H, W, cout):
+        st = _stats_buf(B, x.device)
+        return capi.conv2d(x, w, bias, gn_stats=st, **kw), st
+    return capi.conv2d(x, w, bias, **kw), None
+
+
+def resnet_gen(r, x, out=None, x_stats=None, want_stats=False):
+    """ResnetBlock2D as a coroutine: yields (x, gamma, beta, silu, stats|None) at each GroupNorm and receives the
+    normalised tensor, so a driver can share statistics across tiles (infer/vaehook.py task queue). `stats` are
+    the fused-epilogue (sum, sumsq) of the producing conv when available. Returns (y, stats of y | None)."""
+    h = yield (x, r.g1, r.b1, True, x_stats)
+    h, st = conv_with_stats(h, r.w1, r.c1b, True)
+    h = yield (h, r.g2, r.b2, True, st)
     if r.ws is not None:
         skip = capi.conv2d(x, r.ws, r.sb, ksize=1, pad=(0, 0, 0, 0))
     else:
         skip = x
-    return capi.conv2d(h, r.w2, r.c2b, res=skip, out=out)
+    return conv_with_stats(h, r.w2, r.c2b, want_stats, res=skip, out=out)
 
 
 def drive_plain(gen, eps):
@@ -62,8 +82,10 @@ def drive_plain(gen, eps):
     try:
         req = next(gen)
         while True:
-            x, g, b, silu = req
-            req = gen.send(capi.groupnorm(x, g, b, 32, eps, silu))
+            x, g, b, silu, st = req
+            if st is None:
+                st = capi.groupnorm_stats(x)
+            req = gen.send(capi.groupnorm_apply(x, st, g, b, 32, eps, silu))
     except StopIteration as stop:
         return stop.value
 
@@ -75,13 +97,13 @@ def drive_tiled(gens, eps, n_img):
     reqs = [next(g) for g in gens]
     while True:
         sums, pix = [], []
-        for (x, _, _, _) in reqs:
-            sums.append(capi.groupnorm_stats(x))
+        for (x, _, _, _, st) in reqs:
+            sums.append(st if st is not None else capi.groupnorm_stats(x))
             hw = x.numel() // (x.shape[0] * x.shape[-1])
             pix.append(torch.full((x.shape[0],), float(hw), device=x.device, dtype=torch.float32))
         C = reqs[0][0].shape[-1]
         shared = capi.groupnorm_combine(torch.cat(sums, 0), torch.cat(pix, 0), n_img, C)
-        outs = [capi.groupnorm_apply(x, shared, g, b, 32, eps, silu, shared_mod=n_img) for (x, g, b, silu) in reqs]
+        outs = [capi.groupnorm_apply(x, shared, g, b, 32, eps, silu, shared_mod=n_img) for (x, g, b, silu, _) in reqs]
         nxt, done = [], []
         for g, o in zip(gens, outs):
             try:
@@ -97,7 +119,7 @@ def drive_tiled(gens, eps, n_img):
 
 def resnet_forward(r, x, eps, out=None):
     """x NHWC view -> NHWC (written into `out` if given). GroupNorm+SiLU -> conv1 -> GroupNorm+SiLU -> conv2 + skip."""
-    return drive_plain(resnet_gen(r, x, out), eps)
+    return drive_plain(resnet_gen(r, x, out), eps)[0]
 
 
 class _MidAttn:
@@ -120,7 +142,7 @@ class _MidAttn:
     def gen(self, x):
         B, H, W, C = x.shape
         T = H * W
-        h = yield (x, self.g, self.b, False)
+        h = yield (x, self.g, self.b, False, None)
         qkv = capi.gemm(h.view(B * T, C), self.wqkv, self.bqkv)  # [B*T, 3C]
         q, k, v = (qkv[:, i * C:(i + 1) * C].unflatten(0, (B, T)).unsqueeze(2) for i in range(3))  # [B,T,1,C]
         a = capi.attention_materialised(q, k, v, 1.0 / math.sqrt(C))  # [B,T,1,C]
@@ -162,17 +184,19 @@ class B200Encoder(torch.nn.Module):
         self.conv_out_b = _dev(b, self.dev, torch.float32)
 
     def trunk_gen(self, x):
-        """NCHW image -> NHWC bf16 features after conv_norm_out + SiLU (input of conv_out)."""
+        """NCHW image -> NHWC bf16 features after conv_norm_out + SiLU (input of conv_out). GroupNorm statistics
+        travel with the tensors: every conv whose output feeds a GroupNorm produces them in its epilogue."""
         h = capi.conv_in_nchw(x.contiguous(), self.conv_in_w, self.conv_in_b, self.cfg.block_out_channels[0])
+        st = None
         for res, down in self.levels:
             for r in res:
-                h = yield from resnet_gen(r, h)
-            if down is not None:
-                h = capi.conv2d(h, down[0], down[1], stride=2, pad=(0, 0, 1, 1))  # F.pad(x,(0,1,0,1)) + s2 p0
-        h = yield from resnet_gen(self.mid0, h)
+                h, st = yield from resnet_gen(r, h, x_stats=st, want_stats=True)
+            if down is not None:  # F.pad(x,(0,1,0,1)) + stride-2 conv
+                h, st = conv_with_stats(h, down[0], down[1], True, stride=2, pad=(0, 0, 1, 1))
+        h, _ = yield from resnet_gen(self.mid0, h, x_stats=st)
         h = yield from self.attn.gen(h)
-        h = yield from resnet_gen(self.mid1, h)
-        h = yield (h, self.gno, self.bno, True)
+        h, st = yield from resnet_gen(self.mid1, h, want_stats=True)
+        h = yield (h, self.gno, self.bno, True, st)
         return h
 
     def moments_nhwc(self, x, w=None, b=None):
@@ -225,15 +249,15 @@ class B200Decoder(torch.nn.Module):
     def trunk_gen(self, z):
         ch0 = self.cfg.block_out_channels[-1]
         h = capi.conv_in_nchw(z.contiguous(), self.conv_in_w, self.conv_in_b, ch0)
-        h = yield from resnet_gen(self.mid0, h)
+        h, _ = yield from resnet_gen(self.mid0, h)
         h = yield from self.attn.gen(h)
-        h = yield from resnet_gen(self.mid1, h)
+        h, st = yield from resnet_gen(self.mid1, h, want_stats=True)
         for res, up in self.levels:
             for r in res:
-                h = yield from resnet_gen(r, h)
-            if up is not None:
-                h = capi.conv2d(h, up[0], up[1], upsample2x=True)  # nearest-2x folded into 4 parity convs
-        h = yield (h, self.gno, self.bno, True)
+                h, st = yield from resnet_gen(r, h, x_stats=st, want_stats=True)
+            if up is not None:  # nearest-2x folded into 4 parity convs; all four accumulate into one statistics buffer
+                h, st = conv_with_stats(h, up[0], up[1], True, upsample2x=True)
+        h = yield (h, self.gno, self.bno, True, st)
         return h
 
     def _conv_out(self, h, clamp, out_dtype):

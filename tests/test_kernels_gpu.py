@@ -155,6 +155,36 @@ def test_conv_halo(capi, B, H, W, Cin, Cout, up, mode):
     assert ok
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,up,stride", [(2, 32, 32, 128, 128, False, 1), (1, 16, 128, 64, 128, False, 1),
+                                                      (2, 24, 40, 256, 256, False, 1), (1, 16, 16, 128, 512, False, 1),
+                                                      (2, 16, 16, 128, 128, True, 1), (2, 32, 32, 128, 128, False, 2)])
+def test_conv_fused_groupnorm_stats(capi, B, H, W, Cin, Cout, up, stride):
+    """the conv epilogue also produces (sum, sumsq) per (image, group) of its stored output."""
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight, pack_upsample_weight
+    g = _g(B + H + W + Cin + Cout + 3)
+    x = bf16r(torch.randn(B, H, W, Cin, generator=g))
+    w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+    b = torch.randn(Cout, generator=g)
+    pad = (0, 0, 1, 1) if stride == 2 else (1, 1, 1, 1)
+    OH, OW = (2 * H, 2 * W) if up else (H // stride, W // stride)
+    res = bf16r(torch.randn(B, OH, OW, Cout, generator=g))
+    pw = pack_upsample_weight(w) if up else pack_conv_weight(w)
+    st = torch.full((B, 32, 2), 123.0, device="cuda")
+    out = capi.conv2d(x.cuda().bfloat16(), pw.cuda(), b.cuda(), res=res.cuda().bfloat16(), stride=stride, pad=pad,
+                      upsample2x=up, gn_stats=st)
+    ref = ops.conv2d_nhwc(x, w, b, stride=stride, pad=pad, upsample2x=up) + res
+    assert report("conv (with fused stats)", out, ref, 2e-2 if up else 1e-2)[0]
+    o = out.float().cpu().reshape(B, OH * OW, 32, Cout // 32)
+    sref = torch.stack([o.sum(dim=(1, 3)), o.pow(2).sum(dim=(1, 3))], dim=-1)
+    assert report(f"fused gn stats C={Cout}", st, sref, 1e-3)[0]
+    # and the GroupNorm built on them equals the two-pass one
+    gam, bet = torch.randn(Cout, generator=g).cuda(), torch.randn(Cout, generator=g).cuda()
+    a = capi.groupnorm_apply(out, st, gam, bet, 32, 1e-6, True)
+    bb = capi.groupnorm(out, gam, bet, 32, 1e-6, True)
+    assert report("gn from fused stats", a, bb, 5e-3)[0]
+
+
 def test_conv_residual_silu_concat(capi):
     """residual epilogue + reading a channel slice of a concat buffer + writing into a slice."""
     from oracle import ops
