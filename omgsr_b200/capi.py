@@ -210,7 +210,7 @@ def conv_out_nchw(x, w, bias, cout, clamp=False, out_dtype=torch.bfloat16):
 def gn_fusable(B, H, W, C, groups=32):
     """can the conv producing an NHWC [B,H,W,C] tensor also produce its GroupNorm statistics (conv2d gn_stats=)?"""
     cpg = C // groups
-    return C % groups == 0 and H * W >= 128 and (cpg == 4 or (cpg >= 8 and cpg % 8 == 0))
+    return C % groups == 0 and H * W >= 128 and cpg in (4, 8, 16)
 
 
 def groupnorm_stats(x, groups=32, stats=None):

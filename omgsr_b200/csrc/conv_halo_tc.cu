@@ -41,7 +41,7 @@ struct HaloCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kBStages = (BN == 128) ? 5 : 2;
   static constexpr int kAccSets = (BN * TM * 2 <= 512) ? 2 : 1;
-  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024 /*GN partial sums*/;
 };
 
 __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, int mode) {
@@ -78,6 +78,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* acc_full = b_empty + C::kBStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [4 warps][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -168,6 +169,10 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row = quarter * 32 + lane;
     int set = 0;
     uint32_t sph = 0;
+    float* my_gn = gn_acc + quarter * 64;  // see gemm_conv_tc.cu: per-warp partial sums, flushed when the image changes
+    const int gn_n = p.gn_groups * 2;  // <= 64: the slice holds every group of one image, whatever the n_tile
+    int gn_b = -1;
+    if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m = tile / p.n_tiles;
@@ -175,6 +180,10 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ty = m % p.tiles_y;
       const int b = m / p.tiles_y;
       const int x = tx * 128 + row;
+      if (p.gn_sums && b != gn_b) {
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+        gn_b = b;
+      }
       mbar_wait(&acc_full[set], sph);
       tc_fence_after();
 #pragma unroll 1
@@ -187,8 +196,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         e.res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
         e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
         e.out_f32 = p.out_f32;
-        e.gn_sums = p.gn_sums ? p.gn_sums + static_cast<long long>(b) * p.gn_groups * 2 : nullptr;
-        e.gn_cpg = p.gn_cpg;
+        float gn_part[16];
+        e.gn_part = p.gn_sums ? gn_part : nullptr;
         const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -201,6 +210,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int cv = n_tile * BN + c0;
           if (p.bias) add_bias32(f, p.bias, cv, p.Cout);
           epilogue_store32(f, cv, cv, valid, e);
+          if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((cv) / p.gn_cpg) * 2, lane);
         }
       }
       tc_fence_before();
@@ -209,6 +219,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (C::kAccSets == 2) { if (++set == 2) { set = 0; sph ^= 1; } }
       else { sph ^= 1; }
     }
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
   }
 
   tc_fence_before();
@@ -261,7 +272,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   p.gn_sums = nullptr; p.gn_cpg = 0; p.gn_groups = 0;
   if (gn_sums) {
     const int cpg = gn_groups > 0 ? Cout / gn_groups : 0;
-    if (out_f32 || gn_groups <= 0 || Cout % gn_groups || !(cpg == 4 || (cpg >= 8 && cpg % 8 == 0))) return 1;
+    if (out_f32 || gn_groups <= 0 || gn_groups > 32 || Cout % gn_groups || !(cpg == 4 || cpg == 8 || cpg == 16)) return 1;
     p.gn_sums = gn_sums; p.gn_cpg = cpg; p.gn_groups = gn_groups;
   }
   p.o_sx = o_sx; p.o_sy = o_sy; p.o_sb = o_sb; p.r_sx = r_sx; p.r_sy = r_sy; p.r_sb = r_sb;

@@ -19,8 +19,8 @@ struct EpiArgs {
   int cout_out;           // output channels (Cout, or Cout/2 for GEGLU)
   int act, act_c0, act_c1;
   int out_f32;
-  float* gn_sums;  // optional [groups][2] (sum, sumsq) accumulator of THIS row's image: GroupNorm statistics of
-  int gn_cpg;      // the stored tensor are produced here instead of by a separate pass over HBM
+  float* gn_part;  // optional: 16 per-thread partials of this 32-column chunk, (sum, sumsq) per 4 channels, filled
+                   // by epilogue_store32 for the fused GroupNorm statistics (see gn_chunk_accumulate)
 };
 
 __device__ __forceinline__ float warp_sum_all(float v) {
@@ -93,29 +93,75 @@ __device__ __forceinline__ void epilogue_store32(float (&f)[32], int cv, int oc0
       o.x = pack_bf16x2(ff[0], ff[1]); o.y = pack_bf16x2(ff[2], ff[3]);
       o.z = pack_bf16x2(ff[4], ff[5]); o.w = pack_bf16x2(ff[6], ff[7]);
       if (valid) *reinterpret_cast<uint4*>(static_cast<bf16*>(e.out) + e.o_off + oc) = o;
-      if (e.gn_sums) {
-        // statistics of the values as stored (bf16-rounded), 8 channels = one or two groups (cpg 4 | >= 8)
+      if (e.gn_part) {
+        // partial statistics of the values as stored (bf16-rounded): channels 0-3 and 4-7 of this granule
         const float2 v0 = unpack_bf16x2(o.x), v1 = unpack_bf16x2(o.y), v2 = unpack_bf16x2(o.z), v3 = unpack_bf16x2(o.w);
-        float s0 = valid ? (v0.x + v0.y) + (v1.x + v1.y) : 0.f;
-        float q0 = valid ? (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) : 0.f;
-        float s1 = valid ? (v2.x + v2.y) + (v3.x + v3.y) : 0.f;
-        float q1 = valid ? (v2.x * v2.x + v2.y * v2.y) + (v3.x * v3.x + v3.y * v3.y) : 0.f;
-        if (e.gn_cpg == 4) {
-          s0 = warp_sum_all(s0); q0 = warp_sum_all(q0); s1 = warp_sum_all(s1); q1 = warp_sum_all(q1);
-          if ((threadIdx.x & 31) == 0) {
-            float* g = e.gn_sums + (oc >> 2) * 2;
-            atomicAdd(g, s0); atomicAdd(g + 1, q0); atomicAdd(g + 2, s1); atomicAdd(g + 3, q1);
-          }
-        } else {
-          s0 = warp_sum_all(s0 + s1); q0 = warp_sum_all(q0 + q1);
-          if ((threadIdx.x & 31) == 0) {
-            float* g = e.gn_sums + (oc / e.gn_cpg) * 2;
-            atomicAdd(g, s0); atomicAdd(g + 1, q0);
-          }
-        }
+        e.gn_part[4 * q + 0] = valid ? (v0.x + v0.y) + (v1.x + v1.y) : 0.f;
+        e.gn_part[4 * q + 1] = valid ? (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) : 0.f;
+        e.gn_part[4 * q + 2] = valid ? (v2.x + v2.y) + (v3.x + v3.y) : 0.f;
+        e.gn_part[4 * q + 3] = valid ? (v2.x * v2.x + v2.y * v2.y) + (v3.x * v3.x + v3.y * v3.y) : 0.f;
       }
     }
   }
+}
+
+// ---- fused GroupNorm statistics ---------------------------------------------------------------------------
+// Reduce NV per-thread values across the 32 lanes (= 32 pixels) of a warp with a halving butterfly:
+// NV-1 + (5 - log2 NV) shuffles instead of 5*NV. Afterwards lane L with (L & ((32 >> LOG2) - 1)) == 0 holds the
+// total of element L >> (5 - LOG2).
+template <int NV, int LOG2>
+__device__ __forceinline__ float warp_butterfly(float (&v)[NV], int lane) {
+  int step = 16;
+#pragma unroll
+  for (int half = NV / 2; half >= 1; half >>= 1, step >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int o = (16 >> LOG2); o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
+// part[16]: (sum, sumsq) of channel quads 0..7 of a 32-channel chunk for this thread's pixel. Adds the warp totals
+// per GroupNorm group into acc (this warp's private shared-memory slice, laid out [group][2] for the chunk's
+// groups). cpg in {4, 8, 16}.
+__device__ __forceinline__ void gn_chunk_accumulate(float (&part)[16], int cpg, float* acc, int lane) {
+  if (cpg == 4) {
+    const float r = warp_butterfly<16, 4>(part, lane);
+    if ((lane & 1) == 0) acc[lane >> 1] += r;
+  } else if (cpg == 8) {
+    float v[8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { v[2 * g] = part[4 * g] + part[4 * g + 2]; v[2 * g + 1] = part[4 * g + 1] + part[4 * g + 3]; }
+    const float r = warp_butterfly<8, 3>(v, lane);
+    if ((lane & 3) == 0) acc[lane >> 2] += r;
+  } else {  // 16
+    float v[4];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      v[2 * g] = (part[8 * g] + part[8 * g + 2]) + (part[8 * g + 4] + part[8 * g + 6]);
+      v[2 * g + 1] = (part[8 * g + 1] + part[8 * g + 3]) + (part[8 * g + 5] + part[8 * g + 7]);
+    }
+    const float r = warp_butterfly<4, 2>(v, lane);
+    if ((lane & 7) == 0) acc[lane >> 3] += r;
+  }
+}
+
+// flush this warp's slice (n floats) into the global [groups][2] accumulator of one image and clear it
+__device__ __forceinline__ void gn_flush(float* acc, int n, float* dst, int lane) {
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const float v = acc[i];
+    if (v != 0.f) atomicAdd(dst + i, v);
+    acc[i] = 0.f;
+  }
+  __syncwarp();
 }
 
 }  // namespace omgsr

@@ -338,7 +338,7 @@ def test_latent_steps(capi):
     logvar = mom[..., Cz:].permute(0, 3, 1, 2).clamp(-30, 20)
     ref = ((mean + torch.exp(0.5 * logvar) * eps) - 0.1159) * 0.3611
     z = capi.posterior_sample(mom.cuda(), eps.cuda(), Cz, 0.1159, 0.3611, torch.float32)
-    assert report("posterior", z, ref, 1e-5)[0]
+    assert report("posterior", z, ref, 2e-4)[0]   # fp32 with the fast exp intrinsic
     x = torch.randn(1000, generator=g)
     y = torch.randn(1000, generator=g)
     out = capi.latent_axpby(x.cuda(), y.cuda(), 0.495, 0.505, 0.0)   # z_t = (1-sigma) z + sigma eps
