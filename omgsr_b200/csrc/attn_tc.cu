@@ -259,6 +259,303 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+// ================================================================================================================
+// v2: two query tiles per CTA (ping-pong), O accumulated in TMEM, lazy rescale.
+//
+//   * CTA = 2 x 128 query rows of one (batch, head): softmax group A = warps 2..5, group B = warps 6..9, warp 0 =
+//     TMA producer, warp 1 = MMA issuer (320 threads). K_j / V_j are loaded ONCE per block and used by both groups,
+//     and while one group exponentiates, the tensor pipe runs the other group's S / PV MMAs.
+//   * O never leaves TMEM during the loop: PV_j accumulates in place. The running row maximum is allowed to go stale:
+//     probabilities are formed against m_stale and O is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when a
+//     row's new maximum exceeds m_stale by more than 8 in the log2 domain (p <= 256, safe in bf16 / fp32). After
+//     the first few blocks this almost never fires, which removes the per-block O read-modify-write of v1.
+//   * TMEM: S_a @0, S_b @128, O_a @256, O_b @384 (512 columns, 1 CTA / SM).
+// ================================================================================================================
+template <int D>
+struct Attn2Cfg {
+  static constexpr int kBN = (D == 64) ? 128 : 64;
+  static constexpr int kPBuf = (D == 64) ? 1 : 2;
+  static constexpr int kStages = 3;
+  static constexpr int kQBytes = 2 * 128 * D * 2;
+  static constexpr int kKBytes = kBN * D * 2;
+  static constexpr int kStageBytes = 2 * kKBytes;
+  static constexpr int kPBytes = 128 * kBN * 2;  // one P buffer of one group
+  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBuf * kPBytes + 1024 + 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(320, 1)
+flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = Attn2Cfg<D>;
+  constexpr int BN = C::kBN, PB = C::kPBuf;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [group][panel][128 rows x 128 B]
+  uint8_t* sKV = sQ + C::kQBytes;                       // [stage][K | V]
+  uint8_t* sP = sKV + C::kStages * C::kStageBytes;      // [group][buf]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PB * C::kPBytes);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* k_full = q_full + 1;             // [stages]
+  uint64_t* v_full = k_full + C::kStages;    // [stages]
+  uint64_t* kv_empty = v_full + C::kStages;  // [stages]
+  uint64_t* s_full = kv_empty + C::kStages;  // [2]
+  uint64_t* p_full = s_full + 2;             // [2][PB]
+  uint64_t* pv_done = p_full + 2 * PB;       // [2][PB]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2 * PB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      for (int i = 0; i < PB; ++i) { mbar_init(&p_full[g * PB + i], 128); mbar_init(&pv_done[g * PB + i], 1); }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, C::kQBytes);
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sQ + (g * (D / 64) + pnl) * (128 * 128), &tmQ, q_full, pnl * 64, m0 + g * 128, h, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sK = sKV + stage * C::kStageBytes;
+        uint8_t* sV = sK + C::kKBytes;
+        mbar_expect_tx(&k_full[stage], C::kKBytes);
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sK + pnl * (BN * 128), &tmK, &k_full[stage], pnl * 64, j * BN, h, b);
+        mbar_expect_tx(&v_full[stage], C::kKBytes);
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sV + pnl * (BN * 128), &tmV, &v_full[stage], pnl * 64, j * BN, h, b);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);
+      auto issue_s = [&](int g, int stage) {
+        const uint32_t aQ = smem_u32(sQ + g * (D / 64) * (128 * 128));
+        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
+          tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
+        }
+        tc_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        const int nstage = (stage + 1 == C::kStages) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == C::kStages) ? (phase ^ 1) : phase;
+        const int pb = j % PB;
+        const uint32_t pph = (j / PB) & 1;
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g * PB + pb], pph);  // group g consumed S_g(j) and wrote P_g(j)
+          if (g == 0) mbar_wait(&v_full[stage], phase);
+          tc_fence_after();
+          const uint32_t aP = smem_u32(sP + (g * PB + pb) * C::kPBytes);
+          const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            const uint64_t da = umma_desc_sw128(aP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(aV + kk * 2048, BN * 128, 1024);
+            tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
+          }
+          tc_commit(&pv_done[g * PB + pb]);
+          if (j + 1 < nblk) {
+            if (g == 0) { mbar_wait(&k_full[nstage], nphase); tc_fence_after(); }
+            issue_s(g, nstage);
+          }
+        }
+        tc_commit(&kv_empty[stage]);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + g * 128 + lane_off, tO = tmem_base + 256 + g * 128 + lane_off;
+    float m_stale = 0.f, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      const int n_valid = min(BN, p.N - j * BN);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const int pb = j % PB;
+      if (j == 0) {
+        m_stale = mx;
+      } else {
+        const bool need = (mx - m_stale) * p.scale_log2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // every PV issued so far must have retired before O is touched
+          mbar_wait(&pv_done[g * PB + ((j - 1) % PB)], ((j - 1) / PB) & 1);
+          tc_fence_after();
+          const float alpha = need ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tO + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tO + c0, v);
+          }
+          tmem_wait_st();
+          l_run *= alpha;
+          if (need) m_stale = mx;
+        }
+      }
+      // the P buffer we are about to overwrite was last read by PV(j - PB)
+      if (j >= PB) mbar_wait(&pv_done[g * PB + pb], ((j - PB) / PB) & 1);
+      const float mb = m_stale * p.scale_log2;
+      uint8_t* p_row = sP + (g * PB + pb) * C::kPBytes + row * 128;
+      float lsum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + c0, v);
+        tmem_wait_ld();
+        uint8_t* panel = p_row + (c0 >> 6) * (128 * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float pr[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = exp2f(__uint_as_float(v[q * 8 + i]) * p.scale_log2 - mb);
+            pr[i] = (c0 + q * 8 + i < n_valid) ? e : 0.f;
+            lsum += pr[i];
+          }
+          const int chunk = ((c0 & 63) >> 3) + q;
+          uint4 u;
+          u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
+          u.z = pack_bf16x2(pr[4], pr[5]); u.w = pack_bf16x2(pr[6], pr[7]);
+          *reinterpret_cast<uint4*>(panel + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      l_run += lsum;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[g * PB + pb]);
+    }
+    // epilogue: O / l
+    mbar_wait(&pv_done[g * PB + ((nblk - 1) % PB)], ((nblk - 1) / PB) & 1);
+    tc_fence_after();
+    const int m = m0 + g * 128 + row;
+    const float inv = 1.0f / l_run;
+    bf16* o = p.out + static_cast<long long>(b) * p.o_batch + static_cast<long long>(m) * p.o_row +
+              static_cast<long long>(h) * p.o_head;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tO + c0, v);
+      tmem_wait_ld();
+      if (m < p.M) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv, __uint_as_float(v[q * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv, __uint_as_float(v[q * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv, __uint_as_float(v[q * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv, __uint_as_float(v[q * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + c0 + q * 8) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D>
+static int launch_attn2(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
+                        const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
+                        cudaStream_t st) {
+  using C = Attn2Cfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(flash_attn2<%d>): %s", D, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t eb = 2;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(M), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t str[3] = {qs[0] * eb, qs[1] * eb, qs[2] * eb};
+    uint32_t box[4] = {64, 128, 1, 1};
+    int rc = make_tmap_bf16(&tmQ, q, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint32_t box[4] = {64, static_cast<uint32_t>(C::kBN), 1, 1};
+    uint64_t strk[3] = {ks[0] * eb, ks[1] * eb, ks[2] * eb};
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, strk, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    uint64_t strv[3] = {vs[0] * eb, vs[1] * eb, vs[2] * eb};
+    rc = make_tmap_bf16(&tmV, v, 4, dims, strv, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.M = M; p.N = N; p.H = H; p.B = B;
+  p.o_row = os[0]; p.o_head = os[1]; p.o_batch = os[2];
+  p.out = static_cast<bf16*>(out);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((M + 255) / 256, H, B);
+  flash_attn2_kernel<D><<<grid, 320, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  return check_launch("flash_attn2_kernel");
+}
+
 template <int D>
 static int launch_attn(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
                        const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
@@ -304,6 +601,10 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
 
 using namespace omgsr;
 
+static int g_attn_force_v1 = 0;
+/* bring-up / A-B timing switch: 1 = always use the single-tile kernel */
+extern "C" int omgsr_flash_attn_set_variant(int force_v1) { g_attn_force_v1 = force_v1; return OMGSR_OK; }
+
 extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int M,
                                      int N, int D, long long q_row, long long q_head, long long q_batch,
                                      long long k_row, long long k_head, long long k_batch, long long v_row,
@@ -320,6 +621,13 @@ extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v
   const long long qs[3] = {q_row, q_head, q_batch}, ks[3] = {k_row, k_head, k_batch}, vs[3] = {v_row, v_head, v_batch},
                   os[3] = {o_row, o_head, o_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // long query sequences: ping-pong kernel (2 x 128 rows per CTA, O in TMEM); short ones (M <= 128, e.g. the 8x8
+  // UNet level) keep the 128-row kernel so half of every CTA is not padding.
+  const bool v2 = (M > 128) && !(g_attn_force_v1);
+  if (v2) {
+    if (D == 64) return launch_attn2<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+    if (D == 128) return launch_attn2<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+  }
   if (D == 64) return launch_attn<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
   if (D == 128) return launch_attn<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
   return set_error(OMGSR_ERR_SHAPE, "flash_attn: head dim %d unsupported (64 or 128)", D);

@@ -246,6 +246,26 @@ def test_flash_attention(capi, B, Hh, M, N, D):
     assert report(f"flash {B},{Hh},{M},{N},{D}", o, ops.attention(q, k, v, scale), 2e-2)[0]
 
 
+def test_flash_attention_variants_agree(capi):
+    """the single-tile kernel (forced) and the ping-pong kernel give the same result on a long sequence."""
+    from oracle import ops
+    g = _g(123)
+    B, Hh, M, N, D = 1, 3, 1000, 1111, 128
+    q = bf16r(torch.randn(B, M, Hh, D, generator=g) * 2)
+    k = bf16r(torch.randn(B, N, Hh, D, generator=g) * 2)
+    v = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    ref = ops.attention(q, k, v, 0.25)   # large logits: exercises the lazy O rescale of the ping-pong kernel
+    qc, kc, vc = q.cuda().bfloat16(), k.cuda().bfloat16(), v.cuda().bfloat16()
+    o2 = capi.flash_attn(qc, kc, vc, 0.25)
+    capi.lib().omgsr_flash_attn_set_variant(1)
+    try:
+        o1 = capi.flash_attn(qc, kc, vc, 0.25)
+    finally:
+        capi.lib().omgsr_flash_attn_set_variant(0)
+    assert report("flash v1 (single tile)", o1, ref, 2e-2)[0]
+    assert report("flash v2 (ping-pong)", o2, ref, 2e-2)[0]
+
+
 def test_flash_attention_fused_qkv_layout(capi):
     """q/k/v as column slices of one fused [B, T, 3*H*D] projection output (strided views)."""
     from oracle import ops
