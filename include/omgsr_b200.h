@@ -115,6 +115,10 @@ int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, cons
  * w: fp32 [ksize*ksize*Cin, Cout]. (VAE encoder.conv_in, decoder.conv_in, unet.conv_in) */
 int omgsr_conv_in_nchw(const void* x, int x_f32, const float* w, const float* bias, void* y, int B, int Cin, int H,
                        int W, int Cout, int ksize, long long ldy, void* stream);
+/* im2col of a thin NCHW input for a 3x3/p1 conv: y[b*H*W + pixel, k] (bf16, row length Kpad, Kpad % 64 == 0) with
+ * k = (r*3+s)*Cin + ci and zero fill for k >= 9*Cin; the conv is then omgsr_gemm_bf16 on y with weights packed
+ * [Cout, Kpad] (large images: the 27-tap conv_in of the VAE encoder runs on the tensor cores this way). */
+int omgsr_im2col3x3_nchw(const void* x, int x_f32, void* y, int B, int Cin, int H, int W, int Kpad, void* stream);
 /* conv_out: x NHWC bf16 [B,H,W,Cin] -> y NCHW [B,Cout,H,W] (bf16 or fp32), Cout <= 4, 3x3 p1, optional clamp
  * to [-1,1] (infer/omgsr_s_infer_model.py:85). w: bf16 [Cout, 9*Cin]. (VAE decoder.conv_out) */
 int omgsr_conv_out_nchw(const void* x, const void* w, const float* bias, void* y, int y_f32, int B, int H, int W,
@@ -135,9 +139,11 @@ int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, 
                           int G, float eps, int silu, int stats_mode, int stats_mod, void* stream);
 /* Cross-tile GroupNorm statistics of the tiled VAE (GroupNormParam.summary, infer/vaehook.py:489-508).
  * sums[entries,G,2] = per-(tile,image) (sum, sumsq) with image = entry % n_img; pixels[entries] = pixels of
- * that tile (fp32, device). out[n_img,G,2] = pixel-weighted mean of the per-tile (mean, biased var). */
+ * that tile (fp32, device). out[n_img,G,2] = pixel-weighted mean of the per-tile (mean, biased var).
+ * wsum_out (nullable, [n_img]): when given, out holds the UN-normalised numerators sum_e pixels_e*(mean_e, var_e) and
+ * wsum_out the weights sum_e pixels_e, so partial results of several GPUs can be all-reduced before dividing. */
 int omgsr_groupnorm_combine(const float* sums, const float* pixels, int entries, int n_img, int C, int G, float* out,
-                            void* stream);
+                            float* wsum_out, void* stream);
 /* LayerNorm over the last dim with y = xhat * g + b where g/b are fp32 vectors of length C taken from
  * gamma + (row / rows_per_batch) * gb_stride (gb_stride = 0: shared affine; >0: per-image AdaLN modulation,
  * caller passes g = 1 + scale, b = shift). gamma/beta may be null (no affine). Input row r lives at

@@ -14,6 +14,7 @@ from typing import Callable
 import torch
 
 from omgsr_b200 import capi
+from omgsr_b200 import dist as D
 from omgsr_b200 import weights as W
 from .vaehook import VAEHook
 
@@ -209,7 +210,12 @@ class OMGSR_F_Infer(torch.nn.Module):
         if pe.shape[0] not in (1, nt * B):
             pe, pp = pe.repeat(nt, 1, 1), pp.repeat(nt, 1)
         packed = _pack_latents(tiles, nt * B, C, tile_size, tile_size)
-        pred = self._dit(packed, pe, pp, text_ids, latent_image_ids)  # [nt*B, (T/2)^2, 4C] bf16
+        if D.tile_parallel():  # single large image on several GPUs: each rank runs the DiT on its share of the tiles
+            if pe.shape[0] != 1:
+                raise RuntimeError("tile-parallel mode expects one shared prompt")
+            pred = D.tile_parallel_forward(lambda t: self._dit(t, pe, pp, text_ids, latent_image_ids), packed)
+        else:
+            pred = self._dit(packed, pe, pp, text_ids, latent_image_ids)  # [nt*B, (T/2)^2, 4C] bf16
         T2 = tile_size // 2
         # logical [nt, B, C, T, T] view of the packed prediction: channel c, pixel (y,x) -> token (y/2)*T2 + x/2,
         # feature c*4 + (y%2)*2 + (x%2); not expressible with one stride per axis, so unpack first (kernel)

@@ -18,6 +18,7 @@ import time
 import torch
 
 from omgsr_b200 import capi
+from omgsr_b200 import dist as D
 from omgsr_b200 import weights as W
 from omgsr_b200.engine_unet import B200UNet
 from omgsr_b200.engine_vae import B200AutoencoderKL
@@ -182,7 +183,10 @@ class OMGSR_S_Infer(torch.nn.Module):
         tiles = tiles.reshape(nt * B, C, tile_size, tile_size).contiguous()
         if prompt_embeds.shape[0] not in (1, nt * B):  # per-image prompts: repeat for every tile of that image
             prompt_embeds = prompt_embeds.repeat(nt, 1, 1)
-        eps_t = self.unet.eps_hat_nhwc(tiles, prompt_embeds)  # fp32 NHWC view [nt*B,T,T,C] (ld 8)
+        if D.tile_parallel():  # single large image on several GPUs: each rank denoises its share of the tiles
+            eps_t = D.tile_parallel_forward(lambda t: self.unet.eps_hat_nhwc(t, prompt_embeds)[..., :C], tiles)
+        else:
+            eps_t = self.unet.eps_hat_nhwc(tiles, prompt_embeds)  # fp32 NHWC view [nt*B,T,T,C] (ld 8)
         ld = eps_t.stride(2)
         et = torch.as_strided(eps_t, (nt, B, C, tile_size, tile_size),
                               (B * tile_size * tile_size * ld, tile_size * tile_size * ld, 1, tile_size * ld, ld),
@@ -204,7 +208,7 @@ class OMGSR_S_Infer(torch.nn.Module):
         cz = vae.cfg.latent_channels
         eps = vae.posterior_eps
         if eps is None:
-            eps = torch.randn((B, cz, hh, ww), device=m.device, dtype=torch.float32)
+            eps = D.broadcast_(torch.randn((B, cz, hh, ww), device=m.device, dtype=torch.float32))
         return capi.posterior_sample(m, eps.to(device=m.device, dtype=torch.float32), cz, 0.0,
                                      vae.config.scaling_factor, vae.dtype)
 

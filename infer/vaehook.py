@@ -21,6 +21,12 @@ import torch
 
 from omgsr_b200 import capi
 
+# Tile-parallel mode (additive; omgsr_b200.dist.enable_tile_parallel): with torch.distributed
+# initialised, the tiles of ONE image are dealt round-robin to the ranks; each rank runs only its tiles, the
+# GroupNorm statistics are all-reduced at every site (a [n_img,32,2] message) and the stitched result is summed
+# over ranks. Same numerics as on one GPU.
+from omgsr_b200 import dist as _dist
+
 
 class VAEHook:
     def __init__(self, net, tile_size, is_decoder, fast_decoder, fast_encoder, color_fix, to_gpu=False):
@@ -89,9 +95,15 @@ class VAEHook:
             raise NotImplementedError("VAEHook fast mode (GroupNorm estimation on a downsampled copy) is not built; "
                                       "the reference default and OMGSR's settings use fast_*=False")
         in_boxes, out_boxes = self.split_tiles(height, width)
+        tp = _dist.tile_parallel()
+        mine, shadow = list(range(len(in_boxes))), False
+        if tp:
+            from omgsr_b200.dist import my_tiles
+            mine, shadow = my_tiles(len(in_boxes), torch.distributed.get_rank(), torch.distributed.get_world_size())
         # group tiles of equal padded shape: each group is one batched tensor [n_tiles*N, C, th, tw]
         groups = {}
-        for idx, bx in enumerate(in_boxes):
+        for idx in mine:
+            bx = in_boxes[idx]
             groups.setdefault((bx[3] - bx[2], bx[1] - bx[0]), []).append(idx)
         gens, members, pixels = [], [], []
         for (th, tw), ids in groups.items():
@@ -99,14 +111,18 @@ class VAEHook:
             gens.append(net.forward_gen(stack.contiguous()))
             members.append(ids)
             pixels.append((th, tw))
-        outs = net.run_tiled(gens, [len(m) for m in members], N)
+        outs = net.run_tiled(gens, [len(m) for m in members], N, weight=0.0 if shadow else 1.0, tile_parallel=tp)
         scale = 8 if self.is_decoder else 1
         oh, ow = (height * 8, width * 8) if self.is_decoder else (height // 8, width // 8)
         result = torch.zeros((N, outs[0].shape[1], oh, ow), device=z.device, dtype=torch.float32)
         for out, ids in zip(outs, members):
+            if shadow:
+                break  # this rank only kept the collectives in step; it owns no output region
             for k, i in enumerate(ids):
                 tile = out[k * N:(k + 1) * N]
                 m = self.crop_margins(in_boxes[i], out_boxes[i], self.is_decoder)
                 ob = out_boxes[i]
                 result[:, :, ob[2]:ob[3], ob[0]:ob[1]] = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]]
+        if tp:
+            torch.distributed.all_reduce(result)  # output regions are disjoint: the sum is the stitched image
         return result

@@ -19,7 +19,7 @@ OUT_F32, B_MN_MAJOR, CONV_NO_HALO = 1, 2, 4
 SYMBOLS = [
     "omgsr_version", "omgsr_last_error", "omgsr_destroy", "omgsr_launch_count",
     "omgsr_gemm_bf16", "omgsr_gemm_batched_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
-    "omgsr_conv_in_nchw", "omgsr_conv_out_nchw",
+    "omgsr_conv_in_nchw", "omgsr_conv_out_nchw", "omgsr_im2col3x3_nchw",
     "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_groupnorm_combine", "omgsr_layernorm", "omgsr_softmax_rows",
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
@@ -193,6 +193,25 @@ def conv_in_nchw(x, w, bias, cout, ksize=3, out=None):
     return out
 
 
+def conv_in_gemm(x, w_gemm, bias, out=None):
+    """thin-input 3x3/p1 conv on the tensor cores: im2col (k padded to a multiple of 64) + GEMM.
+    x NCHW (bf16|fp32); w_gemm bf16 [Cout, Kpad] (omgsr_b200.pack.pack_conv_in_gemm_weight); bias fp32 [Cout].
+    -> NHWC bf16 [B,H,W,Cout] (optionally written into the NHWC view `out`, which may be a channel slice)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32)
+    _cuda_bf16(w_gemm, "w_gemm"); _cuda_f32(bias, "bias")
+    B, Cin, H, W = x.shape
+    cout, kpad = w_gemm.shape
+    patches = torch.empty((B * H * W, kpad), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_im2col3x3_nchw(_ptr(x), _i(int(x.dtype == torch.float32)), _ptr(patches), _i(B), _i(Cin), _i(H),
+                                   _i(W), _i(kpad), _stream())
+    _check(rc, "omgsr_im2col3x3_nchw")
+    if out is None:
+        out = torch.empty((B, H, W, cout), device=x.device, dtype=torch.bfloat16)
+    o2 = torch.as_strided(out, (B * H * W, cout), (out.stride(2), 1), out.storage_offset())
+    gemm(patches, w_gemm, bias, out=o2)
+    return out
+
+
 def conv_out_nchw(x, w, bias, cout, clamp=False, out_dtype=torch.bfloat16):
     """x NHWC bf16 -> NCHW (bf16|fp32), 3x3 p1, Cout in {3,4}. w bf16 [Cout, 9*Cin]."""
     _cuda_bf16(x, "x"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias")
@@ -247,15 +266,18 @@ def groupnorm(x, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, stats=N
     return groupnorm_apply(x, stats, gamma, beta, groups, eps, silu, out)
 
 
-def groupnorm_combine(sums, pixels, n_img, C, groups=32):
-    """sums fp32 [entries, groups, 2], pixels fp32 [entries] -> (mean, var) fp32 [n_img, groups, 2]."""
+def groupnorm_combine(sums, pixels, n_img, C, groups=32, raw=False):
+    """sums fp32 [entries, groups, 2], pixels fp32 [entries] -> (mean, var) fp32 [n_img, groups, 2].
+    raw=True -> (numerators [n_img, groups, 2], weight sums [n_img]) for a cross-GPU all-reduce."""
     _cuda_f32(sums, "sums"); _cuda_f32(pixels, "pixels")
     entries = sums.shape[0]
+    sums = sums.contiguous()
     out = torch.empty((n_img, groups, 2), device=sums.device, dtype=torch.float32)
-    rc = _lib.omgsr_groupnorm_combine(_ptr(sums.contiguous()), _ptr(pixels), _i(entries), _i(n_img), _i(C),
-                                      _i(groups), _ptr(out), _stream())
+    wsum = torch.empty((n_img,), device=sums.device, dtype=torch.float32) if raw else None
+    rc = _lib.omgsr_groupnorm_combine(_ptr(sums), _ptr(pixels), _i(entries), _i(n_img), _i(C), _i(groups), _ptr(out),
+                                      _ptr(wsum), _stream())
     _check(rc, "omgsr_groupnorm_combine")
-    return out
+    return (out, wsum) if raw else out
 
 
 def layernorm(x, gamma=None, beta=None, eps=1e-5, rows_per_batch=0, gb_stride=0, out=None):

@@ -160,7 +160,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
 // per entry e = (tile, image b = e % n_img): mean_e, biased var_e; result[b] = sum_e w_e * (mean_e, var_e)
 // with w_e = pixels_e / sum of pixels over the tiles of image b.
 __global__ void gn_combine_kernel(const float* __restrict__ sums, const float* __restrict__ pixels, int entries,
-                                  int n_img, int G, int cpg, float* __restrict__ out) {
+                                  int n_img, int G, int cpg, float* __restrict__ out, float* __restrict__ wsum_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * G) return;
   const int b = i / G, g = i % G;
@@ -173,8 +173,14 @@ __global__ void gn_combine_kernel(const float* __restrict__ sums, const float* _
     m += pixels[e] * mean;
     v += pixels[e] * var;
   }
-  out[2 * i] = m / wsum;
-  out[2 * i + 1] = v / wsum;
+  if (wsum_out) {  // raw numerators: the caller sums them over ranks (tile-parallel VAE) and divides afterwards
+    out[2 * i] = m;
+    out[2 * i + 1] = v;
+    if (g == 0) wsum_out[b] = wsum;
+  } else {
+    out[2 * i] = m / wsum;
+    out[2 * i + 1] = v / wsum;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,6 +338,37 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const float* __restric
       }
     }
     *reinterpret_cast<uint4*>(y + pix * ldy + g * 8) = pack8(acc);
+  }
+}
+
+// im2col for the thin-input 3x3 convs (Cin <= 16): NCHW (bf16|f32) -> patch rows [B*H*W, Kpad] bf16 with
+// k = (r*3 + s)*Cin + ci, zero padded to Kpad (multiple of 64) so the tensor-core GEMM can consume them.
+// One thread writes one 16-byte chunk (8 k values) of one pixel.
+template <typename TIn>
+__global__ void im2col3x3_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, int Cin, int H, int W, int Kpad,
+                                 long long total) {
+  const int chunks = Kpad / 8;
+  const int K = 9 * Cin;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % chunks);
+    const long long pix = i / chunks;
+    const int xx = static_cast<int>(pix % W);
+    const int yy = static_cast<int>((pix / W) % H);
+    const long long b = pix / (static_cast<long long>(W) * H);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ch * 8 + j;
+      float v = 0.f;
+      if (k < K) {
+        const int tap = k / Cin, ci = k - tap * Cin;
+        const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = static_cast<float>(x[((b * Cin + ci) * H + iy) * W + ix]);
+      }
+      f[j] = v;
+    }
+    *reinterpret_cast<uint4*>(y + pix * Kpad + ch * 8) = pack8(f);
   }
 }
 
@@ -587,12 +624,12 @@ extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long
 }
 
 extern "C" int omgsr_groupnorm_combine(const float* sums, const float* pixels, int entries, int n_img, int C, int G,
-                                       float* out, void* stream) {
+                                       float* out, float* wsum_out, void* stream) {
   if (entries <= 0 || n_img <= 0 || entries % n_img || C % G)
     return set_error(OMGSR_ERR_SHAPE, "groupnorm_combine: entries=%d n_img=%d", entries, n_img);
   const int n = n_img * G;
   gn_combine_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, pixels, entries, n_img, G,
-                                                                                 C / G, out);
+                                                                                 C / G, out, wsum_out);
   return check_launch("gn_combine_kernel");
 }
 
@@ -659,6 +696,20 @@ extern "C" int omgsr_conv_in_nchw(const void* x, int x_f32, const float* w, cons
                                                                   static_cast<bf16*>(y), B, Cin, H, W, Cout, ksize,
                                                                   ldy, cg, total);
   return check_launch("conv_in_kernel");
+}
+
+extern "C" int omgsr_im2col3x3_nchw(const void* x, int x_f32, void* y, int B, int Cin, int H, int W, int Kpad,
+                                    void* stream) {
+  if (Cin <= 0 || Cin > 16 || Kpad % 64 || Kpad < 9 * Cin) return set_error(OMGSR_ERR_SHAPE, "im2col3x3: Cin=%d Kpad=%d", Cin, Kpad);
+  const long long total = static_cast<long long>(B) * H * W * (Kpad / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_f32)
+    im2col3x3_kernel<float><<<grid_for(total, 256) * 2, 256, 0, st>>>(static_cast<const float*>(x), static_cast<bf16*>(y),
+                                                                      Cin, H, W, Kpad, total);
+  else
+    im2col3x3_kernel<bf16><<<grid_for(total, 256) * 2, 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y),
+                                                                     Cin, H, W, Kpad, total);
+  return check_launch("im2col3x3_kernel");
 }
 
 template <int COUT, typename TOut>

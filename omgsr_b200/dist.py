@@ -66,3 +66,75 @@ def gather_results(local_items, n_items):
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+# ---- tile-parallel single-image path (reference tile semantics) ---------------------------------
+TILE_PARALLEL = False  # set by enable_tile_parallel(); read by infer/vaehook.py and the _forward_tile methods
+
+
+def enable_tile_parallel(on=True):
+    """spread the latent tiles (denoiser) and the VAE tiles of ONE image over all ranks of the default group."""
+    global TILE_PARALLEL
+    TILE_PARALLEL = bool(on)
+
+
+def tile_parallel():
+    return TILE_PARALLEL and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def broadcast_(t, src=0):
+    if tile_parallel():
+        dist.broadcast(t, src=src)
+    return t
+
+
+def tile_parallel_forward(fn, batch):
+    """run `fn` on this rank's share of `batch` (dim 0 = independent tiles) and all-gather the results back into
+    the original order. fn must map [n, ...] -> [n, ...]."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = batch.shape[0]
+    idx, _ = padded_share(n, rank, world)
+    out = fn(batch[idx].contiguous()).contiguous()
+    g = all_gather_batch(out)  # [world, per, ...]
+    order = torch.tensor([(i % world) * g.shape[1] + i // world for i in range(n)], device=out.device)
+    return g.reshape(world * g.shape[1], *out.shape[1:]).index_select(0, order)
+
+
+def reduce_gn_partials(num, wsum, group=None):
+    """cross-GPU step of the tiled VAE's GroupNorm: every rank holds the pixel-weighted numerators of ITS tiles
+    (sum_e pix_e * (mean_e, var_e)) and the weights (sum_e pix_e); the shared statistics are the all-reduced ratio.
+    One tiny all-reduce ([n_img, 32, 2] + [n_img] floats) per GroupNorm site; nothing else crosses NVLink."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        packed = torch.cat([num.reshape(-1), wsum.reshape(-1)])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        num = packed[: num.numel()].reshape(num.shape)
+        wsum = packed[num.numel():]
+    return num / wsum.clamp_min(1e-30).reshape(-1, 1, 1)
+
+
+def my_tiles(n_tiles, rank, world):
+    """tile indices owned by `rank` (round robin) and whether the rank only shadows a tile (world > n_tiles):
+    a shadow rank runs tile rank % n_tiles with weight 0 so that it stays in lock step with the collectives."""
+    own = list(range(rank, n_tiles, world))
+    if own:
+        return own, False
+    return [rank % n_tiles], True
+
+
+def padded_share(n_items, rank, world):
+    """equal-length index lists for an all_gather over the batch axis: rank r gets items r, r+world, ... padded
+    with its last item (or item 0) up to ceil(n_items / world). Returns (indices, number of real entries)."""
+    per = (n_items + world - 1) // world
+    own = list(range(rank, n_items, world))
+    real = len(own)
+    while len(own) < per:
+        own.append(own[-1] if own else 0)
+    return own, real
+
+
+def all_gather_batch(t, group=None):
+    """concatenate equal-shaped per-rank tensors along dim 0 -> [world, ...] stacked (rank-major)."""
+    world = dist.get_world_size(group)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t.contiguous(), group=group)
+    return torch.stack(out, 0)

@@ -15,7 +15,7 @@ from types import SimpleNamespace
 import torch
 
 from . import capi
-from .pack import pack_conv_in_weight, pack_conv_weight, pack_upsample_weight, pad8
+from .pack import pack_conv_in_gemm_weight, pack_conv_in_weight, pack_conv_weight, pack_upsample_weight, pad8
 
 
 def _dev(t, device, dtype=None):
@@ -90,7 +90,7 @@ def drive_plain(gen, eps):
         return stop.value
 
 
-def drive_tiled(gens, eps, n_img):
+def drive_tiled(gens, eps, n_img, weight=1.0, tile_parallel=False):
     """advance several tile-group coroutines in lock step; at every GroupNorm the per-(tile,image)
     statistics of all groups are combined on the device (pixel-weighted mean of mean and of variance,
     GroupNormParam.summary, infer/vaehook.py:489-508) and applied to every group."""
@@ -100,9 +100,15 @@ def drive_tiled(gens, eps, n_img):
         for (x, _, _, _, st) in reqs:
             sums.append(st if st is not None else capi.groupnorm_stats(x))
             hw = x.numel() // (x.shape[0] * x.shape[-1])
-            pix.append(torch.full((x.shape[0],), float(hw), device=x.device, dtype=torch.float32))
+            pix.append(torch.full((x.shape[0],), float(hw) * weight, device=x.device, dtype=torch.float32))
         C = reqs[0][0].shape[-1]
-        shared = capi.groupnorm_combine(torch.cat(sums, 0), torch.cat(pix, 0), n_img, C)
+        if tile_parallel:
+            # tiles of this image are spread over several GPUs: all-reduce the weighted numerators (tiny), then divide
+            from .dist import reduce_gn_partials
+            num, wsum = capi.groupnorm_combine(torch.cat(sums, 0), torch.cat(pix, 0), n_img, C, raw=True)
+            shared = reduce_gn_partials(num, wsum).contiguous()
+        else:
+            shared = capi.groupnorm_combine(torch.cat(sums, 0), torch.cat(pix, 0), n_img, C)
         outs = [capi.groupnorm_apply(x, shared, g, b, 32, eps, silu, shared_mod=n_img) for (x, g, b, silu, _) in reqs]
         nxt, done = [], []
         for g, o in zip(gens, outs):
@@ -162,6 +168,8 @@ class B200Encoder(torch.nn.Module):
         ch = cfg.block_out_channels
         self.conv_in_w = _dev(pack_conv_in_weight(sd["encoder.conv_in.weight"]), device)
         self.conv_in_b = _dev(pad8(sd["encoder.conv_in.bias"]), device, f32)
+        self.conv_in_wg = _dev(pack_conv_in_gemm_weight(sd["encoder.conv_in.weight"]), device)
+        self.conv_in_bg = _dev(sd["encoder.conv_in.bias"], device, f32)
         self.levels = []
         for i in range(len(ch)):
             res = [_Res(sd, f"encoder.down_blocks.{i}.resnets.{j}", device) for j in range(cfg.layers_per_block)]
@@ -186,7 +194,12 @@ class B200Encoder(torch.nn.Module):
     def trunk_gen(self, x):
         """NCHW image -> NHWC bf16 features after conv_norm_out + SiLU (input of conv_out). GroupNorm statistics
         travel with the tensors: every conv whose output feeds a GroupNorm produces them in its epilogue."""
-        h = capi.conv_in_nchw(x.contiguous(), self.conv_in_w, self.conv_in_b, self.cfg.block_out_channels[0])
+        if x.shape[0] * x.shape[2] * x.shape[3] >= (1 << 16):
+            # 3 -> C conv_in at full image resolution: im2col (K = 27 -> 64) + tensor-core GEMM
+            # (the CUDA-core kernel took 4.7 ms of a 105 ms step at 16 x 512^2)
+            h = capi.conv_in_gemm(x.contiguous(), self.conv_in_wg, self.conv_in_bg)
+        else:
+            h = capi.conv_in_nchw(x.contiguous(), self.conv_in_w, self.conv_in_b, self.cfg.block_out_channels[0])
         st = None
         for res, down in self.levels:
             for r in res:
@@ -211,8 +224,8 @@ class B200Encoder(torch.nn.Module):
         m = capi.conv2d(h, self.conv_out_w, self.conv_out_b, out_f32=True, cout=self.cout)
         return m.permute(0, 3, 1, 2).contiguous()
 
-    def run_tiled(self, gens, tiles_per_group, n_img):
-        return drive_tiled(gens, self.cfg.eps, n_img)
+    def run_tiled(self, gens, tiles_per_group, n_img, weight=1.0, tile_parallel=False):
+        return drive_tiled(gens, self.cfg.eps, n_img, weight, tile_parallel)
 
     def forward(self, x):
         m = self.moments_nhwc(x)  # [B,h,w,2Cz] fp32
@@ -276,8 +289,8 @@ class B200Decoder(torch.nn.Module):
         h = yield from self.trunk_gen(z.to(self.out_dtype))
         return self._conv_out(h, False, torch.float32)
 
-    def run_tiled(self, gens, tiles_per_group, n_img):
-        return drive_tiled(gens, self.cfg.eps, n_img)
+    def run_tiled(self, gens, tiles_per_group, n_img, weight=1.0, tile_parallel=False):
+        return drive_tiled(gens, self.cfg.eps, n_img, weight, tile_parallel)
 
     def forward(self, z, clamp=False):
         h = drive_plain(self.trunk_gen(z), self.cfg.eps)
@@ -311,7 +324,9 @@ class _Posterior:
         B, h, w, _ = self.m.shape
         eps = self.eps
         if eps is None:
-            eps = torch.randn((B, self.cz, h, w), device=self.m.device, dtype=torch.float32, generator=generator)
+            from .dist import broadcast_
+            eps = broadcast_(torch.randn((B, self.cz, h, w), device=self.m.device, dtype=torch.float32,
+                                         generator=generator))
         return capi.posterior_sample(self.m, eps.to(device=self.m.device, dtype=torch.float32), self.cz, 0.0, 1.0,
                                      self.out_dtype)
 

@@ -73,3 +73,15 @@ def pad8(v):
     out = torch.zeros(n8, dtype=torch.float32)
     out[: v.numel()] = v.float()
     return out
+
+
+def pack_conv_in_gemm_weight(w, dtype=torch.bfloat16):
+    """OIHW [Cout, Cin, 3, 3] -> [Cout, Kpad] with k = (r*3+s)*Cin + ci, zero padded to a multiple of 64
+    (B operand of the im2col + GEMM form of a thin-input conv)."""
+    co, ci, r, s = w.shape
+    assert r == 3 and s == 3
+    k = 9 * ci
+    kpad = (k + 63) // 64 * 64
+    out = torch.zeros(co, kpad, dtype=torch.float32)
+    out[:, :k] = w.permute(0, 2, 3, 1).reshape(co, k).float()
+    return out.contiguous().to(dtype)

@@ -57,3 +57,56 @@ def test_shard_indices_cover_everything_once():
         for w in (1, 2, 4, 8):
             got = sorted(i for r in range(w) for i in shard_indices(n, r, w))
             assert got == list(range(n))
+
+
+def _worker_gn(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from omgsr_b200 import dist as D
+    D.init(backend="gloo")
+    g = torch.Generator().manual_seed(7)
+    # 5 tiles of one image (n_img = 2 images in the batch): per-tile mean / var / pixel counts
+    mean = torch.randn(5, 2, 32, generator=g)
+    var = torch.rand(5, 2, 32, generator=g)
+    pix = torch.tensor([400.0, 400.0, 380.0, 361.0, 100.0])
+    mine, shadow = D.my_tiles(5, rank, world)
+    assert not shadow
+    num = torch.stack([sum(pix[t] * mean[t] for t in mine), sum(pix[t] * var[t] for t in mine)], dim=-1)  # [2,32,2]
+    wsum = torch.full((2,), float(sum(pix[t] for t in mine)))
+    shared = D.reduce_gn_partials(num, wsum)
+    ref_mean = (pix[:, None, None] * mean).sum(0) / pix.sum()
+    ref_var = (pix[:, None, None] * var).sum(0) / pix.sum()
+    ok = torch.allclose(shared[..., 0], ref_mean, atol=1e-5) and torch.allclose(shared[..., 1], ref_var, atol=1e-5)
+    # tile-parallel batch forward: order restored after the all-gather, padding entries dropped
+    D.enable_tile_parallel(True)
+    batch = torch.arange(9, dtype=torch.float32).reshape(9, 1) * 10
+    got = D.tile_parallel_forward(lambda t: t + 1, batch)
+    ok = ok and torch.equal(got, batch + 1)
+    if rank == 0:
+        out.put(bool(ok))
+    torch.distributed.destroy_process_group()
+
+
+def test_tile_parallel_groupnorm_reduction_and_batch_split_gloo_world2():
+    """the only cross-GPU arithmetic of the tile-parallel single-image path: pixel-weighted GroupNorm statistics
+    (GroupNormParam.summary semantics, infer/vaehook.py:489-508) reduced over ranks == the single-process value."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_gn, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=120) is True
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+
+def test_shadow_ranks_and_padded_share():
+    from omgsr_b200.dist import my_tiles, padded_share
+    assert my_tiles(4, 5, 8) == ([1], True) and my_tiles(4, 3, 8) == ([3], False)
+    assert my_tiles(9, 1, 8) == ([1], False) and my_tiles(9, 0, 8) == ([0, 8], False)
+    idx, real = padded_share(9, 3, 8)
+    assert idx == [3, 3] and real == 1
+    idx, real = padded_share(9, 0, 8)
+    assert idx == [0, 8] and real == 2

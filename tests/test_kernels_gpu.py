@@ -332,6 +332,14 @@ def test_thin_convs_and_layout(capi):
         for dt in (torch.bfloat16, torch.float32):
             out = capi.conv_in_nchw(x.cuda().to(dt), pack_conv_in_weight(w).cuda(), pad8(b).cuda(), Cout, k)
             assert report(f"conv_in {Cin}->{Cout} {dt}", out, ref)[0]
+    from omgsr_b200.pack import pack_conv_in_gemm_weight
+    for (B, Cin, H, W, Cout) in [(2, 3, 40, 48, 128), (1, 4, 16, 16, 320), (1, 16, 12, 20, 512)]:
+        x = bf16r(torch.randn(B, Cin, H, W, generator=g))
+        w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+        b = torch.randn(Cout, generator=g)
+        ref = torch.nn.functional.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+        out = capi.conv_in_gemm(x.cuda().bfloat16(), pack_conv_in_gemm_weight(w).cuda(), b.cuda())
+        assert report(f"conv_in im2col+gemm {Cin}->{Cout}", out, ref)[0]
     for (B, H, W, Cin, Cout) in [(2, 24, 40, 128, 3), (1, 16, 16, 320, 4)]:
         x = bf16r(torch.randn(B, H, W, Cin, generator=g))
         w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))

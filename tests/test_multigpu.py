@@ -1,0 +1,93 @@
+"""Tile-parallel single-image path on >= 2 GPUs: the latent tiles of the denoiser and the VAE tiles
+of ONE image are spread over the ranks; GroupNorm statistics are all-reduced per site. The result must equal the
+single-GPU result of the same module (up to the atomics' summation order). Skipped on single-GPU boxes; run with
+`gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`."""
+import contextlib
+import io
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _psnr(a, b):
+    mse = (a.float() - b.float()).pow(2).mean().item()
+    return 10 * math.log10(4.0 / max(mse, 1e-20))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    from omgsr_b200 import dist as D
+    D.init(device=torch.device("cuda", rank))
+    from infer.omgsr_s_infer_model import OMGSR_S_Infer
+    from infer.omgsr_f_infer_model import OMGSR_F_Infer
+    from infer.infer_omgsr_f import _prepare_latent_image_ids
+    dev = f"cuda:{rank}"
+    res = {}
+    quiet = lambda: contextlib.redirect_stdout(io.StringIO())
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(5)
+        lq = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).to(dev).bfloat16()
+        # ---- OMGSR-S, tiled VAE + 9 latent tiles ----
+        with quiet():
+            m = OMGSR_S_Infer("random://tiny?seed=3", "random://lora?seed=7", 273, dev, torch.bfloat16)
+            m._init_tiled_vae(encoder_tile_size=64, decoder_tile_size=16)
+        ctx = torch.randn(1, 77, 128, generator=g).to(dev).bfloat16()
+        m.vae.posterior_eps = torch.randn(1, 4, 32, 32, generator=g)
+        with quiet():
+            ref, _ = m(lq, ctx, 16, 8)
+            D.enable_tile_parallel(True)
+            out, _ = m(lq, ctx, 16, 8)
+            D.enable_tile_parallel(False)
+        res["s"] = _psnr(out, ref)
+        # ---- OMGSR-F, tiled VAE + 9 latent tiles ----
+        with quiet():
+            f = OMGSR_F_Infer("random://tiny?seed=2", "random://lora?seed=3&rank=8", dev)
+            f._init_tiled_vae(encoder_tile_size=64, decoder_tile_size=16)
+        pe = torch.randn(1, 32, 256, generator=g).to(dev).bfloat16()
+        pp = torch.randn(1, 64, generator=g).to(dev).bfloat16()
+        tid = torch.zeros(32, 3, device=dev, dtype=torch.bfloat16)
+        ids = _prepare_latent_image_ids(8, 8, dev, torch.bfloat16)
+        f.vae.posterior_eps = torch.randn(1, 16, 32, 32, generator=g)
+        with quiet():
+            ref, _ = f(lq, pe, pp, tid, ids, 16, 8)
+            D.enable_tile_parallel(True)
+            out, _ = f(lq, pe, pp, tid, ids, 16, 8)
+            D.enable_tile_parallel(False)
+        res["f"] = _psnr(out, ref)
+    torch.distributed.barrier()
+    if rank == 0:
+        q.put(res)
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_tile_parallel_matches_single_gpu():
+    world = min(torch.cuda.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    print(f"tile-parallel x{world} vs single GPU: S {res['s']:.2f} dB, F {res['f']:.2f} dB")
+    assert res["s"] >= 45.0 and res["f"] >= 45.0
