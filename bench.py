@@ -28,7 +28,9 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 S512_FLOP_PER_IMAGE = 4.435e12  # enc 1.1167 + UNet 0.8043 + dec 2.5145 TFLOP (2*MAC)
+F1024_FLOP_PER_IMAGE = 89.74e12  # enc 4.8826 + DiT 74.3847 + dec 10.4722 TFLOP
 WORKLOAD = "OMGSR-S-512 bf16 batch 16 (128->512 SR: VAE enc + UNet@t=273 + VAE dec, SD-2.1 shapes)"
+WORKLOAD_F = "OMGSR-F-1024 bf16 batch 4 per GPU (256->1024 SR: FLUX VAE enc + FLUX.1-dev-shape DiT@sigma=0.505 + VAE dec)"
 
 
 def _peaks():
@@ -154,6 +156,91 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------------
+def run_ours_f1024(args):
+    """BASELINE config 4 (not the default N=1 line): OMGSR-F-1024, batch 4 per GPU, image-parallel replicas."""
+    ws, rank, lr = _dist()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the omgsr_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    import torch.distributed as dist
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from infer.infer_omgsr_f import _prepare_latent_image_ids
+    from infer.omgsr_f_infer_model import OMGSR_F_Infer
+    from omgsr_b200 import capi
+    B = args.batch if args.batch != 16 else 4
+    with _quiet():
+        model = OMGSR_F_Infer("random://flux_dev?seed=0", "random://lora?seed=1&rank=64", dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_in = [torch.rand(B, 3, 1024, 1024, generator=g).mul_(2).sub_(1).bfloat16().pin_memory() for _ in range(2)]
+    dev_in = [t.to(dev) for t in host_in]
+    g2 = torch.Generator().manual_seed(1235)
+    pe = torch.randn(1, 512, 4096, generator=g2).to(dev).bfloat16()
+    pp = torch.randn(1, 768, generator=g2).to(dev).bfloat16()
+    tid = torch.zeros(512, 3, device=dev, dtype=torch.bfloat16)
+    ids = _prepare_latent_image_ids(64, 64, dev, torch.bfloat16)
+    host_out = torch.empty(B, 3, 1024, 1024, dtype=torch.bfloat16).pin_memory()
+
+    def step(i, x=None):
+        with torch.no_grad(), _quiet():
+            return model(dev_in[i % 2] if x is None else x, pe, pp, tid, ids, 128, 64)[0]
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    l0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(lr) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    launches = capi.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = step(i, host_in[i % 2].to(dev, non_blocking=True))
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if ws > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0].item()), float(t[1].item())
+    ms_per_step = ms / args.steps
+    burst, sustained, hbm, how = _peaks()
+    step_tflops = F1024_FLOP_PER_IMAGE * B / (ms_per_step * 1e-3) / 1e12
+    if rank == 0:
+        print(json.dumps({
+            "metric": "SR images/sec (OMGSR-F 256->1024)", "value": ws * B / (ms_per_step * 1e-3), "unit": "images/s",
+            "n_gpus": ws, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD_F, "batch_per_gpu": B, "parallelism": f"image-parallel x{ws}",
+                       "l2": "2 rotating input buffers; 24 GB of weights + GB-sized activations per step >> L2",
+                       "step_tflops_algorithmic": step_tflops, "step_frac_of_sustained_peak": step_tflops / sustained},
+            "clocks": clocks.summary(),
+            "e2e": {"value": ws * B * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": B * 3 * 1024 * 1024 * 2, "d2h_bytes_per_step": B * 3 * 1024 * 1024 * 2},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "whole step (DiT GEMMs + flash attention + VAE convs)",
+                         "achieved": step_tflops, "peak": sustained, "unit": "TFLOP/s", "frac": step_tflops / sustained,
+                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})"},
+            "cpu_baseline": None}))
+    if ws > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args):
     ws, rank, lr = _dist()
     if not torch.cuda.is_available():
@@ -263,8 +350,8 @@ def run_ours(args):
 
 
 def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
-    """conv_gemm_tc_kernel on the launch that dominates the step: the VAE decoder's 128->128 3x3 conv at
-    512x512 (7 launches per decode, ~0.62 TFLOP each at batch 16). Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W."""
+    """the launch class that dominates the step: the VAE's 128->128 3x3 conv at 512x512 (12 launches per step,
+    1.24 TFLOP each at batch 16), dispatched to conv_halo_tc_kernel<128,2>. Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W."""
     from omgsr_b200.pack import pack_conv_weight
     C, H = 128, 512
     x = torch.randn(B, H, H, C, device=dev, dtype=torch.bfloat16)
@@ -284,7 +371,7 @@ def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * C * C * 9 * B * H * H
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<128> (3x3, 128->128 ch, 512x512, batch %d)" % B,
+    return {"bound": "tensor", "kernel": "conv_halo_tc_kernel<128,2> (3x3, 128->128 ch, 512x512, batch %d)" % B,
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
 
@@ -297,9 +384,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="s512", choices=["s512", "f1024"],
+                    help="s512 = BASELINE configs[1] (default, the N=1 line); f1024 = configs[3] (OMGSR-F-1024, batch 4/GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "f1024":
+        return run_ours_f1024(args)
     return run_ours(args)
 
 

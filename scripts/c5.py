@@ -2,7 +2,7 @@
 (VAEHook encoder tile 1024 / decoder tile 224 as in the reference's commented default, 3x3 latent tiles of 128)."""
 import contextlib, io, json, os, sys, time
 import torch
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from omgsr_b200 import dist as D
 ws, rank, lr = D.env_world()
 torch.cuda.set_device(lr)

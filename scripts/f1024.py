@@ -2,7 +2,7 @@
 device), 256->1024, batch B per GPU. Prints stage timings and images/s (CUDA events)."""
 import contextlib, io, json, sys, time
 import torch
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from infer.omgsr_f_infer_model import OMGSR_F_Infer, encode_images, _pack_latents
 from infer.infer_omgsr_f import _prepare_latent_image_ids
 from omgsr_b200 import capi

@@ -24,7 +24,7 @@ cat gpurun_out/attn_time.log >> gpurun_out/summary.txt
 timeout 1200 python -m pytest tests/test_pipeline_gpu.py -m gpu -q -s -p no:cacheprovider > gpurun_out/pipeline.log 2>&1
 echo "== pipeline exit $?" >> gpurun_out/summary.txt
 grep -E "relerr|psnr|passed|failed|Error|error" gpurun_out/pipeline.log | tail -30 >> gpurun_out/summary.txt
-timeout 900 python scripts_f1024.py 4 3 > gpurun_out/f1024.log 2>&1
+timeout 900 python scripts/f1024.py 4 3 > gpurun_out/f1024.log 2>&1
 echo "== f1024 exit $?" >> gpurun_out/summary.txt; tail -2 gpurun_out/f1024.log >> gpurun_out/summary.txt
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 echo "== ncu exit $?" >> gpurun_out/summary.txt

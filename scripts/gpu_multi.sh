@@ -7,6 +7,6 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 echo "== bench 2gpu exit $?" >> gpurun_out/summary.txt; cat gpurun_out/bench_2gpu.json >> gpurun_out/summary.txt; tail -3 gpurun_out/bench_2gpu.err >> gpurun_out/summary.txt
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 echo "== bench reference exit $?" >> gpurun_out/summary.txt; cat gpurun_out/bench_ref.json >> gpurun_out/summary.txt
-timeout 900 python scripts_f1024.py 4 3 > gpurun_out/f1024.log 2>&1
+timeout 900 python scripts/f1024.py 4 3 > gpurun_out/f1024.log 2>&1
 echo "== f1024 exit $?" >> gpurun_out/summary.txt; tail -4 gpurun_out/f1024.log >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
