@@ -1,3 +1,5 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys, math, torch
 from omgsr_b200 import capi
 from omgsr_b200.pack import pack_conv_weight

@@ -1,4 +1,7 @@
 """one GroupNorm apply (+stats) at the largest VAE shape and one flash-attention call at the FLUX shape, for ncu."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 import math, torch
 from omgsr_b200 import capi
 x = torch.randn(16, 512, 512, 128, device="cuda", dtype=torch.bfloat16)
