@@ -192,8 +192,10 @@ class OMGSR_S_Infer(torch.nn.Module):
                               (B * tile_size * tile_size * ld, tile_size * tile_size * ld, 1, tile_size * ld, ld),
                               eps_t.storage_offset())
         blended = torch.empty((B, h, w, 8), device=lq_latent.device, dtype=torch.float32)
-        ofs = torch.tensor(offs, dtype=torch.int32, device=lq_latent.device)
-        capi.tile_blend(et, wts, ofs, blended[..., :C].permute(0, 3, 1, 2), tile_size)
+        okey = ("ofs", h, w, tile_size, tile_overlap, str(lq_latent.device))
+        if okey not in self._wts:  # cached: no host->device copy inside a CUDA-graph capture
+            self._wts[okey] = torch.tensor(offs, dtype=torch.int32, device=lq_latent.device)
+        capi.tile_blend(et, wts, self._wts[okey], blended[..., :C].permute(0, 3, 1, 2), tile_size)
         return self._decode_from_eps(lq_latent, blended[..., :C])
 
     def _encode(self, lq_img):
@@ -212,17 +214,70 @@ class OMGSR_S_Infer(torch.nn.Module):
         return capi.posterior_sample(m, eps.to(device=m.device, dtype=torch.float32), cz, 0.0,
                                      vae.config.scaling_factor, vae.dtype)
 
-    def forward(self, lq_img, prompt_embeds, tile_size, tile_overlap):
-        torch.cuda.synchronize()
-        start_time = time.time()
+    # -- CUDA graph replay (additive) ---------------------------------------------------------------------
+    def enable_cuda_graph(self, on=True):
+        """Capture the whole launch sequence (~660 kernels for SD-2.1 shapes) of one (shape, tile setting) into a CUDA
+        graph on first use and replay it afterwards. The reference's use case is batch 1 per image, where the
+        Python/ctypes launch overhead (not the GPU) bounds the latency; every C-ABI entry only enqueues on the
+        current stream, so the sequence is capturable as is. The posterior noise is drawn outside the graph."""
+        self._graphs = {} if on else None
+
+    def _run(self, lq_img, prompt_embeds, tile_size, tile_overlap):
         lq_latent = self._encode(lq_img)
         _, _, h, w = lq_latent.size()
         if h * w <= tile_size * tile_size:
+            return self._forward_no_tile(lq_latent, prompt_embeds), False
+        return self._forward_tile(lq_latent, prompt_embeds, tile_size, tile_overlap), True
+
+    def _run_graphed(self, lq_img, prompt_embeds, tile_size, tile_overlap):
+        if "forward" in self.vae.encoder.__dict__ or D.tile_parallel():
+            raise RuntimeError("CUDA-graph replay supports the plain (untiled-VAE, single-GPU) path only")
+        key = (tuple(lq_img.shape), lq_img.dtype, tuple(prompt_embeds.shape), tile_size, tile_overlap)
+        cz = self.vae.cfg.latent_channels
+        B, _, H, W = lq_img.shape
+        ent = self._graphs.get(key)
+        if ent is None:
+            st = {"x": torch.empty_like(lq_img), "ctx": prompt_embeds.to(torch.bfloat16).clone(),
+                  "eps": torch.empty((B, cz, H // 8, W // 8), device=lq_img.device, dtype=torch.float32)}
+            st["x"].copy_(lq_img)
+            st["eps"].normal_()
+            user_eps = self.vae.posterior_eps
+            self.vae.posterior_eps = st["eps"]
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):  # warm-up: lazy attribute setting / caches happen outside the capture
+                    self.unet.cache_kv = False
+                    self._run(st["x"], st["ctx"], tile_size, tile_overlap)
+                    self.unet.cache_kv = True
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out, tiled = self._run(st["x"], st["ctx"], tile_size, tile_overlap)
+            finally:
+                self.vae.posterior_eps = user_eps
+            ent = self._graphs[key] = (graph, st, out, tiled)
+        graph, st, out, tiled = ent
+        st["x"].copy_(lq_img)
+        st["ctx"].copy_(prompt_embeds)
+        if self.vae.posterior_eps is not None:
+            st["eps"].copy_(self.vae.posterior_eps)
+        else:
+            st["eps"].normal_()
+        graph.replay()
+        return out.clone(), tiled
+
+    def forward(self, lq_img, prompt_embeds, tile_size, tile_overlap):
+        torch.cuda.synchronize()
+        start_time = time.time()
+        if getattr(self, "_graphs", None) is not None:
+            pred_img, tiled = self._run_graphed(lq_img, prompt_embeds, tile_size, tile_overlap)
+        else:
+            pred_img, tiled = self._run(lq_img, prompt_embeds, tile_size, tile_overlap)
+        if not tiled:
             print(f"[Tiled Latent]: the input size is tiny and unnecessary to tile.")
-            pred_img = self._forward_no_tile(lq_latent, prompt_embeds)
         else:
             print(f"[Tiled Latent]: the input size is {lq_img.shape[-2]}x{lq_img.shape[-1]}, need to tiled")
-            pred_img = self._forward_tile(lq_latent, prompt_embeds, tile_size, tile_overlap)
         torch.cuda.synchronize()
         t = time.time() - start_time
         print(f"Inference time per image: {t}s")

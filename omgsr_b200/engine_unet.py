@@ -56,7 +56,7 @@ class _T2D:
         self.kv_cache = None  # (key, kv [B,77,2C])
 
     def cross_kv(self, ctx, ctx_key, B):
-        if self.kv_cache is None or self.kv_cache[0] != (ctx_key, B):
+        if ctx_key is None or self.kv_cache is None or self.kv_cache[0] != (ctx_key, B):
             T = ctx.shape[1]
             ctx2 = ctx.reshape(-1, ctx.shape[-1])
             if ctx2.shape[1] % 64:
@@ -64,6 +64,8 @@ class _T2D:
             kv = capi.gemm(ctx2, self.wkv2).view(ctx.shape[0], T, 2 * self.c)
             if ctx.shape[0] != B:  # batch-1 text broadcast over the image batch
                 kv = kv.expand(B, T, 2 * self.c).contiguous()
+            if ctx_key is None:
+                return kv
             self.kv_cache = ((ctx_key, B), kv)
         return self.kv_cache[1]
 
@@ -103,6 +105,7 @@ class B200UNet(torch.nn.Module):
         if dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("B200UNet: boundary dtype must be bf16 or fp32")
         self.cfg, self.dev, self._dtype = cfg, device, dtype
+        self.cache_kv = True
         self.config = SimpleNamespace(in_channels=cfg.in_channels, out_channels=cfg.out_channels)
         f32 = torch.float32
         ch = cfg.block_out_channels
@@ -180,7 +183,10 @@ class B200UNet(torch.nn.Module):
         B, _, H0, W0 = z.shape
         n = len(ch)
         ctx = ctx.to(device=z.device, dtype=torch.bfloat16).contiguous()
-        ctx_key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
+        # prompt projections are cached across calls unless the launch sequence is being captured into a CUDA graph
+        # (a replayed graph must recompute them from the static prompt buffer)
+        ctx_key = None if torch.cuda.is_current_stream_capturing() or not self.cache_kv else \
+            (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
         res_hw = [(H0 >> l, W0 >> l) for l in range(n)]
         # concat buffers, one per up resnet; skip s lives in the right slice of its consumer's buffer
         nsk = len(self._skip_meta)

@@ -262,3 +262,98 @@ def test_f_tiny_latent_tiling():
     p = psnr(out, ref)
     print(f"F tiled e2e psnr {p:.2f} dB")
     assert p >= 40.0
+
+
+# ----------------------------------------------------------------------------------------------------
+# boundary edge cases
+# ----------------------------------------------------------------------------------------------------
+def test_s_nonsquare_fp32_boundary_and_batch_broadcast():
+    """non-square image, fp32 tensors at the module boundary (weight_dtype=fp32 as infer_omgsr_s.py --weight_dtype
+    fp32 passes), batch 3 with a batch-1 prompt that is broadcast (SURVEY.md §7.3 batch semantics)."""
+    from infer.omgsr_s_infer_model import OMGSR_S_Infer, build_s_state
+    from omgsr_b200 import weights as W
+    from oracle.omgsr_s import OracleS
+    vae_sd, unet_sd, vae_cfg, unet_cfg = build_s_state("random://tiny?seed=9", "random://lora?seed=4")
+    state = {"vae": vae_sd, "unet": unet_sd, "vae_cfg": vae_cfg, "unet_cfg": unet_cfg}
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = OMGSR_S_Infer(state, None, 273, "cuda", torch.float32)
+    oracle = OracleS(vae_sd, unet_sd, vae_cfg, unet_cfg, 273, W.ddpm_alphas_cumprod())
+    g = torch.Generator().manual_seed(17)
+    lq = torch.rand(3, 3, 64, 128, generator=g) * 2 - 1
+    ctx = torch.randn(1, 77, 128, generator=g)
+    eps = torch.randn(3, 4, 8, 16, generator=g)
+    with torch.no_grad():
+        model.vae.posterior_eps = eps
+        with contextlib.redirect_stdout(io.StringIO()):
+            out, _ = model(lq.cuda(), ctx.cuda(), 64, 32)
+        ref = oracle.forward(lq, ctx, 64, 32, eps)
+    assert out.dtype == torch.float32 and out.shape == (3, 3, 64, 128)
+    p = psnr(out, ref)
+    print(f"non-square fp32-boundary batch-3 psnr {p:.2f} dB")
+    assert p >= 40.0
+    assert float(out.max()) <= 1.0 and float(out.min()) >= -1.0   # clamp (infer/omgsr_s_infer_model.py:85)
+
+
+def test_colorfix_pil_wrappers_match_reference_golden():
+    """GPU colour fix through the PIL->PIL API against the reference's own outputs (uint8, truncating conversion):
+    at most one grey level off (fp32 summation order), and identical on >= 99 % of the pixels."""
+    import os
+    import numpy as np
+    from PIL import Image
+    from infer.wavelet_color_fix import adain_color_fix, wavelet_color_fix
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.pt"), weights_only=False)["colorfix_pil"]
+    tgt = Image.fromarray(g["target"].numpy(), "RGB")
+    src = Image.fromarray(g["source"].numpy(), "RGB")
+    for name, fn in (("wavelet", wavelet_color_fix), ("adain", adain_color_fix)):
+        got = np.asarray(fn(tgt, src)).astype(np.int32)
+        ref = g[name].numpy().astype(np.int32)
+        diff = np.abs(got - ref)
+        print(f"{name}: max level diff {diff.max()}, identical {100.0 * (diff == 0).mean():.2f} %")
+        assert diff.max() <= 1 and (diff == 0).mean() >= 0.99
+
+
+def test_driver_script_end_to_end(tmp_path):
+    """the CLI driver (mirror of infer/infer_omgsr_s.py) runs end to end on synthetic images and writes PNGs."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(root, "infer", "infer_omgsr_s.py"), "--sd_path", "random://tiny?seed=0",
+                        "--lora_path", "random://lora?seed=1", "--output_dir", str(out), "--synthetic", "2",
+                        "--process_size", "128", "--align_method", "wavelet"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted(os.listdir(out))
+    assert files == ["synthetic_000.png", "synthetic_001.png"]
+    from PIL import Image
+    im = Image.open(out / files[0])
+    assert im.size == (128, 128)
+    assert "Average inference time" in r.stdout
+
+
+def test_s_cuda_graph_replay_matches_eager():
+    """enable_cuda_graph(): the captured launch sequence replays to the same result for new inputs."""
+    import time
+    model, oracle = _build("random://tiny?seed=0", "random://lora?seed=5")
+    lq1, ctx, eps1 = _inputs(1, 128, 128, 128, 4, seed=1)
+    lq2, _, eps2 = _inputs(1, 128, 128, 128, 4, seed=2)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        model.vae.posterior_eps = eps2
+        ref2, _ = model(lq2.cuda().bfloat16(), ctx.cuda().bfloat16(), 64, 32)
+        model.enable_cuda_graph()
+        model.vae.posterior_eps = eps1
+        model(lq1.cuda().bfloat16(), ctx.cuda().bfloat16(), 64, 32)     # capture on other data
+        model.vae.posterior_eps = eps2
+        out2, _ = model(lq2.cuda().bfloat16(), ctx.cuda().bfloat16(), 64, 32)   # replay
+        t0 = time.perf_counter()
+        for _ in range(5):
+            model(lq2.cuda().bfloat16(), ctx.cuda().bfloat16(), 64, 32)
+        t_graph = (time.perf_counter() - t0) / 5
+        model.enable_cuda_graph(False)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            model(lq2.cuda().bfloat16(), ctx.cuda().bfloat16(), 64, 32)
+        t_eager = (time.perf_counter() - t0) / 5
+    p = psnr(out2, ref2)
+    print(f"graph replay vs eager: {p:.2f} dB; latency eager {t_eager*1e3:.2f} ms, graph {t_graph*1e3:.2f} ms")
+    assert p >= 40.0
