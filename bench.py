@@ -372,7 +372,10 @@ def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
     flops = 2.0 * C * C * 9 * B * H * H
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "conv_halo_tc_kernel<128,2> (3x3, 128->128 ch, 512x512, batch %d)" % B,
-            "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": None,
+            "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this very launch from one `ncu --set full` capture
+            # (profiles/r01/ncu_halo128.txt: 1.0746 + 1.0223 GB; algorithmic input + output = 2 x 1.0737 GB)
+            "traffic": 2.0969e9 if (B, C, H) == (16, 128, 512) else None, "traffic_unit": "bytes/launch",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
 
 

@@ -130,6 +130,7 @@ HALO_CASES = [
     (1, 130, 128, 64, 128, False),
     (1, 32, 128, 128, 128, True),       # nearest-2x + conv: four 2x2 parity convs through the halo kernel
     (2, 64, 96, 64, 256, True),
+    (2, 40, 256, 128, 3, False),        # thin Cout (decoder conv_out) on one masked 128-wide tile
 ]
 
 
@@ -142,15 +143,18 @@ def test_conv_halo(capi, B, H, W, Cin, Cout, up, mode):
     x = bf16r(torch.randn(B, H, W, Cin, generator=g))
     w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
     b = torch.randn(Cout, generator=g)
-    res = bf16r(torch.randn(B, H * (2 if up else 1), W * (2 if up else 1), Cout, generator=g))
-    ref = ops.conv2d_nhwc(x, w, b, upsample2x=up) + res
+    ref = ops.conv2d_nhwc(x, w, b, upsample2x=up)
+    rc = None
+    if Cout % 8 == 0:
+        res = bf16r(torch.randn(B, H * (2 if up else 1), W * (2 if up else 1), Cout, generator=g))
+        ref = ref + res
+        rc = res.cuda().bfloat16()
     pw = pack_upsample_weight(w) if up else pack_conv_weight(w)
-    flags = capi.CONV_HALO_DESC1 if mode == "halo_desc1" else 0
-    xc, wc, bc, rc = x.cuda().bfloat16(), pw.cuda(), b.cuda(), res.cuda().bfloat16()
-    out = capi.conv2d(xc, wc, bc, res=rc, upsample2x=up, flags=flags)
+    xc, wc, bc = x.cuda().bfloat16(), pw.cuda(), b.cuda()
+    out = capi.conv2d(xc, wc, bc, res=rc, upsample2x=up, cout=Cout)
     torch.cuda.synchronize()
     ok, _ = report(f"conv-halo[{mode}] {B}x{H}x{W} {Cin}->{Cout} up={up}", out, ref, 2e-2 if up else 1e-2)
-    gen = capi.conv2d(xc, wc, bc, res=rc, upsample2x=up, flags=capi.CONV_NO_HALO)
+    gen = capi.conv2d(xc, wc, bc, res=rc, upsample2x=up, flags=capi.CONV_NO_HALO, cout=Cout)
     assert report("generic kernel, same problem", gen, ref, 2e-2 if up else 1e-2)[0]
     assert ok
 
