@@ -273,9 +273,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // ================================================================================================================
 template <int D>
 struct Attn2Cfg {
-  static constexpr int kBN = (D == 64) ? 128 : 64;
-  static constexpr int kPBuf = (D == 64) ? 1 : 2;
-  static constexpr int kStages = 3;
+  // 64 keys per block for both head sizes: the whole S row of a thread (64 fp32) is read from TMEM ONCE with one
+  // tcgen05.ld.x64 and kept in registers for the max and the exponentiation (the first version re-read S in a second
+  // pass and waited after every 32 columns: 30 % tensor-pipe activity in ncu)
+  static constexpr int kBN = 64;
+  static constexpr int kPBuf = 2;
+  static constexpr int kStages = (D == 64) ? 4 : 3;
   static constexpr int kQBytes = 2 * 128 * D * 2;
   static constexpr int kKBytes = kBN * D * 2;
   static constexpr int kStageBytes = 2 * kKBytes;
@@ -414,16 +417,21 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
       const int n_valid = min(BN, p.N - j * BN);
-      float mx = -INFINITY;
+      uint32_t sv[64];
+      tmem_ld64(tS, sv);
+      tmem_wait_ld();
+      if (n_valid < BN) {  // ragged last block only: mask the columns that do not exist
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + c0, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 64; ++i)
+          if (i >= n_valid) sv[i] = 0xff800000u;  // -inf
       }
+      float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]);
+#pragma unroll
+      for (int i = 2; i < 64; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+      }
+      const float mx = fmaxf(mx0, mx1);
       const int pb = j % PB;
       if (j == 0) {
         m_stale = mx;
@@ -452,29 +460,20 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j >= PB) mbar_wait(&pv_done[g * PB + pb], ((j - PB) / PB) & 1);
       const float mb = m_stale * p.scale_log2;
       uint8_t* p_row = sP + (g * PB + pb) * C::kPBytes + row * 128;
-      float lsum = 0.f;
+      float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + c0, v);
-        tmem_wait_ld();
-        uint8_t* panel = p_row + (c0 >> 6) * (128 * 128);
+      for (int q = 0; q < 8; ++q) {
+        float pr[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float pr[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float e = exp2f(__uint_as_float(v[q * 8 + i]) * p.scale_log2 - mb);
-            pr[i] = (c0 + q * 8 + i < n_valid) ? e : 0.f;
-            lsum += pr[i];
-          }
-          const int chunk = ((c0 & 63) >> 3) + q;
-          uint4 u;
-          u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
-          u.z = pack_bf16x2(pr[4], pr[5]); u.w = pack_bf16x2(pr[6], pr[7]);
-          *reinterpret_cast<uint4*>(panel + ((chunk ^ (row & 7)) << 4)) = u;
-        }
+        for (int i = 0; i < 8; ++i) pr[i] = exp2f(fmaf(__uint_as_float(sv[q * 8 + i]), p.scale_log2, -mb));  // exp2(-inf) = 0
+        ls0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
+        ls1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
+        uint4 u;
+        u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
+        u.z = pack_bf16x2(pr[4], pr[5]); u.w = pack_bf16x2(pr[6], pr[7]);
+        *reinterpret_cast<uint4*>(p_row + ((q ^ (row & 7)) << 4)) = u;
       }
+      const float lsum = ls0 + ls1;
       l_run += lsum;
       tc_fence_before();
       fence_proxy_async_smem();
