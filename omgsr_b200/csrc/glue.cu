@@ -226,13 +226,19 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float o = (f[i][j] - mean) * rstd;
-          if (gamma) o *= __ldg(gamma + gb + v * 8 + j);
-          if (beta) o += __ldg(beta + gb + v * 8 + j);
-          f[i][j] = o;
+        float gm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, bt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (gamma) {  // 16-byte loads of the affine / modulation vectors (was one scalar load per element)
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + gb + v * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + gb + v * 8 + 4));
+          gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
         }
+        if (beta) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + gb + v * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + gb + v * 8 + 4));
+          bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[i][j] = fmaf((f[i][j] - mean) * rstd, gm[j], bt[j]);
         *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(f[i]);
       }
     }
@@ -639,6 +645,8 @@ extern "C" int omgsr_layernorm(const void* x, void* y, const float* gamma, const
   if (C % 8 || C > 4096) return set_error(OMGSR_ERR_SHAPE, "layernorm: C=%d", C);
   if (ldx <= 0) ldx = C;
   if ((ldx | x_batch_stride) % 8) return set_error(OMGSR_ERR_ALIGN, "layernorm: strides %% 8");
+  if ((gb_stride % 4) || (reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15)
+    return set_error(OMGSR_ERR_ALIGN, "layernorm: gamma/beta must be 16-byte aligned with gb_stride %% 4 == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);

@@ -18,8 +18,9 @@ from types import SimpleNamespace
 import torch
 
 from . import capi
-from .engine_vae import _Res, _dev
-from .pack import pack_conv_in_weight, pack_conv_weight, pack_geglu_weight, pack_upsample_weight, pad8
+from .engine_vae import _Res, _dev, thin_conv_in
+from .pack import (pack_conv_in_gemm_weight, pack_conv_in_weight, pack_conv_weight, pack_geglu_weight,
+                   pack_upsample_weight, pad8)
 
 
 def _timestep_embedding(t, dim):
@@ -122,6 +123,8 @@ class B200UNet(torch.nn.Module):
 
         self.conv_in_w = _dev(pack_conv_in_weight(sd["conv_in.weight"]), device)
         self.conv_in_b = _dev(pad8(sd["conv_in.bias"]), device, f32)
+        self.conv_in_wg = _dev(pack_conv_in_gemm_weight(sd["conv_in.weight"]), device)
+        self.conv_in_bg = _dev(sd["conv_in.bias"], device, f32)
         n = len(ch)
         self.down = []
         for i in range(n):
@@ -202,7 +205,7 @@ class B200UNet(torch.nn.Module):
 
         # ---- down path ----
         s = 0
-        h = capi.conv_in_nchw(z.contiguous(), self.conv_in_w, self.conv_in_b, ch[0], out=skip_home(s))
+        h = thin_conv_in(z, self.conv_in_w, self.conv_in_b, self.conv_in_wg, self.conv_in_bg, ch[0], out=skip_home(s))
         s += 1
         for i, (layers, ds) in enumerate(self.down):
             for r, t in layers:

@@ -44,6 +44,14 @@ class _Res:
             self.sb = _dev(sd[name + ".conv_shortcut.bias"], device, f32)
 
 
+def thin_conv_in(x, w_simt, b_simt, w_gemm, b_gemm, cout, out=None):
+    """3x3 conv from a thin NCHW input (Cin <= 16) to NHWC bf16. From 64 Ki pixels on: im2col (K padded to a multiple
+    of 64) + tensor-core GEMM; below that the direct CUDA-core kernel (launch-latency bound either way)."""
+    if x.shape[0] * x.shape[2] * x.shape[3] >= (1 << 16):
+        return capi.conv_in_gemm(x.contiguous(), w_gemm, b_gemm, out=out)
+    return capi.conv_in_nchw(x.contiguous(), w_simt, b_simt, cout, out=out)
+
+
 def _stats_buf(x_like_B, device):
     return torch.empty((x_like_B, 32, 2), device=device, dtype=torch.float32)
 
@@ -194,12 +202,10 @@ class B200Encoder(torch.nn.Module):
     def trunk_gen(self, x):
         """NCHW image -> NHWC bf16 features after conv_norm_out + SiLU (input of conv_out). GroupNorm statistics
         travel with the tensors: every conv whose output feeds a GroupNorm produces them in its epilogue."""
-        if x.shape[0] * x.shape[2] * x.shape[3] >= (1 << 16):
-            # 3 -> C conv_in at full image resolution: im2col (K = 27 -> 64) + tensor-core GEMM
-            # (the CUDA-core kernel took 4.7 ms of a 105 ms step at 16 x 512^2)
-            h = capi.conv_in_gemm(x.contiguous(), self.conv_in_wg, self.conv_in_bg)
-        else:
-            h = capi.conv_in_nchw(x.contiguous(), self.conv_in_w, self.conv_in_b, self.cfg.block_out_channels[0])
+        # 3 -> C conv_in at full image resolution runs as im2col (K = 27 -> 64) + tensor-core GEMM
+        # (the CUDA-core kernel took 4.7 ms of a 105 ms step at 16 x 512^2)
+        h = thin_conv_in(x, self.conv_in_w, self.conv_in_b, self.conv_in_wg, self.conv_in_bg,
+                         self.cfg.block_out_channels[0])
         st = None
         for res, down in self.levels:
             for r in res:
@@ -242,6 +248,8 @@ class B200Decoder(torch.nn.Module):
         ch = list(reversed(cfg.block_out_channels))
         self.conv_in_w = _dev(pack_conv_in_weight(sd["decoder.conv_in.weight"]), device)
         self.conv_in_b = _dev(pad8(sd["decoder.conv_in.bias"]), device, f32)
+        self.conv_in_wg = _dev(pack_conv_in_gemm_weight(sd["decoder.conv_in.weight"]), device)
+        self.conv_in_bg = _dev(sd["decoder.conv_in.bias"], device, f32)
         self.mid0 = _Res(sd, "decoder.mid_block.resnets.0", device)
         self.attn = _MidAttn(sd, "decoder.mid_block.attentions.0", device)
         self.mid1 = _Res(sd, "decoder.mid_block.resnets.1", device)
@@ -261,7 +269,7 @@ class B200Decoder(torch.nn.Module):
 
     def trunk_gen(self, z):
         ch0 = self.cfg.block_out_channels[-1]
-        h = capi.conv_in_nchw(z.contiguous(), self.conv_in_w, self.conv_in_b, ch0)
+        h = thin_conv_in(z, self.conv_in_w, self.conv_in_b, self.conv_in_wg, self.conv_in_bg, ch0)
         h, _ = yield from resnet_gen(self.mid0, h)
         h = yield from self.attn.gen(h)
         h, st = yield from resnet_gen(self.mid1, h, want_stats=True)
