@@ -161,3 +161,38 @@ def test_ddpm_alpha_matches_survey_constant():
     from omgsr_b200 import weights as W
     a = W.ddpm_alphas_cumprod()[273].item()
     assert abs(a - 0.6357423) < 1e-6
+
+
+def test_mid_timestep_search_matches_reference_loop():
+    """vectorised SNR sweep == the reference's per-timestep python loop (mid_timestep/mid_timestep_sd.py:59-80,
+    mid_timestep_flux.py:94-108), restated here literally on random latents."""
+    import math
+    from mid_timestep.calibrate import MidTimestepSearch, ddpm_tables, flux_tables
+    from omgsr_b200 import weights as W
+    from infer.omgsr_f_infer_model import get_flux_setting_timesteps
+    g = torch.Generator().manual_seed(3)
+    abar = W.ddpm_alphas_cumprod()
+    sigmas = get_flux_setting_timesteps()
+    for family in ("sd", "flux"):
+        sig, noise = ddpm_tables(abar) if family == "sd" else flux_tables(sigmas)
+        search = MidTimestepSearch(sig, noise)
+        acc = {t: 0.0 for t in range(999, -1, -1)}
+        n = 0
+        for _ in range(3):
+            hq = torch.randn(2, 4, 8, 8, generator=g)
+            lq = hq + 0.6 * torch.randn(2, 4, 8, 8, generator=g)
+            search.update(hq, lq)
+            for t in acc:
+                if family == "sd":
+                    s2, n2 = math.sqrt(abar[t]) ** 2, math.sqrt(1 - abar[t]) ** 2
+                else:
+                    s2, n2 = (1 - sigmas[-(t + 1)]) ** 2, sigmas[-(t + 1)] ** 2
+                snr1 = torch.mean(hq ** 2) * s2 / n2 if n2 > 0 else torch.tensor(float("inf"))
+                snr2 = torch.mean(hq ** 2) / torch.mean((lq - hq) ** 2)
+                acc[t] += torch.abs(snr1 - snr2).item() * 2
+            n += 2
+        ref = {t: acc[t] / n for t in acc}
+        t_ref = min(ref, key=ref.get)
+        t_got, loss, _ = search.result()
+        assert t_got == t_ref, (family, t_got, t_ref)
+        assert abs(loss - ref[t_ref]) <= 1e-4 * max(1.0, ref[t_ref])
