@@ -60,6 +60,10 @@ int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias, const void
                     long long M, int N, int K, long long lda, long long ldd, long long ldr, int act, int gate_rows,
                     int flags, int force_bn, void* stream);
 
+/* 1: route the 256-wide GEMMs / convolutions to the CTA-pair kernel (tcgen05 cta_group::2, M = 256 per cluster of
+ * two CTAs, each CTA streaming half of the weight tile); 0: single-CTA kernel. Process-wide switch. */
+int omgsr_set_gemm_2cta(int on);
+
 /* Row-batched linear layer: D[b, m, :] = epi(A[b, m, :] * Wt^T) for b < batch, with independent batch strides
  * for A / D / res (tokens of one image may live inside a longer joint [text; image] sequence), a per-batch
  * gate vector gate[b * gate_ld + n], and the activation restricted to output columns [act_c0, act_c1)

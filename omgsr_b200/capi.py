@@ -24,7 +24,7 @@ SYMBOLS = [
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
-    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant",
+    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta",
 ]
 
 

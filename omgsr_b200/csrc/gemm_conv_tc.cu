@@ -311,6 +311,220 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes a 256 x 256 output tile with ONE tcgen05.mma per
+// K-step (M = 256, N = 256). Each CTA loads its own 128-pixel A tile and HALF (128 rows) of the weight tile, holds its
+// own 128 x 256 fp32 accumulator in TMEM and runs its own epilogue. Versus the single-CTA kernel the per-CTA
+// L2->SMEM stream per k-block drops from 48 KB to 32 KB and the shared-memory operand reads per MMA from 12 KB to 8 KB.
+// Only the leader CTA (rank 0) issues MMAs; TMA bytes of both CTAs are credited to the leader's full barriers; the
+// MMA completion is multicast to the empty / accumulator-full barriers of both CTAs.
+// ------------------------------------------------------------------------------------------------
+struct Cfg2 {
+  static constexpr int kABytes = kBM * kBK * 2;     // 16 KB: this CTA's 128 pixels
+  static constexpr int kBBytes = 128 * kBK * 2;     // 16 KB: this CTA's half of the 256-row weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const ConvGemmParams p) {
+  using C = Cfg2;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;                        // [kStages]  (the leader's are the live ones)
+  uint64_t* empty_bar = bars + C::kStages;          // [kStages]  per CTA
+  uint64_t* acc_full = bars + 2 * C::kStages;       // [2]        per CTA
+  uint64_t* acc_empty = bars + 2 * C::kStages + 2;  // [2]        leader's: 4 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 2);   // one arrival per CTA's producer (the leader's carries the expected bytes)
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int total_pairs = m_pairs * p.n_tiles;
+  const int num_kb = p.R * p.S * p.kc_per_tap;
+  const int tw = 1 << p.log_tw, th = 1 << p.log_th;
+  const int tb = kBM >> (p.log_tw + p.log_th);
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        const int n_tile = pt % p.n_tiles;
+        const int m = 2 * (pt / p.n_tiles) + static_cast<int>(rank);
+        const bool dummy = m >= m_tiles;  // odd tile count: the pair's second half loads zeros and stores nothing
+        const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, tbi = m / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * tw, y0 = ty * th, b0 = dummy ? p.B : tbi * tb;
+        int kb = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            int c1, c2, c3, c4, cbase;
+            if (!p.stride2) {
+              cbase = 0; c1 = x0 + s - p.pad_l; c2 = y0 + r - p.pad_t; c3 = b0; c4 = 0;
+            } else {
+              const int dy = r - p.pad_t, dx = s - p.pad_l;
+              const int py = dy & 1, px = dx & 1;
+              cbase = px * p.pair_off; c1 = x0 + ((dx - px) >> 1); c2 = py; c3 = y0 + ((dy - py) >> 1); c4 = b0;
+            }
+            for (int kc = 0; kc < p.kc_per_tap; ++kc, ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * C::kStageBytes;
+              uint8_t* sb = sa + C::kABytes;
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (p.a_bytes + C::kBBytes));
+              else mbar_arrive_remote(&full_bar[stage], 0);
+              tma2_load_5d(sa, &tmA, &full_bar[stage], cbase + kc * kBK, c1, c2, c3, c4);
+              tma2_load_4d(sb, &tmB, &full_bar[stage], kb * kBK, n_tile * BN + static_cast<int>(rank) * 128, 0, 0);
+              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t db = umma_desc_sw128(sa + C::kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) tc_mma2_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_commit2_mc(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit2_mc(&acc_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int xl = row & (tw - 1);
+    const int yl = (row >> p.log_tw) & (th - 1);
+    const int bl = row >> (p.log_tw + p.log_th);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float* my_gn = gn_acc + quarter * 64;
+    const int gn_n = p.gn_groups * 2;
+    int gn_b = -1;
+    if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      const int n_tile = pt % p.n_tiles;
+      const int m = 2 * (pt / p.n_tiles) + static_cast<int>(rank);
+      const bool dummy = m >= m_tiles;
+      const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, tbi = m / (p.tiles_x * p.tiles_y);
+      const int x = tx * tw + xl, y = ty * th + yl, b = tbi * tb + bl;
+      if (p.gn_sums && !dummy && tbi != gn_b) {
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+        gn_b = tbi;
+      }
+      const bool valid = !dummy && (x < p.W) && (y < p.H) && (b < p.B);
+      EpiArgs e;
+      e.bias = p.bias;
+      e.out = p.out;
+      e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+      e.res_row = (p.res && valid) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+      const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : min(b, p.B - 1)) : 0;
+      e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
+      e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
+      e.out_f32 = p.out_f32;
+      float gn_part[16];
+      e.gn_part = p.gn_sums ? gn_part : nullptr;
+
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        float f[32];
+        tmem_ld32(t_row + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) add_bias32(f, p.bias, n_tile * BN + c0, p.Cout);
+        epilogue_store32(f, n_tile * BN + c0, n_tile * BN + c0, valid, e);
+        if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((n_tile * BN + c0) / p.gn_cpg) * 2, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&acc_empty[acc]);
+        else mbar_arrive_remote(&acc_empty[acc], 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+static int g_use_2cta = 0;
+
+static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg2::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_tc2): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const long long pairs = static_cast<long long>((m_tiles + 1) / 2) * p.n_tiles;
+  const int max_clusters = sm_count() / 2;
+  const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
+  conv_gemm_tc2_kernel<<<2 * clusters, kThreads, Cfg2::kSmemBytes, st>>>(tmA, tmB, p);
+  return check_launch("conv_gemm_tc2_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int ilog2(int v) {
@@ -478,6 +692,13 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
     wd[0] = d.w_ld; wd[1] = d.Cout; wd[2] = 1; wd[3] = 1;
     ws[0] = d.w_ld * eb; ws[1] = ws[0] * d.Cout; ws[2] = ws[1];
     wb[0] = kBK; wb[1] = bn; wb[2] = 1; wb[3] = 1;
+    if (bn == 256 && g_use_2cta && !geglu && m_tiles >= 2) {
+      // CTA-pair kernel: each CTA of the pair loads half (128 rows) of the 256-row weight tile
+      wb[1] = 128;
+      rc = make_tmap_bf16(&tmB, d.w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      return launch_cfg2(tmA, tmB, p, st);
+    }
   } else if (!d.b_mn_major) {
     wd[0] = d.Cin; wd[1] = d.b_rows; wd[2] = d.H; wd[3] = d.B;
     ws[0] = d.b_row * eb; ws[1] = d.b_head * eb; ws[2] = d.b_batch * eb;
@@ -501,6 +722,9 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
 }  // namespace omgsr
 
 using namespace omgsr;
+
+/* 1: route 256-wide weight-stationary GEMMs / convs to the CTA-pair (cta_group::2) kernel */
+extern "C" int omgsr_set_gemm_2cta(int on) { omgsr::g_use_2cta = on; return OMGSR_OK; }
 
 extern "C" int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias, const void* res, const float* gate,
                                void* D, long long M, int N, int K, long long lda, long long ldd, long long ldr,

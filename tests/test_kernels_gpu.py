@@ -472,3 +472,49 @@ def test_colorfix(capi):
     from oracle import colorfix
     assert report("wavelet", capi.wavelet_fix(c.cuda(), s.cuda()), colorfix.wavelet_reconstruction(c, s), 1e-5)[0]
     assert report("adain", capi.adain_fix(c.cuda(), s.cuda()), colorfix.adaptive_instance_normalization(c, s), 1e-4)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# CTA-pair (cta_group::2) kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def two_cta(capi):
+    capi.lib().omgsr_set_gemm_2cta(1)
+    yield
+    capi.lib().omgsr_set_gemm_2cta(0)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 256), (384, 512, 192), (4096, 1280, 1280), (1000, 256, 320)])
+def test_gemm_two_cta(capi, two_cta, M, N, K):
+    from oracle import ops
+    g = _g(M + N + K + 2)
+    a = bf16r(torch.randn(M, K, generator=g))
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g)
+    res = bf16r(torch.randn(M, N, generator=g))
+    out = capi.gemm(a.cuda().bfloat16(), w.cuda().bfloat16(), b.cuda(), res=res.cuda().bfloat16(), act=capi.ACT_SILU)
+    torch.cuda.synchronize()
+    assert report(f"gemm 2cta {M}x{N}x{K}", out, torch.nn.functional.silu(ops.linear(a, w, b)) + res)[0]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,up", [(2, 32, 32, 256, 256, 1, False), (1, 24, 40, 128, 512, 1, False),
+                                                      (3, 16, 16, 128, 256, 2, False), (1, 16, 16, 256, 256, 1, True),
+                                                      (1, 8, 8, 320, 1280, 1, False)])
+def test_conv_two_cta(capi, two_cta, B, H, W, Cin, Cout, stride, up):
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight, pack_upsample_weight
+    g = _g(B + H + W + Cin + Cout + 5)
+    x = bf16r(torch.randn(B, H, W, Cin, generator=g))
+    w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+    b = torch.randn(Cout, generator=g)
+    pad = (0, 0, 1, 1) if stride == 2 else (1, 1, 1, 1)
+    ref = ops.conv2d_nhwc(x, w, b, stride=stride, pad=pad, upsample2x=up)
+    pw = pack_upsample_weight(w) if up else pack_conv_weight(w)
+    st = torch.zeros(B, 32, 2, device="cuda") if (Cout // 32 in (8, 16) and ref.shape[1] * ref.shape[2] >= 128) else None
+    out = capi.conv2d(x.cuda().bfloat16(), pw.cuda(), b.cuda(), stride=stride, pad=pad, upsample2x=up, gn_stats=st)
+    torch.cuda.synchronize()
+    assert report(f"conv 2cta {B}x{H}x{W} {Cin}->{Cout} s{stride} up={up}", out, ref, 2e-2 if up else 1e-2)[0]
+    if st is not None:
+        o = out.float().cpu().reshape(B, -1, 32, Cout // 32)
+        sref = torch.stack([o.sum(dim=(1, 3)), o.pow(2).sum(dim=(1, 3))], dim=-1)
+        assert report("2cta fused gn stats", st, sref, 1e-3)[0]
