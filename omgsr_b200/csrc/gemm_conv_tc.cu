@@ -318,19 +318,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // Only the leader CTA (rank 0) issues MMAs; TMA bytes of both CTAs are credited to the leader's full barriers; the
 // MMA completion is multicast to the empty / accumulator-full barriers of both CTAs.
 // ------------------------------------------------------------------------------------------------
+template <int BN>
 struct Cfg2 {
-  static constexpr int kABytes = kBM * kBK * 2;     // 16 KB: this CTA's 128 pixels
-  static constexpr int kBBytes = 128 * kBK * 2;     // 16 KB: this CTA's half of the 256-row weight tile
+  static constexpr int kABytes = kBM * kBK * 2;           // 16 KB: this CTA's 128 pixels
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;      // this CTA's half of the BN-row weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 6;
+  static constexpr int kStages = (BN >= 256) ? 6 : 7;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 1024;
 };
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const ConvGemmParams p) {
-  using C = Cfg2;
-  constexpr int BN = 256;
+  using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -403,7 +404,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (p.a_bytes + C::kBBytes));
               else mbar_arrive_remote(&full_bar[stage], 0);
               tma2_load_5d(sa, &tmA, &full_bar[stage], cbase + kc * kBK, c1, c2, c3, c4);
-              tma2_load_4d(sb, &tmB, &full_bar[stage], kb * kBK, n_tile * BN + static_cast<int>(rank) * 128, 0, 0);
+              tma2_load_4d(sb, &tmB, &full_bar[stage], kb * kBK, n_tile * BN + static_cast<int>(rank) * (BN / 2), 0, 0);
               if (++stage == C::kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -442,6 +443,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int xl = row & (tw - 1);
     const int yl = (row >> p.log_tw) & (th - 1);
     const int bl = row >> (p.log_tw + p.log_th);
+    const bool geglu = (p.act == OMGSR_ACT_GEGLU);
+    const int out_bn = geglu ? BN / 2 : BN;
     int acc = 0;
     uint32_t acc_phase = 0;
     float* my_gn = gn_acc + quarter * 64;
@@ -466,7 +469,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       e.res_row = (p.res && valid) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
       const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : min(b, p.B - 1)) : 0;
       e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
-      e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
+      e.Cout = p.Cout; e.cout_out = geglu ? p.Cout / 2 : p.Cout; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
       e.out_f32 = p.out_f32;
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
@@ -475,15 +478,30 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < out_bn; c0 += 32) {
         uint32_t v[32];
         float f[32];
         tmem_ld32(t_row + c0, v);
-        tmem_wait_ld();
+        if (geglu) {
+          uint32_t gg[32];
+          float gf[32];
+          tmem_ld32(t_row + BN / 2 + c0, gg);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) add_bias32(f, p.bias, n_tile * BN + c0, p.Cout);
-        epilogue_store32(f, n_tile * BN + c0, n_tile * BN + c0, valid, e);
+          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gf[j] = __uint_as_float(gg[j]); }
+          if (p.bias) {
+            add_bias32(f, p.bias, n_tile * BN + c0, p.Cout);
+            add_bias32(gf, p.bias, n_tile * BN + BN / 2 + c0, p.Cout);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_f(gf[j]);
+        } else {
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) add_bias32(f, p.bias, n_tile * BN + c0, p.Cout);
+        }
+        epilogue_store32(f, n_tile * BN + c0, n_tile * out_bn + c0, valid, e);
         if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((n_tile * BN + c0) / p.gn_cpg) * 2, lane);
       }
       tc_fence_before();
@@ -505,13 +523,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-static int g_use_2cta = 0;
+// measured on B200 (profiles/r01/gemm_1cta_vs_2cta.txt): +7..19 % over the single-CTA kernel on every 256-wide shape
+static int g_use_2cta = 1;
 
+template <int BN>
 static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg2::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg2<BN>::kSmemBytes);
     if (e != cudaSuccess)
       return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_tc2): %s", cudaGetErrorString(e));
     attr_set = true;
@@ -520,7 +540,7 @@ static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   const long long pairs = static_cast<long long>((m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
-  conv_gemm_tc2_kernel<<<2 * clusters, kThreads, Cfg2::kSmemBytes, st>>>(tmA, tmB, p);
+  conv_gemm_tc2_kernel<BN><<<2 * clusters, kThreads, Cfg2<BN>::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_gemm_tc2_kernel");
 }
 
@@ -692,12 +712,14 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
     wd[0] = d.w_ld; wd[1] = d.Cout; wd[2] = 1; wd[3] = 1;
     ws[0] = d.w_ld * eb; ws[1] = ws[0] * d.Cout; ws[2] = ws[1];
     wb[0] = kBK; wb[1] = bn; wb[2] = 1; wb[3] = 1;
-    if (bn == 256 && g_use_2cta && !geglu && m_tiles >= 2) {
-      // CTA-pair kernel: each CTA of the pair loads half (128 rows) of the 256-row weight tile
-      wb[1] = 128;
+    if (g_use_2cta && (bn == 256 || bn == 160 || bn == 128) && (d.Cout % bn == 0) && m_tiles >= 2) {
+      // CTA-pair kernel: each CTA of the pair loads half of the bn-row weight tile
+      wb[1] = bn / 2;
       rc = make_tmap_bf16(&tmB, d.w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
-      return launch_cfg2(tmA, tmB, p, st);
+      if (bn == 256) return launch_cfg2<256>(tmA, tmB, p, st);
+      if (bn == 160) return launch_cfg2<160>(tmA, tmB, p, st);
+      return launch_cfg2<128>(tmA, tmB, p, st);
     }
   } else if (!d.b_mn_major) {
     wd[0] = d.Cin; wd[1] = d.b_rows; wd[2] = d.H; wd[3] = d.B;

@@ -477,14 +477,16 @@ def test_colorfix(capi):
 # ------------------------------------------------------------------------------------------------
 # CTA-pair (cta_group::2) kernel
 # ------------------------------------------------------------------------------------------------
-@pytest.fixture
-def two_cta(capi):
+@pytest.fixture(params=["pair", "single"])
+def two_cta(capi, request):
+    """the CTA-pair kernel is the default; 'single' forces the one-CTA kernel so both stay covered."""
+    capi.lib().omgsr_set_gemm_2cta(1 if request.param == "pair" else 0)
+    yield request.param
     capi.lib().omgsr_set_gemm_2cta(1)
-    yield
-    capi.lib().omgsr_set_gemm_2cta(0)
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 256), (384, 512, 192), (4096, 1280, 1280), (1000, 256, 320)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 256), (384, 512, 192), (4096, 1280, 1280), (1000, 256, 320),
+                                   (700, 320, 320), (515, 640, 128), (300, 128, 256)])
 def test_gemm_two_cta(capi, two_cta, M, N, K):
     from oracle import ops
     g = _g(M + N + K + 2)
@@ -499,7 +501,8 @@ def test_gemm_two_cta(capi, two_cta, M, N, K):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride,up", [(2, 32, 32, 256, 256, 1, False), (1, 24, 40, 128, 512, 1, False),
                                                       (3, 16, 16, 128, 256, 2, False), (1, 16, 16, 256, 256, 1, True),
-                                                      (1, 8, 8, 320, 1280, 1, False)])
+                                                      (1, 8, 8, 320, 1280, 1, False), (2, 16, 16, 320, 320, 1, False),
+                                                      (1, 32, 32, 256, 128, 1, False)])
 def test_conv_two_cta(capi, two_cta, B, H, W, Cin, Cout, stride, up):
     from oracle import ops
     from omgsr_b200.pack import pack_conv_weight, pack_upsample_weight
@@ -510,7 +513,7 @@ def test_conv_two_cta(capi, two_cta, B, H, W, Cin, Cout, stride, up):
     pad = (0, 0, 1, 1) if stride == 2 else (1, 1, 1, 1)
     ref = ops.conv2d_nhwc(x, w, b, stride=stride, pad=pad, upsample2x=up)
     pw = pack_upsample_weight(w) if up else pack_conv_weight(w)
-    st = torch.zeros(B, 32, 2, device="cuda") if (Cout // 32 in (8, 16) and ref.shape[1] * ref.shape[2] >= 128) else None
+    st = torch.zeros(B, 32, 2, device="cuda") if (Cout // 32 in (4, 8, 16) and ref.shape[1] * ref.shape[2] >= 128) else None
     out = capi.conv2d(x.cuda().bfloat16(), pw.cuda(), b.cuda(), stride=stride, pad=pad, upsample2x=up, gn_stats=st)
     torch.cuda.synchronize()
     assert report(f"conv 2cta {B}x{H}x{W} {Cin}->{Cout} s{stride} up={up}", out, ref, 2e-2 if up else 1e-2)[0]
@@ -518,3 +521,16 @@ def test_conv_two_cta(capi, two_cta, B, H, W, Cin, Cout, stride, up):
         o = out.float().cpu().reshape(B, -1, 32, Cout // 32)
         sref = torch.stack([o.sum(dim=(1, 3)), o.pow(2).sum(dim=(1, 3))], dim=-1)
         assert report("2cta fused gn stats", st, sref, 1e-3)[0]
+
+
+def test_geglu_two_cta(capi, two_cta):
+    from oracle import ops
+    from omgsr_b200.pack import pack_geglu_weight
+    g = _g(77)
+    M, K, F_ = 512, 320, 1280
+    a = bf16r(torch.randn(M, K, generator=g))
+    w = bf16r(torch.randn(2 * F_, K, generator=g) / math.sqrt(K))
+    b = torch.randn(2 * F_, generator=g)
+    wi, bi = pack_geglu_weight(w, b, 256)
+    out = capi.gemm(a.cuda().bfloat16(), wi.cuda().bfloat16(), bi.cuda(), act=capi.ACT_GEGLU, force_bn=256)
+    assert report(f"geglu [{two_cta}]", out, ops.geglu(a, w, b))[0]
