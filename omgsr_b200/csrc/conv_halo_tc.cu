@@ -16,6 +16,8 @@
 
 namespace omgsr {
 
+extern const char* g_trace_variant;
+
 struct HaloParams {
   int tiles_x, tiles_y, B;    // tiles_y counts groups of TM rows
   int W, H;                   // output extents
@@ -24,7 +26,7 @@ struct HaloParams {
   int R, S, pad_t, pad_l, Cin;
   int pw;                     // halo pitch in pixels = 128 + S - 1
   int a_bytes;                // bytes of one halo load
-  int desc_mode;              // 1: put (addr >> 7) & 7 into the descriptor base-offset field
+  int debug;                  // experiment knob (OMGSR_HALO_DEBUG): 1 no stores, 2 no epilogue, 4 no MMA
   long long o_sx, o_sy, o_sb, r_sx, r_sy, r_sb;
   void* out;
   const float* bias;
@@ -148,9 +150,11 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int t = 0; t < TM; ++t) {
                 const uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc_mma_ss(acc0 + t * BN, halo_desc(a_addr + k * 32, p.desc_mode),
+                for (int k = 0; k < 4; ++k) {
+                  if (p.debug & 4) continue;
+                  tc_mma_ss(acc0 + t * BN, umma_desc_sw128(a_addr + k * 32, 16, 1024),
                             umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (c | tap | k) != 0);
+                }
               }
               tc_commit(&b_empty[bs]);
               if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
@@ -184,32 +188,54 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
         gn_b = b;
       }
+      // residual rows of this thread's TM pixels: pulled into L2 now, then loaded one 32-channel chunk ahead of use
+      EpiArgs e;
+      e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
+      e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
+      e.out_f32 = p.out_f32;
+      float gn_part[16];
+      e.gn_part = p.gn_sums ? gn_part : nullptr;
+      uint4 rr[4] = {}, rn[4] = {};
+      if (p.res) {
+#pragma unroll
+        for (int t = TM - 1; t >= 0; --t) {
+          const int y = ty * TM + t;
+          e.res_row = p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx);
+          prefetch_res_row(e, n_tile * BN, BN, (x < p.W) && (y < p.H));
+        }
+        load_res32(rr, e, n_tile * BN, (x < p.W) && (ty * TM < p.H));  // e.res_row is row t = 0 here
+      }
       mbar_wait(&acc_full[set], sph);
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < TM; ++t) {
         const int y = ty * TM + t;
-        const bool valid = (x < p.W) && (y < p.H);
-        EpiArgs e;
-        e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
+        const bool valid = (x < p.W) && (y < p.H) && !(p.debug & 1);
+        if (p.debug & 2) continue;
         e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
-        e.res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
-        e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
-        e.out_f32 = p.out_f32;
-        float gn_part[16];
-        e.gn_part = p.gn_sums ? gn_part : nullptr;
+        const bf16* res_this = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
         const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           float f[32];
           tmem_ld32(t_row + c0, v);
+          if (c0 + 32 < BN) {
+            e.res_row = res_this;
+            load_res32(rn, e, n_tile * BN + c0 + 32, valid);
+          } else if (t + 1 < TM) {
+            e.res_row = p.res ? res_this + p.r_sy : nullptr;
+            load_res32(rn, e, n_tile * BN, (x < p.W) && (y + 1 < p.H));
+          }
+          e.res_row = res_this;
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           const int cv = n_tile * BN + c0;
           if (p.bias) add_bias32(f, p.bias, cv, p.Cout);
-          epilogue_store32(f, cv, cv, valid, e);
+          epilogue_store32(f, cv, cv, valid, e, rr);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
           if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((cv) / p.gn_cpg) * 2, lane);
         }
       }
@@ -230,6 +256,243 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2, see gemm_conv_tc.cu): the two CTAs of a cluster each own one halo tile (TM rows x
+// 128 pixels) and HALF (64 rows) of every 128-row weight block; one M=256 tcgen05.mma per (tap, row, K-step) covers
+// both. At N = 128 the single-CTA MMA reads 4 KB of A + 4 KB of B from shared memory per 64 cycles (the 128 B/clk
+// limit); the pair reads 4 + 2 KB per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int TM>
+struct Halo2Cfg {
+  static constexpr int kABytes = (((TM + 2) * 130 * 128) + 1023) / 1024 * 1024;
+  static constexpr int kAStages = 2;
+  static constexpr int kBBytes = 64 * 128;  // this CTA's half of the 128-row weight block
+  static constexpr int kBStages = 8;
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024;
+};
+
+template <int TM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const HaloParams p) {
+  using C = Halo2Cfg<TM>;
+  constexpr int BN = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::kAStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::kBStages * C::kBBytes);
+  uint64_t* a_full = bars;                      // leader's are live (2 arrivals)
+  uint64_t* a_empty = a_full + C::kAStages;     // per CTA
+  uint64_t* b_full = a_empty + C::kAStages;     // leader's
+  uint64_t* b_empty = b_full + C::kBStages;     // per CTA
+  uint64_t* acc_full = b_empty + C::kBStages;   // per CTA
+  uint64_t* acc_empty = acc_full + 2;           // leader's: 8 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::kAStages; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&b_full[i], 2); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int halo_tiles = p.tiles_x * p.tiles_y * p.B;
+  const int total_pairs = (halo_tiles + 1) >> 1;   // n_tiles == 1 (Cout <= 128)
+  const int taps = p.R * p.S;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        int m = 2 * pt + static_cast<int>(rank);
+        const bool dummy = m >= halo_tiles;
+        const int tx = m % p.tiles_x; m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int b = dummy ? p.B : m / p.tiles_y;
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (rank == 0) mbar_expect_tx(&a_full[as], 2 * p.a_bytes);
+          else mbar_arrive_remote(&a_full[as], 0);
+          tma2_load_5d(sA + as * C::kABytes, &tmA, &a_full[as], c * 64, tx * 128 - p.pad_l, ty * TM - p.pad_t, b, 0);
+          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * C::kBBytes);
+            else mbar_arrive_remote(&b_full[bs], 0);
+            tma2_load_4d(sB + bs * C::kBBytes, &tmB, &b_full[bs], tap * p.Cin + c * 64, static_cast<int>(rank) * 64, 0, 0);
+            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      int as = 0, bs = 0, set = 0;
+      uint32_t aph = 0, bph = 0, sph = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        mbar_wait(&acc_empty[set], sph ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + set * (TM * BN);
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + as * C::kABytes);
+          int tap = 0;
+          for (int r = 0; r < p.R; ++r) {
+            for (int s = 0; s < p.S; ++s, ++tap) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(sB + bs * C::kBBytes);
+#pragma unroll
+              for (int t = 0; t < TM; ++t) {
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (p.debug & 4) continue;
+                  tc_mma2_ss(acc0 + t * BN, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                             umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (c | tap | k) != 0);
+                }
+              }
+              tc_commit2_mc(&b_empty[bs]);
+              if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+            }
+          }
+          tc_commit2_mc(&a_empty[as]);
+          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+        }
+        tc_commit2_mc(&acc_full[set]);
+        if (++set == 2) { set = 0; sph ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int set = 0;
+    uint32_t sph = 0;
+    float* my_gn = gn_acc + quarter * 64;
+    const int gn_n = p.gn_groups * 2;
+    int gn_b = -1;
+    if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      int m = 2 * pt + static_cast<int>(rank);
+      const bool dummy = m >= halo_tiles;
+      const int tx = m % p.tiles_x; m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int b = dummy ? 0 : m / p.tiles_y;
+      const int x = tx * 128 + row;
+      if (p.gn_sums && !dummy && b != gn_b) {
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+        gn_b = b;
+      }
+      // residual rows of this thread's TM pixels: pulled into L2 now, then loaded one 32-channel chunk ahead of use
+      EpiArgs e;
+      e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
+      e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
+      e.out_f32 = p.out_f32;
+      float gn_part[16];
+      e.gn_part = p.gn_sums ? gn_part : nullptr;
+      uint4 rr[4] = {}, rn[4] = {};
+      const bool use_res = p.res && !dummy;
+      if (use_res) {
+#pragma unroll
+        for (int t = TM - 1; t >= 0; --t) {
+          const int y = ty * TM + t;
+          e.res_row = p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx);
+          prefetch_res_row(e, 0, BN, (x < p.W) && (y < p.H));
+        }
+        load_res32(rr, e, 0, (x < p.W) && (ty * TM < p.H));  // e.res_row is row t = 0 here
+      }
+      mbar_wait(&acc_full[set], sph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < TM; ++t) {
+        const int y = ty * TM + t;
+        const bool valid = !dummy && (x < p.W) && (y < p.H) && !(p.debug & 1);
+        if (p.debug & 2) continue;
+        e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+        const bf16* res_this = use_res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+        const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          float f[32];
+          tmem_ld32(t_row + c0, v);
+          if (c0 + 32 < BN) {
+            e.res_row = res_this;
+            load_res32(rn, e, c0 + 32, valid);
+          } else if (t + 1 < TM) {
+            e.res_row = use_res ? res_this + p.r_sy : nullptr;
+            load_res32(rn, e, 0, !dummy && (x < p.W) && (y + 1 < p.H));
+          }
+          e.res_row = res_this;
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) add_bias32(f, p.bias, c0, p.Cout);
+          epilogue_store32(f, c0, c0, valid, e, rr);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+          if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + (c0 / p.gn_cpg) * 2, lane);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&acc_empty[set]);
+        else mbar_arrive_remote(&acc_empty[set], 0);
+      }
+      if (++set == 2) { set = 0; sph ^= 1; }
+    }
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+int g_halo_2cta = 1;
+
+template <int TM>
+static int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
+  using C = Halo2Cfg<TM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_tc2_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_halo2<%d>): %s", TM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long halo_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B;
+  const long long pairs = (halo_tiles + 1) / 2;
+  const int max_clusters = sm_count() / 2;
+  const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
+  g_trace_variant = "halo_pair128";
+  conv_halo_tc2_kernel<TM><<<2 * clusters, 192, C::kSmemBytes, st>>>(tmA, tmB, p);
+  return check_launch("conv_halo_tc2_kernel");
+}
+
 template <int BN, int TM>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
   using C = HaloCfg<BN, TM>;
@@ -243,6 +506,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
   }
   const long long total = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles;
   const int grid = total < sm_count() ? static_cast<int>(total) : sm_count();
+  g_trace_variant = "halo_single128";
   conv_halo_tc_kernel<BN, TM><<<grid, 192, C::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_halo_tc_kernel");
 }
@@ -272,7 +536,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   p.n_tiles = (Cout + bn - 1) / bn; p.Cout = Cout; p.chunks = Cin / 64; p.R = R; p.S = S; p.pad_t = pad_t; p.pad_l = pad_l;
   p.Cin = Cin; p.pw = 128 + S - 1;
   p.a_bytes = 128 * p.pw * (TM + R - 1);
-  p.desc_mode = 0;
+  { static const int dbg = getenv("OMGSR_HALO_DEBUG") ? atoi(getenv("OMGSR_HALO_DEBUG")) : 0; p.debug = dbg; }
   p.gn_sums = nullptr; p.gn_cpg = 0; p.gn_groups = 0;
   if (gn_sums) {
     const int cpg = gn_groups > 0 ? Cout / gn_groups : 0;
@@ -292,10 +556,11 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   if (rc) return rc;
   uint64_t wd[4] = {static_cast<uint64_t>(w_ld), static_cast<uint64_t>(Cout), 1, 1};
   uint64_t ws[3] = {w_ld * eb, w_ld * eb * Cout, w_ld * eb * Cout};
-  uint32_t wb[4] = {64, static_cast<uint32_t>(bn), 1, 1};
+  const bool pair = g_halo_2cta && p.n_tiles == 1 && static_cast<long long>(p.tiles_x) * p.tiles_y * p.B >= 2;
+  uint32_t wb[4] = {64, static_cast<uint32_t>(pair ? 64 : bn), 1, 1};
   rc = make_tmap_bf16(&tmB, w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  if (bn == 256) return launch_halo<256, TM>(tmA, tmB, p, st);
+  if (pair) return launch_halo2<TM>(tmA, tmB, p, st);
   return launch_halo<128, TM>(tmA, tmB, p, st);
 }
 

@@ -21,6 +21,8 @@
 // Replaces the cuDNN / cuBLAS calls underneath diffusers' Conv2d / Linear modules that the reference
 // reaches from infer/omgsr_s_infer_model.py:75-84,173 and infer/omgsr_f_infer_model.py:16,191-211.
 #include "common.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include "epilogue.cuh"
 #include "../../include/omgsr_b200.h"
 
@@ -264,6 +266,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
 
+      uint4 rr[4] = {}, rn[4] = {};
+      prefetch_res_row(e, t.n_tile * out_bn, out_bn, valid);
+      load_res32(rr, e, t.n_tile * out_bn, valid);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -272,6 +277,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t v[32];
         float f[32];
         tmem_ld32(t_row + c0, v);
+        if (c0 + 32 < out_bn) load_res32(rn, e, t.n_tile * out_bn + c0 + 32, valid);
         if (geglu) {
           uint32_t g[32];
           float gf[32];
@@ -291,7 +297,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) add_bias32(f, p.bias, t.n_tile * BN + c0, p.Cout);
         }
-        epilogue_store32(f, t.n_tile * BN + c0, t.n_tile * out_bn + c0, valid, e);
+        epilogue_store32(f, t.n_tile * BN + c0, t.n_tile * out_bn + c0, valid, e, rr);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rr[q] = rn[q];
         if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((t.n_tile * BN + c0) / p.gn_cpg) * 2, lane);
       }
       tc_fence_before();
@@ -474,6 +482,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
 
+      uint4 rr[4] = {}, rn[4] = {};
+      prefetch_res_row(e, n_tile * out_bn, out_bn, valid);
+      load_res32(rr, e, n_tile * out_bn, valid);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -482,6 +493,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t v[32];
         float f[32];
         tmem_ld32(t_row + c0, v);
+        if (c0 + 32 < out_bn) load_res32(rn, e, n_tile * out_bn + c0 + 32, valid);
         if (geglu) {
           uint32_t gg[32];
           float gf[32];
@@ -501,7 +513,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) add_bias32(f, p.bias, n_tile * BN + c0, p.Cout);
         }
-        epilogue_store32(f, n_tile * BN + c0, n_tile * out_bn + c0, valid, e);
+        epilogue_store32(f, n_tile * BN + c0, n_tile * out_bn + c0, valid, e, rr);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rr[q] = rn[q];
         if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((n_tile * BN + c0) / p.gn_cpg) * 2, lane);
       }
       tc_fence_before();
@@ -525,6 +539,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 // measured on B200 (profiles/r01/gemm_1cta_vs_2cta.txt): +7..19 % over the single-CTA kernel on every 256-wide shape
 static int g_use_2cta = 1;
+extern const char* g_trace_variant;
 
 template <int BN>
 static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, cudaStream_t st) {
@@ -540,6 +555,7 @@ static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   const long long pairs = static_cast<long long>((m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
+  g_trace_variant = BN == 256 ? "pair256" : BN == 160 ? "pair160" : "pair128";
   conv_gemm_tc2_kernel<BN><<<2 * clusters, kThreads, Cfg2<BN>::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_gemm_tc2_kernel");
 }
@@ -566,6 +582,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
   }
   const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
+  g_trace_variant = BN == 256 ? "single256" : BN == 160 ? "single160" : BN == 128 ? "single128" : "single64";
   conv_gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_gemm_tc_kernel");
 }
@@ -610,7 +627,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
                   long long x_sb, long long o_sx, long long o_sy, long long o_sb, long long r_sx, long long r_sy,
                   long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, cudaStream_t st);
 
-static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
+static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   if (d.Cin % kBK) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: K/Cin=%d must be a multiple of %d", d.Cin, kBK);
   if ((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.w) | reinterpret_cast<uintptr_t>(d.y) |
        reinterpret_cast<uintptr_t>(d.res)) & 15)
@@ -741,12 +758,35 @@ static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
   }
 }
 
+// OMGSR_TRACE=1: time every GEMM / convolution launch with CUDA events (serialising) and print its shape, the
+// kernel variant that served it and the achieved TFLOP/s to stderr - the per-layer table under profiles/.
+const char* g_trace_variant = "";
+static int run_conv_gemm(const ConvDesc& d, cudaStream_t st) {
+  static const bool trace = getenv("OMGSR_TRACE") != nullptr;
+  if (!trace) return run_conv_gemm_impl(d, st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  const int rc = run_conv_gemm_impl(d, st);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const double flops = 2.0 * d.B * d.H * d.W * d.Cout * d.Cin * d.R * d.S;
+  fprintf(stderr, "TRACE %s B=%d H=%d W=%d Cin=%d Cout=%d k=%dx%d s2=%d flat=%d batched=%d act=%d res=%d gn=%d %.4f ms %.0f TFLOP/s\n",
+          g_trace_variant, d.B, d.H, d.W, d.Cin, d.Cout, d.R, d.S, d.stride2, d.flat, d.b_batched, d.act,
+          d.res ? 1 : 0, d.gn_sums ? 1 : 0, ms, flops / ms * 1e-9);
+  return rc;
+}
+
 }  // namespace omgsr
 
 using namespace omgsr;
 
 /* 1: route 256-wide weight-stationary GEMMs / convs to the CTA-pair (cta_group::2) kernel */
-extern "C" int omgsr_set_gemm_2cta(int on) { omgsr::g_use_2cta = on; return OMGSR_OK; }
+namespace omgsr { extern int g_halo_2cta; }
+extern "C" int omgsr_set_gemm_2cta(int on) { omgsr::g_use_2cta = on; omgsr::g_halo_2cta = on; return OMGSR_OK; }
 
 extern "C" int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias, const void* res, const float* gate,
                                void* D, long long M, int N, int K, long long lda, long long ldd, long long ldr,

@@ -131,13 +131,16 @@ HALO_CASES = [
     (1, 32, 128, 128, 128, True),       # nearest-2x + conv: four 2x2 parity convs through the halo kernel
     (2, 64, 96, 64, 256, True),
     (2, 40, 256, 128, 3, False),        # thin Cout (decoder conv_out) on one masked 128-wide tile
+    (1, 6, 128, 64, 128, False),        # three halo tiles: the CTA pair's odd tail (one dummy tile)
+    (3, 10, 300, 192, 128, False),      # 45 tiles, ragged x, three K chunks
 ]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,up", HALO_CASES)
-@pytest.mark.parametrize("mode", ["halo"])
+@pytest.mark.parametrize("mode", ["pair", "single"])
 def test_conv_halo(capi, B, H, W, Cin, Cout, up, mode):
     from oracle import ops
+    capi.lib().omgsr_set_gemm_2cta(1 if mode == "pair" else 0)
     from omgsr_b200.pack import pack_conv_weight, pack_upsample_weight
     g = _g(B * 7 + H + W + Cin + Cout)
     x = bf16r(torch.randn(B, H, W, Cin, generator=g))
@@ -155,6 +158,7 @@ def test_conv_halo(capi, B, H, W, Cin, Cout, up, mode):
     torch.cuda.synchronize()
     ok, _ = report(f"conv-halo[{mode}] {B}x{H}x{W} {Cin}->{Cout} up={up}", out, ref, 2e-2 if up else 1e-2)
     gen = capi.conv2d(xc, wc, bc, res=rc, upsample2x=up, flags=capi.CONV_NO_HALO, cout=Cout)
+    capi.lib().omgsr_set_gemm_2cta(1)
     assert report("generic kernel, same problem", gen, ref, 2e-2 if up else 1e-2)[0]
     assert ok
 
