@@ -43,7 +43,7 @@ struct HaloCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kBStages = (BN == 128) ? 5 : 2;
   static constexpr int kAccSets = (BN * TM * 2 <= 512) ? 2 : 1;
-  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024 /*GN partial sums*/;
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024 /*GN partial sums*/ + 16 * BN /*bias slices*/;
 };
 
 __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, int mode) {
@@ -174,11 +174,18 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int set = 0;
     uint32_t sph = 0;
     float* my_gn = gn_acc + quarter * 64;  // see gemm_conv_tc.cu: per-warp partial sums, flushed when the image changes
+    float* my_bias = gn_acc + 256 + quarter * BN;
+    int bias_tile = -1;
+    const int epi_mode = epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
     const int gn_n = p.gn_groups * 2;  // <= 64: the slice holds every group of one image, whatever the n_tile
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
+      if (p.bias && n_tile != bias_tile) {
+        stage_bias<BN>(my_bias, p.bias, n_tile * BN, p.Cout, lane);
+        bias_tile = n_tile;
+      }
       int m = tile / p.n_tiles;
       const int tx = m % p.tiles_x; m /= p.tiles_x;
       const int ty = m % p.tiles_y;
@@ -220,22 +227,26 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t v[32];
           float f[32];
           tmem_ld32(t_row + c0, v);
-          if (c0 + 32 < BN) {
-            e.res_row = res_this;
-            load_res32(rn, e, n_tile * BN + c0 + 32, valid);
-          } else if (t + 1 < TM) {
-            e.res_row = p.res ? res_this + p.r_sy : nullptr;
-            load_res32(rn, e, n_tile * BN, (x < p.W) && (y + 1 < p.H));
+          if (p.res) {
+            if (c0 + 32 < BN) {
+              e.res_row = res_this;
+              load_res32(rn, e, n_tile * BN + c0 + 32, valid);
+            } else if (t + 1 < TM) {
+              e.res_row = res_this + p.r_sy;
+              load_res32(rn, e, n_tile * BN, (x < p.W) && (y + 1 < p.H));
+            }
           }
           e.res_row = res_this;
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           const int cv = n_tile * BN + c0;
-          if (p.bias) add_bias32(f, p.bias, cv, p.Cout);
-          epilogue_store32(f, cv, cv, valid, e, rr);
+          if (p.bias) add_bias32_s(f, my_bias + c0);
+          epilogue_store32_m(epi_mode, f, cv, cv, valid, e, rr);
+          if (p.res) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+            for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+          }
           if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((cv) / p.gn_cpg) * 2, lane);
         }
       }
@@ -268,7 +279,7 @@ struct Halo2Cfg {
   static constexpr int kAStages = 2;
   static constexpr int kBBytes = 64 * 128;  // this CTA's half of the 128-row weight block
   static constexpr int kBStages = 8;
-  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024;
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024 + 16 * 128;
 };
 
 template <int TM>
@@ -387,6 +398,9 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int set = 0;
     uint32_t sph = 0;
     float* my_gn = gn_acc + quarter * 64;
+    float* my_bias = gn_acc + 256 + quarter * BN;
+    if (p.bias) stage_bias<BN>(my_bias, p.bias, 0, p.Cout, lane);
+    const int epi_mode = epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
     const int gn_n = p.gn_groups * 2;
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
@@ -434,21 +448,25 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint32_t v[32];
           float f[32];
           tmem_ld32(t_row + c0, v);
-          if (c0 + 32 < BN) {
-            e.res_row = res_this;
-            load_res32(rn, e, c0 + 32, valid);
-          } else if (t + 1 < TM) {
-            e.res_row = use_res ? res_this + p.r_sy : nullptr;
-            load_res32(rn, e, 0, !dummy && (x < p.W) && (y + 1 < p.H));
+          if (use_res) {
+            if (c0 + 32 < BN) {
+              e.res_row = res_this;
+              load_res32(rn, e, c0 + 32, valid);
+            } else if (t + 1 < TM) {
+              e.res_row = res_this + p.r_sy;
+              load_res32(rn, e, 0, (x < p.W) && (y + 1 < p.H));
+            }
           }
           e.res_row = res_this;
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) add_bias32(f, p.bias, c0, p.Cout);
-          epilogue_store32(f, c0, c0, valid, e, rr);
+          if (p.bias) add_bias32_s(f, my_bias + c0);
+          epilogue_store32_m(epi_mode, f, c0, c0, valid, e, rr);
+          if (p.res) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+            for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+          }
           if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + (c0 / p.gn_cpg) * 2, lane);
         }
       }

@@ -53,6 +53,30 @@ __device__ __forceinline__ void add_bias32(float (&f)[32], const float* bias, in
   }
 }
 
+// Bias staged in shared memory: each epilogue warp keeps the BN bias values of its current n-tile in a private slice,
+// refilled (before the accumulator wait, so the latency is hidden) only when the n-tile changes. Reading the bias
+// with __ldg per chunk cost an L2 round trip per chunk: with > 200 KB of the SM's L1/shared carve-out given to the
+// operand ring, the few KB of L1 left are thrashed by the residual / output streams.
+template <int N>
+__device__ __forceinline__ void stage_bias(float* slice, const float* bias, int c_first, int Cout, int lane) {
+  __syncwarp();
+  float v[(N + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (N + 31) / 32; ++i) v[i] = __ldg(bias + min(c_first + lane + 32 * i, Cout - 1));  // all in flight
+#pragma unroll
+  for (int i = 0; i < (N + 31) / 32; ++i)
+    if (lane + 32 * i < N) slice[lane + 32 * i] = v[i];
+  __syncwarp();
+}
+__device__ __forceinline__ void add_bias32_s(float (&f)[32], const float* slice) {
+  const float4* bp = reinterpret_cast<const float4*>(slice);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = bp[q];
+    f[4 * q + 0] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+  }
+}
+
 // Residual operand of one 32-column chunk (4 x 16 B of this thread's row). The kernels issue these loads one chunk
 // AHEAD of their use (and before the tcgen05.ld wait): inside epilogue_store32 they sat behind the previous
 // granule's store, which the compiler must assume may alias, so every 16-byte load exposed a full HBM round trip
@@ -125,6 +149,73 @@ __device__ __forceinline__ void epilogue_store32(float (&f)[32], int cv, int oc0
         e.gn_part[4 * q + 3] = valid ? (v2.x * v2.x + v2.y * v2.y) + (v3.x * v3.x + v3.y * v3.y) : 0.f;
       }
     }
+  }
+}
+
+// Compile-time specialisations of epilogue_store32 for the option sets the two pipelines actually use. The generic
+// version above is if-converted by the compiler into ~330 issued (mostly predicated-off) instructions per chunk;
+// with one epilogue warp per scheduler that, not the tensor pipe, bounded every K <= ~1500 layer (ncu source view:
+// 58 % of all samples inside the chunk body). The specialised bodies issue ~100.
+template <int ACT, bool GATE, bool RES, bool GN>
+__device__ __forceinline__ void epilogue_store32_t(float (&f)[32], int cv, int oc0, bool valid, const EpiArgs& e,
+                                                   const uint4 (&rr4)[4]) {
+  if (ACT != OMGSR_ACT_NONE && cv >= e.act_c0 && cv < e.act_c1) act32<ACT>(f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int oc = oc0 + q * 8;
+    if (oc >= e.cout_out) break;  // warp-uniform
+    float* ff = f + q * 8;
+    if (GATE) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.gate_row + oc));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.gate_row + oc + 4));
+      ff[0] *= g0.x; ff[1] *= g0.y; ff[2] *= g0.z; ff[3] *= g0.w;
+      ff[4] *= g1.x; ff[5] *= g1.y; ff[6] *= g1.z; ff[7] *= g1.w;
+    }
+    if (RES) {  // rows that are not stored may add stale registers: harmless, they are never written
+      const uint4 rr = rr4[q];
+      const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                   r3 = unpack_bf16x2(rr.w);
+      ff[0] += r0.x; ff[1] += r0.y; ff[2] += r1.x; ff[3] += r1.y;
+      ff[4] += r2.x; ff[5] += r2.y; ff[6] += r3.x; ff[7] += r3.y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(ff[0], ff[1]); o.y = pack_bf16x2(ff[2], ff[3]);
+    o.z = pack_bf16x2(ff[4], ff[5]); o.w = pack_bf16x2(ff[6], ff[7]);
+    if (valid) *reinterpret_cast<uint4*>(static_cast<bf16*>(e.out) + e.o_off + oc) = o;
+    if (GN) {
+      const float2 v0 = unpack_bf16x2(o.x), v1 = unpack_bf16x2(o.y), v2 = unpack_bf16x2(o.z), v3 = unpack_bf16x2(o.w);
+      e.gn_part[4 * q + 0] = valid ? (v0.x + v0.y) + (v1.x + v1.y) : 0.f;
+      e.gn_part[4 * q + 1] = valid ? (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) : 0.f;
+      e.gn_part[4 * q + 2] = valid ? (v2.x + v2.y) + (v3.x + v3.y) : 0.f;
+      e.gn_part[4 * q + 3] = valid ? (v2.x * v2.x + v2.y * v2.y) + (v3.x * v3.x + v3.y * v3.y) : 0.f;
+    }
+  }
+}
+
+// option set -> specialisation id (0 = generic). Computed once per thread, warp-uniform.
+enum : int { EPI_GENERIC = 0, EPI_PLAIN, EPI_RES, EPI_GN, EPI_RES_GN, EPI_GELU_TANH, EPI_GATE_RES, EPI_SILU };
+__device__ __forceinline__ int epilogue_mode(int act, bool gate, bool res, bool out_f32, bool gn) {
+  if (out_f32) return EPI_GENERIC;
+  if (act == OMGSR_ACT_NONE || act == OMGSR_ACT_GEGLU) {  // GEGLU: the kernels fold the gate half before the store
+    if (gate) return (res && !gn) ? EPI_GATE_RES : EPI_GENERIC;
+    return gn ? (res ? EPI_RES_GN : EPI_GN) : (res ? EPI_RES : EPI_PLAIN);
+  }
+  if (gate || res || gn) return EPI_GENERIC;
+  if (act == OMGSR_ACT_GELU_TANH) return EPI_GELU_TANH;
+  if (act == OMGSR_ACT_SILU) return EPI_SILU;
+  return EPI_GENERIC;
+}
+__device__ __forceinline__ void epilogue_store32_m(int mode, float (&f)[32], int cv, int oc0, bool valid,
+                                                   const EpiArgs& e, const uint4 (&rr)[4]) {
+  switch (mode) {
+    case EPI_PLAIN: epilogue_store32_t<OMGSR_ACT_NONE, false, false, false>(f, cv, oc0, valid, e, rr); break;
+    case EPI_RES: epilogue_store32_t<OMGSR_ACT_NONE, false, true, false>(f, cv, oc0, valid, e, rr); break;
+    case EPI_GN: epilogue_store32_t<OMGSR_ACT_NONE, false, false, true>(f, cv, oc0, valid, e, rr); break;
+    case EPI_RES_GN: epilogue_store32_t<OMGSR_ACT_NONE, false, true, true>(f, cv, oc0, valid, e, rr); break;
+    case EPI_GELU_TANH: epilogue_store32_t<OMGSR_ACT_GELU_TANH, false, false, false>(f, cv, oc0, valid, e, rr); break;
+    case EPI_GATE_RES: epilogue_store32_t<OMGSR_ACT_NONE, true, true, false>(f, cv, oc0, valid, e, rr); break;
+    case EPI_SILU: epilogue_store32_t<OMGSR_ACT_SILU, false, false, false>(f, cv, oc0, valid, e, rr); break;
+    default: epilogue_store32(f, cv, oc0, valid, e, rr); break;
   }
 }
 

@@ -65,7 +65,8 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    1024 /*fused GroupNorm partial sums: 4 warps x 64 floats*/;
+                                    1024 /*fused GroupNorm partial sums: 4 warps x 64 floats*/ +
+                                    16 * BN /*bias slices: 4 warps x BN floats*/;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -243,11 +244,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // n_tile) and is flushed to HBM (atomics) only when that pair changes: consecutive tiles of a persistent CTA
     // mostly stay within one image, so atomics drop by ~14x versus one flush per tile.
     float* my_gn = gn_acc + quarter * 64;
+    float* my_bias = gn_acc + 256 + quarter * BN;
+    int bias_tile = -1;
+    const int epi_mode = epilogue_mode(p.act, p.gate != nullptr, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
     const int gn_n = p.gn_groups * 2;  // <= 64: the slice holds every group of one image, whatever the n_tile
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(tile, p);
+      if (p.bias && t.n_tile != bias_tile) {
+        stage_bias<BN>(my_bias, p.bias, t.n_tile * BN, p.Cout, lane);
+        bias_tile = t.n_tile;
+      }
       const int x = t.tx * tw + xl, y = t.ty * th + yl, b = t.tbi * tb + bl;
       if (p.gn_sums && t.tbi != gn_b) {
         if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
@@ -277,7 +285,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t v[32];
         float f[32];
         tmem_ld32(t_row + c0, v);
-        if (c0 + 32 < out_bn) load_res32(rn, e, t.n_tile * out_bn + c0 + 32, valid);
+        if (p.res && c0 + 32 < out_bn) load_res32(rn, e, t.n_tile * out_bn + c0 + 32, valid);
         if (geglu) {
           uint32_t g[32];
           float gf[32];
@@ -286,8 +294,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gf[j] = __uint_as_float(g[j]); }
           if (p.bias) {
-            add_bias32(f, p.bias, t.n_tile * BN + c0, p.Cout);            // value columns (row-permuted weight)
-            add_bias32(gf, p.bias, t.n_tile * BN + BN / 2 + c0, p.Cout);  // gate columns
+            add_bias32_s(f, my_bias + c0);            // value columns (row-permuted weight)
+            add_bias32_s(gf, my_bias + BN / 2 + c0);  // gate columns
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_f(gf[j]);
@@ -295,11 +303,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) add_bias32(f, p.bias, t.n_tile * BN + c0, p.Cout);
+          if (p.bias) add_bias32_s(f, my_bias + c0);
         }
-        epilogue_store32(f, t.n_tile * BN + c0, t.n_tile * out_bn + c0, valid, e, rr);
+        epilogue_store32_m(epi_mode, f, t.n_tile * BN + c0, t.n_tile * out_bn + c0, valid, e, rr);
+        if (p.res) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+        }
         if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((t.n_tile * BN + c0) / p.gn_cpg) * 2, lane);
       }
       tc_fence_before();
@@ -332,7 +342,7 @@ struct Cfg2 {
   static constexpr int kBBytes = (BN / 2) * kBK * 2;      // this CTA's half of the BN-row weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 6 : 7;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 1024 + 16 * BN;
 };
 
 template <int BN>
@@ -456,11 +466,18 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     float* my_gn = gn_acc + quarter * 64;
+    float* my_bias = gn_acc + 256 + quarter * BN;
+    int bias_tile = -1;
+    const int epi_mode = epilogue_mode(p.act, p.gate != nullptr, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
     const int gn_n = p.gn_groups * 2;
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
       const int n_tile = pt % p.n_tiles;
+      if (p.bias && n_tile != bias_tile) {
+        stage_bias<BN>(my_bias, p.bias, n_tile * BN, p.Cout, lane);
+        bias_tile = n_tile;
+      }
       const int m = 2 * (pt / p.n_tiles) + static_cast<int>(rank);
       const bool dummy = m >= m_tiles;
       const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, tbi = m / (p.tiles_x * p.tiles_y);
@@ -493,7 +510,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t v[32];
         float f[32];
         tmem_ld32(t_row + c0, v);
-        if (c0 + 32 < out_bn) load_res32(rn, e, n_tile * out_bn + c0 + 32, valid);
+        if (p.res && c0 + 32 < out_bn) load_res32(rn, e, n_tile * out_bn + c0 + 32, valid);
         if (geglu) {
           uint32_t gg[32];
           float gf[32];
@@ -502,8 +519,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gf[j] = __uint_as_float(gg[j]); }
           if (p.bias) {
-            add_bias32(f, p.bias, n_tile * BN + c0, p.Cout);
-            add_bias32(gf, p.bias, n_tile * BN + BN / 2 + c0, p.Cout);
+            add_bias32_s(f, my_bias + c0);
+            add_bias32_s(gf, my_bias + BN / 2 + c0);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_f(gf[j]);
@@ -511,11 +528,13 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) add_bias32(f, p.bias, n_tile * BN + c0, p.Cout);
+          if (p.bias) add_bias32_s(f, my_bias + c0);
         }
-        epilogue_store32(f, n_tile * BN + c0, n_tile * out_bn + c0, valid, e, rr);
+        epilogue_store32_m(epi_mode, f, n_tile * BN + c0, n_tile * out_bn + c0, valid, e, rr);
+        if (p.res) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+        }
         if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((n_tile * BN + c0) / p.gn_cpg) * 2, lane);
       }
       tc_fence_before();

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -p no:cacheprovider > gpurun_out/k_all.log 2>&1
+echo "== kernel tests exit $?" > gpurun_out/summary_k.txt; tail -5 gpurun_out/k_all.log >> gpurun_out/summary_k.txt
+bash scripts/gpu_epi_probe.sh > /dev/null 2>&1
+cp gpurun_out/summary.txt gpurun_out/summary_probe.txt
+TRACE_LINES=45 bash scripts/gpu_res.sh > /dev/null 2>&1
+cat gpurun_out/summary_k.txt gpurun_out/summary_probe.txt gpurun_out/summary.txt
