@@ -220,7 +220,10 @@ def test_conv_residual_silu_concat(capi):
 
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,Hh,M,N,D", [(1, 1, 128, 128, 64), (2, 5, 256, 256, 64), (2, 5, 1024, 77, 64),
-                                         (1, 2, 200, 300, 64), (1, 1, 256, 256, 512), (1, 3, 256, 320, 128)])
+                                         (1, 2, 200, 300, 64), (1, 1, 256, 256, 512), (1, 3, 256, 320, 128),
+                                         # rows of >= 1024 scores: register-resident softmax (2 / 4 / 8 float4 per thread)
+                                         (1, 1, 256, 1024, 512), (1, 1, 128, 1990, 64), (1, 1, 128, 4096, 512),
+                                         (1, 1, 128, 5000, 64)])
 def test_attention_materialised(capi, B, Hh, M, N, D):
     from oracle import ops
     g = _g(B + Hh + M + N + D)
