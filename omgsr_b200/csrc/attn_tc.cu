@@ -269,7 +269,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 //     probabilities are formed against m_stale and O is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when a
 //     row's new maximum exceeds m_stale by more than 8 in the log2 domain (p <= 256, safe in bf16 / fp32). After
 //     the first few blocks this almost never fires, which removes the per-block O read-modify-write of v1.
-//   * TMEM: S_a @0, S_b @128, O_a @256, O_b @384 (512 columns, 1 CTA / SM).
+//   * TMEM: S_a[2] @0/@64, S_b[2] @128/@192 (double-buffered scores), O_a @256, O_b @384 (512 columns, 1 CTA / SM).
 // ================================================================================================================
 template <int D>
 struct Attn2Cfg {
@@ -283,8 +283,17 @@ struct Attn2Cfg {
   static constexpr int kKBytes = kBN * D * 2;
   static constexpr int kStageBytes = 2 * kKBytes;
   static constexpr int kPBytes = 128 * kBN * 2;  // one P buffer of one group
-  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBuf * kPBytes + 1024 + 256;
+  // d = 64: the row sums l = sum_j p_j come out of the PV MMA itself. V is extended by 16 all-ones columns (a constant
+  // 8 KB shared-memory panel reached through the descriptor's leading-dimension offset), so O gets a 65th column that
+  // holds exactly the sum of the bf16 probabilities the MMA consumed, is accumulated / rescaled with O, and costs
+  // the softmax warps no FADD at all. (d = 128 has no TMEM room for 2 x 144 columns next to the double-buffered S.)
+  static constexpr bool kOnesCol = (D == 64);
+  static constexpr int kOnesBytes = kOnesCol ? kBN * 128 : 0;
+  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + 2 * kPBuf * kPBytes + kOnesBytes + 1024 + 256;
 };
+
+// (ex2.approx.ftz.bf16x2 was tried for the exponentials: ptxas lowers it to TWO scalar MUFU.EX2.BF16 ops, one per
+// half, so it saves no MUFU issue slots and adds pack / permute work.)
 
 template <int D>
 __global__ void __launch_bounds__(320, 1)
@@ -297,13 +306,14 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sQ = smem;                                   // [group][panel][128 rows x 128 B]
   uint8_t* sKV = sQ + C::kQBytes;                       // [stage][K | V]
   uint8_t* sP = sKV + C::kStages * C::kStageBytes;      // [group][buf]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PB * C::kPBytes);
+  uint8_t* sOnes = sP + 2 * PB * C::kPBytes;            // [64 keys x 128 B] of bf16 1.0 (d = 64 only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::kOnesBytes);
   uint64_t* q_full = bars;                   // 1
   uint64_t* k_full = q_full + 1;             // [stages]
   uint64_t* v_full = k_full + C::kStages;    // [stages]
   uint64_t* kv_empty = v_full + C::kStages;  // [stages]
-  uint64_t* s_full = kv_empty + C::kStages;  // [2]
-  uint64_t* p_full = s_full + 2;             // [2][PB]
+  uint64_t* s_full = kv_empty + C::kStages;  // [2 groups][2 S buffers]
+  uint64_t* p_full = s_full + 4;             // [2][PB]
   uint64_t* pv_done = p_full + 2 * PB;       // [2][PB]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2 * PB);
 
@@ -318,7 +328,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(q_full, 1);
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1);
+      mbar_init(&s_full[g * 2], 1);
+      mbar_init(&s_full[g * 2 + 1], 1);
       for (int i = 0; i < PB; ++i) { mbar_init(&p_full[g * PB + i], 128); mbar_init(&pv_done[g * PB + i], 1); }
     }
     fence_barrier_init();
@@ -326,6 +337,11 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  if (C::kOnesCol) {
+    for (int i = threadIdx.x; i < C::kOnesBytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -359,23 +375,28 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
-      const uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);
-      auto issue_s = [&](int g, int stage) {
+      const uint32_t idesc_o = umma_idesc_bf16(128, C::kOnesCol ? D + 16 : D, 0, 1);
+      // S_g(j) goes to buffer j & 1 of group g: the scores of block j + 1 are issued BEFORE waiting for the
+      // probabilities of block j, so the tensor pipe computes them while the group is still exponentiating block j
+      // (single S buffer: 403 / 727 TFLOP/s at d = 64 / 128; double-buffered: 448 / 743). Serving the groups in
+      // whatever order their P becomes ready (mbarrier.test_wait polling) was tried and is SLOWER (383 / 647): the
+      // polling thread steals issue slots from the two softmax warps on its scheduler.
+      auto issue_s = [&](int g, int stage, int buf) {
         const uint32_t aQ = smem_u32(sQ + g * (D / 64) * (128 * 128));
         const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
-          tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
+          tc_mma_ss(tmem_base + g * 128 + buf * BN, da, db, idesc_s, kk != 0);
         }
-        tc_commit(&s_full[g]);
+        tc_commit(&s_full[g * 2 + buf]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
+      issue_s(0, 0, 0);
+      issue_s(1, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
@@ -383,6 +404,14 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t nphase = (stage + 1 == C::kStages) ? (phase ^ 1) : phase;
         const int pb = j % PB;
         const uint32_t pph = (j / PB) & 1;
+        if (j + 1 < nblk) {
+          // buffer (j + 1) & 1 was last read by softmax(j - 1), which finished before p_full(j - 1) (waited below,
+          // one iteration ago)
+          mbar_wait(&k_full[nstage], nphase);
+          tc_fence_after();
+          issue_s(0, nstage, (j + 1) & 1);
+          issue_s(1, nstage, (j + 1) & 1);
+        }
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&p_full[g * PB + pb], pph);  // group g consumed S_g(j) and wrote P_g(j)
           if (g == 0) mbar_wait(&v_full[stage], phase);
@@ -392,14 +421,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk) {
             const uint64_t da = umma_desc_sw128(aP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(aV + kk * 2048, BN * 128, 1024);
+            // second 64-wide N atom: the next d panel (d = 128) or the all-ones panel (d = 64)
+            const uint32_t lbo = C::kOnesCol ? smem_u32(sOnes) - aV : BN * 128;
+            const uint64_t db = umma_desc_sw128(aV + kk * 2048, lbo, 1024);
             tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
           }
           tc_commit(&pv_done[g * PB + pb]);
-          if (j + 1 < nblk) {
-            if (g == 0) { mbar_wait(&k_full[nstage], nphase); tc_fence_after(); }
-            issue_s(g, nstage);
-          }
         }
         tc_commit(&kv_empty[stage]);
         stage = nstage;
@@ -414,11 +441,11 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tS = tmem_base + g * 128 + lane_off, tO = tmem_base + 256 + g * 128 + lane_off;
     float m_stale = 0.f, l_run = 0.f;
     for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[g], j & 1);
+      mbar_wait(&s_full[g * 2 + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
       const int n_valid = min(BN, p.N - j * BN);
       uint32_t sv[64];
-      tmem_ld64(tS, sv);
+      tmem_ld64(tS + (j & 1) * BN, sv);
       tmem_wait_ld();
       if (n_valid < BN) {  // ragged last block only: mask the columns that do not exist
 #pragma unroll
@@ -443,7 +470,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_fence_after();
           const float alpha = need ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
 #pragma unroll
-          for (int c0 = 0; c0 < D; c0 += 32) {
+          for (int c0 = 0; c0 < (C::kOnesCol ? D + 32 : D); c0 += 32) {  // + the row-sum column(s) at D
             uint32_t v[32];
             tmem_ld32(tO + c0, v);
             tmem_wait_ld();
@@ -466,8 +493,10 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float pr[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) pr[i] = exp2f(fmaf(__uint_as_float(sv[q * 8 + i]), p.scale_log2, -mb));  // exp2(-inf) = 0
-        ls0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
-        ls1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
+        if (!C::kOnesCol) {
+          ls0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
+          ls1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
+        }
         uint4 u;
         u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
         u.z = pack_bf16x2(pr[4], pr[5]); u.w = pack_bf16x2(pr[6], pr[7]);
@@ -483,6 +512,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&pv_done[g * PB + ((nblk - 1) % PB)], ((nblk - 1) / PB) & 1);
     tc_fence_after();
     const int m = m0 + g * 128 + row;
+    if (C::kOnesCol) {  // l = the ones column of O
+      uint32_t lv[16];
+      tmem_ld16(tO + D, lv);
+      tmem_wait_ld();
+      l_run = __uint_as_float(lv[0]);
+    }
     const float inv = 1.0f / l_run;
     bf16* o = p.out + static_cast<long long>(b) * p.o_batch + static_cast<long long>(m) * p.o_row +
               static_cast<long long>(h) * p.o_head;
