@@ -606,20 +606,31 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
   return check_launch("conv_gemm_tc_kernel");
 }
 
-static int pick_bn(int Cout, long long m_tiles, int forced, bool geglu, bool mn_major) {
+static int pick_bn(int Cout, long long m_tiles, int forced, bool geglu, bool mn_major, bool pair_ok) {
   if (forced > 0) return forced;
   if (mn_major) return (Cout % 128 == 0) ? 128 : 64;
+  // Cost model per candidate width (a divisor of Cout): waves x max(MMA cycles, operand bytes / L2->SM port rate) per
+  // 64-deep k-block. One CTA streams 16 KB of A plus its share of B (the CTA pair splits B) at ~64 B/clk; the MMAs of
+  // a k-block take 2 * bn cycles. Many-wave problems come out at the widest tile (least operand traffic per output
+  // column); skinny ones (UNet 8x8 / 16x16 levels: M = 1024..4096) now get 128/160-wide pair tiles on fewer SMs
+  // instead of 64-wide tiles on all of them, which were L2-port bound (1280->1280 3x3 @8x8: 130 us at BN = 64).
   const int cands[4] = {256, 160, 128, 64};
-  // widest tile that divides Cout and still gives every SM a tile; otherwise the narrowest divisor
-  int narrowest = 0;
+  int best = 0;
+  double best_cost = 0.0;
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     if (Cout % bn) continue;
     if (geglu && (bn % 64)) continue;
-    narrowest = bn;
-    if (m_tiles * (Cout / bn) >= sm_count()) return bn;
+    const bool pair = pair_ok && bn >= 128 && m_tiles >= 2;
+    const long long n_tiles = Cout / bn;
+    const long long ctas = pair ? 2 * ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+    const long long waves = (ctas + sm_count() - 1) / sm_count();
+    const double bytes = 16384.0 + (pair ? 64.0 : 128.0) * bn;
+    const double mma = 2.0 * bn, port = bytes / 64.0;
+    const double cost = static_cast<double>(waves) * (mma > port ? mma : port);
+    if (!best || cost < best_cost) { best = bn; best_cost = cost; }
   }
-  if (narrowest) return narrowest;
+  if (best) return best;
   return 64;  // ragged Cout: 64-wide tiles, last one masked
 }
 
@@ -705,7 +716,7 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   }
 
   const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_b;
-  const int bn = pick_bn(d.Cout, m_tiles, d.force_bn, geglu, d.b_mn_major);
+  const int bn = pick_bn(d.Cout, m_tiles, d.force_bn, geglu, d.b_mn_major, g_use_2cta && !d.b_batched);
   if (bn != 256 && bn != 160 && bn != 128 && bn != 64) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: BN=%d", bn);
   if (geglu && ((bn % 64) || (d.Cout % bn)))
     return set_error(OMGSR_ERR_SHAPE, "conv_gemm: GEGLU needs Cout %% BN == 0 and BN %% 64 == 0");
