@@ -32,6 +32,7 @@ struct HaloParams {
   const float* bias;
   const bf16* res;
   int act, out_f32;
+  int out_vec32, res_vec32;
   float* gn_sums;
   int gn_cpg, gn_groups;
 };
@@ -199,10 +200,10 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       EpiArgs e;
       e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
       e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
-      e.out_f32 = p.out_f32;
+      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32;
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
-      uint4 rr[4] = {}, rn[4] = {};
+      uint4 rr[4] = {};
       if (p.res) {
 #pragma unroll
         for (int t = TM - 1; t >= 0; --t) {
@@ -222,33 +223,10 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
         const bf16* res_this = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
         const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          float f[32];
-          tmem_ld32(t_row + c0, v);
-          if (p.res) {
-            if (c0 + 32 < BN) {
-              e.res_row = res_this;
-              load_res32(rn, e, n_tile * BN + c0 + 32, valid);
-            } else if (t + 1 < TM) {
-              e.res_row = res_this + p.r_sy;
-              load_res32(rn, e, n_tile * BN, (x < p.W) && (y + 1 < p.H));
-            }
-          }
-          e.res_row = res_this;
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          const int cv = n_tile * BN + c0;
-          if (p.bias) add_bias32_s(f, my_bias + c0);
-          epilogue_store32_m(epi_mode, f, cv, cv, valid, e, rr);
-          if (p.res) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rr[q] = rn[q];
-          }
-          if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((cv) / p.gn_cpg) * 2, lane);
-        }
+        e.res_row = res_this;
+        const bf16* next_res = (p.res && t + 1 < TM) ? res_this + p.r_sy : nullptr;
+        epilogue_row_m<false>(epi_mode, t_row, BN, 0, n_tile * BN, n_tile * BN, valid, e, next_res, n_tile * BN,
+                              (x < p.W) && (y + 1 < p.H), p.bias ? my_bias : nullptr, rr, my_gn, p.gn_cpg, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -419,10 +397,10 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       EpiArgs e;
       e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
       e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
-      e.out_f32 = p.out_f32;
+      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32;
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
-      uint4 rr[4] = {}, rn[4] = {};
+      uint4 rr[4] = {};
       const bool use_res = p.res && !dummy;
       if (use_res) {
 #pragma unroll
@@ -443,32 +421,10 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
         const bf16* res_this = use_res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
         const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          float f[32];
-          tmem_ld32(t_row + c0, v);
-          if (use_res) {
-            if (c0 + 32 < BN) {
-              e.res_row = res_this;
-              load_res32(rn, e, c0 + 32, valid);
-            } else if (t + 1 < TM) {
-              e.res_row = res_this + p.r_sy;
-              load_res32(rn, e, 0, (x < p.W) && (y + 1 < p.H));
-            }
-          }
-          e.res_row = res_this;
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) add_bias32_s(f, my_bias + c0);
-          epilogue_store32_m(epi_mode, f, c0, c0, valid, e, rr);
-          if (p.res) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rr[q] = rn[q];
-          }
-          if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + (c0 / p.gn_cpg) * 2, lane);
-        }
+        e.res_row = res_this;
+        const bf16* next_res = (use_res && t + 1 < TM) ? res_this + p.r_sy : nullptr;
+        epilogue_row_m<false>(epi_mode, t_row, BN, 0, 0, 0, valid, e, next_res, 0, (x < p.W) && (y + 1 < p.H),
+                              p.bias ? my_bias : nullptr, rr, my_gn, p.gn_cpg, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -563,6 +519,8 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   }
   p.o_sx = o_sx; p.o_sy = o_sy; p.o_sb = o_sb; p.r_sx = r_sx; p.r_sy = r_sy; p.r_sb = r_sb;
   p.out = y; p.bias = bias; p.res = static_cast<const bf16*>(res); p.act = act; p.out_f32 = out_f32;
+  p.out_vec32 = !out_f32 && (reinterpret_cast<uintptr_t>(y) % 32 == 0) && ((o_sx | o_sy | o_sb) % 16 == 0);
+  p.res_vec32 = res && (reinterpret_cast<uintptr_t>(res) % 32 == 0) && ((r_sx | r_sy | r_sb) % 16 == 0);
   if (static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles > 0x7fffffffLL) return 1;
   CUtensorMap tmA, tmB;
   const uint64_t eb = 2;

@@ -19,6 +19,8 @@ struct EpiArgs {
   int cout_out;           // output channels (Cout, or Cout/2 for GEGLU)
   int act, act_c0, act_c1;
   int out_f32;
+  int vec32;       // bf16 output rows are 32-byte aligned at every 16-channel granule pair: one 256-bit store each
+  int res_vec32;   // same for the residual rows: 256-bit loads
   float* gn_part;  // optional: 16 per-thread partials of this 32-column chunk, (sum, sumsq) per 4 channels, filled
                    // by epilogue_store32 for the fused GroupNorm statistics (see gn_chunk_accumulate)
 };
@@ -68,6 +70,22 @@ __device__ __forceinline__ void stage_bias(float* slice, const float* bias, int 
     if (lane + 32 * i < N) slice[lane + 32 * i] = v[i];
   __syncwarp();
 }
+// Split form for the persistent kernels: the loads of the NEXT tile's bias are issued before the current tile's chunk
+// loop and committed to the slice after it, so their L2 latency never sits on the epilogue's critical path.
+template <int N>
+__device__ __forceinline__ void bias_prefetch(float (&v)[(N + 31) / 32], const float* bias, int c_first, int Cout,
+                                              int lane) {
+#pragma unroll
+  for (int i = 0; i < (N + 31) / 32; ++i) v[i] = __ldg(bias + min(c_first + lane + 32 * i, Cout - 1));
+}
+template <int N>
+__device__ __forceinline__ void bias_commit(float* slice, const float (&v)[(N + 31) / 32], int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < (N + 31) / 32; ++i)
+    if (lane + 32 * i < N) slice[lane + 32 * i] = v[i];
+  __syncwarp();
+}
 __device__ __forceinline__ void add_bias32_s(float (&f)[32], const float* slice) {
   const float4* bp = reinterpret_cast<const float4*>(slice);
 #pragma unroll
@@ -81,11 +99,32 @@ __device__ __forceinline__ void add_bias32_s(float (&f)[32], const float* slice)
 // AHEAD of their use (and before the tcgen05.ld wait): inside epilogue_store32 they sat behind the previous
 // granule's store, which the compiler must assume may alias, so every 16-byte load exposed a full HBM round trip
 // (measured: 128->128 @512^2 conv 2.11 ms with a residual vs 1.31 ms without).
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256). A thread of the epilogue owns one output row, so a 16-byte
+// store covers HALF a 32-byte sector and the other half arrives with a later instruction: every sector reached L2 as
+// two partial writes (measured: K = 64 GEMM, i.e. pure epilogue, 2.4 TB/s of output). 32 bytes per thread writes
+// whole sectors.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p)
+               : "memory");
+}
+
 __device__ __forceinline__ void load_res32(uint4 (&rr)[4], const EpiArgs& e, int oc0, bool valid) {
   if (e.res_row && valid) {
+    if (e.res_vec32 && oc0 + 32 <= e.cout_out) {
+      ld_global_256(e.res_row + oc0, rr[0], rr[1]);
+      ld_global_256(e.res_row + oc0 + 16, rr[2], rr[3]);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (oc0 + q * 8 < e.cout_out) rr[q] = *reinterpret_cast<const uint4*>(e.res_row + oc0 + q * 8);
+      for (int q = 0; q < 4; ++q)
+        if (oc0 + q * 8 < e.cout_out) rr[q] = *reinterpret_cast<const uint4*>(e.res_row + oc0 + q * 8);
+    }
   }
 }
 
@@ -160,34 +199,48 @@ template <int ACT, bool GATE, bool RES, bool GN>
 __device__ __forceinline__ void epilogue_store32_t(float (&f)[32], int cv, int oc0, bool valid, const EpiArgs& e,
                                                    const uint4 (&rr4)[4]) {
   if (ACT != OMGSR_ACT_NONE && cv >= e.act_c0 && cv < e.act_c1) act32<ACT>(f);
+  uint4 o[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int oc = oc0 + q * 8;
-    if (oc >= e.cout_out) break;  // warp-uniform
     float* ff = f + q * 8;
-    if (GATE) {
+    if (GATE && oc < e.cout_out) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.gate_row + oc));
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.gate_row + oc + 4));
       ff[0] *= g0.x; ff[1] *= g0.y; ff[2] *= g0.z; ff[3] *= g0.w;
       ff[4] *= g1.x; ff[5] *= g1.y; ff[6] *= g1.z; ff[7] *= g1.w;
     }
-    if (RES) {  // rows that are not stored may add stale registers: harmless, they are never written
+    if (RES) {  // rows / granules that are not stored may add stale registers: harmless, they are never written
       const uint4 rr = rr4[q];
       const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
                    r3 = unpack_bf16x2(rr.w);
       ff[0] += r0.x; ff[1] += r0.y; ff[2] += r1.x; ff[3] += r1.y;
       ff[4] += r2.x; ff[5] += r2.y; ff[6] += r3.x; ff[7] += r3.y;
     }
-    uint4 o;
-    o.x = pack_bf16x2(ff[0], ff[1]); o.y = pack_bf16x2(ff[2], ff[3]);
-    o.z = pack_bf16x2(ff[4], ff[5]); o.w = pack_bf16x2(ff[6], ff[7]);
-    if (valid) *reinterpret_cast<uint4*>(static_cast<bf16*>(e.out) + e.o_off + oc) = o;
-    if (GN) {
-      const float2 v0 = unpack_bf16x2(o.x), v1 = unpack_bf16x2(o.y), v2 = unpack_bf16x2(o.z), v3 = unpack_bf16x2(o.w);
-      e.gn_part[4 * q + 0] = valid ? (v0.x + v0.y) + (v1.x + v1.y) : 0.f;
-      e.gn_part[4 * q + 1] = valid ? (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) : 0.f;
-      e.gn_part[4 * q + 2] = valid ? (v2.x + v2.y) + (v3.x + v3.y) : 0.f;
-      e.gn_part[4 * q + 3] = valid ? (v2.x * v2.x + v2.y * v2.y) + (v3.x * v3.x + v3.y * v3.y) : 0.f;
+    o[q].x = pack_bf16x2(ff[0], ff[1]); o[q].y = pack_bf16x2(ff[2], ff[3]);
+    o[q].z = pack_bf16x2(ff[4], ff[5]); o[q].w = pack_bf16x2(ff[6], ff[7]);
+  }
+  bf16* orow = static_cast<bf16*>(e.out) + e.o_off + oc0;
+  if (e.vec32 && oc0 + 32 <= e.cout_out) {  // warp-uniform
+    if (valid) {
+      st_global_256(orow, o[0], o[1]);
+      st_global_256(orow + 16, o[2], o[3]);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (valid && oc0 + q * 8 < e.cout_out) *reinterpret_cast<uint4*>(orow + q * 8) = o[q];
+  }
+  if (GN) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool on = valid && oc0 + q * 8 < e.cout_out;
+      const float2 v0 = unpack_bf16x2(o[q].x), v1 = unpack_bf16x2(o[q].y), v2 = unpack_bf16x2(o[q].z),
+                   v3 = unpack_bf16x2(o[q].w);
+      e.gn_part[4 * q + 0] = on ? (v0.x + v0.y) + (v1.x + v1.y) : 0.f;
+      e.gn_part[4 * q + 1] = on ? (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) : 0.f;
+      e.gn_part[4 * q + 2] = on ? (v2.x + v2.y) + (v3.x + v3.y) : 0.f;
+      e.gn_part[4 * q + 3] = on ? (v2.x * v2.x + v2.y * v2.y) + (v3.x * v3.x + v3.y * v3.y) : 0.f;
     }
   }
 }
@@ -276,6 +329,110 @@ __device__ __forceinline__ void gn_flush(float* acc, int n, float* dst, int lane
     acc[i] = 0.f;
   }
   __syncwarp();
+}
+
+
+// ---- one accumulator row segment, specialised per option set ------------------------------------------------
+// n_cols output columns of this thread's row, read from TMEM at t_row in 32-column chunks.
+//   cv0      first accumulator column (absolute; activation range and GroupNorm group index are relative to it)
+//   oc0      first output channel
+//   bias_s   this warp's shared-memory bias slice for columns [cv0, ...), or null
+//   gate_off GEGLU: TMEM column / bias-slice offset of the gate half
+//   rr       residual of the FIRST chunk, loaded by the caller before it waited for the accumulator; on return it
+//            holds the first chunk of next_res (if any), so the residual stream stays one chunk ahead across rows
+// The option set is a template parameter so that the chunk loop contains no dispatch at all: with the switch inside
+// the loop every chunk paid an indirect branch plus ~20 register moves (ncu source view, K = 64 GEMM).
+template <int MODE>
+struct EpiTraits {
+  static constexpr bool kGeneric = MODE == EPI_GENERIC;
+  static constexpr bool kRes = MODE == EPI_RES || MODE == EPI_RES_GN || MODE == EPI_GATE_RES;
+  static constexpr bool kGn = MODE == EPI_GN || MODE == EPI_RES_GN;
+  static constexpr bool kGate = MODE == EPI_GATE_RES;
+  static constexpr int kAct = MODE == EPI_GELU_TANH ? OMGSR_ACT_GELU_TANH : (MODE == EPI_SILU ? OMGSR_ACT_SILU : OMGSR_ACT_NONE);
+};
+
+template <int MODE, bool GEGLU>
+__device__ __forceinline__ void epilogue_row(uint32_t t_row, int n_cols, int gate_off, int cv0, int oc0, bool valid,
+                                             EpiArgs& e, const bf16* next_res, int next_oc0, bool next_valid,
+                                             const float* bias_s, uint4 (&rr)[4], float* gn_slice, int gn_cpg,
+                                             int lane) {
+  using T = EpiTraits<MODE>;
+  const bool has_res = T::kGeneric ? (e.res_row != nullptr) : T::kRes;
+  const bool has_gn = T::kGeneric ? (gn_slice != nullptr && e.gn_part != nullptr) : T::kGn;
+  float gn_part[16];
+  float* const gn_keep = e.gn_part;
+  e.gn_part = has_gn ? gn_part : nullptr;
+  uint4 rn[4] = {};
+#pragma unroll 1
+  for (int c0 = 0; c0 < n_cols; c0 += 32) {
+    uint32_t v[32];
+    float f[32];
+    tmem_ld32(t_row + c0, v);
+    if (has_res) {
+      if (c0 + 32 < n_cols) {
+        load_res32(rn, e, oc0 + c0 + 32, valid);
+      } else if (next_res) {
+        const bf16* keep = e.res_row;
+        e.res_row = next_res;
+        load_res32(rn, e, next_oc0, next_valid);
+        e.res_row = keep;
+      }
+    }
+    if (GEGLU) {
+      uint32_t g[32];
+      float gf[32];
+      tmem_ld32(t_row + gate_off + c0, g);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gf[j] = __uint_as_float(g[j]); }
+      if (bias_s) {
+        add_bias32_s(f, bias_s + c0);              // value columns (row-permuted weight)
+        add_bias32_s(gf, bias_s + gate_off + c0);  // gate columns
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_f(gf[j]);
+    } else {
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (bias_s) add_bias32_s(f, bias_s + c0);
+    }
+    if (T::kGeneric) epilogue_store32(f, cv0 + c0, oc0 + c0, valid, e, rr);
+    else epilogue_store32_t<T::kAct, T::kGate, T::kRes, T::kGn>(f, cv0 + c0, oc0 + c0, valid, e, rr);
+    if (has_res) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rr[q] = rn[q];
+    }
+    if (has_gn) gn_chunk_accumulate(gn_part, gn_cpg, gn_slice + ((cv0 + c0) / gn_cpg) * 2, lane);
+  }
+  e.gn_part = gn_keep;
+}
+
+// run-time option set -> specialised row routine (once per accumulator row, outside the chunk loop)
+template <bool GEGLU>
+__device__ __forceinline__ void epilogue_row_m(int mode, uint32_t t_row, int n_cols, int gate_off, int cv0, int oc0,
+                                               bool valid, EpiArgs& e, const bf16* next_res, int next_oc0,
+                                               bool next_valid, const float* bias_s, uint4 (&rr)[4], float* gn_slice,
+                                               int gn_cpg, int lane) {
+#define OMGSR_EPI_ROW(M)                                                                                              \
+  epilogue_row<M, GEGLU>(t_row, n_cols, gate_off, cv0, oc0, valid, e, next_res, next_oc0, next_valid, bias_s, rr,     \
+                         gn_slice, gn_cpg, lane)
+  if (GEGLU) {  // only the plain and the generic set occur with GEGLU
+    if (mode == EPI_PLAIN) OMGSR_EPI_ROW(EPI_PLAIN);
+    else OMGSR_EPI_ROW(EPI_GENERIC);
+    return;
+  }
+  switch (mode) {
+    case EPI_PLAIN: OMGSR_EPI_ROW(EPI_PLAIN); break;
+    case EPI_RES: OMGSR_EPI_ROW(EPI_RES); break;
+    case EPI_GN: OMGSR_EPI_ROW(EPI_GN); break;
+    case EPI_RES_GN: OMGSR_EPI_ROW(EPI_RES_GN); break;
+    case EPI_GELU_TANH: OMGSR_EPI_ROW(EPI_GELU_TANH); break;
+    case EPI_GATE_RES: OMGSR_EPI_ROW(EPI_GATE_RES); break;
+    case EPI_SILU: OMGSR_EPI_ROW(EPI_SILU); break;
+    default: OMGSR_EPI_ROW(EPI_GENERIC); break;
+  }
+#undef OMGSR_EPI_ROW
 }
 
 }  // namespace omgsr

@@ -48,6 +48,7 @@ struct ConvGemmParams {
   int act_c0, act_c1;  // the activation is applied to output columns in [act_c0, act_c1) only
   int act;             // OMGSR_ACT_*
   int out_f32;
+  int out_vec32, res_vec32;  // output / residual rows allow 256-bit accesses (see epilogue.cuh)
   int a_bytes;         // bytes one A box delivers (tb may be clamped to B)
   float* gn_sums;      // optional fused GroupNorm statistics of the output: [B][groups][2]
   int gn_cpg, gn_groups;
@@ -252,10 +253,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(tile, p);
-      if (p.bias && t.n_tile != bias_tile) {
+      if (p.bias && t.n_tile != bias_tile) {  // first tile only: later ones are prefetched below
         stage_bias<BN>(my_bias, p.bias, t.n_tile * BN, p.Cout, lane);
         bias_tile = t.n_tile;
       }
+      float bias_nx[(BN + 31) / 32];
+      const int next_tile = tile + gridDim.x;
+      const int next_n = next_tile < total_tiles ? next_tile % p.n_tiles : bias_tile;
+      if (p.bias && next_n != bias_tile) bias_prefetch<BN>(bias_nx, p.bias, next_n * BN, p.Cout, lane);
       const int x = t.tx * tw + xl, y = t.ty * th + yl, b = t.tbi * tb + bl;
       if (p.gn_sums && t.tbi != gn_b) {
         if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
@@ -270,52 +275,31 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : b) : 0;
       e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
       e.Cout = p.Cout; e.cout_out = cout_out; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
-      e.out_f32 = p.out_f32;
+      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32;
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
 
-      uint4 rr[4] = {}, rn[4] = {};
+      uint4 rr[4] = {};
       prefetch_res_row(e, t.n_tile * out_bn, out_bn, valid);
       load_res32(rr, e, t.n_tile * out_bn, valid);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < out_bn; c0 += 32) {
-        uint32_t v[32];
-        float f[32];
-        tmem_ld32(t_row + c0, v);
-        if (p.res && c0 + 32 < out_bn) load_res32(rn, e, t.n_tile * out_bn + c0 + 32, valid);
-        if (geglu) {
-          uint32_t g[32];
-          float gf[32];
-          tmem_ld32(t_row + BN / 2 + c0, g);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gf[j] = __uint_as_float(g[j]); }
-          if (p.bias) {
-            add_bias32_s(f, my_bias + c0);            // value columns (row-permuted weight)
-            add_bias32_s(gf, my_bias + BN / 2 + c0);  // gate columns
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_f(gf[j]);
-        } else {
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) add_bias32_s(f, my_bias + c0);
-        }
-        epilogue_store32_m(epi_mode, f, t.n_tile * BN + c0, t.n_tile * out_bn + c0, valid, e, rr);
-        if (p.res) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
-        }
-        if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((t.n_tile * BN + c0) / p.gn_cpg) * 2, lane);
-      }
+      const float* bias_s = p.bias ? my_bias : nullptr;
+      if (geglu)
+        epilogue_row_m<true>(epi_mode, t_row, out_bn, BN / 2, t.n_tile * BN, t.n_tile * out_bn, valid, e, nullptr, 0,
+                             false, bias_s, rr, my_gn, p.gn_cpg, lane);
+      else
+        epilogue_row_m<false>(epi_mode, t_row, out_bn, 0, t.n_tile * BN, t.n_tile * out_bn, valid, e, nullptr, 0,
+                              false, bias_s, rr, my_gn, p.gn_cpg, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.bias && next_n != bias_tile) {
+        bias_commit<BN>(my_bias, bias_nx, lane);
+        bias_tile = next_n;
+      }
     }
     if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
   }
@@ -474,10 +458,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
       const int n_tile = pt % p.n_tiles;
-      if (p.bias && n_tile != bias_tile) {
+      if (p.bias && n_tile != bias_tile) {  // first tile only: later ones are prefetched below
         stage_bias<BN>(my_bias, p.bias, n_tile * BN, p.Cout, lane);
         bias_tile = n_tile;
       }
+      float bias_nx[(BN + 31) / 32];
+      const int next_pt = pt + num_clusters;
+      const int next_n = next_pt < total_pairs ? next_pt % p.n_tiles : bias_tile;
+      if (p.bias && next_n != bias_tile) bias_prefetch<BN>(bias_nx, p.bias, next_n * BN, p.Cout, lane);
       const int m = 2 * (pt / p.n_tiles) + static_cast<int>(rank);
       const bool dummy = m >= m_tiles;
       const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, tbi = m / (p.tiles_x * p.tiles_y);
@@ -495,48 +483,23 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : min(b, p.B - 1)) : 0;
       e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
       e.Cout = p.Cout; e.cout_out = geglu ? p.Cout / 2 : p.Cout; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
-      e.out_f32 = p.out_f32;
+      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32;
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
 
-      uint4 rr[4] = {}, rn[4] = {};
+      uint4 rr[4] = {};
       prefetch_res_row(e, n_tile * out_bn, out_bn, valid);
       load_res32(rr, e, n_tile * out_bn, valid);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < out_bn; c0 += 32) {
-        uint32_t v[32];
-        float f[32];
-        tmem_ld32(t_row + c0, v);
-        if (p.res && c0 + 32 < out_bn) load_res32(rn, e, n_tile * out_bn + c0 + 32, valid);
-        if (geglu) {
-          uint32_t gg[32];
-          float gf[32];
-          tmem_ld32(t_row + BN / 2 + c0, gg);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gf[j] = __uint_as_float(gg[j]); }
-          if (p.bias) {
-            add_bias32_s(f, my_bias + c0);
-            add_bias32_s(gf, my_bias + BN / 2 + c0);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_f(gf[j]);
-        } else {
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) add_bias32_s(f, my_bias + c0);
-        }
-        epilogue_store32_m(epi_mode, f, n_tile * BN + c0, n_tile * out_bn + c0, valid, e, rr);
-        if (p.res) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rr[q] = rn[q];
-        }
-        if (p.gn_sums) gn_chunk_accumulate(gn_part, p.gn_cpg, my_gn + ((n_tile * BN + c0) / p.gn_cpg) * 2, lane);
-      }
+      const float* bias_s = p.bias ? my_bias : nullptr;
+      if (geglu)
+        epilogue_row_m<true>(epi_mode, t_row, out_bn, BN / 2, n_tile * BN, n_tile * out_bn, valid, e, nullptr, 0,
+                             false, bias_s, rr, my_gn, p.gn_cpg, lane);
+      else
+        epilogue_row_m<false>(epi_mode, t_row, out_bn, 0, n_tile * BN, n_tile * out_bn, valid, e, nullptr, 0,
+                              false, bias_s, rr, my_gn, p.gn_cpg, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -544,6 +507,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         else mbar_arrive_remote(&acc_empty[acc], 0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.bias && next_n != bias_tile) {
+        bias_commit<BN>(my_bias, bias_nx, lane);
+        bias_tile = next_n;
+      }
     }
     if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
   }
@@ -702,6 +669,8 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   p.o_sx = d.o_sx; p.o_sy = d.o_sy; p.o_sb = d.o_sb; p.r_sx = d.r_sx; p.r_sy = d.r_sy; p.r_sb = d.r_sb;
   p.out = d.y; p.bias = d.bias; p.res = static_cast<const bf16*>(d.res);
   p.gate = d.gate; p.gate_rows = d.gate_rows; p.act = d.act; p.out_f32 = d.out_f32;
+  p.out_vec32 = !d.out_f32 && (reinterpret_cast<uintptr_t>(d.y) % 32 == 0) && ((d.o_sx | d.o_sy | d.o_sb) % 16 == 0);
+  p.res_vec32 = d.res && (reinterpret_cast<uintptr_t>(d.res) % 32 == 0) && ((d.r_sx | d.r_sy | d.r_sb) % 16 == 0);
   p.gate_ld = d.gate_ld > 0 ? d.gate_ld : (geglu ? d.Cout / 2 : d.Cout);
   p.act_c0 = d.act_c1 > d.act_c0 ? d.act_c0 : 0; p.act_c1 = d.act_c1 > d.act_c0 ? d.act_c1 : 0x7fffffff;
   p.a_bytes = kBK * 2 * tw * th * tb_box;

@@ -8,7 +8,7 @@ res = len(sys.argv) > 4 and sys.argv[4] == "1"
 act = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
 w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) / math.sqrt(K)
-bias = torch.zeros(N, device="cuda")
+bias = None if (len(sys.argv) > 6 and sys.argv[6] == "nobias") else torch.zeros(N, device="cuda")
 No = N // 2 if act == capi.ACT_GEGLU else N
 out = torch.empty(M, No, device="cuda", dtype=torch.bfloat16)
 r = torch.randn(M, No, device="cuda", dtype=torch.bfloat16) if res else None
