@@ -351,7 +351,8 @@ def run_ours(args):
 
 def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
     """the launch class that dominates the step: the VAE's 128->128 3x3 conv at 512x512 (12 launches per step,
-    1.24 TFLOP each at batch 16), dispatched to conv_halo_tc_kernel<128,2>. Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W."""
+    1.24 TFLOP each at batch 16), dispatched to conv_halo_tc2_kernel<2> (CTA-pair input-halo kernel).
+    Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W."""
     from omgsr_b200.pack import pack_conv_weight
     C, H = 128, 512
     x = torch.randn(B, H, H, C, device=dev, dtype=torch.bfloat16)
@@ -371,11 +372,11 @@ def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * C * C * 9 * B * H * H
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_halo_tc_kernel<128,2> (3x3, 128->128 ch, 512x512, batch %d)" % B,
+    return {"bound": "tensor", "kernel": "conv_halo_tc2_kernel<2> (3x3, 128->128 ch, 512x512, batch %d)" % B,
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this very launch from one `ncu --set full` capture
-            # (profiles/r01/ncu_halo128.txt: 1.0746 + 1.0223 GB; algorithmic input + output = 2 x 1.0737 GB)
-            "traffic": 2.0969e9 if (B, C, H) == (16, 128, 512) else None, "traffic_unit": "bytes/launch",
+            # (profiles/r01/ncu_halo_pair128.txt: 1.0743 + 1.0346 GB; algorithmic input + output = 2 x 1.0737 GB)
+            "traffic": 2.1089e9 if (B, C, H) == (16, 128, 512) else None, "traffic_unit": "bytes/launch",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
 
 

@@ -351,7 +351,8 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               const uint32_t b_addr = smem_u32(sB + bs * C::kBBytes);
 #pragma unroll
               for (int t = 0; t < TM; ++t) {
-                const uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
+                uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
+                if (p.debug & 8) a_addr = a_base + static_cast<uint32_t>((((t + r) * p.pw + s) & ~7) * 128);  // timing only
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (p.debug & 4) continue;
