@@ -223,6 +223,27 @@ int omgsr_nchw_to_nhwc(const void* x, int x_f32, void* y, int B, int C, int H, i
 int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f32, int B, int C, int H, int W, int clamp,
                        void* stream);
 
+/* ---- driver-side image pre/post-processing --------------------------------
+ * The reference prepares its input on the CPU with PIL (infer/infer_omgsr_s.py:76-90):
+ *   img.resize((w*upscale, h*upscale))  [Pillow default filter = BICUBIC]; img.resize((w - w%8, h - h%8), LANCZOS);
+ *   to_tensor(img).to(weight_dtype) * 2 - 1
+ * and converts the result back with clip(x*0.5+0.5, 0, 1).float() -> ToPILImage (:96-98). These entries restate
+ * that chain for 8-bit RGB on the device, bit-exactly (Pillow's resampler is fixed-point integer arithmetic). */
+#define OMGSR_RESIZE_BICUBIC 0
+#define OMGSR_RESIZE_LANCZOS 1
+/* HOST-only helper: Pillow's per-axis tables (precompute_coeffs + normalize_coeffs_8bpc). bounds: [out_size][2] =
+ * (first tap, tap count); coeffs: [out_size][ksize] 22-bit fixed point. bounds == NULL: only *ksize is returned. */
+int omgsr_resample_coeffs(int in_size, int out_size, int filter, int* bounds, int* coeffs, int max_ksize, int* ksize);
+/* device bytes omgsr_resize_u8 needs (horizontal-pass intermediate + the four tables) */
+long long omgsr_resize_u8_workspace(int src_h, int src_w, int dst_h, int dst_w, int filter);
+/* src: [src_h, src_w, 3] u8 (device, dense) -> dst: [dst_h, dst_w, 3] u8; == PIL.Image.resize(..., filter) for RGB */
+int omgsr_resize_u8(const void* src, int src_h, int src_w, void* dst, int dst_h, int dst_w, int filter,
+                    void* workspace, long long workspace_bytes, void* stream);
+/* [H, W, 3] u8 -> [1, 3, H, W] bf16 (or fp32): to_tensor(img).to(dtype) * 2 - 1 with the reference's rounding order */
+int omgsr_u8_to_input(const void* hwc_u8, void* nchw, int out_f32, int H, int W, void* stream);
+/* [3, H, W] bf16|fp32 in [-1, 1] -> [H, W, 3] u8: clip(x*0.5+0.5, 0, 1).float().mul(255).byte() (truncating) */
+int omgsr_output_to_u8(const void* nchw, int in_f32, void* hwc_u8, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,27 @@ def preprocess(img, process_size, upscale):
     return img.resize((nw, nh), Image.LANCZOS), resize_flag, (ow, oh)
 
 
+def preprocess_gpu(img, process_size, upscale, device, dtype):
+    """the same chain as `preprocess` + `pil_to_model_input`, on the device: the decoded image is uploaded once as
+    uint8 and resampled by kernels that reproduce Pillow's fixed-point resampler bit for bit (omgsr_resize_u8).
+    -> (lq_u8 [H, W, 3] uint8 CUDA tensor on the output grid, model input [1, 3, H, W], resize_flag, original size)"""
+    from omgsr_b200 import capi
+    ow, oh = img.size
+    x = torch.from_numpy(np.asarray(img.convert("RGB"), dtype=np.uint8).copy()).to(device)
+    resize_flag = False
+    w, h = ow, oh
+    if ow < process_size // upscale or oh < process_size // upscale:
+        s = (process_size // upscale) / min(ow, oh)
+        w, h = int(s * ow), int(s * oh)
+        x = capi.resize_u8(x, (h, w), capi.RESIZE_BICUBIC)
+        resize_flag = True
+    w, h = w * upscale, h * upscale
+    x = capi.resize_u8(x, (h, w), capi.RESIZE_BICUBIC)
+    nw, nh = w - w % 8, h - h % 8
+    x = capi.resize_u8(x, (nh, nw), capi.RESIZE_LANCZOS)
+    return x, capi.u8_to_input(x, dtype), resize_flag, (ow, oh)
+
+
 def pil_to_model_input(img, device, dtype):
     arr = np.asarray(img.convert("RGB"), dtype=np.uint8)
     x = torch.from_numpy(arr.copy()).to(device).permute(2, 0, 1).unsqueeze(0)
@@ -52,6 +73,8 @@ def finish(output, lq_pil, align_method, resize_flag, orig_size, upscale, save_p
     """de-normalise, clip, colour-align against the LQ image and save. The colour fix runs on the GPU
     (infer/wavelet_color_fix.py) with the reference's uint8 truncation semantics."""
     from .wavelet_color_fix import _cuda_to_pil, adain_color_fix, wavelet_color_fix
+    if torch.is_tensor(lq_pil):  # GPU pre-processing path: the LQ image is a uint8 [H, W, 3] device tensor
+        lq_pil = Image.fromarray(lq_pil.cpu().numpy(), mode="RGB")
     out = torch.clip(output * 0.5 + 0.5, 0, 1).float()
     pil = _cuda_to_pil(out[:1].clone())
     if align_method == "adain":
@@ -60,6 +83,26 @@ def finish(output, lq_pil, align_method, resize_flag, orig_size, upscale, save_p
         pil = wavelet_color_fix(target=pil, source=lq_pil)
     if resize_flag:
         pil = pil.resize((int(upscale * orig_size[0]), int(upscale * orig_size[1])))
+    if save_path:
+        pil.save(save_path)
+    return pil
+
+
+def finish_gpu(output, lq_u8, align_method, resize_flag, orig_size, upscale, save_path):
+    """`finish` without the host round trips: the model output is quantised to uint8 on the device with the
+    reference's truncation (omgsr_output_to_u8), colour-aligned against the uint8 LQ tensor from `preprocess_gpu`
+    (same values as to_tensor of the PIL images the reference feeds its colour fix), and crosses PCIe once as uint8."""
+    from omgsr_b200 import capi
+    from .wavelet_color_fix import adaptive_instance_normalization, wavelet_reconstruction
+    out_u8 = capi.output_to_u8(output[:1].contiguous())
+    if align_method in ("adain", "wavelet"):
+        tgt = out_u8.permute(2, 0, 1).float().div_(255.0).unsqueeze(0).contiguous()
+        src = lq_u8.permute(2, 0, 1).float().div_(255.0).unsqueeze(0).contiguous()
+        fixed = adaptive_instance_normalization(tgt, src) if align_method == "adain" else wavelet_reconstruction(tgt, src)
+        out_u8 = fixed.squeeze(0).clamp_(0.0, 1.0).mul(255).byte().permute(1, 2, 0).contiguous()
+    if resize_flag:
+        out_u8 = capi.resize_u8(out_u8, (int(upscale * orig_size[1]), int(upscale * orig_size[0])), capi.RESIZE_BICUBIC)
+    pil = Image.fromarray(out_u8.cpu().numpy(), mode="RGB")
     if save_path:
         pil.save(save_path)
     return pil

@@ -49,15 +49,19 @@ def main(args):
     print(f"There are {len(items)} images.")
     total_time = 0
     for bname, img in items:
-        lq, resize_flag, orig = dc.preprocess(img, args.process_size, args.upscale)
+        if args.host_preprocess:
+            lq, resize_flag, orig = dc.preprocess(img, args.process_size, args.upscale)
+            lq_img = dc.pil_to_model_input(lq, args.device, args.weight_dtype)
+        else:  # same chain on the device, bit-identical to PIL (omgsr_resize_u8)
+            lq, lq_img, resize_flag, orig = dc.preprocess_gpu(img, args.process_size, args.upscale, args.device,
+                                                             args.weight_dtype)
         tile_size = args.process_size // 8
         tile_overlap = tile_size // 2
         with torch.no_grad():
-            lq_img = dc.pil_to_model_input(lq, args.device, args.weight_dtype)
             output_image, t = net_sr(lq_img, prompt_embeds, tile_size, tile_overlap)
             total_time += t
-        dc.finish(output_image, lq, args.align_method, resize_flag, orig, args.upscale,
-                  os.path.join(args.output_dir, bname))
+        (dc.finish if args.host_preprocess else dc.finish_gpu)(output_image, lq, args.align_method, resize_flag, orig,
+                                                               args.upscale, os.path.join(args.output_dir, bname))
     print(f"Average inference time: {total_time / max(len(items), 1)}s")
 
 
@@ -74,6 +78,8 @@ if __name__ == "__main__":
     ap.add_argument("--weight_dtype", type=str, default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--prompt", type=str, nargs="+", default="")
     ap.add_argument("--mid_timestep", type=int, default=273)
+    ap.add_argument("--host_preprocess", action="store_true",
+                    help="resize / colour-align through PIL on the host like the reference (default: on the GPU)")
     ap.add_argument("--synthetic", type=int, default=0, help="run on N seeded synthetic LQ images")
     ap.add_argument("--prompt_embeds", type=str, default="", help="precomputed [1,77,D] prompt embeddings (.pt)")
     a = ap.parse_args()

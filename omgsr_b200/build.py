@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libomgsr_b200.so")
-SOURCES = ["capi.cu", "gemm_conv_tc.cu", "conv_halo_tc.cu", "attn_tc.cu", "glue.cu", "colorfix.cu"]
+SOURCES = ["capi.cu", "gemm_conv_tc.cu", "conv_halo_tc.cu", "attn_tc.cu", "glue.cu", "colorfix.cu", "resize.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",

@@ -25,6 +25,7 @@ SYMBOLS = [
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
     "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta",
+    "omgsr_resample_coeffs", "omgsr_resize_u8_workspace", "omgsr_resize_u8", "omgsr_u8_to_input", "omgsr_output_to_u8",
 ]
 
 
@@ -36,6 +37,7 @@ def _load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.omgsr_last_error.restype = ctypes.c_char_p
     lib.omgsr_launch_count.restype = ctypes.c_longlong
+    lib.omgsr_resize_u8_workspace.restype = ctypes.c_longlong
     return lib
 
 
@@ -507,3 +509,61 @@ def attention_materialised(q, k, v, scale):
     s = bgemm_qk(q, k)
     p = softmax_rows(s, n, scale)
     return bgemm_pv(p, v)
+
+
+# ------------------------------------------------------------------------------------------------
+# driver-side image pre/post-processing (bit-exact with PIL for 8-bit RGB)
+# ------------------------------------------------------------------------------------------------
+RESIZE_BICUBIC, RESIZE_LANCZOS = 0, 1
+
+
+def resample_coeffs(in_size, out_size, flt):
+    """host-only: Pillow's (bounds [out,2], coeffs [out,ksize]) tables as numpy int32 arrays."""
+    import numpy as np
+    k = ctypes.c_int(0)
+    _check(_lib.omgsr_resample_coeffs(_i(in_size), _i(out_size), _i(flt), None, None, _i(0), ctypes.byref(k)),
+           "omgsr_resample_coeffs")
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    coeffs = np.zeros((out_size, k.value), dtype=np.int32)
+    _check(_lib.omgsr_resample_coeffs(_i(in_size), _i(out_size), _i(flt), bounds.ctypes.data_as(ctypes.c_void_p),
+                                      coeffs.ctypes.data_as(ctypes.c_void_p), _i(k.value), ctypes.byref(k)),
+           "omgsr_resample_coeffs")
+    return bounds, coeffs
+
+
+def resize_u8(img, size_hw, flt=RESIZE_BICUBIC):
+    """img: uint8 [H, W, 3] CUDA tensor -> uint8 [h, w, 3]; equals PIL.Image.resize((w, h), filter) bit for bit."""
+    assert img.is_cuda and img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()
+    H, W = img.shape[:2]
+    h, w = size_hw
+    if (h, w) == (H, W):
+        return img.clone()  # PIL returns a copy when the size does not change
+    nbytes = int(_lib.omgsr_resize_u8_workspace(_i(H), _i(W), _i(h), _i(w), _i(flt)))
+    ws = torch.empty(nbytes, device=img.device, dtype=torch.uint8)
+    out = torch.empty((h, w, 3), device=img.device, dtype=torch.uint8)
+    _check(_lib.omgsr_resize_u8(_ptr(img), _i(H), _i(W), _ptr(out), _i(h), _i(w), _i(flt), _ptr(ws), _ll(nbytes),
+                                _stream()), "omgsr_resize_u8")
+    return out
+
+
+def u8_to_input(img, dtype=torch.bfloat16):
+    """uint8 [H, W, 3] -> [1, 3, H, W] in [-1, 1]: to_tensor(img).to(dtype) * 2 - 1."""
+    assert img.is_cuda and img.dtype == torch.uint8 and img.is_contiguous() and dtype in (torch.bfloat16, torch.float32)
+    H, W = img.shape[:2]
+    out = torch.empty((1, 3, H, W), device=img.device, dtype=dtype)
+    _check(_lib.omgsr_u8_to_input(_ptr(img), _ptr(out), _i(dtype == torch.float32), _i(H), _i(W), _stream()),
+           "omgsr_u8_to_input")
+    return out
+
+
+def output_to_u8(x):
+    """[3, H, W] (or [1, 3, H, W]) bf16|fp32 model output -> uint8 [H, W, 3] (clip(x*0.5+0.5,0,1)*255, truncated)."""
+    if x.dim() == 4:
+        assert x.shape[0] == 1
+        x = x[0]
+    assert x.is_cuda and x.is_contiguous() and x.shape[0] == 3 and x.dtype in (torch.bfloat16, torch.float32)
+    H, W = x.shape[1:]
+    out = torch.empty((H, W, 3), device=x.device, dtype=torch.uint8)
+    _check(_lib.omgsr_output_to_u8(_ptr(x), _i(x.dtype == torch.float32), _ptr(out), _i(H), _i(W), _stream()),
+           "omgsr_output_to_u8")
+    return out
