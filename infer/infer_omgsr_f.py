@@ -53,6 +53,13 @@ def main(args):
     os.makedirs(args.output_dir, exist_ok=True)
     print(f"There are {len(items)} images.")
     total_time = 0
+    if args.batch_size > 1 and not args.host_preprocess:
+        ts, to = args.process_size // 8, args.process_size // 16
+        total_time, n = dc.run_batched(
+            items, lambda x: omgsr(x, prompt_embeds, pooled, text_ids, latent_image_ids, ts, to), args, args.device,
+            args.weight_dtype)
+        print(f"Average inference time: {total_time / max(n, 1)}s")
+        return
     for bname, img in items:
         if args.host_preprocess:
             lq, resize_flag, orig = dc.preprocess(img, args.process_size, args.upscale)
@@ -84,6 +91,7 @@ if __name__ == "__main__":
     ap.add_argument("--prompt", type=str, default="")
     ap.add_argument("--mid_timestep", type=int, default=244)
     ap.add_argument("--guidance_scale", type=float, default=1.0)
+    ap.add_argument("--batch_size", type=int, default=1, help="stack up to N same-size images per forward")
     ap.add_argument("--host_preprocess", action="store_true",
                     help="resize / colour-align through PIL on the host like the reference (default: on the GPU)")
     ap.add_argument("--synthetic", type=int, default=0)

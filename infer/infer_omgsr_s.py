@@ -48,6 +48,12 @@ def main(args):
     os.makedirs(args.output_dir, exist_ok=True)
     print(f"There are {len(items)} images.")
     total_time = 0
+    if args.batch_size > 1 and not args.host_preprocess:
+        ts, to = args.process_size // 8, args.process_size // 16
+        total_time, n = dc.run_batched(items, lambda x: net_sr(x, prompt_embeds, ts, to), args, args.device,
+                                       args.weight_dtype)
+        print(f"Average inference time: {total_time / max(n, 1)}s")
+        return
     for bname, img in items:
         if args.host_preprocess:
             lq, resize_flag, orig = dc.preprocess(img, args.process_size, args.upscale)
@@ -78,6 +84,7 @@ if __name__ == "__main__":
     ap.add_argument("--weight_dtype", type=str, default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--prompt", type=str, nargs="+", default="")
     ap.add_argument("--mid_timestep", type=int, default=273)
+    ap.add_argument("--batch_size", type=int, default=1, help="stack up to N same-size images per forward")
     ap.add_argument("--host_preprocess", action="store_true",
                     help="resize / colour-align through PIL on the host like the reference (default: on the GPU)")
     ap.add_argument("--synthetic", type=int, default=0, help="run on N seeded synthetic LQ images")

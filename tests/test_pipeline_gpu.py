@@ -329,6 +329,16 @@ def test_driver_script_end_to_end(tmp_path):
     im = Image.open(out / files[0])
     assert im.size == (128, 128)
     assert "Average inference time" in r.stdout
+    # batched loop (3 same-size images, batches of 2 + 1) and the host (PIL) pre/post-processing path
+    for extra, sub in ((["--batch_size", "2", "--synthetic", "3"], "b2"), (["--host_preprocess", "--synthetic", "1"], "host")):
+        out2 = tmp_path / sub
+        r = subprocess.run([sys.executable, os.path.join(root, "infer", "infer_omgsr_s.py"), "--sd_path",
+                            "random://tiny?seed=0", "--lora_path", "random://lora?seed=1", "--output_dir", str(out2),
+                            "--process_size", "128", "--align_method", "adain"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert len(os.listdir(out2)) == int(extra[-1])
+        assert Image.open(out2 / "synthetic_000.png").size == (128, 128)
 
 
 def test_s_cuda_graph_replay_matches_eager():
