@@ -172,6 +172,7 @@ __global__ void gn_combine_kernel(const float* __restrict__ sums, const float* _
   const int b = i / G, g = i % G;
   float wsum = 0.f, m = 0.f, v = 0.f;
   for (int e = b; e < entries; e += n_img) {
+    if (!(pixels[e] > 0.f)) continue;  // zero-weight entry (a shadow rank's duplicate tile): contributes nothing
     const float n = pixels[e] * cpg;
     const float mean = sums[(static_cast<long long>(e) * G + g) * 2] / n;
     const float var = fmaxf(sums[(static_cast<long long>(e) * G + g) * 2 + 1] / n - mean * mean, 0.f);

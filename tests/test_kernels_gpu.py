@@ -541,3 +541,23 @@ def test_geglu_two_cta(capi, two_cta):
     wi, bi = pack_geglu_weight(w, b, 256)
     out = capi.gemm(a.cuda().bfloat16(), wi.cuda().bfloat16(), bi.cuda(), act=capi.ACT_GEGLU, force_bn=256)
     assert report(f"geglu [{two_cta}]", out, ops.geglu(a, w, b))[0]
+
+
+def test_groupnorm_combine_zero_weight_entries(capi):
+    """tile-parallel shadow ranks contribute duplicate tiles with weight 0 (pixels = 0): they must drop out of the
+    combine instead of producing 0/0 (found at 8 GPUs: 4 decoder tiles, 4 shadow ranks -> NaN image)."""
+    g = _g(77)
+    n_img, G, C = 2, 32, 128
+    x = [bf16r(torch.randn(n_img, 12, 10 + 3 * i, C, generator=g)).cuda().bfloat16() for i in range(3)]
+    sums = torch.cat([capi.groupnorm_stats(t, G) for t in x], 0)
+    pix = torch.cat([torch.full((n_img,), float(t.shape[1] * t.shape[2]), device="cuda") for t in x], 0)
+    ref = capi.groupnorm_combine(sums[:2 * n_img].contiguous(), pix[:2 * n_img].contiguous(), n_img, C)
+    pix0 = pix.clone()
+    pix0[2 * n_img:] = 0.0  # third tile group: weight 0
+    got = capi.groupnorm_combine(sums, pix0, n_img, C)
+    assert torch.isfinite(got).all() and torch.equal(got, ref)
+    num, wsum = capi.groupnorm_combine(sums, pix0, n_img, C, raw=True)
+    assert torch.isfinite(num).all() and torch.equal(wsum, pix[:n_img] + pix[n_img:2 * n_img])
+    zero = torch.zeros_like(pix)  # a rank that holds ONLY shadows: all-zero numerators, not NaN
+    num, wsum = capi.groupnorm_combine(sums, zero, n_img, C, raw=True)
+    assert float(num.abs().max()) == 0.0 and float(wsum.abs().max()) == 0.0

@@ -78,7 +78,8 @@ def _worker(rank, world, port, q):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_tile_parallel_matches_single_gpu():
-    world = min(torch.cuda.device_count(), 4)
+    # up to 8 ranks: the tiny decoder has only 4 tiles, so ranks 4..7 run zero-weight shadow tiles
+    world = min(torch.cuda.device_count(), 8)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
