@@ -119,7 +119,7 @@ int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, cons
  * w: fp32 [ksize*ksize*Cin, Cout]. (VAE encoder.conv_in, decoder.conv_in, unet.conv_in) */
 int omgsr_conv_in_nchw(const void* x, int x_f32, const float* w, const float* bias, void* y, int B, int Cin, int H,
                        int W, int Cout, int ksize, long long ldy, void* stream);
-/* im2col of a thin NCHW input for a 3x3/p1 conv: y[b*H*W + pixel, k] (bf16, row length Kpad, Kpad % 64 == 0) with
+/* im2col of a thin NCHW input for a 3x3/p1 conv: y[b*H*W + pixel, k] (bf16, row length Kpad, Kpad % 8 == 0) with
  * k = (r*3+s)*Cin + ci and zero fill for k >= 9*Cin; the conv is then omgsr_gemm_bf16 on y with weights packed
  * [Cout, Kpad] (large images: the 27-tap conv_in of the VAE encoder runs on the tensor cores this way). */
 int omgsr_im2col3x3_nchw(const void* x, int x_f32, void* y, int B, int Cin, int H, int W, int Kpad, void* stream);

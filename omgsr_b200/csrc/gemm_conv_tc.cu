@@ -625,7 +625,12 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
                   long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, cudaStream_t st);
 
 static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
-  if (d.Cin % kBK) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: K/Cin=%d must be a multiple of %d", d.Cin, kBK);
+  // K need not fill the last 64-deep k-block of a plain GEMM (R = S = 1, K-major B): the tensor maps carry the true
+  // K as their inner extent and TMA zero-fills the rest of the box for BOTH operands (used by the K = 32 im2col form
+  // of the 3-channel conv_in). With taps, a partial block would run into the next tap's weights.
+  const bool ragged_k = (d.Cin % kBK) != 0;
+  if (ragged_k && (d.R * d.S != 1 || d.b_mn_major || d.stride2 || (d.Cin % 8)))
+    return set_error(OMGSR_ERR_SHAPE, "conv_gemm: K/Cin=%d must be a multiple of %d (or of 8 for a plain GEMM)", d.Cin, kBK);
   if ((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.w) | reinterpret_cast<uintptr_t>(d.y) |
        reinterpret_cast<uintptr_t>(d.res)) & 15)
     return set_error(OMGSR_ERR_ALIGN, "conv_gemm: pointers must be 16-byte aligned");
@@ -663,7 +668,7 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   p.log_tw = ilog2(tw); p.log_th = ilog2(th);
   p.tiles_x = (d.W + tw - 1) / tw; p.tiles_y = (d.H + th - 1) / th; p.tiles_b = (d.B + tb - 1) / tb;
   p.W = d.W; p.H = d.H; p.B = d.B;
-  p.Cout = d.Cout; p.kc_per_tap = d.Cin / kBK; p.R = d.R; p.S = d.S; p.pad_t = d.pad_t; p.pad_l = d.pad_l;
+  p.Cout = d.Cout; p.kc_per_tap = (d.Cin + kBK - 1) / kBK; p.R = d.R; p.S = d.S; p.pad_t = d.pad_t; p.pad_l = d.pad_l;
   p.stride2 = d.stride2; p.pair_off = static_cast<int>(d.x_sx);
   p.b_batched = d.b_batched; p.b_mn_major = d.b_mn_major;
   p.o_sx = d.o_sx; p.o_sy = d.o_sy; p.o_sb = d.o_sb; p.r_sx = d.r_sx; p.r_sy = d.r_sy; p.r_sb = d.r_sb;

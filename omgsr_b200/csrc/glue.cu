@@ -413,7 +413,7 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const float* __restric
 }
 
 // im2col for the thin-input 3x3 convs (Cin <= 16): NCHW (bf16|f32) -> patch rows [B*H*W, Kpad] bf16 with
-// k = (r*3 + s)*Cin + ci, zero padded to Kpad (multiple of 64) so the tensor-core GEMM can consume them.
+// k = (r*3 + s)*Cin + ci, zero padded to Kpad (multiple of 8; the GEMM zero-fills its k-blocks beyond Kpad).
 // One thread writes one 16-byte chunk (8 k values) of one pixel.
 template <typename TIn>
 __global__ void im2col3x3_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, int Cin, int H, int W, int Kpad,
@@ -785,7 +785,7 @@ extern "C" int omgsr_conv_in_nchw(const void* x, int x_f32, const float* w, cons
 
 extern "C" int omgsr_im2col3x3_nchw(const void* x, int x_f32, void* y, int B, int Cin, int H, int W, int Kpad,
                                     void* stream) {
-  if (Cin <= 0 || Cin > 16 || Kpad % 64 || Kpad < 9 * Cin) return set_error(OMGSR_ERR_SHAPE, "im2col3x3: Cin=%d Kpad=%d", Cin, Kpad);
+  if (Cin <= 0 || Cin > 16 || Kpad % 8 || Kpad < 9 * Cin) return set_error(OMGSR_ERR_SHAPE, "im2col3x3: Cin=%d Kpad=%d", Cin, Kpad);
   const long long total = static_cast<long long>(B) * H * W * (Kpad / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_f32)

@@ -76,12 +76,13 @@ def pad8(v):
 
 
 def pack_conv_in_gemm_weight(w, dtype=torch.bfloat16):
-    """OIHW [Cout, Cin, 3, 3] -> [Cout, Kpad] with k = (r*3+s)*Cin + ci, zero padded to a multiple of 64
-    (B operand of the im2col + GEMM form of a thin-input conv)."""
+    """OIHW [Cout, Cin, 3, 3] -> [Cout, Kpad] with k = (r*3+s)*Cin + ci, zero padded to a multiple of 32
+    (B operand of the im2col + GEMM form of a thin-input conv; the GEMM's TMA boxes zero-fill up to the next 64, so
+    a 3-channel conv_in streams 32 instead of 64 patch columns per pixel)."""
     co, ci, r, s = w.shape
     assert r == 3 and s == 3
     k = 9 * ci
-    kpad = (k + 63) // 64 * 64
+    kpad = (k + 31) // 32 * 32
     out = torch.zeros(co, kpad, dtype=torch.float32)
     out[:, :k] = w.permute(0, 2, 3, 1).reshape(co, k).float()
     return out.contiguous().to(dtype)

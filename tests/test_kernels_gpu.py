@@ -493,7 +493,9 @@ def two_cta(capi, request):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 256), (384, 512, 192), (4096, 1280, 1280), (1000, 256, 320),
-                                   (700, 320, 320), (515, 640, 128), (300, 128, 256)])
+                                   (700, 320, 320), (515, 640, 128), (300, 128, 256),
+                                   # K not a multiple of the 64-deep k-block: TMA zero-fills both operands
+                                   (300, 128, 32), (515, 256, 160), (256, 320, 40)])
 def test_gemm_two_cta(capi, two_cta, M, N, K):
     from oracle import ops
     g = _g(M + N + K + 2)
