@@ -42,9 +42,11 @@ struct HaloCfg {
   static constexpr int kABytes = (((TM + 2) * 130 * 128) + 1023) / 1024 * 1024;
   static constexpr int kAStages = 2;
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBStages = (BN == 128) ? 5 : 2;
+  static constexpr int kBStages = (BN == 128) ? 5 : (BN <= 32 ? 8 : 2);
   static constexpr int kAccSets = (BN * TM * 2 <= 512) ? 2 : 1;
-  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024 /*GN partial sums*/ + 16 * BN /*bias slices*/;
+  static constexpr int kBiasSlice = BN < 32 ? 32 : BN;  // floats per epilogue warp (a chunk reads 32)
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024 /*GN partial sums*/ +
+                                    16 * kBiasSlice /*bias slices*/;
 };
 
 __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, int mode) {
@@ -175,7 +177,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int set = 0;
     uint32_t sph = 0;
     float* my_gn = gn_acc + quarter * 64;  // see gemm_conv_tc.cu: per-warp partial sums, flushed when the image changes
-    float* my_bias = gn_acc + 256 + quarter * BN;
+    float* my_bias = gn_acc + 256 + quarter * C::kBiasSlice;
     int bias_tile = -1;
     const int epi_mode = epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
     const int gn_n = p.gn_groups * 2;  // <= 64: the slice holds every group of one image, whatever the n_tile
@@ -533,10 +535,13 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   if (rc) return rc;
   uint64_t wd[4] = {static_cast<uint64_t>(w_ld), static_cast<uint64_t>(Cout), 1, 1};
   uint64_t ws[3] = {w_ld * eb, w_ld * eb * Cout, w_ld * eb * Cout};
-  const bool pair = g_halo_2cta && p.n_tiles == 1 && static_cast<long long>(p.tiles_x) * p.tiles_y * p.B >= 2;
-  uint32_t wb[4] = {64, static_cast<uint32_t>(pair ? 64 : bn), 1, 1};
+  // thin Cout (decoder conv_out 128 -> 3): N = 16 MMAs, bound by the 4 KB A read per MMA (32 instead of 64 cycles)
+  const bool thin = Cout <= 16;
+  const bool pair = !thin && g_halo_2cta && p.n_tiles == 1 && static_cast<long long>(p.tiles_x) * p.tiles_y * p.B >= 2;
+  uint32_t wb[4] = {64, static_cast<uint32_t>(thin ? 16 : (pair ? 64 : bn)), 1, 1};
   rc = make_tmap_bf16(&tmB, w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
+  if (thin) return launch_halo<16, TM>(tmA, tmB, p, st);
   if (pair) return launch_halo2<TM>(tmA, tmB, p, st);
   return launch_halo<128, TM>(tmA, tmB, p, st);
 }
