@@ -49,22 +49,10 @@ struct HaloCfg {
                                     16 * kBiasSlice /*bias slices*/;
 };
 
-__device__ __forceinline__ uint64_t halo_desc(uint32_t addr, int mode) {
-  // The 128B swizzle is a function of the absolute shared-memory address bits [4:6] ^ [7:9], so an operand view that
-  // starts at any 128-byte row of a 1024-byte aligned, TMA-written tile needs NO base-offset correction
-  // (verified on B200: setting the base-offset field to (addr >> 7) & 7 gives wrong results).
-  (void)mode;
-  return umma_desc_sw128(addr, 16, 1024);
-}
-
-__device__ __forceinline__ float halo_act(float v, int act) {
-  switch (act) {
-    case OMGSR_ACT_SILU: return silu_f(v);
-    case OMGSR_ACT_GELU_ERF: return gelu_erf_f(v);
-    case OMGSR_ACT_GELU_TANH: return gelu_tanh_f(v);
-    default: return v;
-  }
-}
+// NOTE on the shifted operand views: the 128B swizzle is a function of the absolute shared-memory address bits
+// [4:6] ^ [7:9], so an operand view that starts at any 128-byte row of a 1024-byte aligned, TMA-written tile needs NO
+// base-offset correction in its descriptor (verified on B200: setting the base-offset field to (addr >> 7) & 7 gives
+// wrong results), and aligning the views to whole 8-row swizzle atoms does not change the MMA rate either.
 
 template <int BN, int TM>
 __global__ void __launch_bounds__(192, 1)
@@ -353,8 +341,7 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               const uint32_t b_addr = smem_u32(sB + bs * C::kBBytes);
 #pragma unroll
               for (int t = 0; t < TM; ++t) {
-                uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
-                if (p.debug & 8) a_addr = a_base + static_cast<uint32_t>((((t + r) * p.pw + s) & ~7) * 128);  // timing only
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (p.debug & 4) continue;

@@ -70,15 +70,6 @@ struct Cfg {
                                     16 * BN /*bias slices: 4 warps x BN floats*/;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case OMGSR_ACT_SILU: return silu_f(v);
-    case OMGSR_ACT_GELU_ERF: return gelu_erf_f(v);
-    case OMGSR_ACT_GELU_TANH: return gelu_tanh_f(v);
-    default: return v;
-  }
-}
-
 struct TileCoord {
   int n_tile, tx, ty, tbi;
 };
