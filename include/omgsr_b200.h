@@ -112,6 +112,15 @@ int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, cons
                            int W, int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b,
                            int pad_r, int upsample2x, int act, long long ldx, long long ldy, long long ldr,
                            float* gn_sums, int gn_groups, int flags, int force_bn, void* stream);
+/* GroupNorm + SiLU of the INPUT fused into a 3x3 / stride 1 / pad 1 convolution: y = conv(silu(a[b,c] * x + s[b,c])) with
+ * gn_in_coef [B, Cin] float2 from omgsr_groupnorm_coef (the diffusers ResnetBlock2D pattern norm -> SiLU -> conv,
+ * infer/vaehook.py:384-413 custom_group_norm + F.silu before each conv task). The normalised tensor is never written:
+ * the transform runs on the operand tile in shared memory. Only on the CTA-pair input-halo path: W >= 96,
+ * Cin % 64 == 0, 16 < Cout <= 128, at least two 2x128-pixel tiles; anything else returns OMGSR_ERR_SHAPE (the caller
+ * then uses omgsr_groupnorm_apply + omgsr_conv2d_nhwc_bf16). Other arguments as omgsr_conv2d_nhwc_bf16. */
+int omgsr_conv2d_gn_nhwc_bf16(const void* x, const float* gn_in_coef, const void* w, const float* bias, const void* res,
+                              void* y, int B, int H, int W, int Cin, int Cout, long long ldx, long long ldy,
+                              long long ldr, float* gn_sums, int gn_groups, void* stream);
 
 /* ---- thin convolutions (CUDA cores; too few channels for the tensor pipe) --------------------- */
 
@@ -138,6 +147,10 @@ int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats, int B, lon
  * stats_mode 0: stats[B,G,2] = (sum, sumsq) from omgsr_groupnorm_stats on this tensor.
  * stats_mode 1: stats[stats_mod,G,2] = (mean, var) from omgsr_groupnorm_combine, row = batch index % stats_mod.
  * coef_scratch: caller-provided B*C float2 (8*B*C bytes) for the per-(image, channel) affine coefficients. */
+/* only the coefficient stage of omgsr_groupnorm_apply: coef[B, C] float2 = (rstd * gamma, beta - mean * rstd * gamma),
+ * for a consumer that applies the normalisation itself (omgsr_conv2d_gn_nhwc_bf16). Same stats_mode convention. */
+int omgsr_groupnorm_coef(const float* stats, const float* gamma, const float* beta, void* coef, int B, long long HW,
+                         int C, int G, float eps, int stats_mode, int stats_mod, void* stream);
 int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,
                           const float* gamma, const float* beta, void* coef_scratch, int B, long long HW, int C,
                           int G, float eps, int silu, int stats_mode, int stats_mod, void* stream);

@@ -25,6 +25,7 @@ SYMBOLS = [
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
     "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta",
+    "omgsr_groupnorm_coef", "omgsr_conv2d_gn_nhwc_bf16",
     "omgsr_resample_coeffs", "omgsr_resize_u8_workspace", "omgsr_resize_u8", "omgsr_u8_to_input", "omgsr_output_to_u8",
 ]
 
@@ -268,6 +269,46 @@ def groupnorm(x, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, stats=N
     """x: [B, ..., C] NHWC bf16 (channel stride = x.stride(-2)). Two launches: stats, apply(+SiLU)."""
     stats = groupnorm_stats(x, groups, stats)
     return groupnorm_apply(x, stats, gamma, beta, groups, eps, silu, out)
+
+
+def groupnorm_coef(stats, gamma, beta, B, HW, groups=32, eps=1e-6, shared_mod=0):
+    """per-(image, channel) affine coefficients (rstd*gamma, beta - mean*rstd*gamma): fp32 [B, C, 2]."""
+    _cuda_f32(stats, "stats"); _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta")
+    C = gamma.numel()
+    coef = torch.empty((B, C, 2), device=stats.device, dtype=torch.float32)
+    rc = _lib.omgsr_groupnorm_coef(_ptr(stats), _ptr(gamma), _ptr(beta), _ptr(coef), _i(B), _ll(HW), _i(C), _i(groups),
+                                   _f(eps), _i(1 if shared_mod else 0), _i(max(shared_mod, 1)), _stream())
+    _check(rc, "omgsr_groupnorm_coef")
+    return coef
+
+
+def conv_gn_in_fusable(B, H, W, Cin, Cout):
+    """can omgsr_conv2d_gn_nhwc_bf16 serve this 3x3/s1/p1 conv (CTA-pair input-halo path)?"""
+    tiles = ((W + 127) // 128) * ((H + 1) // 2) * B
+    return W >= 96 and Cin % 64 == 0 and 16 < Cout <= 128 and tiles >= 2 and not os.environ.get("OMGSR_NO_GN_IN_FUSION")
+
+
+def conv2d_gn(x, coef, w, bias, res=None, out=None, gn_stats=None, gn_groups=32):
+    """conv3x3(silu(groupnorm(x))) with the normalisation applied to the operand tile inside the kernel.
+    x NHWC bf16 view (raw, un-normalised), coef fp32 [B, Cin, 2] from groupnorm_coef."""
+    _cuda_bf16(x, "x"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias"); _cuda_f32(coef, "coef")
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
+    assert coef.is_contiguous() and coef.shape == (B, Cin, 2)
+    if out is None:
+        out = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16)
+    assert out.stride(3) == 1 and out.stride(1) == W * out.stride(2) and out.stride(0) == H * out.stride(1)
+    ldr = 0
+    if res is not None:
+        _cuda_bf16(res, "res")
+        assert res.shape == out.shape and res.stride(3) == 1 and res.stride(1) == W * res.stride(2)
+        ldr = res.stride(2)
+    rc = _lib.omgsr_conv2d_gn_nhwc_bf16(_ptr(x), _ptr(coef), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), _i(B), _i(H),
+                                        _i(W), _i(Cin), _i(Cout), _ll(x.stride(2)), _ll(out.stride(2)), _ll(ldr),
+                                        _ptr(gn_stats), _i(gn_groups), _stream())
+    _check(rc, "omgsr_conv2d_gn_nhwc_bf16")
+    return out
 
 
 def groupnorm_combine(sums, pixels, n_img, C, groups=32, raw=False):

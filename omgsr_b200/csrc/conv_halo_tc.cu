@@ -35,6 +35,8 @@ struct HaloParams {
   int out_vec32, res_vec32;
   float* gn_sums;
   int gn_cpg, gn_groups;
+  const float2* gn_in;        // optional [B][Cin] (scale, shift): GroupNorm + SiLU applied to the INPUT (pair kernel)
+  int IH, IW;                 // input extents (validity of halo pixels for the input transform)
 };
 
 template <int BN, int TM>
@@ -250,8 +252,14 @@ struct Halo2Cfg {
   static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 256 + 1024 + 16 * 128;
 };
 
-template <int TM>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+// XF = true adds four TRANSFORM warps (320 threads): the input of the convolution is the raw output of the previous
+// layer and its GroupNorm + SiLU is applied to the halo tile in shared memory, between the TMA load and the MMAs
+// (y = silu(a[b,c] * x + s[b,c]) with the per-(image, channel) coefficients of gn_coef_kernel; halo pixels outside
+// the image stay zero = the conv's zero padding). This removes the separate normalise pass: 2 x 1 GB of HBM traffic
+// per 128-channel layer at 512^2 x 16. Each CTA's halo load then signals its OWN barrier; the transform warps
+// publish the tile through the leader's a_ready barrier (cluster-scope release / acquire).
+template <int TM, bool XF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XF ? 320 : 192, 1)
 conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const HaloParams p) {
   using C = Halo2Cfg<TM>;
@@ -267,7 +275,8 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* b_empty = b_full + C::kBStages;     // per CTA
   uint64_t* acc_full = b_empty + C::kBStages;   // per CTA
   uint64_t* acc_empty = acc_full + 2;           // leader's: 8 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* a_ready = acc_empty + 2;            // XF: leader's [stage][half], 8 arrivals (4 transform warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2 * C::kAStages);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,7 +284,12 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < C::kAStages; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::kAStages; ++i) {
+      mbar_init(&a_full[i], XF ? 1 : 2);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_ready[2 * i], 8);
+      mbar_init(&a_ready[2 * i + 1], 8);
+    }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&b_full[i], 2); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_barrier_init();
@@ -306,9 +320,14 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int b = dummy ? p.B : m / p.tiles_y;
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&a_empty[as], aph ^ 1);
-          if (rank == 0) mbar_expect_tx(&a_full[as], 2 * p.a_bytes);
-          else mbar_arrive_remote(&a_full[as], 0);
-          tma2_load_5d(sA + as * C::kABytes, &tmA, &a_full[as], c * 64, tx * 128 - p.pad_l, ty * TM - p.pad_t, b, 0);
+          if (XF) {  // own barrier: this CTA's transform warps consume the tile first
+            mbar_expect_tx(&a_full[as], p.a_bytes);
+            tma_load_5d(sA + as * C::kABytes, &tmA, &a_full[as], c * 64, tx * 128 - p.pad_l, ty * TM - p.pad_t, b, 0);
+          } else {
+            if (rank == 0) mbar_expect_tx(&a_full[as], 2 * p.a_bytes);
+            else mbar_arrive_remote(&a_full[as], 0);
+            tma2_load_5d(sA + as * C::kABytes, &tmA, &a_full[as], c * 64, tx * 128 - p.pad_l, ty * TM - p.pad_t, b, 0);
+          }
           if (++as == C::kAStages) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < taps; ++tap) {
             mbar_wait(&b_empty[bs], bph ^ 1);
@@ -330,11 +349,15 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tc_fence_after();
         const uint32_t acc0 = tmem_base + set * (TM * BN);
         for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait(&a_full[as], aph);
+          // XF: the transform publishes the halo tile in two halves (first TM rows, then the rest): the r = 0 taps only
+          // read rows [0, TM) and start while the lower rows are still being normalised
+          if (XF) mbar_wait_cluster(&a_ready[2 * as], aph);
+          else mbar_wait(&a_full[as], aph);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + as * C::kABytes);
           int tap = 0;
           for (int r = 0; r < p.R; ++r) {
+            if (XF && r == 1) { mbar_wait_cluster(&a_ready[2 * as + 1], aph); tc_fence_after(); }
             for (int s = 0; s < p.S; ++s, ++tap) {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
@@ -360,7 +383,86 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (++set == 2) { set = 0; sph ^= 1; }
       }
     }
-  } else {
+  } else if (XF && warp >= 6) {
+    // ================= input transform (warps 6..9): GroupNorm + SiLU on the halo tile, in place =================
+    const int tid = threadIdx.x - 192;  // 0..127
+    const int j = tid & 7;              // 16-byte unit (8 channels) of a 128-byte pixel row: fixed per thread
+    const int p0 = tid >> 3;            // first halo pixel of this thread; then every 16th
+    const int n_pix = (TM + p.R - 1) * p.pw;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      int m = 2 * pt + static_cast<int>(rank);
+      const bool dummy = m >= halo_tiles;
+      const int tx = m % p.tiles_x; m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int b = dummy ? 0 : m / p.tiles_y;
+      const int x0 = tx * 128 - p.pad_l, y0 = ty * TM - p.pad_t;
+      for (int c = 0; c < p.chunks; ++c) {
+        float ca[8], cb[8];
+        if (!dummy) {
+          const float4* cf = reinterpret_cast<const float4*>(p.gn_in + static_cast<long long>(b) * p.Cin + c * 64 + j * 8);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(cf + q);
+            ca[2 * q] = v.x; cb[2 * q] = v.y; ca[2 * q + 1] = v.z; cb[2 * q + 1] = v.w;
+          }
+        }
+        mbar_wait(&a_full[as], aph);
+        bool half_sent = false;
+        if (!dummy) {
+          uint8_t* tile = sA + as * C::kABytes;
+          // four independent pixels per iteration (loads, math and stores of the four interleave): one transform
+          // warp per scheduler has nothing else to hide the LDS / MUFU latencies behind
+          int hx = p0, hy = 0;
+          const int half_pix = TM * p.pw;  // rows [0, TM): everything the r = 0 taps read
+          for (int pix = p0; pix < n_pix; pix += 64) {
+            if (!half_sent && pix - p0 >= half_pix) {  // warp-uniform: every lane's remaining pixels are >= half_pix
+              half_sent = true;
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(&a_ready[2 * as], 0);
+            }
+            uint4* u[4];
+            uint4 v[4];
+            bool on[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int pi = pix + 16 * i;
+              const int xx = x0 + hx, yy = y0 + hy;
+              // outside the image: TMA wrote zeros = the conv padding, which must stay zero
+              on[i] = pi < n_pix && xx >= 0 && xx < p.IW && yy >= 0 && yy < p.IH;
+              u[i] = reinterpret_cast<uint4*>(tile + pi * 128 + ((j ^ (pi & 7)) << 4));
+              if (on[i]) v[i] = *u[i];
+              hx += 16;
+              if (hx >= p.pw) { hx -= p.pw; ++hy; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float f[8];
+              const float2 f0 = unpack_bf16x2(v[i].x), f1 = unpack_bf16x2(v[i].y), f2 = unpack_bf16x2(v[i].z),
+                           f3 = unpack_bf16x2(v[i].w);
+              f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] = silu_f(fmaf(f[q], ca[q], cb[q]));
+              v[i].x = pack_bf16x2(f[0], f[1]); v[i].y = pack_bf16x2(f[2], f[3]);
+              v[i].z = pack_bf16x2(f[4], f[5]); v[i].w = pack_bf16x2(f[6], f[7]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (on[i]) *u[i] = v[i];
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          if (!half_sent) mbar_arrive_cluster(&a_ready[2 * as], 0);  // dummy tile / loop too short to split
+          mbar_arrive_cluster(&a_ready[2 * as + 1], 0);
+        }
+        if (++as == C::kAStages) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     int set = 0;
@@ -437,12 +539,12 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 int g_halo_2cta = 1;
 
-template <int TM>
+template <int TM, bool XF>
 static int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
   using C = Halo2Cfg<TM>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_tc2_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_tc2_kernel<TM, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess)
       return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_halo2<%d>): %s", TM, cudaGetErrorString(e));
@@ -452,8 +554,8 @@ static int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ha
   const long long pairs = (halo_tiles + 1) / 2;
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
-  g_trace_variant = "halo_pair128";
-  conv_halo_tc2_kernel<TM><<<2 * clusters, 192, C::kSmemBytes, st>>>(tmA, tmB, p);
+  g_trace_variant = XF ? "halo_pair128_gn" : "halo_pair128";
+  conv_halo_tc2_kernel<TM, XF><<<2 * clusters, XF ? 320 : 192, C::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_halo_tc2_kernel");
 }
 
@@ -479,7 +581,8 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
 int try_conv_halo(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int IH, int IW,
                   int OH, int OW, int Cin, int Cout, int R, int S, int pad_t, int pad_l, long long x_sx, long long x_sy,
                   long long x_sb, long long o_sx, long long o_sy, long long o_sb, long long r_sx, long long r_sy,
-                  long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, cudaStream_t st) {
+                  long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, const float* gn_in,
+                  cudaStream_t st) {
   if (R * S < 4 || R > 3 || S > 3) return 1;
   if (OW < 96) return 1;                        // a 128-pixel row tile would be mostly padding
   // Cout = 128, or a thin Cout < 128 served by one 128-wide tile whose missing weight rows TMA zero-fills and whose
@@ -502,6 +605,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   p.a_bytes = 128 * p.pw * (TM + R - 1);
   { static const int dbg = getenv("OMGSR_HALO_DEBUG") ? atoi(getenv("OMGSR_HALO_DEBUG")) : 0; p.debug = dbg; }
   p.gn_sums = nullptr; p.gn_cpg = 0; p.gn_groups = 0;
+  p.gn_in = reinterpret_cast<const float2*>(gn_in); p.IH = IH; p.IW = IW;
   if (gn_sums) {
     const int cpg = gn_groups > 0 ? Cout / gn_groups : 0;
     if (out_f32 || gn_groups <= 0 || gn_groups > 32 || Cout % gn_groups || !(cpg == 4 || cpg == 8 || cpg == 16)) return 1;
@@ -529,7 +633,11 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   rc = make_tmap_bf16(&tmB, w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (thin) return launch_halo<16, TM>(tmA, tmB, p, st);
-  if (pair) return launch_halo2<TM>(tmA, tmB, p, st);
+  if (gn_in) {
+    if (!pair) return set_error(OMGSR_ERR_SHAPE, "conv_halo: the fused input GroupNorm needs the CTA-pair halo kernel (16 < Cout <= 128, >= 2 tiles)");
+    return launch_halo2<TM, true>(tmA, tmB, p, st);
+  }
+  if (pair) return launch_halo2<TM, false>(tmA, tmB, p, st);
   return launch_halo<128, TM>(tmA, tmB, p, st);
 }
 

@@ -602,6 +602,7 @@ struct ConvDesc {
   int act, gate_rows, force_bn, out_f32;
   long long gate_ld; int act_c0, act_c1;
   float* gn_sums; int gn_groups;
+  const float* gn_in;  // optional [B][Cin][2] input GroupNorm coefficients (+SiLU), halo pair kernel only
   long long w_ld;  // elements per weight row (R*S*Cin)
   // batched B operand (attention)
   int b_batched, b_mn_major, flat;
@@ -613,7 +614,8 @@ struct ConvDesc {
 int try_conv_halo(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int IH, int IW,
                   int OH, int OW, int Cin, int Cout, int R, int S, int pad_t, int pad_l, long long x_sx, long long x_sy,
                   long long x_sb, long long o_sx, long long o_sy, long long o_sb, long long r_sx, long long r_sy,
-                  long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, cudaStream_t st);
+                  long long r_sb, long long w_ld, int act, int out_f32, float* gn_sums, int gn_groups, const float* gn_in,
+                  cudaStream_t st);
 
 static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   // K need not fill the last 64-deep k-block of a plain GEMM (R = S = 1, K-major B): the tensor maps carry the true
@@ -632,9 +634,12 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
     // wide stride-1 3x3 / 2x2 layers: input-halo kernel (conv_halo_tc.cu); returns 1 when not eligible
     const int rc = try_conv_halo(d.x, d.w, d.bias, d.res, d.y, d.B, d.IH, d.IW, d.H, d.W, d.Cin, d.Cout, d.R, d.S,
                                  d.pad_t, d.pad_l, d.x_sx, d.x_sy, d.x_sb, d.o_sx, d.o_sy, d.o_sb, d.r_sx, d.r_sy,
-                                 d.r_sb, d.w_ld, d.act, d.out_f32, d.gn_sums, d.gn_groups, st);
+                                 d.r_sb, d.w_ld, d.act, d.out_f32, d.gn_sums, d.gn_groups, d.gn_in, st);
     if (rc != 1) return rc;
   }
+  if (d.gn_in)
+    return set_error(OMGSR_ERR_SHAPE, "conv2d: the fused input GroupNorm is only available on the input-halo path "
+                                      "(3x3 stride 1, W >= 96, Cin %% 64 == 0, 16 < Cout <= 128)");
 
   // tile shape {tw, th, tb} (powers of two, product 128): minimise the padded pixel count, prefer wide rows
   int tw = 128, th = 1, tb = 1;
@@ -842,11 +847,33 @@ extern "C" int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batc
   return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
 }
 
+static int conv2d_impl(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H, int W,
+                       int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b, int pad_r,
+                       int upsample2x, int act, long long ldx, long long ldy, long long ldr, float* gn_sums,
+                       int gn_groups, const float* gn_in, int flags, int force_bn, void* stream);
+
 extern "C" int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* res, void* y,
                                       int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad_t,
                                       int pad_l, int pad_b, int pad_r, int upsample2x, int act, long long ldx,
                                       long long ldy, long long ldr, float* gn_sums, int gn_groups, int flags,
                                       int force_bn, void* stream) {
+  return conv2d_impl(x, w, bias, res, y, B, H, W, Cin, Cout, ksize, stride, pad_t, pad_l, pad_b, pad_r, upsample2x, act,
+                     ldx, ldy, ldr, gn_sums, gn_groups, nullptr, flags, force_bn, stream);
+}
+
+extern "C" int omgsr_conv2d_gn_nhwc_bf16(const void* x, const float* gn_in_coef, const void* w, const float* bias,
+                                         const void* res, void* y, int B, int H, int W, int Cin, int Cout,
+                                         long long ldx, long long ldy, long long ldr, float* gn_sums, int gn_groups,
+                                         void* stream) {
+  if (!gn_in_coef) return set_error(OMGSR_ERR_SHAPE, "conv2d_gn: gn_in_coef is required");
+  return conv2d_impl(x, w, bias, res, y, B, H, W, Cin, Cout, 3, 1, 1, 1, 1, 1, 0, OMGSR_ACT_NONE, ldx, ldy, ldr, gn_sums,
+                     gn_groups, gn_in_coef, 0, 0, stream);
+}
+
+static int conv2d_impl(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H, int W,
+                       int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b, int pad_r,
+                       int upsample2x, int act, long long ldx, long long ldy, long long ldr, float* gn_sums,
+                       int gn_groups, const float* gn_in, int flags, int force_bn, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: empty problem");
   if (ksize != 1 && ksize != 3) return set_error(OMGSR_ERR_SHAPE, "conv2d: ksize must be 1 or 3");
   if (stride != 1 && stride != 2) return set_error(OMGSR_ERR_SHAPE, "conv2d: stride must be 1 or 2");
@@ -857,7 +884,7 @@ extern "C" int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float*
   d.x_sx = ldx; d.x_sy = ldx * W; d.x_sb = ldx * W * H;
   d.act = act; d.force_bn = force_bn; d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
   d.halo_mode = (flags & OMGSR_CONV_NO_HALO) ? 0 : 1;
-  d.gn_sums = gn_sums; d.gn_groups = gn_groups;
+  d.gn_sums = gn_sums; d.gn_groups = gn_groups; d.gn_in = gn_in;
   if (gn_sums) {
     if (gn_groups <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: gn_groups must be > 0 with gn_sums");
     cudaError_t e = cudaMemsetAsync(gn_sums, 0, sizeof(float) * 2 * gn_groups * B, st);

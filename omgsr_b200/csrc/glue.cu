@@ -694,6 +694,16 @@ extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long
   return check_launch("gn_apply_kernel");
 }
 
+extern "C" int omgsr_groupnorm_coef(const float* stats, const float* gamma, const float* beta, void* coef, int B,
+                                   long long HW, int C, int G, float eps, int stats_mode, int stats_mod, void* stream) {
+  if (C % 8 || C % G) return set_error(OMGSR_ERR_SHAPE, "groupnorm_coef: C=%d G=%d", C, G);
+  if (stats_mode && stats_mod <= 0) return set_error(OMGSR_ERR_SHAPE, "groupnorm_coef: stats_mod must be > 0");
+  if (!coef || (reinterpret_cast<uintptr_t>(coef) & 15)) return set_error(OMGSR_ERR_ALIGN, "groupnorm_coef: coef must be 16-byte aligned");
+  gn_coef_kernel<<<(B * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, gamma, beta, static_cast<float2*>(coef), B, HW, C, G, eps, stats_mode, stats_mod);
+  return check_launch("gn_coef_kernel");
+}
+
 extern "C" int omgsr_groupnorm_combine(const float* sums, const float* pixels, int entries, int n_img, int C, int G,
                                        float* out, float* wsum_out, void* stream) {
   if (entries <= 0 || n_img <= 0 || entries % n_img || C % G)

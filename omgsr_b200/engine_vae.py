@@ -56,9 +56,33 @@ def _stats_buf(x_like_B, device):
     return torch.empty((x_like_B, 32, 2), device=device, dtype=torch.float32)
 
 
+class GnDeferred:
+    """a GroupNorm + SiLU that has NOT been applied: the raw tensor plus the per-(image, channel) coefficients. The
+    consuming 3x3 conv normalises its operand tiles in shared memory (capi.conv2d_gn), so the normalised tensor never
+    exists in HBM."""
+    __slots__ = ("x", "coef")
+
+    def __init__(self, x, coef):
+        self.x, self.coef = x, coef
+
+
+def _deferrable(x, silu, fuse_cout):
+    """may the GroupNorm of NHWC view `x` be left to a following plain 3x3 conv with `fuse_cout` output channels?"""
+    if not (silu and fuse_cout):
+        return False
+    B, H, W, C = x.shape
+    dense = x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
+    return dense and capi.conv_gn_in_fusable(B, H, W, C, fuse_cout)
+
+
 def conv_with_stats(x, w, bias, want_stats, **kw):
     """conv2d that also returns the GroupNorm (sum, sumsq) statistics of its output when the shape allows the fused
-    epilogue path (None otherwise: the consumer then runs the separate statistics kernel)."""
+    epilogue path (None otherwise: the consumer then runs the separate statistics kernel). `x` may be a GnDeferred."""
+    if isinstance(x, GnDeferred):
+        assert not (kw.get("upsample2x") or kw.get("stride", 1) != 1)
+        B, H, W, _ = x.x.shape
+        st = _stats_buf(B, x.x.device) if want_stats and capi.gn_fusable(B, H, W, w.shape[0]) else None
+        return capi.conv2d_gn(x.x, x.coef, w, bias, res=kw.get("res"), out=kw.get("out"), gn_stats=st), st
     B, H, W = x.shape[0], x.shape[1], x.shape[2]
     if kw.get("upsample2x"):
         H, W = 2 * H, 2 * W
@@ -75,9 +99,11 @@ def resnet_gen(r, x, out=None, x_stats=None, want_stats=False):
     """ResnetBlock2D as a coroutine: yields (x, gamma, beta, silu, stats|None) at each GroupNorm and receives the
     normalised tensor, so a driver can share statistics across tiles (infer/vaehook.py task queue). `stats` are
     the fused-epilogue (sum, sumsq) of the producing conv when available. Returns (y, stats of y | None)."""
-    h = yield (x, r.g1, r.b1, True, x_stats)
+    # 6th field: Cout of the plain 3x3 conv that consumes the normalised tensor (the driver may then defer the
+    # normalisation to that conv, see GnDeferred)
+    h = yield (x, r.g1, r.b1, True, x_stats, r.w1.shape[0])
     h, st = conv_with_stats(h, r.w1, r.c1b, True)
-    h = yield (h, r.g2, r.b2, True, st)
+    h = yield (h, r.g2, r.b2, True, st, r.w2.shape[0])
     if r.ws is not None:
         skip = capi.conv2d(x, r.ws, r.sb, ksize=1, pad=(0, 0, 0, 0))
     else:
@@ -90,10 +116,14 @@ def drive_plain(gen, eps):
     try:
         req = next(gen)
         while True:
-            x, g, b, silu, st = req
+            x, g, b, silu, st, *rest = req
             if st is None:
                 st = capi.groupnorm_stats(x)
-            req = gen.send(capi.groupnorm_apply(x, st, g, b, 32, eps, silu))
+            if _deferrable(x, silu, rest[0] if rest else None):
+                hw = x.shape[1] * x.shape[2]
+                req = gen.send(GnDeferred(x, capi.groupnorm_coef(st, g, b, x.shape[0], hw, 32, eps)))
+            else:
+                req = gen.send(capi.groupnorm_apply(x, st, g, b, 32, eps, silu))
     except StopIteration as stop:
         return stop.value
 
@@ -105,7 +135,7 @@ def drive_tiled(gens, eps, n_img, weight=1.0, tile_parallel=False):
     reqs = [next(g) for g in gens]
     while True:
         sums, pix = [], []
-        for (x, _, _, _, st) in reqs:
+        for (x, _, _, _, st, *_rest) in reqs:
             sums.append(st if st is not None else capi.groupnorm_stats(x))
             hw = x.numel() // (x.shape[0] * x.shape[-1])
             pix.append(torch.full((x.shape[0],), float(hw) * weight, device=x.device, dtype=torch.float32))
@@ -117,7 +147,13 @@ def drive_tiled(gens, eps, n_img, weight=1.0, tile_parallel=False):
             shared = reduce_gn_partials(num, wsum).contiguous()
         else:
             shared = capi.groupnorm_combine(torch.cat(sums, 0), torch.cat(pix, 0), n_img, C)
-        outs = [capi.groupnorm_apply(x, shared, g, b, 32, eps, silu, shared_mod=n_img) for (x, g, b, silu, _) in reqs]
+        outs = []
+        for (x, g, b, silu, _st, *rest) in reqs:
+            if _deferrable(x, silu, rest[0] if rest else None):
+                coef = capi.groupnorm_coef(shared, g, b, x.shape[0], x.shape[1] * x.shape[2], 32, eps, shared_mod=n_img)
+                outs.append(GnDeferred(x, coef))
+            else:
+                outs.append(capi.groupnorm_apply(x, shared, g, b, 32, eps, silu, shared_mod=n_img))
         nxt, done = [], []
         for g, o in zip(gens, outs):
             try:

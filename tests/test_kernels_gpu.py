@@ -563,3 +563,40 @@ def test_groupnorm_combine_zero_weight_entries(capi):
     zero = torch.zeros_like(pix)  # a rank that holds ONLY shadows: all-zero numerators, not NaN
     num, wsum = capi.groupnorm_combine(sums, zero, n_img, C, raw=True)
     assert float(num.abs().max()) == 0.0 and float(wsum.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(2, 8, 128, 64, 128, False), (1, 33, 200, 128, 128, True),
+                                                (2, 40, 256, 256, 128, True), (1, 7, 130, 64, 64, False),
+                                                (3, 10, 300, 192, 128, False)])
+def test_conv_fused_input_groupnorm(capi, B, H, W, Cin, Cout, res):
+    """conv3x3(silu(groupnorm(x))) with the normalisation applied to the operand tile in shared memory
+    (omgsr_conv2d_gn_nhwc_bf16) == the two-pass form, and == the fp32 oracle. Covers ragged x, odd row counts, an odd
+    number of tiles (dummy CTA of the pair) and image borders (halo pixels must stay zero AFTER the transform)."""
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight
+    g = _g(B * 11 + H + W + Cin + Cout)
+    x = bf16r(torch.randn(B, H, W, Cin, generator=g) * 1.5 + 0.3)
+    gamma, beta = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.2
+    w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+    b = torch.randn(Cout, generator=g)
+    r = bf16r(torch.randn(B, H, W, Cout, generator=g)) if res else None
+    assert capi.conv_gn_in_fusable(B, H, W, Cin, Cout)
+    xc, wc, bc = x.cuda().bfloat16(), pack_conv_weight(w).cuda(), b.cuda()
+    gc, btc = gamma.cuda(), beta.cuda()
+    rc = r.cuda().bfloat16() if res else None
+    st = capi.groupnorm_stats(xc, 32)
+    two_pass = capi.conv2d(capi.groupnorm_apply(xc, st, gc, btc, 32, 1e-6, True), wc, bc, res=rc)
+    coef = capi.groupnorm_coef(st, gc, btc, B, H * W, 32, 1e-6)
+    stats_out = torch.empty(B, 32, 2, device="cuda") if Cout % 32 == 0 and Cout // 32 in (4, 8, 16) else None
+    fused = capi.conv2d_gn(xc, coef, wc, bc, res=rc, gn_stats=stats_out)
+    torch.cuda.synchronize()
+    assert report("fused vs two-pass", fused, two_pass.float().cpu(), 2e-3)[0]
+    ref = ops.conv2d_nhwc(bf16r(torch.nn.functional.silu(ops.groupnorm_nhwc(x, gamma, beta, 32, 1e-6))), w, b)
+    if res:
+        ref = ref + r
+    assert report(f"conv(silu(gn(x))) {B}x{H}x{W} {Cin}->{Cout}", fused, ref)[0]
+    if stats_out is not None:
+        f32 = fused.float()
+        s_ref = torch.stack([f32.reshape(B, H * W, 32, Cout // 32).sum((1, 3)),
+                             (f32 * f32).reshape(B, H * W, 32, Cout // 32).sum((1, 3))], -1)
+        assert report("fused output statistics", stats_out, s_ref.cpu(), 1e-3)[0]
