@@ -349,34 +349,40 @@ def run_ours(args):
     return 0
 
 
+HALO_GN_TRAFFIC = 2.1089e9  # bytes per launch, updated from profiles/r01/ncu_halo_pair128_gn.txt
+
+
 def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
-    """the launch class that dominates the step: the VAE's 128->128 3x3 conv at 512x512 (12 launches per step,
-    1.24 TFLOP each at batch 16), dispatched to conv_halo_tc2_kernel<2> (CTA-pair input-halo kernel).
-    Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W."""
+    """the launch class that dominates the step: the VAE's GroupNorm+SiLU -> 3x3 conv 128->128 at 512x512 (11 launches
+    per step, 1.24 TFLOP each at batch 16), served by conv_halo_tc2_kernel<2,true> (CTA-pair input-halo kernel with the
+    normalisation applied to the operand tile in shared memory). Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W."""
     from omgsr_b200.pack import pack_conv_weight
     C, H = 128, 512
     x = torch.randn(B, H, H, C, device=dev, dtype=torch.bfloat16)
     w = pack_conv_weight(torch.randn(C, C, 3, 3) / 34.0).to(dev)
     b = torch.zeros(C, device=dev)
+    coef = capi.groupnorm_coef(capi.groupnorm_stats(x, 32), torch.ones(C, device=dev), torch.zeros(C, device=dev), B,
+                               H * H, 32, 1e-6)
     out = torch.empty_like(x)
     for _ in range(3):
-        capi.conv2d(x, w, b, out=out)
+        capi.conv2d_gn(x, coef, w, b, out=out)
     torch.cuda.synchronize()
     n = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
-        capi.conv2d(x, w, b, out=out)
+        capi.conv2d_gn(x, coef, w, b, out=out)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * C * C * 9 * B * H * H
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_halo_tc2_kernel<2> (3x3, 128->128 ch, 512x512, batch %d)" % B,
+    return {"bound": "tensor", "kernel": "conv_halo_tc2_kernel<2,true> (GroupNorm+SiLU -> 3x3, 128->128 ch, 512x512, "
+                                         "batch %d)" % B,
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this very launch from one `ncu --set full` capture
-            # (profiles/r01/ncu_halo_pair128.txt: 1.0743 + 1.0346 GB; algorithmic input + output = 2 x 1.0737 GB)
-            "traffic": 2.1089e9 if (B, C, H) == (16, 128, 512) else None, "traffic_unit": "bytes/launch",
+            # (profiles/r01/ncu_halo_pair128_gn.txt); algorithmic input + output = 2 x 1.0737 GB
+            "traffic": HALO_GN_TRAFFIC if (B, C, H) == (16, 128, 512) else None, "traffic_unit": "bytes/launch",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
 
 

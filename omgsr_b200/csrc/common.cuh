@@ -282,6 +282,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+// remote arrive without the implicit .release fence (the default form compiles to MEMBAR.ALL.GPU): for producers whose
+// data is consumed inside their OWN CTA (by the tensor core after fence.proxy.async) and only the count travels
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t"
+      "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [r];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 // cluster-scope release / acquire forms for a barrier that orders one CTA's shared-memory writes before work the
 // OTHER CTA triggers (the GroupNorm transform of the CTA-pair halo kernel)
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
