@@ -349,7 +349,7 @@ def run_ours(args):
     return 0
 
 
-HALO_GN_TRAFFIC = 2.1089e9  # bytes per launch, updated from profiles/r01/ncu_halo_pair128_gn.txt
+HALO_GN_TRAFFIC = 2.1099e9  # bytes per launch, updated from profiles/r01/ncu_halo_pair128_gn.txt
 
 
 def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
