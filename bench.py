@@ -364,6 +364,9 @@ def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
     coef = capi.groupnorm_coef(capi.groupnorm_stats(x, 32), torch.ones(C, device=dev), torch.zeros(C, device=dev), B,
                                H * H, 32, 1e-6)
     out = torch.empty_like(x)
+    # the burst peak is a cold-start figure: let the board leave the power-capped state of the timed steps first
+    torch.cuda.synchronize()
+    time.sleep(3.0)
     for _ in range(3):
         capi.conv2d_gn(x, coef, w, b, out=out)
     torch.cuda.synchronize()
