@@ -79,7 +79,7 @@ def conv_with_stats(x, w, bias, want_stats, **kw):
     """conv2d that also returns the GroupNorm (sum, sumsq) statistics of its output when the shape allows the fused
     epilogue path (None otherwise: the consumer then runs the separate statistics kernel). `x` may be a GnDeferred."""
     if isinstance(x, GnDeferred):
-        assert not (kw.get("upsample2x") or kw.get("stride", 1) != 1)
+        assert set(kw) <= {"res", "out"}, f"a deferred GroupNorm feeds a plain 3x3 conv only, got {sorted(kw)}"
         B, H, W, _ = x.x.shape
         st = _stats_buf(B, x.x.device) if want_stats and capi.gn_fusable(B, H, W, w.shape[0]) else None
         return capi.conv2d_gn(x.x, x.coef, w, bias, res=kw.get("res"), out=kw.get("out"), gn_stats=st), st
