@@ -116,7 +116,7 @@ def run_batched(items, run_model, args, device, dtype):
     except for the GroupNorm atomics' summation order)."""
     import concurrent.futures as cf
     total_time, n_done = 0.0, 0
-    pool = cf.ThreadPoolExecutor(max_workers=2)
+    pool = cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2))  # PNG encoding releases the GIL in zlib
     saves = []
 
     def flush(batch):
