@@ -18,6 +18,7 @@ resume. No device<->host traffic happens inside the call.
 import math
 
 import torch
+import torch.nn.functional as F
 
 from omgsr_b200 import capi
 
@@ -91,9 +92,9 @@ class VAEHook:
         net = self.net
         N, _, height, width = z.shape
         print(f'[Tiled VAE]: input_size: {z.shape}, tile_size: {self.tile_size}, padding: {self.pad}')
-        if self.fast_mode:
-            raise NotImplementedError("VAEHook fast mode (GroupNorm estimation on a downsampled copy) is not built; "
-                                      "the reference default and OMGSR's settings use fast_*=False")
+        if self.fast_mode and self.color_fix:
+            raise NotImplementedError("VAEHook fast encoder with color_fix=True (statistics estimated only up to the "
+                                      "first downsample) is not built; OMGSR uses color_fix=False")
         in_boxes, out_boxes = self.split_tiles(height, width)
         tp = _dist.tile_parallel()
         mine, shadow = list(range(len(in_boxes))), False
@@ -111,7 +112,19 @@ class VAEHook:
             gens.append(net.forward_gen(stack.contiguous()))
             members.append(ids)
             pixels.append((th, tw))
-        outs = net.run_tiled(gens, [len(m) for m in members], N, weight=0.0 if shadow else 1.0, tile_parallel=tp)
+        if self.fast_mode:
+            # fast mode (reference :714-735): GroupNorm statistics are estimated ONCE on a copy of the input downsampled
+            # to the tile size (nearest-exact, per-channel mean / std restored, clamped to the input range) and replayed
+            # by every tile, so the tiles need no cross-tile (or cross-GPU) statistics exchange
+            print(f'[Tiled VAE]: Fast mode enabled, estimating group norm parameters on a downsampled copy')
+            zf = z.float()
+            down = F.interpolate(zf, scale_factor=self.tile_size / max(height, width), mode='nearest-exact')
+            std_old, mean_old = torch.std_mean(zf, dim=[0, 2, 3], keepdim=True)
+            std_new, mean_new = torch.std_mean(down, dim=[0, 2, 3], keepdim=True)
+            down = torch.clamp((down - mean_new) / std_new * std_old + mean_old, min=zf.min(), max=zf.max())
+            outs = net.run_tiled_fast(gens, N, down.to(z.dtype).contiguous())
+        else:
+            outs = net.run_tiled(gens, [len(m) for m in members], N, weight=0.0 if shadow else 1.0, tile_parallel=tp)
         scale = 8 if self.is_decoder else 1
         oh, ow = (height * 8, width * 8) if self.is_decoder else (height // 8, width // 8)
         result = torch.zeros((N, outs[0].shape[1], oh, ow), device=z.device, dtype=torch.float32)

@@ -84,6 +84,15 @@ def conv_with_stats(x, w, bias, want_stats, **kw):
         st = _stats_buf(B, x.x.device) if want_stats and capi.gn_fusable(B, H, W, w.shape[0]) else None
         return capi.conv2d_gn(x.x, x.coef, w, bias, res=kw.get("res"), out=kw.get("out"), gn_stats=st), st
     B, H, W = x.shape[0], x.shape[1], x.shape[2]
+    if kw.get("stride", 1) == 2 and (H % 2 or W % 2):
+        # odd extents (VAEHook fast mode estimates on a downsampled copy of arbitrary size): the stride-2 kernel views
+        # the input as pixel pairs, so run it on a copy zero-padded to even extents - the same zeros the (0,1,0,1)
+        # padding of the reference's Downsample2D supplies - and drop the one extra output row / column
+        xp = torch.zeros((B, H + H % 2, W + W % 2, x.shape[3]), device=x.device, dtype=x.dtype)
+        xp[:, :H, :W] = x
+        y = capi.conv2d(xp, w, bias, **kw)
+        oh, ow = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
+        return y[:, :oh, :ow].contiguous(), None
     if kw.get("upsample2x"):
         H, W = 2 * H, 2 * W
     elif kw.get("stride", 1) == 2:
@@ -165,6 +174,43 @@ def drive_tiled(gens, eps, n_img, weight=1.0, tile_parallel=False):
                 raise RuntimeError("tile coroutines fell out of step")
             return done
         reqs = nxt
+
+
+def drive_record(gen, eps):
+    """VAEHook fast mode, first pass (infer/vaehook.py:637-676): run the coroutine on the downsampled copy with
+    ordinary per-tensor statistics and record (mean, biased var) per (image, group) at every GroupNorm site."""
+    sites = []
+    try:
+        req = next(gen)
+        while True:
+            x, g, b, silu, st, *_rest = req
+            if st is None:
+                st = capi.groupnorm_stats(x)
+            n = float(x.shape[1] * x.shape[2] * (x.shape[3] // 32))
+            mean = st[..., 0] / n
+            sites.append(torch.stack([mean, (st[..., 1] / n - mean * mean).clamp_min_(0.0)], -1).contiguous())
+            req = gen.send(capi.groupnorm_apply(x, st, g, b, 32, eps, silu))
+    except StopIteration:
+        return sites
+
+
+def drive_fixed(gen, eps, n_img, sites):
+    """VAEHook fast mode, tile pass: every GroupNorm site applies the statistics recorded by drive_record
+    ([n_img, 32, 2] (mean, var) rows shared by batch index % n_img), so the tiles never synchronise."""
+    k = 0
+    try:
+        req = next(gen)
+        while True:
+            x, g, b, silu, _st, *rest = req
+            shared = sites[k]
+            k += 1
+            if _deferrable(x, silu, rest[0] if rest else None):
+                coef = capi.groupnorm_coef(shared, g, b, x.shape[0], x.shape[1] * x.shape[2], 32, eps, shared_mod=n_img)
+                req = gen.send(GnDeferred(x, coef))
+            else:
+                req = gen.send(capi.groupnorm_apply(x, shared, g, b, 32, eps, silu, shared_mod=n_img))
+    except StopIteration as stop:
+        return stop.value
 
 
 def resnet_forward(r, x, eps, out=None):
@@ -269,6 +315,11 @@ class B200Encoder(torch.nn.Module):
     def run_tiled(self, gens, tiles_per_group, n_img, weight=1.0, tile_parallel=False):
         return drive_tiled(gens, self.cfg.eps, n_img, weight, tile_parallel)
 
+    def run_tiled_fast(self, gens, n_img, estimate_input):
+        """VAEHook fast mode: statistics from one pass over `estimate_input`, replayed by every tile group."""
+        sites = drive_record(self.forward_gen(estimate_input), self.cfg.eps)
+        return [drive_fixed(g, self.cfg.eps, n_img, sites) for g in gens]
+
     def forward(self, x):
         m = self.moments_nhwc(x)  # [B,h,w,2Cz] fp32
         return m.permute(0, 3, 1, 2).contiguous().to(self.out_dtype)
@@ -335,6 +386,11 @@ class B200Decoder(torch.nn.Module):
 
     def run_tiled(self, gens, tiles_per_group, n_img, weight=1.0, tile_parallel=False):
         return drive_tiled(gens, self.cfg.eps, n_img, weight, tile_parallel)
+
+    def run_tiled_fast(self, gens, n_img, estimate_input):
+        """VAEHook fast mode: statistics from one pass over `estimate_input`, replayed by every tile group."""
+        sites = drive_record(self.forward_gen(estimate_input), self.cfg.eps)
+        return [drive_fixed(g, self.cfg.eps, n_img, sites) for g in gens]
 
     def forward(self, z, clamp=False):
         h = drive_plain(self.trunk_gen(z), self.cfg.eps)

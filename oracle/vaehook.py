@@ -1,6 +1,6 @@
 """Oracle restatement of the reference's tiled VAE (infer/vaehook.py) — TEST INFRASTRUCTURE ONLY.
 
-Semantics reproduced (non-fast mode, the reference's and OMGSR's default):
+Semantics reproduced (non-fast mode, the reference's and OMGSR's default; fast mode: tiled_forward_fast):
   * inputs with max(H, W) <= 2*pad + tile_size bypass tiling (:554-556); pad = 32 px (encoder) / 11 latent px
     (decoder) (:546)
   * tile planner split_tiles (:577-634) / get_best_tile_size (:562-575)
@@ -76,6 +76,69 @@ class _SharedGroupNorm:
         y = (xr - mean[..., None]) / torch.sqrt(var[..., None] + 1e-6)
         y = y.reshape(x.shape)
         return y * weight.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+
+
+class _EstimatedGroupNorm:
+    """fast mode (infer/vaehook.py:637-676, 714-735): the first pass over a downsampled copy records (var, mean) per
+    (image, group) at every GroupNorm site (GroupNormParam.from_tile :511-534); every tile then replays them in site
+    order, so the tiles are independent of each other."""
+
+    def __init__(self):
+        self.sites = []
+        self.recording = True
+        self.k = 0
+
+    def __call__(self, x, groups, weight, bias, eps):
+        b = x.shape[0]
+        xr = x.reshape(b, groups, -1)
+        if self.recording:
+            self.sites.append(torch.var_mean(xr, dim=2, unbiased=False))
+            var, mean = self.sites[-1]
+        else:
+            var, mean = self.sites[self.k]
+            self.k += 1
+        y = ((xr - mean[..., None]) / torch.sqrt(var[..., None] + 1e-6)).reshape(x.shape)
+        return y * weight.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+
+
+def _stitch(x, results, ins, outs, is_decoder):
+    _, _, h, w = x.shape
+    oh, ow = (h * 8, w * 8) if is_decoder else (h // 8, w // 8)
+    out = torch.zeros((x.shape[0], results[0].shape[1], oh, ow), dtype=torch.float32)
+    for i, tile in enumerate(results):
+        scaled = [v * 8 if is_decoder else v // 8 for v in ins[i]]
+        m = [outs[i][k] - scaled[k] for k in range(4)]
+        ob = outs[i]
+        out[:, :, ob[2]:ob[3], ob[0]:ob[1]] = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]].float()
+    return out
+
+
+def tiled_forward_fast(fn, x, tile_size, is_decoder):
+    """VAEHook with fast_encoder / fast_decoder = True (color_fix False)."""
+    pad = 11 if is_decoder else 32
+    _, _, h, w = x.shape
+    if max(h, w) <= 2 * pad + tile_size:
+        return fn(x)
+    ins, outs = split_tiles(h, w, tile_size, is_decoder)
+    # downsample to the tile size with nearest-exact, then restore the per-channel mean / std the resampling distorted
+    # and clamp to the original range (:716-731)
+    down = F.interpolate(x, scale_factor=tile_size / max(h, w), mode="nearest-exact")
+    std_old, mean_old = torch.std_mean(x, dim=[0, 2, 3], keepdim=True)
+    std_new, mean_new = torch.std_mean(down, dim=[0, 2, 3], keepdim=True)
+    down = torch.clamp((down - mean_new) / std_new * std_old + mean_old, min=x.min(), max=x.max())
+    hook = _EstimatedGroupNorm()
+    prev = nets.GN_HOOK
+    nets.GN_HOOK = hook
+    try:
+        fn(down)
+        hook.recording = False
+        results = []
+        for bx in ins:
+            hook.k = 0
+            results.append(fn(x[:, :, bx[2]:bx[3], bx[0]:bx[1]]))
+    finally:
+        nets.GN_HOOK = prev
+    return _stitch(x, results, ins, outs, is_decoder)
 
 
 def tiled_forward(fn, x, tile_size, is_decoder):

@@ -156,6 +156,9 @@ def main():
         gold["dec_in_sum"] = z.double().sum()
         gold["enc_tiled"] = hook_e(x)   # [1, 8, 24, 20] pre-quant moments, fp32
         gold["dec_tiled"] = hook_d(z)   # [1, 3, 320, 384]
+        # fast mode (GroupNorm statistics estimated once on a nearest-exact downsampled copy, infer/vaehook.py:714-735)
+        gold["enc_tiled_fast"] = vaehook.VAEHook(build_stub(sd, cfg, False), 64, False, False, True, False)(x)
+        gold["dec_tiled_fast"] = vaehook.VAEHook(build_stub(sd, cfg, True), 16, True, True, False, False)(z)
         gold["enc_split"] = hook_e.split_tiles(192, 160)
         gold["dec_split"] = hook_d.split_tiles(40, 48)
         # untiled references from the oracle nets for the same inputs (pre quant_conv / no post_quant)
@@ -165,6 +168,8 @@ def main():
     torch.save(gold, os.path.join(OUT, "vaehook_fixtures.pt"))
     print("enc tiled vs untiled max diff", (gold["enc_tiled"] - gold["enc_untiled_oracle"]).abs().max().item())
     print("dec tiled vs untiled max diff", (gold["dec_tiled"] - gold["dec_untiled_oracle"]).abs().max().item())
+    print("enc fast vs exact tiled max diff", (gold["enc_tiled_fast"] - gold["enc_tiled"]).abs().max().item())
+    print("dec fast vs exact tiled max diff", (gold["dec_tiled_fast"] - gold["dec_tiled"]).abs().max().item())
     print("wrote vaehook_fixtures.pt", os.path.getsize(os.path.join(OUT, "vaehook_fixtures.pt")))
 
 

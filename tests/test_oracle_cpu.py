@@ -129,6 +129,13 @@ def test_vaehook_oracle_matches_reference_vaehook():
     assert enc.shape == g["enc_tiled"].shape and dec.shape == g["dec_tiled"].shape
     assert (enc - g["enc_tiled"]).abs().max() < 2e-4, (enc - g["enc_tiled"]).abs().max()
     assert (dec - g["dec_tiled"]).abs().max() < 2e-4, (dec - g["dec_tiled"]).abs().max()
+    # fast mode: statistics estimated once on a nearest-exact downsampled copy, then replayed by every tile
+    with torch.no_grad():
+        enc_f = ov.tiled_forward_fast(lambda t: nets.vae_encode_moments(sd, cfg, t), x, 64, False)
+        dec_f = ov.tiled_forward_fast(lambda t: nets.vae_decode(sd, cfg, t), z, 16, True)
+    assert (enc_f - g["enc_tiled_fast"]).abs().max() < 2e-4, (enc_f - g["enc_tiled_fast"]).abs().max()
+    assert (dec_f - g["dec_tiled_fast"]).abs().max() < 2e-4, (dec_f - g["dec_tiled_fast"]).abs().max()
+    assert (enc_f - enc).abs().max() > 1e-2  # and it really is a different result from the exact mode
 
 
 def test_weight_tables_reproduce_public_parameter_counts():

@@ -142,6 +142,15 @@ def test_tiled_vae_matches_reference_vaehook():
           f"tiled dec psnr vs reference vaehook {p_dec:.2f} dB (tiled-vs-untiled {psnr(g['dec_tiled'], g['dec_untiled_oracle']):.2f} dB)")
     assert e_enc <= 2e-2
     assert p_dec >= 40.0
+    # fast mode (statistics estimated on a downsampled copy) against the reference's own fast-mode output
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        enc_f = VAEHook(vae.encoder, 64, False, False, True, False, True)(x.cuda().bfloat16())
+        dec_f = VAEHook(vae.decoder, 16, True, True, False, False, True)(z.cuda().bfloat16())
+    e_enc_f, p_dec_f = relerr(enc_f, g["enc_tiled_fast"]), psnr(dec_f, g["dec_tiled_fast"])
+    print(f"fast mode: enc relerr {e_enc_f:.4f} (fast-vs-exact {relerr(g['enc_tiled_fast'], g['enc_tiled']):.4f}); "
+          f"dec psnr {p_dec_f:.2f} dB (fast-vs-exact {psnr(g['dec_tiled_fast'], g['dec_tiled']):.2f} dB)")
+    assert e_enc_f <= 2e-2
+    assert p_dec_f >= 40.0
     # small inputs bypass tiling and must equal the plain forward
     xs = torch.rand(1, 3, 64, 64, generator=gen) * 2 - 1
     with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
