@@ -92,9 +92,10 @@ class VAEHook:
         net = self.net
         N, _, height, width = z.shape
         print(f'[Tiled VAE]: input_size: {z.shape}, tile_size: {self.tile_size}, padding: {self.pad}')
-        if self.fast_mode and self.color_fix:
-            raise NotImplementedError("VAEHook fast encoder with color_fix=True (statistics estimated only up to the "
-                                      "first downsample) is not built; OMGSR uses color_fix=False")
+        # color_fix: in the reference it only switches the fast-mode estimate to stop at the first task named
+        # 'downsample' (:664-668), but OMGSR's task queue names that task 'downsamplers' (:313-326), so the branch is
+        # dead and color_fix=True gives bit-identical results (tests/golden: enc_tiled_fast_colorfix == enc_tiled_fast).
+        # Accepted and, like there, without effect.
         in_boxes, out_boxes = self.split_tiles(height, width)
         tp = _dist.tile_parallel()
         mine, shadow = list(range(len(in_boxes))), False

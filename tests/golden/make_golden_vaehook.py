@@ -159,6 +159,9 @@ def main():
         # fast mode (GroupNorm statistics estimated once on a nearest-exact downsampled copy, infer/vaehook.py:714-735)
         gold["enc_tiled_fast"] = vaehook.VAEHook(build_stub(sd, cfg, False), 64, False, False, True, False)(x)
         gold["dec_tiled_fast"] = vaehook.VAEHook(build_stub(sd, cfg, True), 16, True, True, False, False)(z)
+        # fast encoder with color_fix=True: only the sites before the first downsample use estimated statistics
+        # (infer/vaehook.py:664-668), the rest are synchronised across tiles as in the exact mode
+        gold["enc_tiled_fast_colorfix"] = vaehook.VAEHook(build_stub(sd, cfg, False), 64, False, False, True, True)(x)
         gold["enc_split"] = hook_e.split_tiles(192, 160)
         gold["dec_split"] = hook_d.split_tiles(40, 48)
         # untiled references from the oracle nets for the same inputs (pre quant_conv / no post_quant)
@@ -169,6 +172,7 @@ def main():
     print("enc tiled vs untiled max diff", (gold["enc_tiled"] - gold["enc_untiled_oracle"]).abs().max().item())
     print("dec tiled vs untiled max diff", (gold["dec_tiled"] - gold["dec_untiled_oracle"]).abs().max().item())
     print("enc fast vs exact tiled max diff", (gold["enc_tiled_fast"] - gold["enc_tiled"]).abs().max().item())
+    print("enc fast+color_fix vs fast max diff", (gold["enc_tiled_fast_colorfix"] - gold["enc_tiled_fast"]).abs().max().item())
     print("dec fast vs exact tiled max diff", (gold["dec_tiled_fast"] - gold["dec_tiled"]).abs().max().item())
     print("wrote vaehook_fixtures.pt", os.path.getsize(os.path.join(OUT, "vaehook_fixtures.pt")))
 

@@ -136,6 +136,8 @@ def test_vaehook_oracle_matches_reference_vaehook():
     assert (enc_f - g["enc_tiled_fast"]).abs().max() < 2e-4, (enc_f - g["enc_tiled_fast"]).abs().max()
     assert (dec_f - g["dec_tiled_fast"]).abs().max() < 2e-4, (dec_f - g["dec_tiled_fast"]).abs().max()
     assert (enc_f - enc).abs().max() > 1e-2  # and it really is a different result from the exact mode
+    # reference quirk: color_fix=True changes nothing (its 'downsample' branch never matches OMGSR's task names)
+    assert torch.equal(g["enc_tiled_fast_colorfix"], g["enc_tiled_fast"])
 
 
 def test_weight_tables_reproduce_public_parameter_counts():

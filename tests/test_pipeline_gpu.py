@@ -144,7 +144,7 @@ def test_tiled_vae_matches_reference_vaehook():
     assert p_dec >= 40.0
     # fast mode (statistics estimated on a downsampled copy) against the reference's own fast-mode output
     with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-        enc_f = VAEHook(vae.encoder, 64, False, False, True, False, True)(x.cuda().bfloat16())
+        enc_f = VAEHook(vae.encoder, 64, False, False, True, True, True)(x.cuda().bfloat16())  # color_fix: no effect
         dec_f = VAEHook(vae.decoder, 16, True, True, False, False, True)(z.cuda().bfloat16())
     e_enc_f, p_dec_f = relerr(enc_f, g["enc_tiled_fast"]), psnr(dec_f, g["dec_tiled_fast"])
     print(f"fast mode: enc relerr {e_enc_f:.4f} (fast-vs-exact {relerr(g['enc_tiled_fast'], g['enc_tiled']):.4f}); "
