@@ -10,6 +10,10 @@
 //   traffic per 2x128 output pixels, C=128: 4 rows x 130 px x 256 B + 295 KB weights = 428 KB
 //   (generic kernel: 2 x 18 k-blocks x 32 KB = 1152 KB).
 // Warp roles as in gemm_conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+// Three instantiations: conv_halo_tc2_kernel<2,false> (CTA pair, the default for 16 < Cout <= 128),
+// conv_halo_tc2_kernel<2,true> (the same plus four transform warps that apply the INPUT's GroupNorm + SiLU to the halo
+// tile in shared memory, omgsr_conv2d_gn_nhwc_bf16) and the single-CTA conv_halo_tc_kernel<BN,2> (BN = 16 for thin
+// Cout such as the decoder's conv_out, BN = 128 for single-tile problems).
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "../../include/omgsr_b200.h"

@@ -14,9 +14,13 @@
 //   attention GEMMs the B operand is a per-(batch, head) matrix, either K-major (Q K^T) or MN-major
 //   (P V, V read in place as [kv, d]).
 // * Warp-specialised persistent kernel, one CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer
-//   (single elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=16), warps 2..5 = epilogue
-//   (tcgen05.ld -> bias/activation/gate/residual -> bf16|f32 -> global). smem ring of kStages, two TMEM
+//   (single elected thread, tcgen05.mma, M=128 per CTA, N=BN, K=16), warps 2..5 = epilogue
+//   (tcgen05.ld -> bias/activation/gate/residual -> bf16|f32 -> global, epilogue.cuh). smem ring of kStages, two TMEM
 //   accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * Two forms: conv_gemm_tc2_kernel (default) pairs two CTAs of a cluster on one cta_group::2 MMA (M = 256: each CTA
+//   loads its own A tile and HALF of the weight tile; 92.6 % tensor-pipe activity at N = 256), conv_gemm_tc_kernel is
+//   the single-CTA form for batched / MN-major B operands, ragged Cout and one-tile problems. The tile width BN is
+//   chosen by a small cost model (pick_bn). A plain GEMM may have K that does not fill the last 64-deep k-block.
 //
 // Replaces the cuDNN / cuBLAS calls underneath diffusers' Conv2d / Linear modules that the reference
 // reaches from infer/omgsr_s_infer_model.py:75-84,173 and infer/omgsr_f_infer_model.py:16,191-211.
