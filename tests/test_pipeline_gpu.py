@@ -376,3 +376,39 @@ def test_s_cuda_graph_replay_matches_eager():
     p = psnr(out2, ref2)
     print(f"graph replay vs eager: {p:.2f} dB; latency eager {t_eager*1e3:.2f} ms, graph {t_graph*1e3:.2f} ms")
     assert p >= 40.0
+
+
+def test_f_full_size_1024_properties():
+    """BASELINE config 4 shapes (FLUX.1-dev widths, 19 + 38 blocks, 1024x1024 images): the fp32 oracle cannot run this
+    in test time (90 TFLOP per image), so the full-size path is checked through size-independent properties:
+    finite and bounded output; two identical images in one batch give the same result (to the rounding noise of the
+    fp32 GroupNorm atomics); an image's result does not depend on what else is in the batch; the 2x2 latent
+    pack / unpack round trip is exact at full size."""
+    from infer.omgsr_f_infer_model import OMGSR_F_Infer, _pack_latents, _unpack_latents
+    from infer.infer_omgsr_f import _prepare_latent_image_ids
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = OMGSR_F_Infer("random://flux_dev?seed=0", "random://lora?seed=1&rank=64", "cuda")
+    g = torch.Generator().manual_seed(77)
+    x0 = (torch.rand(1, 3, 1024, 1024, generator=g) * 2 - 1)
+    x1 = (torch.rand(1, 3, 1024, 1024, generator=g) * 2 - 1)
+    pe = torch.randn(1, 512, 4096, generator=g).cuda().bfloat16()
+    pp = torch.randn(1, 768, generator=g).cuda().bfloat16()
+    tid = torch.zeros(512, 3, device="cuda", dtype=torch.bfloat16)
+    ids = _prepare_latent_image_ids(64, 64, "cuda", torch.bfloat16)
+    eps1 = torch.randn(1, 16, 128, 128, generator=g)
+    run = lambda x, eps: model(x.cuda().bfloat16(), pe, pp, tid, ids, 128, 64)[0].float().cpu()
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        model.vae.posterior_eps = torch.cat([eps1, eps1, eps1], 0)
+        out = run(torch.cat([x0, x0, x1], 0), None)
+        model.vae.posterior_eps = eps1
+        alone = run(x0, None)
+    assert out.shape == (3, 3, 1024, 1024) and torch.isfinite(out).all()
+    assert out.abs().max() < 50 and out.std() > 1e-3
+    p_same, p_alone, p_other = psnr(out[0:1], out[1:2]), psnr(out[0:1], alone), psnr(out[0:1], out[2:3])
+    print(f"F-1024 full size: twin images {p_same:.1f} dB, batched vs alone {p_alone:.1f} dB, different image {p_other:.1f} dB")
+    assert p_same >= 40.0 and p_alone >= 40.0
+    assert p_other < 30.0  # and the output really depends on the input
+    z = torch.randn(2, 16, 128, 128, generator=g).cuda().bfloat16()
+    packed = _pack_latents(z, 2, 16, 128, 128)
+    assert packed.shape == (2, 4096, 64)
+    assert torch.equal(_unpack_latents(packed, 1024, 1024, 8), z)
