@@ -50,6 +50,9 @@ const char* omgsr_last_error(void);
 int omgsr_destroy(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 long long omgsr_launch_count(void);
+/* name of the kernel variant that served the most recent GEMM / convolution call of this process (diagnostics:
+ * bench.py names the kernel its roofline figure was measured on). */
+const char* omgsr_last_variant(void);
 
 /* ---- contractions (tcgen05 + TMEM + TMA) ------------------------------------------------------ */
 
@@ -104,14 +107,21 @@ int omgsr_flash_attn_set_variant(int force_v1);
  * upsample in front of a 3x3/p1 conv (weights must be packed by pack_upsample_weight: 4 x [Cout, 4*Cin]).
  * Replaces cuDNN under diffusers ResnetBlock2D/Downsample2D/Upsample2D in the VAE and UNet
  * (infer/omgsr_s_infer_model.py:84,173; infer/vaehook.py:248-329 lists the same layers). Cin % 64 == 0.
- * epi: +bias -> act -> +res. gn_sums (nullable): fp32 [B, gn_groups, 2]; the call zeroes it and the epilogue
- * accumulates (sum, sum of squares) of the STORED bf16 output per (image, group), i.e. the statistics pass of the
- * GroupNorm that follows the conv costs no extra trip over HBM (needs >= 128 output pixels per image and
- * Cout/gn_groups in {4, 8, 16, ...}; otherwise OMGSR_ERR_SHAPE). */
+ * epi: +bias -> act -> +res. gn_sums (nullable): fp32 [B, gn_groups, 2] = (sum, sum of squares) of the STORED bf16
+ * output per (image, group), produced by the epilogue, i.e. the statistics pass of the GroupNorm that follows the conv
+ * costs no extra trip over HBM (needs >= 128 output pixels per image and Cout/gn_groups in {4, 8, 16}; otherwise
+ * OMGSR_ERR_SHAPE). The sums are bit-reproducible: every epilogue warp writes its partial sums to its own slot of
+ * gn_scratch (caller-provided fp32 workspace of >= omgsr_gn_scratch_floats(B, gn_groups, upsample2x ? 4 : 1) floats;
+ * the call zeroes it) and a fixed-order reduction kernel folds the slots into gn_sums - no floating-point atomics. */
 int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H,
                            int W, int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b,
                            int pad_r, int upsample2x, int act, long long ldx, long long ldy, long long ldr,
-                           float* gn_sums, int gn_groups, int flags, int force_bn, void* stream);
+                           float* gn_sums, int gn_groups, float* gn_scratch, long long gn_scratch_floats, int flags,
+                           int force_bn, void* stream);
+/* workspace size (in floats) for the deterministic GroupNorm statistics of `launches` kernel launches over B images
+ * with G groups: omgsr_conv2d_nhwc_bf16 / omgsr_conv2d_gn_nhwc_bf16 (launches = 4 with upsample2x, else 1) and
+ * omgsr_groupnorm_stats (launches = 1). Host-only; depends on the SM count of the current device. */
+long long omgsr_gn_scratch_floats(int B, int G, int launches);
 /* GroupNorm + SiLU of the INPUT fused into a 3x3 / stride 1 / pad 1 convolution: y = conv(silu(a[b,c] * x + s[b,c])) with
  * gn_in_coef [B, Cin] float2 from omgsr_groupnorm_coef (the diffusers ResnetBlock2D pattern norm -> SiLU -> conv,
  * infer/vaehook.py:384-413 custom_group_norm + F.silu before each conv task). The normalised tensor is never written:
@@ -120,7 +130,8 @@ int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, cons
  * then uses omgsr_groupnorm_apply + omgsr_conv2d_nhwc_bf16). Other arguments as omgsr_conv2d_nhwc_bf16. */
 int omgsr_conv2d_gn_nhwc_bf16(const void* x, const float* gn_in_coef, const void* w, const float* bias, const void* res,
                               void* y, int B, int H, int W, int Cin, int Cout, long long ldx, long long ldy,
-                              long long ldr, float* gn_sums, int gn_groups, void* stream);
+                              long long ldr, float* gn_sums, int gn_groups, float* gn_scratch,
+                              long long gn_scratch_floats, void* stream);
 
 /* ---- thin convolutions (CUDA cores; too few channels for the tensor pipe) --------------------- */
 
@@ -139,9 +150,10 @@ int omgsr_conv_out_nchw(const void* x, const void* w, const float* bias, void* y
 
 /* ---- normalisation / glue (HBM-bound) --------------------------------------------------------- */
 
-/* GroupNorm statistics: stats[B, G, 2] = (sum, sum of squares) over (HW, C/G). Zeroes stats first. */
+/* GroupNorm statistics: stats[B, G, 2] = (sum, sum of squares) over (HW, C/G). Bit-reproducible: per-block partial
+ * sums go to `scratch` (>= omgsr_gn_scratch_floats(B, G, 1) floats, caller-provided) and are reduced in a fixed order. */
 int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats, int B, long long HW, int C, int G,
-                          void* stream);
+                          float* scratch, long long scratch_floats, void* stream);
 /* y = (x - mean) * rstd * gamma + beta, optional SiLU. (diffusers GroupNorm+SiLU pairs: VAE eps 1e-6,
  * UNet eps 1e-5; infer/vaehook.py:384-413 restates the same op as custom_group_norm.)
  * stats_mode 0: stats[B,G,2] = (sum, sumsq) from omgsr_groupnorm_stats on this tensor.

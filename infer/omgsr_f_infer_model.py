@@ -20,6 +20,9 @@ from .vaehook import VAEHook
 
 
 def encode_images(pixels: torch.Tensor, vae: torch.nn.Module, weight_dtype):
+    fused = getattr(vae, "encode_scaled", None)
+    if fused is not None:  # B200AutoencoderKL: shift / scale applied inside the posterior-sample kernel
+        return fused(pixels.to(vae.dtype)).to(weight_dtype)
     pixel_latents = vae.encode(pixels.to(vae.dtype)).latent_dist.sample()
     pixel_latents = (pixel_latents - vae.config.shift_factor) * vae.config.scaling_factor
     return pixel_latents.to(weight_dtype)
@@ -113,6 +116,8 @@ class OMGSR_F_Infer(torch.nn.Module):
             raise RuntimeError("OMGSR_F_Infer (omgsr_b200) needs a CUDA device: the hot path has no CPU fallback")
         from omgsr_b200.engine_flux import B200FluxTransformer
         from omgsr_b200.engine_vae import B200AutoencoderKL
+        from .omgsr_s_infer_model import _select_device
+        _select_device(device)
         print("Loading adapers...")
         vae_sd, flux_sd, vae_cfg, flux_cfg = build_f_state(flux_path, lora_path, weight_dtype, device)
         self.vae_scale_factor = 2 ** (len(vae_cfg.block_out_channels) - 1)

@@ -25,6 +25,14 @@ from omgsr_b200.engine_vae import B200AutoencoderKL
 from .vaehook import VAEHook
 
 
+def _select_device(device):
+    """make `device` the current CUDA device of this process: the C-ABI kernels launch on the current device / stream
+    (the reference's drivers pass --device cuda:N, infer/infer_omgsr_s.py:116)."""
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is not None:
+        torch.cuda.set_device(d)
+
+
 def _parse_spec(spec):
     body = spec[len("random://"):]
     name, _, q = body.partition("?")
@@ -75,6 +83,7 @@ class OMGSR_S_Infer(torch.nn.Module):
         super().__init__()
         if not torch.cuda.is_available():
             raise RuntimeError("OMGSR_S_Infer (omgsr_b200) needs a CUDA device: the hot path has no CPU fallback")
+        _select_device(device)
         vae_sd, unet_sd, vae_cfg, unet_cfg = build_s_state(sd_path, lora_path)
         self.mid_timestep = mid_timestep
         self.scheduler = _Scheduler()
@@ -184,6 +193,8 @@ class OMGSR_S_Infer(torch.nn.Module):
         if prompt_embeds.shape[0] not in (1, nt * B):  # per-image prompts: repeat for every tile of that image
             prompt_embeds = prompt_embeds.repeat(nt, 1, 1)
         if D.tile_parallel():  # single large image on several GPUs: each rank denoises its share of the tiles
+            if prompt_embeds.shape[0] != 1:
+                raise RuntimeError("tile-parallel mode expects one shared prompt")
             eps_t = D.tile_parallel_forward(lambda t: self.unet.eps_hat_nhwc(t, prompt_embeds)[..., :C], tiles)
         else:
             eps_t = self.unet.eps_hat_nhwc(tiles, prompt_embeds)  # fp32 NHWC view [nt*B,T,T,C] (ld 8)
@@ -249,12 +260,13 @@ class OMGSR_S_Infer(torch.nn.Module):
                 with torch.cuda.stream(side):  # warm-up: lazy attribute setting / caches happen outside the capture
                     self.unet.cache_kv = False
                     self._run(st["x"], st["ctx"], tile_size, tile_overlap)
-                    self.unet.cache_kv = True
                 torch.cuda.current_stream().wait_stream(side)
+                self.unet.cache_kv = True
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     out, tiled = self._run(st["x"], st["ctx"], tile_size, tile_overlap)
             finally:
+                self.unet.cache_kv = True
                 self.vae.posterior_eps = user_eps
             ent = self._graphs[key] = (graph, st, out, tiled)
         graph, st, out, tiled = ent

@@ -35,7 +35,10 @@ def _digest(paths):
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "omgsr_b200.h")]
+    # every header the sources include: editing epilogue.cuh (or any other .cuh / .h) must trigger a rebuild
+    inc = os.path.join(HERE, "..", "include")
+    deps = srcs + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
+        sorted(os.path.join(inc, f) for f in os.listdir(inc) if f.endswith(".h"))
     stamp = os.path.join(LIBDIR, "build.sha256")
     dig = _digest(deps)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:

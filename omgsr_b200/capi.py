@@ -17,7 +17,8 @@ OUT_F32, B_MN_MAJOR, CONV_NO_HALO = 1, 2, 4
 
 # every symbol include/omgsr_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
-    "omgsr_version", "omgsr_last_error", "omgsr_destroy", "omgsr_launch_count",
+    "omgsr_version", "omgsr_last_error", "omgsr_destroy", "omgsr_launch_count", "omgsr_last_variant",
+    "omgsr_gn_scratch_floats",
     "omgsr_gemm_bf16", "omgsr_gemm_batched_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
     "omgsr_conv_in_nchw", "omgsr_conv_out_nchw", "omgsr_im2col3x3_nchw",
     "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_groupnorm_combine", "omgsr_layernorm", "omgsr_softmax_rows",
@@ -39,6 +40,8 @@ def _load():
     lib.omgsr_last_error.restype = ctypes.c_char_p
     lib.omgsr_launch_count.restype = ctypes.c_longlong
     lib.omgsr_resize_u8_workspace.restype = ctypes.c_longlong
+    lib.omgsr_gn_scratch_floats.restype = ctypes.c_longlong
+    lib.omgsr_last_variant.restype = ctypes.c_char_p
     return lib
 
 
@@ -72,6 +75,17 @@ def version():
 
 def launch_count():
     return int(_lib.omgsr_launch_count())
+
+
+def last_conv_variant():
+    """name of the kernel variant that served the most recent GEMM / convolution call (diagnostics)."""
+    return (_lib.omgsr_last_variant() or b"").decode()
+
+
+def _gn_scratch(B, groups, launches, device):
+    """workspace for the deterministic (atomic-free) GroupNorm statistics: per-warp / per-block partial sums."""
+    n = int(_lib.omgsr_gn_scratch_floats(_i(B), _i(groups), _i(launches)))
+    return torch.empty(n, device=device, dtype=torch.float32), n
 
 
 def _cuda_bf16(t, name):
@@ -168,11 +182,12 @@ def conv2d(x, w, bias=None, res=None, ksize=3, stride=1, pad=(1, 1, 1, 1), upsam
         _cuda_bf16(res, "res")
         assert res.shape[:3] == (B, OH, OW) and res.stride(3) == 1
         ldr = res.stride(2)
+    scratch, n_scr = _gn_scratch(B, gn_groups, 4 if upsample2x else 1, x.device) if gn_stats is not None else (None, 0)
     rc = _lib.omgsr_conv2d_nhwc_bf16(_ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), _i(B), _i(H), _i(W),
                                      _i(Cin), _i(Cout), _i(ksize), _i(stride), _i(pad[0]), _i(pad[1]), _i(pad[2]),
                                      _i(pad[3]), _i(1 if upsample2x else 0), _i(act), _ll(x.stride(2)),
                                      _ll(out.stride(2)), _ll(ldr), _ptr(gn_stats),
-                                     _i(gn_groups if gn_stats is not None else 0),
+                                     _i(gn_groups if gn_stats is not None else 0), _ptr(scratch), _ll(n_scr),
                                      _i((OUT_F32 if out.dtype == torch.float32 else 0) | flags), _i(force_bn),
                                      _stream())
     _check(rc, "omgsr_conv2d_nhwc_bf16")
@@ -244,8 +259,9 @@ def groupnorm_stats(x, groups=32, stats=None):
     HW = x.numel() // (B * C)
     if stats is None:
         stats = torch.empty((B, groups, 2), device=x.device, dtype=torch.float32)
+    scratch, n_scr = _gn_scratch(B, groups, 1, x.device)
     rc = _lib.omgsr_groupnorm_stats(_ptr(x), _ll(x.stride(-2)), _ptr(stats), _i(B), _ll(HW), _i(C), _i(groups),
-                                    _stream())
+                                    _ptr(scratch), _ll(n_scr), _stream())
     _check(rc, "omgsr_groupnorm_stats")
     return stats
 
@@ -304,9 +320,10 @@ def conv2d_gn(x, coef, w, bias, res=None, out=None, gn_stats=None, gn_groups=32)
         _cuda_bf16(res, "res")
         assert res.shape == out.shape and res.stride(3) == 1 and res.stride(1) == W * res.stride(2)
         ldr = res.stride(2)
+    scratch, n_scr = _gn_scratch(B, gn_groups, 1, x.device) if gn_stats is not None else (None, 0)
     rc = _lib.omgsr_conv2d_gn_nhwc_bf16(_ptr(x), _ptr(coef), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), _i(B), _i(H),
                                         _i(W), _i(Cin), _i(Cout), _ll(x.stride(2)), _ll(out.stride(2)), _ll(ldr),
-                                        _ptr(gn_stats), _i(gn_groups), _stream())
+                                        _ptr(gn_stats), _i(gn_groups), _ptr(scratch), _ll(n_scr), _stream())
     _check(rc, "omgsr_conv2d_gn_nhwc_bf16")
     return out
 

@@ -554,13 +554,8 @@ static int launch_attn2(const void* q, const void* k, const void* v, void* out, 
                         const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
                         cudaStream_t st) {
   using C = Attn2Cfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(flash_attn2<%d>): %s", D, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&flash_attn2_kernel<D>), C::kSmemBytes, &attr_done, "flash_attn2")) return rc;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t eb = 2;
   {
@@ -595,13 +590,8 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
                        const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
                        cudaStream_t st) {
   using C = AttnCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(flash_attn<%d>): %s", D, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&flash_attn_kernel<D>), C::kSmemBytes, &attr_done, "flash_attn")) return rc;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t eb = 2;
   {

@@ -72,14 +72,27 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }
 
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {};  // per device: a process may drive any device of the box (infer_omgsr_s.py --device cuda:N)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = (dev < 0 || dev >= 64) ? 0 : dev;
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+
+int ensure_smem_attr(const void* func, int bytes, unsigned long long* done_mask, const char* what) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = (dev < 0 || dev >= 64) ? 0 : dev;
+  if ((*done_mask >> dev) & 1ull) return OMGSR_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+  *done_mask |= 1ull << dev;
+  return OMGSR_OK;
 }
 
 }  // namespace omgsr
@@ -88,3 +101,5 @@ extern "C" int omgsr_version(void) { return 100; }
 extern "C" const char* omgsr_last_error(void) { return omgsr::g_err; }
 extern "C" int omgsr_destroy(void) { return OMGSR_OK; }
 extern "C" long long omgsr_launch_count(void) { return omgsr::g_launches.load(); }
+namespace omgsr { extern const char* g_trace_variant; }
+extern "C" const char* omgsr_last_variant(void) { return omgsr::g_trace_variant; }

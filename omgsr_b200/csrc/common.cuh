@@ -32,7 +32,14 @@ EncodeTiledFn get_encode_tiled();
 // for dims 1..rank-1 (dim 0 is contiguous).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
-int sm_count();
+int sm_count();  // of the CURRENT device
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): *done_mask has one bit per device
+int ensure_smem_attr(const void* func, int bytes, unsigned long long* done_mask, const char* what);
+// deterministic GroupNorm statistics (epilogue.cuh gn_flush / glue.cu gn_finalize_kernel): slots per image in the
+// scratch buffer = 4 epilogue warps x the largest grid any persistent kernel launches
+inline int gn_slots_per_image() { return sm_count() * 4; }
+// out[b][i] = sum over (launch l, slot s) of scratch[((l * B + b) * slots + s) * n + i], in a fixed order
+int launch_gn_finalize(const float* scratch, int launches, int B, int slots, int n, float* out, cudaStream_t st);
 
 // ----------------------------------------------------------------------------------------------
 // small device utilities

@@ -38,7 +38,7 @@ struct HaloParams {
   int act, out_f32;
   int out_vec32, res_vec32;
   float* gn_sums;
-  int gn_cpg, gn_groups;
+  int gn_cpg, gn_groups, gn_slots;  // gn_sums: scratch [image][gn_slots][groups * 2], see gn_flush (epilogue.cuh)
   const float2* gn_in;        // optional [B][Cin] (scale, shift): GroupNorm + SiLU applied to the INPUT (pair kernel)
   int IH, IW;                 // input extents (validity of halo pixels for the input transform)
 };
@@ -189,7 +189,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b = m / p.tiles_y;
       const int x = tx * 128 + row;
       if (p.gn_sums && b != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
         gn_b = b;
       }
       // residual rows of this thread's TM pixels: pulled into L2 now, then loaded one 32-channel chunk ahead of use
@@ -230,7 +230,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (C::kAccSets == 2) { if (++set == 2) { set = 0; sph ^= 1; } }
       else { sph ^= 1; }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -489,7 +489,7 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int b = dummy ? 0 : m / p.tiles_y;
       const int x = tx * 128 + row;
       if (p.gn_sums && !dummy && b != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
         gn_b = b;
       }
       // residual rows of this thread's TM pixels: pulled into L2 now, then loaded one 32-channel chunk ahead of use
@@ -533,7 +533,7 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if (++set == 2) { set = 0; sph ^= 1; }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -549,14 +549,9 @@ int g_halo_2cta = 1;
 template <int TM, bool XF>
 static int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
   using C = Halo2Cfg<TM>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_tc2_kernel<TM, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess)
-      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_halo2<%d>): %s", TM, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_tc2_kernel<TM, XF>), C::kSmemBytes, &attr_done,
+                                "conv_halo_tc2")) return rc;
   const long long halo_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B;
   const long long pairs = (halo_tiles + 1) / 2;
   const int max_clusters = sm_count() / 2;
@@ -569,14 +564,9 @@ static int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ha
 template <int BN, int TM>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
   using C = HaloCfg<BN, TM>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_tc_kernel<BN, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess)
-      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_halo<%d,%d>): %s", BN, TM, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_tc_kernel<BN, TM>), C::kSmemBytes, &attr_done,
+                                "conv_halo_tc")) return rc;
   const long long total = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles;
   const int grid = total < sm_count() ? static_cast<int>(total) : sm_count();
   g_trace_variant = "halo_single128";
@@ -616,7 +606,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   if (gn_sums) {
     const int cpg = gn_groups > 0 ? Cout / gn_groups : 0;
     if (out_f32 || gn_groups <= 0 || gn_groups > 32 || Cout % gn_groups || !(cpg == 4 || cpg == 8 || cpg == 16)) return 1;
-    p.gn_sums = gn_sums; p.gn_cpg = cpg; p.gn_groups = gn_groups;
+    p.gn_sums = gn_sums; p.gn_cpg = cpg; p.gn_groups = gn_groups; p.gn_slots = gn_slots_per_image();
   }
   p.o_sx = o_sx; p.o_sy = o_sy; p.o_sb = o_sb; p.r_sx = r_sx; p.r_sy = r_sy; p.r_sb = r_sb;
   p.out = y; p.bias = bias; p.res = static_cast<const bf16*>(res); p.act = act; p.out_f32 = out_f32;

@@ -322,12 +322,19 @@ __device__ __forceinline__ void gn_chunk_accumulate(float (&part)[16], int cpg, 
   }
 }
 
-// flush this warp's slice (n floats) into the global [groups][2] accumulator of one image and clear it
-__device__ __forceinline__ void gn_flush(float* acc, int n, float* dst, int lane) {
+// Deterministic statistics: each epilogue warp owns ONE slot per image in a scratch buffer laid out
+// [image][slot = CTA * 4 + warp][groups * 2] and writes its partial sums there with plain stores (a warp leaves an image
+// at most once: the persistent tile loops visit the images in increasing order). Slots nobody writes stay zero (the
+// host zeroes the scratch), and gn_finalize_kernel (glue.cu) adds the slots of an image in a fixed order. The first
+// version used fp32 atomicAdd into one [groups][2] cell per image: the arrival order changed from run to run and with
+// it the rounding (1-3 dB of PSNR noise on the amplifying random-init nets).
+__device__ __forceinline__ float* gn_slot(float* scratch, int image, int n, int quarter, int slots) {
+  return scratch + (static_cast<long long>(image) * slots + blockIdx.x * 4 + quarter) * n;  // slots >= gridDim.x * 4
+}
+__device__ __forceinline__ void gn_flush(float* acc, int n, float* slot, int lane) {
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
-    const float v = acc[i];
-    if (v != 0.f) atomicAdd(dst + i, v);
+    slot[i] = acc[i];
     acc[i] = 0.f;
   }
   __syncwarp();

@@ -55,7 +55,7 @@ struct ConvGemmParams {
   int out_vec32, res_vec32;  // output / residual rows allow 256-bit accesses (see epilogue.cuh)
   int a_bytes;         // bytes one A box delivers (tb may be clamped to B)
   float* gn_sums;      // optional fused GroupNorm statistics of the output: [B][groups][2]
-  int gn_cpg, gn_groups;
+  int gn_cpg, gn_groups, gn_slots;  // gn_sums: scratch [image][gn_slots][groups * 2], see gn_flush (epilogue.cuh)
 };
 
 constexpr int kBM = 128;
@@ -258,7 +258,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.bias && next_n != bias_tile) bias_prefetch<BN>(bias_nx, p.bias, next_n * BN, p.Cout, lane);
       const int x = t.tx * tw + xl, y = t.ty * th + yl, b = t.tbi * tb + bl;
       if (p.gn_sums && t.tbi != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
         gn_b = t.tbi;
       }
       const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
@@ -296,7 +296,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bias_tile = next_n;
       }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -466,7 +466,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, tbi = m / (p.tiles_x * p.tiles_y);
       const int x = tx * tw + xl, y = ty * th + yl, b = tbi * tb + bl;
       if (p.gn_sums && !dummy && tbi != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
         gn_b = tbi;
       }
       const bool valid = !dummy && (x < p.W) && (y < p.H) && (b < p.B);
@@ -507,7 +507,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         bias_tile = next_n;
       }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, p.gn_sums + static_cast<long long>(gn_b) * gn_n, lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -524,14 +524,8 @@ extern const char* g_trace_variant;
 
 template <int BN>
 static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg2<BN>::kSmemBytes);
-    if (e != cudaSuccess)
-      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_tc2): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_gemm_tc2_kernel<BN>), Cfg2<BN>::kSmemBytes, &attr_done, "conv_gemm_tc2")) return rc;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const long long pairs = static_cast<long long>((m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = sm_count() / 2;
@@ -553,14 +547,8 @@ static int ilog2(int v) {
 template <int BN>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess)
-      return set_error(OMGSR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm<%d>): %s", BN, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_gemm_tc_kernel<BN>), C::kSmemBytes, &attr_done, "conv_gemm")) return rc;
   const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   g_trace_variant = BN == 256 ? "single256" : BN == 160 ? "single160" : BN == 128 ? "single128" : "single64";
@@ -686,7 +674,7 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
     if (d.out_f32 || geglu || tb != 1 || d.gn_groups <= 0 || d.gn_groups > 32 || d.Cout % d.gn_groups || !(cpg == 4 || cpg == 8 || cpg == 16) || (d.Cout % 32))
       return set_error(OMGSR_ERR_SHAPE, "conv_gemm: fused GroupNorm statistics unsupported for this shape (Cout=%d groups=%d tb=%d)",
                        d.Cout, d.gn_groups, tb);
-    p.gn_sums = d.gn_sums; p.gn_cpg = cpg; p.gn_groups = d.gn_groups;
+    p.gn_sums = d.gn_sums; p.gn_cpg = cpg; p.gn_groups = d.gn_groups; p.gn_slots = gn_slots_per_image();
   }
 
   const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_b;
@@ -854,30 +842,32 @@ extern "C" int omgsr_bgemm_bf16(const void* A, const void* Bm, void* D, int batc
 static int conv2d_impl(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H, int W,
                        int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b, int pad_r,
                        int upsample2x, int act, long long ldx, long long ldy, long long ldr, float* gn_sums,
-                       int gn_groups, const float* gn_in, int flags, int force_bn, void* stream);
+                       int gn_groups, float* gn_scratch, long long gn_scratch_floats, const float* gn_in, int flags,
+                       int force_bn, void* stream);
 
 extern "C" int omgsr_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* res, void* y,
                                       int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad_t,
                                       int pad_l, int pad_b, int pad_r, int upsample2x, int act, long long ldx,
-                                      long long ldy, long long ldr, float* gn_sums, int gn_groups, int flags,
-                                      int force_bn, void* stream) {
+                                      long long ldy, long long ldr, float* gn_sums, int gn_groups, float* gn_scratch,
+                                      long long gn_scratch_floats, int flags, int force_bn, void* stream) {
   return conv2d_impl(x, w, bias, res, y, B, H, W, Cin, Cout, ksize, stride, pad_t, pad_l, pad_b, pad_r, upsample2x, act,
-                     ldx, ldy, ldr, gn_sums, gn_groups, nullptr, flags, force_bn, stream);
+                     ldx, ldy, ldr, gn_sums, gn_groups, gn_scratch, gn_scratch_floats, nullptr, flags, force_bn, stream);
 }
 
 extern "C" int omgsr_conv2d_gn_nhwc_bf16(const void* x, const float* gn_in_coef, const void* w, const float* bias,
                                          const void* res, void* y, int B, int H, int W, int Cin, int Cout,
                                          long long ldx, long long ldy, long long ldr, float* gn_sums, int gn_groups,
-                                         void* stream) {
+                                         float* gn_scratch, long long gn_scratch_floats, void* stream) {
   if (!gn_in_coef) return set_error(OMGSR_ERR_SHAPE, "conv2d_gn: gn_in_coef is required");
   return conv2d_impl(x, w, bias, res, y, B, H, W, Cin, Cout, 3, 1, 1, 1, 1, 1, 0, OMGSR_ACT_NONE, ldx, ldy, ldr, gn_sums,
-                     gn_groups, gn_in_coef, 0, 0, stream);
+                     gn_groups, gn_scratch, gn_scratch_floats, gn_in_coef, 0, 0, stream);
 }
 
 static int conv2d_impl(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H, int W,
                        int Cin, int Cout, int ksize, int stride, int pad_t, int pad_l, int pad_b, int pad_r,
                        int upsample2x, int act, long long ldx, long long ldy, long long ldr, float* gn_sums,
-                       int gn_groups, const float* gn_in, int flags, int force_bn, void* stream) {
+                       int gn_groups, float* gn_scratch, long long gn_scratch_floats, const float* gn_in, int flags,
+                       int force_bn, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: empty problem");
   if (ksize != 1 && ksize != 3) return set_error(OMGSR_ERR_SHAPE, "conv2d: ksize must be 1 or 3");
   if (stride != 1 && stride != 2) return set_error(OMGSR_ERR_SHAPE, "conv2d: stride must be 1 or 2");
@@ -888,11 +878,19 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, const vo
   d.x_sx = ldx; d.x_sy = ldx * W; d.x_sb = ldx * W * H;
   d.act = act; d.force_bn = force_bn; d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
   d.halo_mode = (flags & OMGSR_CONV_NO_HALO) ? 0 : 1;
-  d.gn_sums = gn_sums; d.gn_groups = gn_groups; d.gn_in = gn_in;
+  d.gn_sums = nullptr; d.gn_groups = gn_groups; d.gn_in = gn_in;
+  // deterministic fused statistics: the kernels write per-warp partial sums into gn_scratch [launch][image][slot][2G]
+  // (zeroed here: slots of CTAs that never see an image stay zero), gn_finalize folds them into gn_sums afterwards
+  const int gn_launches = upsample2x ? 4 : 1;
+  const long long gn_per_launch = static_cast<long long>(B) * gn_slots_per_image() * 2 * gn_groups;
   if (gn_sums) {
     if (gn_groups <= 0) return set_error(OMGSR_ERR_SHAPE, "conv2d: gn_groups must be > 0 with gn_sums");
-    cudaError_t e = cudaMemsetAsync(gn_sums, 0, sizeof(float) * 2 * gn_groups * B, st);
+    if (!gn_scratch || gn_scratch_floats < gn_launches * gn_per_launch)
+      return set_error(OMGSR_ERR_SHAPE, "conv2d: gn_scratch needs %lld floats (omgsr_gn_scratch_floats), got %lld",
+                       gn_launches * gn_per_launch, gn_scratch ? gn_scratch_floats : 0LL);
+    cudaError_t e = cudaMemsetAsync(gn_scratch, 0, sizeof(float) * gn_launches * gn_per_launch, st);
     if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "conv2d gn memset: %s", cudaGetErrorString(e));
+    d.gn_sums = gn_scratch;
   }
   if (upsample2x) {
     // nearest-2x + 3x3/p1 == four 2x2 convolutions on the un-upsampled input (weights pre-collapsed
@@ -911,9 +909,11 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, const vo
         const long long shift = py * OW + px;
         d.y = static_cast<char*>(y) + shift * ldy * esz;
         d.res = res ? static_cast<const bf16*>(res) + shift * ldr : nullptr;
+        if (gn_sums) d.gn_sums = gn_scratch + (py * 2 + px) * gn_per_launch;
         int rc = run_conv_gemm(d, st);
         if (rc) return rc;
       }
+    if (gn_sums) return launch_gn_finalize(gn_scratch, 4, B, gn_slots_per_image(), 2 * gn_groups, gn_sums, st);
     return OMGSR_OK;
   }
   const int OHh = (H + pad_t + pad_b - ksize) / stride + 1;
@@ -924,5 +924,7 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, const vo
   d.o_sx = ldy; d.o_sy = ldy * OWw; d.o_sb = ldy * OWw * OHh;
   d.r_sx = ldr; d.r_sy = ldr * OWw; d.r_sb = ldr * OWw * OHh;
   d.w_ld = static_cast<long long>(ksize) * ksize * Cin;
-  return run_conv_gemm(d, st);
+  const int rc = run_conv_gemm(d, st);
+  if (rc || !gn_sums) return rc;
+  return launch_gn_finalize(gn_scratch, 1, B, gn_slots_per_image(), 2 * gn_groups, gn_sums, st);
 }

@@ -42,21 +42,21 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics: stats[b, g] = (sum, sumsq). Thread owns one 8-channel vector column and walks
-// pixels; per-channel partials are folded into per-group shared bins, then one global atomic per bin.
+// pixels. Bit-reproducible: the per-thread channel sums are folded per group in a FIXED order inside the block
+// (shared-memory table, no atomics), every block writes its (sum, sumsq) per group to its own scratch slot
+// [image][block][2G], and gn_finalize_kernel adds the slots in a fixed order.
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ stats, long long HW,
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ scratch, long long HW,
                                 int C, int G, int vpr, int rows_per_iter, int blocks_per_img) {
-  extern __shared__ float bins[];  // [G*2]
+  extern __shared__ float tab[];  // [2][rows_per_iter][C]: per-(row lane, channel) sum / sum of squares
   const int b = blockIdx.x / blocks_per_img;
   const int blk = blockIdx.x % blocks_per_img;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) bins[i] = 0.f;
-  __syncthreads();
   const int v = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
-  float s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (threadIdx.x < vpr * rows_per_iter) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     const bf16* base = x + static_cast<long long>(b) * HW * ldx + v * 8;
     const long long step = static_cast<long long>(blocks_per_img) * rows_per_iter;
     long long r = static_cast<long long>(blk) * rows_per_iter + r0;
@@ -77,16 +77,61 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
     }
-    const int cpg = C / G;
+    float* ts = tab + (static_cast<long long>(r0) * C + v * 8);
+    float* tq = ts + static_cast<long long>(rows_per_iter) * C;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cpg;
-      atomicAdd(&bins[2 * g], s[j]);
-      atomicAdd(&bins[2 * g + 1], q[j]);
-    }
+    for (int j = 0; j < 8; ++j) { ts[j] = s[j]; tq[j] = q[j]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[static_cast<long long>(b) * 2 * G + i], bins[i]);
+  const int cpg = C / G;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+    const int g = i >> 1;
+    const float* t = tab + (i & 1) * static_cast<long long>(rows_per_iter) * C + g * cpg;
+    float acc = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r)
+      for (int c = 0; c < cpg; ++c) acc += t[r * C + c];
+    scratch[(static_cast<long long>(b) * blocks_per_img + blk) * 2 * G + i] = acc;
+  }
+}
+
+// out[b][i] = sum over (launch l, slot s) of scratch[((l * B + b) * slots + s) * n + i]; one block per image, the
+// (l, s) range is split over blockDim.x / n thread groups in a fixed interleaving, each thread adds its share in a
+// fixed order (four independent chains), and the groups are combined in index order: same bits every run.
+__global__ void gn_finalize_kernel(const float* __restrict__ scratch, int launches, int B, int slots, int n,
+                                   float* __restrict__ out) {
+  extern __shared__ float part[];  // [P][n]
+  const int b = blockIdx.x;
+  const int P = blockDim.x / n;
+  const int i = threadIdx.x % n, pid = threadIdx.x / n;
+  const long long total = static_cast<long long>(launches) * slots;
+  if (pid < P) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    auto at = [&](long long k) {
+      const long long l = k / slots, sl = k % slots;
+      return __ldg(scratch + ((l * B + b) * slots + sl) * n + i);
+    };
+    long long k = pid;
+    for (; k + 3LL * P < total; k += 4LL * P) {
+      const float v0 = at(k), v1 = at(k + P), v2 = at(k + 2LL * P), v3 = at(k + 3LL * P);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; k < total; k += P) a0 += at(k);
+    part[pid * n + i] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (threadIdx.x < n) {
+    float acc = 0.f;
+    for (int q = 0; q < P; ++q) acc += part[q * n + threadIdx.x];
+    out[static_cast<long long>(b) * n + threadIdx.x] = acc;
+  }
+}
+
+int launch_gn_finalize(const float* scratch, int launches, int B, int slots, int n, float* out, cudaStream_t st) {
+  if (n <= 0 || n > 1024) return set_error(OMGSR_ERR_SHAPE, "gn_finalize: 2 * groups = %d out of range", n);
+  const int threads = 1024;
+  const int P = threads / n;
+  gn_finalize_kernel<<<B, threads, static_cast<size_t>(P) * n * sizeof(float), st>>>(scratch, launches, B, slots, n, out);
+  return check_launch("gn_finalize_kernel");
 }
 
 // GroupNorm apply, stage 1: per-(image, channel) affine coefficients  y = x * a + b  with
@@ -644,13 +689,18 @@ static int grid_for(long long work_items, int threads) {
 
 using namespace omgsr;
 
+extern "C" long long omgsr_gn_scratch_floats(int B, int G, int launches) {
+  if (B <= 0 || G <= 0 || launches <= 0) return 0;
+  const long long conv = static_cast<long long>(launches) * B * gn_slots_per_image() * 2 * G;
+  const long long stats = (static_cast<long long>(sm_count()) * 8 + B) * 2 * G;
+  return conv > stats ? conv : stats;
+}
+
 extern "C" int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats, int B, long long HW, int C, int G,
-                                     void* stream) {
-  if (C % 8 || C % G || G > 512 || C / 8 > 1024) return set_error(OMGSR_ERR_SHAPE, "groupnorm_stats: C=%d G=%d", C, G);
+                                     float* scratch, long long scratch_floats, void* stream) {
+  if (C % 8 || C % G || G > 512 || C > 4096) return set_error(OMGSR_ERR_SHAPE, "groupnorm_stats: C=%d G=%d", C, G);
   if (ldx % 8) return set_error(OMGSR_ERR_ALIGN, "groupnorm_stats: ldx %% 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * B, st);
-  if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "groupnorm_stats memset: %s", cudaGetErrorString(e));
   const int vpr = C / 8;
   int rows_per_iter = 256 / vpr;
   if (rows_per_iter < 1) rows_per_iter = 1;
@@ -659,9 +709,15 @@ extern "C" int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats,
   const long long max_bpi = (HW + rows_per_iter - 1) / rows_per_iter;
   if (bpi > max_bpi) bpi = max_bpi;
   if (bpi < 1) bpi = 1;
-  gn_stats_kernel<<<static_cast<unsigned>(bpi * B), threads, 2 * G * sizeof(float), st>>>(
-      static_cast<const bf16*>(x), ldx, stats, HW, C, G, vpr, rows_per_iter, static_cast<int>(bpi));
-  return check_launch("gn_stats_kernel");
+  if (!scratch || scratch_floats < bpi * B * 2 * G)
+    return set_error(OMGSR_ERR_SHAPE, "groupnorm_stats: scratch needs %lld floats (omgsr_gn_scratch_floats), got %lld",
+                     bpi * B * 2 * G, scratch ? scratch_floats : 0LL);
+  const size_t smem = 2ull * rows_per_iter * C * sizeof(float);  // <= 32 KB
+  gn_stats_kernel<<<static_cast<unsigned>(bpi * B), threads, smem, st>>>(
+      static_cast<const bf16*>(x), ldx, scratch, HW, C, G, vpr, rows_per_iter, static_cast<int>(bpi));
+  int rc = check_launch("gn_stats_kernel");
+  if (rc) return rc;
+  return launch_gn_finalize(scratch, 1, B, static_cast<int>(bpi), 2 * G, stats, st);
 }
 
 extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, const float* stats,

@@ -54,21 +54,28 @@ class _T2D:
         self.wff1, self.bff1 = _dev(wi, device, bf), _dev(bi, device, f32)
         self.wff2, self.bff2 = g(tb + ".ff.net.2.weight", bf), g(tb + ".ff.net.2.bias")
         self.c = c
-        self.kv_cache = None  # (key, kv [B,77,2C])
+        self.kv_cache = None  # (prompt tensor, its _version, B, kv [B,77,2C])
 
     def cross_kv(self, ctx, ctx_key, B):
-        if ctx_key is None or self.kv_cache is None or self.kv_cache[0] != (ctx_key, B):
-            T = ctx.shape[1]
-            ctx2 = ctx.reshape(-1, ctx.shape[-1])
-            if ctx2.shape[1] % 64:
-                raise RuntimeError("cross_attention_dim must be a multiple of 64")
-            kv = capi.gemm(ctx2, self.wkv2).view(ctx.shape[0], T, 2 * self.c)
-            if ctx.shape[0] != B:  # batch-1 text broadcast over the image batch
-                kv = kv.expand(B, T, 2 * self.c).contiguous()
-            if ctx_key is None:
-                return kv
-            self.kv_cache = ((ctx_key, B), kv)
-        return self.kv_cache[1]
+        """K/V projections of the prompt. ctx_key = (the caller's prompt tensor object, its _version) or None.
+        The cache holds a strong reference to that tensor and hits only on the SAME object at the SAME version, so a
+        freed temporary whose address the allocator hands to the next prompt can never alias it (the first
+        version keyed on data_ptr() of a converted temporary)."""
+        c = self.kv_cache
+        if ctx_key is not None and c is not None and c[0] is ctx_key[0] and c[1] == ctx_key[1] and c[2] == B:
+            return c[3]
+        T = ctx.shape[1]
+        ctx2 = ctx.reshape(-1, ctx.shape[-1])
+        if ctx2.shape[1] % 64:
+            raise RuntimeError("cross_attention_dim must be a multiple of 64")
+        kv = capi.gemm(ctx2, self.wkv2).view(ctx.shape[0], T, 2 * self.c)
+        if ctx.shape[0] != B:  # batch-1 text broadcast over the image batch (SURVEY.md §7.3)
+            if ctx.shape[0] != 1:
+                raise RuntimeError(f"prompt batch {ctx.shape[0]} does not match the latent batch {B}")
+            kv = kv.expand(B, T, 2 * self.c).contiguous()
+        if ctx_key is not None:
+            self.kv_cache = (ctx_key[0], ctx_key[1], B, kv)
+        return kv
 
     def forward(self, x, ctx, ctx_key, out):
         B, H, W, C = x.shape
@@ -106,6 +113,7 @@ class B200UNet(torch.nn.Module):
         if dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("B200UNet: boundary dtype must be bf16 or fp32")
         self.cfg, self.dev, self._dtype = cfg, device, dtype
+        self.mid_timestep = mid_timestep
         self.cache_kv = True
         self.config = SimpleNamespace(in_channels=cfg.in_channels, out_channels=cfg.out_channels)
         f32 = torch.float32
@@ -185,11 +193,11 @@ class B200UNet(torch.nn.Module):
         eps = cfg.norm_eps
         B, _, H0, W0 = z.shape
         n = len(ch)
+        src = ctx  # the caller's tensor object: cache identity (kept alive by the cache itself)
         ctx = ctx.to(device=z.device, dtype=torch.bfloat16).contiguous()
         # prompt projections are cached across calls unless the launch sequence is being captured into a CUDA graph
         # (a replayed graph must recompute them from the static prompt buffer)
-        ctx_key = None if torch.cuda.is_current_stream_capturing() or not self.cache_kv else \
-            (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
+        ctx_key = None if torch.cuda.is_current_stream_capturing() or not self.cache_kv else (src, src._version)
         res_hw = [(H0 >> l, W0 >> l) for l in range(n)]
         # concat buffers, one per up resnet; skip s lives in the right slice of its consumer's buffer
         nsk = len(self._skip_meta)
@@ -254,7 +262,14 @@ class B200UNet(torch.nn.Module):
         return resnet_forward(r, x, eps, out=out)
 
     def forward(self, sample, timestep=None, encoder_hidden_states=None, **kw):
-        """diffusers-style call: returns an object with `.sample` (NCHW, boundary dtype)."""
+        """diffusers-style call: returns an object with `.sample` (NCHW, boundary dtype). The time embedding is folded
+        into the conv biases at construction (the reference always calls the UNet at self.mid_timestep,
+        infer/omgsr_s_infer_model.py:75-79,132), so any other timestep is an error, not a silent mismatch."""
+        if timestep is not None:
+            t = float(timestep.reshape(-1)[0]) if torch.is_tensor(timestep) else float(timestep)
+            if t != float(self.mid_timestep):
+                raise ValueError(f"B200UNet was built for timestep {self.mid_timestep} (time embedding folded into the "
+                                 f"weights); got timestep={t}. Construct a new module for another timestep.")
         e = self.eps_hat_nhwc(sample, encoder_hidden_states)
         out = e[..., :self.cfg.out_channels].permute(0, 3, 1, 2).contiguous().to(self._dtype)
         return SimpleNamespace(sample=out)

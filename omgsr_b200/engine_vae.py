@@ -420,14 +420,15 @@ class _Posterior:
     def __init__(self, moments_nhwc_f32, cz, out_dtype, eps=None):
         self.m, self.cz, self.out_dtype, self.eps = moments_nhwc_f32, cz, out_dtype, eps
 
-    def sample(self, generator=None):
+    def sample(self, generator=None, shift=0.0, scale=1.0):
+        """mean + std * eps; `shift` / `scale` fold the caller's (z - shift_factor) * scaling_factor into the kernel."""
         B, h, w, _ = self.m.shape
         eps = self.eps
         if eps is None:
             from .dist import broadcast_
             eps = broadcast_(torch.randn((B, self.cz, h, w), device=self.m.device, dtype=torch.float32,
                                          generator=generator))
-        return capi.posterior_sample(self.m, eps.to(device=self.m.device, dtype=torch.float32), self.cz, 0.0, 1.0,
+        return capi.posterior_sample(self.m, eps.to(device=self.m.device, dtype=torch.float32), self.cz, shift, scale,
                                      self.out_dtype)
 
     def mode(self):
@@ -476,6 +477,11 @@ class B200AutoencoderKL(torch.nn.Module):
         else:
             m = self.encoder.moments_nhwc(x)
         return SimpleNamespace(latent_dist=_Posterior(m, self.cfg.latent_channels, self._dtype, self.posterior_eps))
+
+    def encode_scaled(self, x):
+        """(encode(x).latent_dist.sample() - shift_factor) * scaling_factor in one posterior kernel
+        (infer/omgsr_f_infer_model.py:15-18 / infer/omgsr_s_infer_model.py:173)."""
+        return self.encode(x).latent_dist.sample(shift=self.config.shift_factor, scale=self.config.scaling_factor)
 
     def decode(self, z, return_dict=True):
         z = z.to(self._dtype)

@@ -1,316 +1,14 @@
-"""Architecture configs and state-dict construction for the nets on the OMGSR inference path.
+"""State-dict construction for the nets on the OMGSR inference path: synthetic specs (re-exported from `omgsr_synth`)
+plus the PEFT-style LoRA merge the product path applies at load time.
 
-Key names are the diffusers 0.34.0 state-dict names, so a real
-`diffusion_pytorch_model.safetensors` can be fed to the engines unchanged. Because neither the HF checkpoints
-nor diffusers/peft exist offline, `random_*_state_dict` builds seeded random-init tensors of exactly those
-shapes, and `random_lora` / `merge_lora` reproduce PEFT's `merge_and_unload`
-(W <- W + (alpha/r) * B A, alpha = r; reference: infer/omgsr_s_infer_model.py:16-23, LoRA targets
-train/train_omgsr_s.py:61-72,89-100 and train/train_omgsr_f.py:155-169).
+`merge_lora` reproduces PEFT's `merge_and_unload` (W <- W + (alpha/r) * B A, alpha = r; reference:
+infer/omgsr_s_infer_model.py:16-23, infer/omgsr_f_infer_model.py:115-118). The oracle carries its own restatement
+(oracle/lora.py); tests/test_oracle_cpu.py checks that the two agree.
 """
-import math
-from dataclasses import dataclass, field
-from typing import Dict, Tuple
-
 import torch
 
-
-# ------------------------------------------------------------------------------------------------
-# configs
-# ------------------------------------------------------------------------------------------------
-@dataclass
-class VAEConfig:
-    in_channels: int = 3
-    out_channels: int = 3
-    latent_channels: int = 4
-    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
-    layers_per_block: int = 2
-    norm_num_groups: int = 32
-    scaling_factor: float = 0.18215
-    shift_factor: float = 0.0
-    use_quant_conv: bool = True
-    eps: float = 1e-6
-
-
-@dataclass
-class UNetConfig:
-    in_channels: int = 4
-    out_channels: int = 4
-    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
-    down_has_attn: Tuple[bool, ...] = (True, True, True, False)
-    layers_per_block: int = 2
-    num_heads: Tuple[int, ...] = (5, 10, 20, 20)  # "attention_head_dim" used as head count => d = 64
-    cross_attention_dim: int = 1024
-    norm_num_groups: int = 32
-    norm_eps: float = 1e-5
-
-    @property
-    def time_embed_dim(self):
-        return 4 * self.block_out_channels[0]
-
-
-@dataclass
-class FluxConfig:
-    in_channels: int = 64
-    num_layers: int = 19
-    num_single_layers: int = 38
-    num_heads: int = 24
-    head_dim: int = 128
-    joint_attention_dim: int = 4096
-    pooled_projection_dim: int = 768
-    axes_dims_rope: Tuple[int, ...] = (16, 56, 56)
-    guidance_embeds: bool = True
-    mlp_ratio: int = 4
-
-    @property
-    def dim(self):
-        return self.num_heads * self.head_dim
-
-
-SD21_VAE = VAEConfig()
-FLUX_VAE = VAEConfig(latent_channels=16, scaling_factor=0.3611, shift_factor=0.1159, use_quant_conv=False)
-SD21_UNET = UNetConfig()
-FLUX_DEV = FluxConfig()
-# reduced-width / reduced-depth variants with the same topology, used by the CPU-sized parity tests
-TINY_VAE = VAEConfig(block_out_channels=(64, 64, 128, 128))
-TINY_FLUX_VAE = VAEConfig(latent_channels=16, scaling_factor=0.3611, shift_factor=0.1159, use_quant_conv=False,
-                          block_out_channels=(64, 64, 128, 128))
-TINY_UNET = UNetConfig(block_out_channels=(64, 128, 256, 256), num_heads=(1, 2, 4, 4), cross_attention_dim=128)
-TINY_FLUX = FluxConfig(num_layers=2, num_single_layers=3, num_heads=4, joint_attention_dim=256,
-                       pooled_projection_dim=64, axes_dims_rope=(16, 56, 56))
-
-
-# ------------------------------------------------------------------------------------------------
-# shape tables
-# ------------------------------------------------------------------------------------------------
-def _conv(sd, name, cin, cout, k):
-    sd[name + ".weight"] = (cout, cin, k, k)
-    sd[name + ".bias"] = (cout,)
-
-
-def _lin(sd, name, cin, cout, bias=True):
-    sd[name + ".weight"] = (cout, cin)
-    if bias:
-        sd[name + ".bias"] = (cout,)
-
-
-def _norm(sd, name, c):
-    sd[name + ".weight"] = (c,)
-    sd[name + ".bias"] = (c,)
-
-
-def _resnet(sd, name, cin, cout, temb=None):
-    _norm(sd, name + ".norm1", cin)
-    _conv(sd, name + ".conv1", cin, cout, 3)
-    if temb:
-        _lin(sd, name + ".time_emb_proj", temb, cout)
-    _norm(sd, name + ".norm2", cout)
-    _conv(sd, name + ".conv2", cout, cout, 3)
-    if cin != cout:
-        _conv(sd, name + ".conv_shortcut", cin, cout, 1)
-
-
-def _vae_attn(sd, name, c):
-    _norm(sd, name + ".group_norm", c)
-    for p in ("to_q", "to_k", "to_v", "to_out.0"):
-        _lin(sd, f"{name}.{p}", c, c)
-
-
-def vae_shapes(cfg: VAEConfig) -> Dict[str, tuple]:
-    sd = {}
-    ch = cfg.block_out_channels
-    # encoder
-    _conv(sd, "encoder.conv_in", cfg.in_channels, ch[0], 3)
-    cin = ch[0]
-    for i, co in enumerate(ch):
-        for j in range(cfg.layers_per_block):
-            _resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", cin, co)
-            cin = co
-        if i < len(ch) - 1:
-            _conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3)
-    _resnet(sd, "encoder.mid_block.resnets.0", ch[-1], ch[-1])
-    _vae_attn(sd, "encoder.mid_block.attentions.0", ch[-1])
-    _resnet(sd, "encoder.mid_block.resnets.1", ch[-1], ch[-1])
-    _norm(sd, "encoder.conv_norm_out", ch[-1])
-    _conv(sd, "encoder.conv_out", ch[-1], 2 * cfg.latent_channels, 3)
-    # decoder
-    rev = list(reversed(ch))
-    _conv(sd, "decoder.conv_in", cfg.latent_channels, rev[0], 3)
-    _resnet(sd, "decoder.mid_block.resnets.0", rev[0], rev[0])
-    _vae_attn(sd, "decoder.mid_block.attentions.0", rev[0])
-    _resnet(sd, "decoder.mid_block.resnets.1", rev[0], rev[0])
-    cin = rev[0]
-    for i, co in enumerate(rev):
-        for j in range(cfg.layers_per_block + 1):
-            _resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", cin, co)
-            cin = co
-        if i < len(ch) - 1:
-            _conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", co, co, 3)
-    _norm(sd, "decoder.conv_norm_out", rev[-1])
-    _conv(sd, "decoder.conv_out", rev[-1], cfg.out_channels, 3)
-    if cfg.use_quant_conv:
-        _conv(sd, "quant_conv", 2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
-        _conv(sd, "post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
-    return sd
-
-
-def _transformer2d(sd, name, c, ctx):
-    _norm(sd, name + ".norm", c)
-    _lin(sd, name + ".proj_in", c, c)
-    tb = name + ".transformer_blocks.0"
-    _norm(sd, tb + ".norm1", c)
-    for p in ("to_q", "to_k", "to_v"):
-        _lin(sd, f"{tb}.attn1.{p}", c, c, bias=False)
-    _lin(sd, tb + ".attn1.to_out.0", c, c)
-    _norm(sd, tb + ".norm2", c)
-    _lin(sd, tb + ".attn2.to_q", c, c, bias=False)
-    _lin(sd, tb + ".attn2.to_k", ctx, c, bias=False)
-    _lin(sd, tb + ".attn2.to_v", ctx, c, bias=False)
-    _lin(sd, tb + ".attn2.to_out.0", c, c)
-    _norm(sd, tb + ".norm3", c)
-    _lin(sd, tb + ".ff.net.0.proj", c, 8 * c)
-    _lin(sd, tb + ".ff.net.2", 4 * c, c)
-    _lin(sd, name + ".proj_out", c, c)
-
-
-def unet_shapes(cfg: UNetConfig) -> Dict[str, tuple]:
-    sd = {}
-    ch = cfg.block_out_channels
-    te = cfg.time_embed_dim
-    _lin(sd, "time_embedding.linear_1", ch[0], te)
-    _lin(sd, "time_embedding.linear_2", te, te)
-    _conv(sd, "conv_in", cfg.in_channels, ch[0], 3)
-    skips = [ch[0]]
-    cin = ch[0]
-    for i, co in enumerate(ch):
-        for j in range(cfg.layers_per_block):
-            _resnet(sd, f"down_blocks.{i}.resnets.{j}", cin, co, te)
-            if cfg.down_has_attn[i]:
-                _transformer2d(sd, f"down_blocks.{i}.attentions.{j}", co, cfg.cross_attention_dim)
-            cin = co
-            skips.append(co)
-        if i < len(ch) - 1:
-            _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", co, co, 3)
-            skips.append(co)
-    _resnet(sd, "mid_block.resnets.0", ch[-1], ch[-1], te)
-    _transformer2d(sd, "mid_block.attentions.0", ch[-1], cfg.cross_attention_dim)
-    _resnet(sd, "mid_block.resnets.1", ch[-1], ch[-1], te)
-    rev = list(reversed(ch))
-    rev_attn = list(reversed(cfg.down_has_attn))
-    for i, co in enumerate(rev):
-        for j in range(cfg.layers_per_block + 1):
-            skip = skips.pop()
-            _resnet(sd, f"up_blocks.{i}.resnets.{j}", cin + skip, co, te)
-            if rev_attn[i]:
-                _transformer2d(sd, f"up_blocks.{i}.attentions.{j}", co, cfg.cross_attention_dim)
-            cin = co
-        if i < len(ch) - 1:
-            _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", co, co, 3)
-    _norm(sd, "conv_norm_out", ch[0])
-    _conv(sd, "conv_out", ch[0], cfg.out_channels, 3)
-    return sd
-
-
-def flux_shapes(cfg: FluxConfig) -> Dict[str, tuple]:
-    sd = {}
-    d = cfg.dim
-    hd = cfg.head_dim
-    _lin(sd, "x_embedder", cfg.in_channels, d)
-    _lin(sd, "context_embedder", cfg.joint_attention_dim, d)
-    for e, cin in (("timestep_embedder", 256), ("guidance_embedder", 256), ("text_embedder", cfg.pooled_projection_dim)):
-        if e == "guidance_embedder" and not cfg.guidance_embeds:
-            continue
-        _lin(sd, f"time_text_embed.{e}.linear_1", cin, d)
-        _lin(sd, f"time_text_embed.{e}.linear_2", d, d)
-    for i in range(cfg.num_layers):
-        b = f"transformer_blocks.{i}"
-        _lin(sd, b + ".norm1.linear", d, 6 * d)
-        _lin(sd, b + ".norm1_context.linear", d, 6 * d)
-        for p in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"):
-            _lin(sd, f"{b}.attn.{p}", d, d)
-        for p in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
-            sd[f"{b}.attn.{p}.weight"] = (hd,)
-        for ff in ("ff", "ff_context"):
-            _lin(sd, f"{b}.{ff}.net.0.proj", d, cfg.mlp_ratio * d)
-            _lin(sd, f"{b}.{ff}.net.2", cfg.mlp_ratio * d, d)
-    for i in range(cfg.num_single_layers):
-        b = f"single_transformer_blocks.{i}"
-        _lin(sd, b + ".norm.linear", d, 3 * d)
-        _lin(sd, b + ".proj_mlp", d, cfg.mlp_ratio * d)
-        _lin(sd, b + ".proj_out", d + cfg.mlp_ratio * d, d)
-        for p in ("to_q", "to_k", "to_v"):
-            _lin(sd, f"{b}.attn.{p}", d, d)
-        for p in ("norm_q", "norm_k"):
-            sd[f"{b}.attn.{p}.weight"] = (hd,)
-    _lin(sd, "norm_out.linear", d, 2 * d)
-    _lin(sd, "proj_out", d, cfg.in_channels)
-    return sd
-
-
-# ------------------------------------------------------------------------------------------------
-# random init (synthetic weights: there is no network access for checkpoints)
-# ------------------------------------------------------------------------------------------------
-def random_state_dict(shapes: Dict[str, tuple], seed: int, dtype=torch.float32, out_gain: Dict[str, float] = None,
-                      device="cpu"):
-    """Variance-preserving init: conv/linear weights ~ N(0, 1/fan_in), biases ~ N(0, 0.02^2), norm affine
-    ~ (1 + N(0, 0.1^2), N(0, 0.1^2)). `out_gain` rescales selected layers (substring match) so that the
-    end-to-end outputs have O(1) range and the PSNR / relative-error bars are meaningful."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    rn = lambda shp: torch.randn(shp, generator=g, device=device)
-    sd = {}
-    for name, shp in shapes.items():
-        if name.endswith(".weight") and len(shp) >= 2:
-            fan_in = 1
-            for s in shp[1:]:
-                fan_in *= s
-            t = rn(shp) / math.sqrt(fan_in)
-        elif name.endswith(".weight"):
-            t = 1.0 + 0.1 * rn(shp)
-        else:
-            is_norm = name.replace(".bias", ".weight") in shapes and len(shapes[name.replace(".bias", ".weight")]) == 1
-            t = (0.1 if is_norm else 0.02) * rn(shp)
-        if out_gain:
-            for key, gain in out_gain.items():
-                if key in name and name.endswith(".weight") and len(shp) >= 2:
-                    t = t * gain
-        sd[name] = t.to(dtype)
-    return sd
-
-
-# LoRA target modules by suffix (train/train_omgsr_s.py:61-72,89-100; train/train_omgsr_f.py:155-169)
-LORA_TARGETS_SD = ("conv1", "conv2", "conv_in", "conv_shortcut", "conv", "conv_out", "to_q", "to_k", "to_v", "to_out.0")
-LORA_TARGETS_FLUX = ("x_embedder", "attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0", "attn.add_q_proj",
-                     "attn.add_k_proj", "attn.add_v_proj", "attn.to_add_out", "ff.net.0.proj", "ff.net.2",
-                     "ff_context.net.0.proj", "ff_context.net.2")
-
-
-def lora_target_names(shapes: Dict[str, tuple], targets, prefix=""):
-    out = []
-    for name in shapes:
-        if not name.endswith(".weight") or len(shapes[name]) < 2 or not name.startswith(prefix):
-            continue
-        mod = name[: -len(".weight")]
-        if any(mod == t or mod.endswith("." + t) for t in targets):
-            out.append(mod)
-    return out
-
-
-def random_lora(shapes, targets, rank, seed, prefix="", b_std=0.02, device="cpu"):
-    """PEFT-format adapter tensors {module: (A, B)}: Linear A [r,in], B [out,r]; Conv2d A [r,Cin,k,k]
-    (same kernel as the base conv), B [Cout,r,1,1]. A ~ N(0, 1/r) ('gaussian' init, train_omgsr_s.py:78);
-    PEFT zero-inits B, here B ~ N(0, b_std^2) so that the merge is actually exercised."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    rn = lambda shp: torch.randn(shp, generator=g, device=device)
-    ad = {}
-    for mod in lora_target_names(shapes, targets, prefix):
-        shp = shapes[mod + ".weight"]
-        if len(shp) == 4:
-            a = rn((rank, shp[1], shp[2], shp[3])) / rank
-            b = rn((shp[0], rank, 1, 1)) * b_std
-        else:
-            a = rn((rank, shp[1])) / rank
-            b = rn((shp[0], rank)) * b_std
-        ad[mod] = (a, b)
-    return ad
+from omgsr_synth import *  # noqa: F401,F403  (configs, shape tables, random init, ddpm_alphas_cumprod)
+from omgsr_synth import _conv, _lin, _norm  # noqa: F401
 
 
 def merge_lora(sd, adapter, scale=1.0):
@@ -325,10 +23,3 @@ def merge_lora(sd, adapter, scale=1.0):
             delta = b.float() @ a.float()
         out[mod + ".weight"] = (w + scale * delta).to(sd[mod + ".weight"].dtype)
     return out
-
-
-def ddpm_alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
-    """SD-2.1-base DDPMScheduler: scaled-linear betas (the reference only reads alphas_cumprod[273],
-    infer/omgsr_s_infer_model.py:13-14)."""
-    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
-    return torch.cumprod(1.0 - betas, dim=0)

@@ -104,7 +104,7 @@ def vae_decode(sd, cfg, z):
 # ------------------------------------------------------------------------------------------------
 def timestep_embedding(t, dim, flip_sin_to_cos=True, max_period=10000.0):
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t.float()[:, None] * freqs[None]
     emb = torch.cat([torch.sin(args), torch.cos(args)], dim=-1)
     if flip_sin_to_cos:
@@ -143,7 +143,7 @@ def unet_forward(sd, cfg, x, timestep, ctx):
     b = x.shape[0]
     ch = cfg.block_out_channels
     eps = cfg.norm_eps
-    t = torch.full((b,), float(timestep), dtype=torch.float32)
+    t = torch.full((b,), float(timestep), dtype=torch.float32, device=x.device)
     temb = timestep_embedding(t, ch[0]).to(x.dtype)
     temb = _lin(sd, "time_embedding.linear_2", F.silu(_lin(sd, "time_embedding.linear_1", temb)))
     if ctx.shape[0] != b:
@@ -187,7 +187,7 @@ def flux_rope(ids, axes_dims, theta=10000.0):
     cos_out, sin_out = [], []
     pos = ids.double()
     for i, d in enumerate(axes_dims):
-        freqs = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64) / d))
+        freqs = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64, device=ids.device) / d))
         ang = pos[:, i:i + 1] * freqs[None]
         cos_out.append(ang.cos().repeat_interleave(2, dim=1).float())
         sin_out.append(ang.sin().repeat_interleave(2, dim=1).float())
@@ -209,7 +209,7 @@ def _rms(x, w, eps=1e-6):
 
 def _sincos256(v):
     half = 128
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=v.device) / half)
     args = v.float()[:, None] * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)  # flip_sin_to_cos=True
 
@@ -233,15 +233,18 @@ def flux_forward(sd, cfg, hidden_states, timestep, guidance, pooled, encoder_hid
     H = cfg.num_heads
     dt = hidden_states.dtype
     B = hidden_states.shape[0]
+    dev = hidden_states.device
     x = _lin(sd, "x_embedder", hidden_states)
-    t = timestep.to(dt).expand(B) * 1000
+    # diffusers casts timestep / guidance to the hidden dtype BEFORE the x1000 (bf16 weights => the net is conditioned
+    # on bf16(0.5051) * 1000 = 504, fp32 weights => 505.11); the fp32 evaluation is the parity target
+    t = timestep.to(device=dev, dtype=dt).expand(B) * 1000
     temb = _mlp_embed(sd, "time_text_embed.timestep_embedder", _sincos256(t).to(dt))
     if cfg.guidance_embeds:
-        g = guidance.to(dt) * 1000
+        g = guidance.to(device=dev, dtype=dt) * 1000
         temb = temb + _mlp_embed(sd, "time_text_embed.guidance_embedder", _sincos256(g).to(dt))
     temb = temb + _mlp_embed(sd, "time_text_embed.text_embedder", pooled)
     c = _lin(sd, "context_embedder", encoder_hidden_states)
-    cos, sin = flux_rope(torch.cat([txt_ids, img_ids], dim=0).float(), cfg.axes_dims_rope)
+    cos, sin = flux_rope(torch.cat([txt_ids, img_ids], dim=0).float().to(dev), cfg.axes_dims_rope)
     st = F.silu(temb)
     n_txt = c.shape[1]
     for i in range(cfg.num_layers):

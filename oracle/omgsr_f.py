@@ -35,6 +35,11 @@ class OracleF:
         self.t_curr, self.t_prev = sched[-(mid_timestep + 1)], sched[-1]
         self.guidance_scale = guidance_scale
 
+    def to(self, device=None, dtype=None):
+        mv = lambda sd: {k: v.to(device=device, dtype=dtype if v.is_floating_point() else None) for k, v in sd.items()}
+        self.vae_sd, self.flux_sd = mv(self.vae_sd), mv(self.flux_sd)
+        return self
+
     def encode(self, lq_img, eps_noise):
         mom = nets.vae_encode_moments(self.vae_sd, self.vae_cfg, lq_img)
         z = nets.posterior_sample(mom, eps_noise)
@@ -43,7 +48,7 @@ class OracleF:
     def dit(self, packed, prompt_embeds, pooled, text_ids, img_ids):
         b = packed.shape[0]
         return nets.flux_forward(self.flux_sd, self.flux_cfg, packed, torch.tensor([self.t_curr]),
-                                 torch.full((b,), self.guidance_scale), pooled.expand(b, -1),
+                                 torch.full((b,), float(self.guidance_scale)), pooled.expand(b, -1),
                                  prompt_embeds.expand(b, -1, -1), text_ids, img_ids)
 
     def forward_no_tile(self, z, prompt_embeds, pooled, text_ids, img_ids):
@@ -57,9 +62,9 @@ class OracleF:
     def forward_tile(self, z, prompt_embeds, pooled, text_ids, img_ids, tile_size, tile_overlap):
         _, _, h, w = z.shape
         tile_size = min(tile_size, min(h, w))
-        wts = gaussian_weights(tile_size, tile_size)
-        noise = torch.zeros(z.shape)
-        contrib = torch.zeros(z.shape)
+        wts = gaussian_weights(tile_size, tile_size).to(z.device)
+        noise = torch.zeros(z.shape, device=z.device)
+        contrib = torch.zeros(z.shape, device=z.device)
         for ox, oy in tile_offsets(h, w, tile_size, tile_overlap):
             tile = z[:, :, oy:oy + tile_size, ox:ox + tile_size]
             v = unpack_latents(self.dit(pack_latents(tile), prompt_embeds, pooled, text_ids, img_ids), tile_size, tile_size)

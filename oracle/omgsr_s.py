@@ -58,6 +58,13 @@ class OracleS:
         self.mid_timestep = mid_timestep
         self.alpha_t = alphas_cumprod[mid_timestep]
 
+    def to(self, device=None, dtype=None):
+        """move / cast the weights (the GPU-eager arm of bench.py and the full-size parity tests run the oracle on
+        the device: fp32 with TF32 off for parity, bf16 as the PyTorch-eager baseline)."""
+        mv = lambda sd: {k: v.to(device=device, dtype=dtype if v.is_floating_point() else None) for k, v in sd.items()}
+        self.vae_sd, self.unet_sd = mv(self.vae_sd), mv(self.unet_sd)
+        return self
+
     def encode(self, lq_img, eps_noise):
         mom = nets.vae_encode_moments(self.vae_sd, self.vae_cfg, lq_img)
         return nets.posterior_sample(mom, eps_noise) * self.vae_cfg.scaling_factor  # :173
@@ -73,10 +80,10 @@ class OracleS:
     def forward_tile(self, lq_latent, prompt_embeds, tile_size, tile_overlap):
         _, _, h, w = lq_latent.shape
         tile_size = min(tile_size, min(h, w))
-        wts = gaussian_weights(tile_size, tile_size)
+        wts = gaussian_weights(tile_size, tile_size).to(lq_latent.device)
         offs = tile_offsets(h, w, tile_size, tile_overlap)
-        noise = torch.zeros(lq_latent.shape)
-        contrib = torch.zeros(lq_latent.shape)
+        noise = torch.zeros(lq_latent.shape, device=lq_latent.device)
+        contrib = torch.zeros(lq_latent.shape, device=lq_latent.device)
         for ox, oy in offs:  # each tile is a batch-1 denoiser call (:129-133)
             tile = lq_latent[:, :, oy:oy + tile_size, ox:ox + tile_size]
             out = nets.unet_forward(self.unet_sd, self.unet_cfg, tile, self.mid_timestep, prompt_embeds)

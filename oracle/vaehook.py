@@ -68,7 +68,7 @@ class _SharedGroupNorm:
         var, mean = torch.var_mean(xr, dim=2, unbiased=False)  # per (b, group)
         self.slots[i] = (var, mean, x.shape[2] * x.shape[3])
         self.barrier.wait()
-        pix = torch.tensor([s[2] for s in self.slots], dtype=torch.float32)
+        pix = torch.tensor([s[2] for s in self.slots], dtype=torch.float32, device=x.device)
         wts = pix / pix.sum()
         var = sum(w * s[0] for w, s in zip(wts, self.slots))
         mean = sum(w * s[1] for w, s in zip(wts, self.slots))
@@ -104,7 +104,7 @@ class _EstimatedGroupNorm:
 def _stitch(x, results, ins, outs, is_decoder):
     _, _, h, w = x.shape
     oh, ow = (h * 8, w * 8) if is_decoder else (h // 8, w // 8)
-    out = torch.zeros((x.shape[0], results[0].shape[1], oh, ow), dtype=torch.float32)
+    out = torch.zeros((x.shape[0], results[0].shape[1], oh, ow), dtype=torch.float32, device=x.device)
     for i, tile in enumerate(results):
         scaled = [v * 8 if is_decoder else v // 8 for v in ins[i]]
         m = [outs[i][k] - scaled[k] for k in range(4)]
@@ -174,7 +174,7 @@ def tiled_forward(fn, x, tile_size, is_decoder):
     if errors:
         raise errors[0]
     oh, ow = (h * 8, w * 8) if is_decoder else (h // 8, w // 8)
-    out = torch.zeros((x.shape[0], results[0].shape[1], oh, ow), dtype=torch.float32)
+    out = torch.zeros((x.shape[0], results[0].shape[1], oh, ow), dtype=torch.float32, device=x.device)
     for i, tile in enumerate(results):
         scaled = [v * 8 if is_decoder else v // 8 for v in ins[i]]
         m = [outs[i][k] - scaled[k] for k in range(4)]

@@ -205,3 +205,65 @@ def test_mid_timestep_search_matches_reference_loop():
         t_got, loss, _ = search.result()
         assert t_got == t_ref, (family, t_got, t_ref)
         assert abs(loss - ref[t_ref]) <= 1e-4 * max(1.0, ref[t_ref])
+
+
+def test_lora_merge_is_adapter_forward():
+    """oracle/lora.py (PEFT merge rule, restated independently) == what the un-merged adapter computes:
+    base(x) + B(A(x)) for a Linear and for a 3x3 Conv2d (stride / padding of the base conv on A, 1x1 B); and the product
+    path's merge (omgsr_b200.weights.merge_lora) produces the same weights."""
+    import torch.nn.functional as F
+    from omgsr_b200 import weights as W
+    from oracle import lora as OL
+    g = torch.Generator().manual_seed(3)
+    r = 4
+    # Linear
+    w, b = torch.randn(24, 16, generator=g), torch.randn(24, generator=g)
+    a, bb = torch.randn(r, 16, generator=g), torch.randn(24, r, generator=g)
+    x = torch.randn(5, 16, generator=g)
+    merged = OL.merge_lora({"m.weight": w, "m.bias": b}, {"m": (a, bb)})
+    assert torch.allclose(F.linear(x, merged["m.weight"], b), OL.adapter_forward(x, w, b, a, bb), atol=1e-5)
+    # Conv2d 3x3, stride 2, padding 1
+    w, b = torch.randn(12, 8, 3, 3, generator=g), torch.randn(12, generator=g)
+    a, bb = torch.randn(r, 8, 3, 3, generator=g), torch.randn(12, r, 1, 1, generator=g)
+    x = torch.randn(2, 8, 10, 10, generator=g)
+    merged_c = OL.merge_lora({"c.weight": w}, {"c": (a, bb)})
+    assert torch.allclose(F.conv2d(x, merged_c["c.weight"], b, stride=2, padding=1),
+                          OL.adapter_forward(x, w, b, a, bb, stride=2, padding=1), atol=1e-4)
+    # lora_alpha != r scales the delta
+    m2 = OL.merge_lora({"c.weight": w}, {"c": (a, bb)}, lora_alpha=2 * r)
+    assert torch.allclose(m2["c.weight"] - w, 2 * (merged_c["c.weight"] - w), atol=1e-5)
+    # product merge == oracle merge
+    prod = W.merge_lora({"c.weight": w, "m.weight": merged["m.weight"]}, {"c": (a, bb)})
+    assert torch.allclose(prod["c.weight"], merged_c["c.weight"], atol=1e-6)
+
+
+def test_oracle_synth_states_equal_product_states():
+    """bench.py's reference arm builds its weights through oracle/synth.py without importing the product package;
+    they must be the very tensors build_s_state / build_f_state give the CUDA path."""
+    from infer.omgsr_s_infer_model import build_s_state
+    from infer.omgsr_f_infer_model import build_f_state
+    from oracle import synth
+    pv, pu, pvc, puc = build_s_state("random://tiny?seed=0", "random://lora?seed=1")
+    ov, ou, ovc, ouc = synth.s_state("tiny", 0, 1)
+    assert pvc == ovc and puc == ouc and set(pv) == set(ov) and set(pu) == set(ou)
+    assert all(torch.allclose(pv[k], ov[k], atol=1e-6) for k in pv) and all(torch.allclose(pu[k], ou[k], atol=1e-6) for k in pu)
+    pv, pf, _, pfc = build_f_state("random://tiny?seed=0", "random://lora?seed=1&rank=8", torch.float32)
+    ov, of_, _, ofc = synth.f_state("tiny", 0, 1, 8, torch.float32)
+    assert pfc == ofc and all(torch.allclose(pf[k], of_[k], atol=1e-6) for k in pf)
+    assert all(torch.allclose(pv[k], ov[k], atol=1e-6) for k in pv)
+
+
+def test_reference_arm_does_not_load_the_cuda_library():
+    """`bench.py --impl reference` must not import omgsr_b200 / infer (the CPU arm dlopen()ed the .so)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, types; sys.argv=['bench.py']; import importlib.util as u; "
+            f"s=u.spec_from_file_location('bench', r'{os.path.join(root, 'bench.py')}'); b=u.module_from_spec(s); s.loader.exec_module(b); "
+            "o=b._oracle_s(); x=b._s_inputs(1); "
+            "bad=[m for m in sys.modules if m.startswith(('omgsr_b200','infer'))]; "
+            "maps=open('/proc/self/maps').read(); "
+            "print('BAD', bad, 'libomgsr' in maps)")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "BAD [] False" in r.stdout, r.stdout
