@@ -1,0 +1,220 @@
+// mma_probe.cu — stand-alone tcgen05.mma issue-rate probe (round-2 design input for the 128-channel halo convolution).
+//
+// One elected thread per CTA (pair) issues a fixed pattern of tcgen05.mma instructions on whatever is in shared
+// memory, commits, waits, and reports clock64 cycles per pattern. All 148 SMs run the same loop, so clocks / power are
+// those of a real kernel. Optional interference: extra warps that read-modify-write shared memory (the GroupNorm
+// transform of conv_halo_tc2_kernel<2,true>) and a TMA stream into a ring (operand refills).
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I omgsr_b200/csrc scripts/mma_probe.cu \
+//        omgsr_b200/csrc/capi.cu -o scripts/mma_probe
+//   ./scripts/mma_probe            # prints one line per pattern
+//
+// Patterns (M is 128 rows per CTA in every case):
+//   single N=256 / N=128 / N=64     cta_group::1: A 4 KB + B N*32 B of shared-memory operand reads per instruction
+//   pair   N=256 / N=128 / N=64     cta_group::2: A 4 KB + B N*16 B per CTA per instruction
+//   pair   mix 128,256,256,128      the row-shared schedule: for a fixed tap column the (output row, tap row) pairs that
+//                                   read the same input row share one instruction (N = 256 = two accumulators)
+//   a_views = k                     the A descriptor cycles through k start addresses 128 B apart (shifted halo views)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "common.cuh"
+
+using namespace omgsr;
+
+namespace omgsr { const char* g_trace_variant = ""; }  // capi.cu (linked for make_tmap_bf16) refers to it
+
+struct ProbeParams {
+  int pair;        // 0: cta_group::1, 1: cta_group::2
+  int pattern[8];  // N of each instruction of the pattern (0 terminates)
+  int a_views;     // number of distinct A start rows cycled through
+  int iters;       // pattern repetitions (each instruction is issued 4x: the K = 64 block)
+  int xf_warps;    // extra warps doing LDS / FMA / tanh / STS on a 64 KB region (0 = none)
+  int tma;         // 1: a producer thread streams 16 KB boxes into a 4-deep ring (not consumed)
+  long long* cycles;  // [gridDim.x]
+};
+
+constexpr int kSmem = 200 * 1024;
+
+__global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ CUtensorMap tm, const ProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 80 KB: A views
+  uint8_t* sB = smem + 80 * 1024;     // 48 KB: B blocks
+  uint8_t* sX = smem + 128 * 1024;    // 64 KB: transform / TMA scratch
+  __shared__ uint64_t done_bar, ring_bar[4];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = p.pair ? cluster_ctarank() : 0;
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i * 2654435761u >> 20 & 0x00ff00ffu);  // small bf16 values
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&ring_bar[i], 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) {
+    if (p.pair) { tmem_alloc2(&tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if (p.pair) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  __shared__ volatile int stop;
+  if (threadIdx.x == 0) stop = 0;
+  __syncthreads();
+
+  if (warp == 0 && lane == 0) {
+    if (!p.pair || rank == 0) {
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+      long long t0 = clock64();
+      int view = 0;
+      for (int it = 0; it < p.iters; ++it) {
+        for (int j = 0; j < 8 && p.pattern[j]; ++j) {
+          const int N = p.pattern[j];
+          const uint32_t idesc = umma_idesc_bf16(p.pair ? 256 : 128, N, 0, 0);
+          const uint32_t a_addr = a0 + view * 128;
+          if (++view >= p.a_views) view = 0;
+          const uint32_t d = tmem_base + ((j & 1) ? 256 : 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(b0 + (j & 3) * 4096 + k * 32, 16, 1024);
+            if (p.pair) tc_mma2_ss(d, da, db, idesc, 1);
+            else tc_mma_ss(d, da, db, idesc, 1);
+          }
+        }
+        if ((it & 63) == 63) {  // bound the number of uncommitted instructions like a real pipeline does
+          if (p.pair) tc_commit2_mc(&done_bar); else tc_commit(&done_bar);
+          mbar_wait(&done_bar, (it >> 6) & 1);
+        }
+      }
+      long long t1 = clock64();
+      p.cycles[blockIdx.x] = t1 - t0;
+      stop = 1;
+      if (p.pair) {  // tell the peer CTA (its interference warps keep running while the leader issues)
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(remote) : "r"(smem_u32(const_cast<int*>(&stop))));
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(1) : "memory");
+      }
+    }
+  } else if (warp == 2 && lane == 0 && p.tma) {
+    // four 16 KB boxes in flight, re-issued as they land (operand refills of a real pipeline: ~40 B/clk)
+    int n = 0;
+    for (int s = 0; s < 4; ++s, ++n) {
+      mbar_expect_tx(&ring_bar[s], 16384);
+      tma_load_2d(sX + s * 16384, &tm, &ring_bar[s], 0, (n * 128 + blockIdx.x * 4096) & 0x3ffff);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    while (true) {
+      mbar_wait(&ring_bar[s], ph);
+      if (stop) break;
+      mbar_expect_tx(&ring_bar[s], 16384);
+      tma_load_2d(sX + s * 16384, &tm, &ring_bar[s], 0, (n * 128 + blockIdx.x * 4096) & 0x3ffff);
+      ++n;
+      if (++s == 4) { s = 0; ph ^= 1; }
+    }
+    // drain the loads still in flight before the CTA may exit
+    for (int k = 1; k < 4; ++k) {
+      if (++s == 4) { s = 0; ph ^= 1; }
+      mbar_wait(&ring_bar[s], ph);
+    }
+  } else if (warp >= 4 && warp < 4 + p.xf_warps) {
+    // GroupNorm + SiLU transform stand-in: 16-byte units, y = silu(a x + b) in place
+    const int tid = threadIdx.x - 128;
+    int off = tid * 16;
+    const int span = 48 * 1024;
+    while (!stop) {
+      uint4* u = reinterpret_cast<uint4*>(sX + 16384 * (p.tma ? 0 : 0) + (off % span));
+      uint4 v = *u;
+      float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+      f0.x = silu_f(fmaf(f0.x, 1.01f, 0.1f)); f0.y = silu_f(fmaf(f0.y, 1.01f, 0.1f));
+      f1.x = silu_f(fmaf(f1.x, 1.01f, 0.1f)); f1.y = silu_f(fmaf(f1.y, 1.01f, 0.1f));
+      f2.x = silu_f(fmaf(f2.x, 1.01f, 0.1f)); f2.y = silu_f(fmaf(f2.y, 1.01f, 0.1f));
+      f3.x = silu_f(fmaf(f3.x, 1.01f, 0.1f)); f3.y = silu_f(fmaf(f3.y, 1.01f, 0.1f));
+      v.x = pack_bf16x2(f0.x, f0.y); v.y = pack_bf16x2(f1.x, f1.y); v.z = pack_bf16x2(f2.x, f2.y); v.w = pack_bf16x2(f3.x, f3.y);
+      *u = v;
+      off += p.xf_warps * 32 * 16;
+    }
+  }
+  __syncthreads();
+  tc_fence_before();
+  if (p.pair) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (p.pair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static double run(const char* name, int pair, std::initializer_list<int> pat, int a_views, int xf, int tma,
+                  const CUtensorMap& tm, long long* d_cycles) {
+  ProbeParams p{};
+  p.pair = pair; p.a_views = a_views; p.iters = 4096; p.xf_warps = xf; p.tma = tma; p.cycles = d_cycles;
+  int j = 0;
+  double nominal = 0;  // tensor-pipe cycles of one pattern at full rate: N / 2 per K = 16 instruction, 4 per block
+  for (int n : pat) { p.pattern[j++] = n; nominal += 4 * n / 2.0; }
+  cudaMemset(d_cycles, 0, 148 * sizeof(long long));
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(148); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = kSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaEventRecord(e0);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, probe_kernel, tm, p);
+  cudaEventRecord(e1);
+  cudaError_t err2 = cudaDeviceSynchronize();
+  if (err != cudaSuccess || err2 != cudaSuccess) {
+    printf("%-46s FAILED: %s / %s\n", name, cudaGetErrorString(err), cudaGetErrorString(err2));
+    return 0;
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<long long> h(148);
+  cudaMemcpy(h.data(), d_cycles, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double sum = 0; int cnt = 0;
+  for (long long c : h) if (c > 0) { sum += c; ++cnt; }
+  const double cyc = sum / cnt / p.iters;
+  printf("%-46s a_views=%d xf=%d tma=%d : %7.1f cycles / pattern (nominal %5.0f) -> tensor pipe %5.1f %%   [%.2f ms]\n", name,
+         a_views, xf, tma, cyc, nominal, 100.0 * nominal / cyc, ms);
+  return cyc;
+}
+
+int main() {
+  long long* d_cycles;
+  cudaMalloc(&d_cycles, 148 * sizeof(long long));
+  void* gbuf;
+  cudaMalloc(&gbuf, 64ull << 20);
+  cudaMemset(gbuf, 0, 64ull << 20);
+  CUtensorMap tm;
+  uint64_t dims[2] = {64, (64ull << 20) / 128};
+  uint64_t str[1] = {128};
+  uint32_t box[2] = {64, 128};
+  if (make_tmap_bf16(&tm, gbuf, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("tensor map failed\n"); return 1; }
+  for (int rep = 0; rep < 2; ++rep) {  // first round warms the clocks
+    run("single N=256", 0, {256}, 1, 0, 0, tm, d_cycles);
+    run("single N=128", 0, {128}, 1, 0, 0, tm, d_cycles);
+    run("single N=64", 0, {64}, 1, 0, 0, tm, d_cycles);
+    run("pair   N=256", 1, {256}, 1, 0, 0, tm, d_cycles);
+    run("pair   N=128", 1, {128}, 1, 0, 0, tm, d_cycles);
+    run("pair   N=64", 1, {64}, 1, 0, 0, tm, d_cycles);
+    run("pair   N=128 shifted views", 1, {128}, 6, 0, 0, tm, d_cycles);
+    run("pair   N=256 shifted views", 1, {256}, 6, 0, 0, tm, d_cycles);
+    run("pair   mix 128,256,256,128", 1, {128, 256, 256, 128}, 4, 0, 0, tm, d_cycles);
+    run("single mix 128,256,256,128", 0, {128, 256, 256, 128}, 4, 0, 0, tm, d_cycles);
+    run("pair   N=128 + TMA", 1, {128}, 6, 0, 1, tm, d_cycles);
+    run("pair   N=128 + transform", 1, {128}, 6, 4, 0, tm, d_cycles);
+    run("pair   N=128 + TMA + transform", 1, {128}, 6, 4, 1, tm, d_cycles);
+    run("pair   mix + TMA", 1, {128, 256, 256, 128}, 4, 0, 1, tm, d_cycles);
+    run("pair   mix + TMA + transform", 1, {128, 256, 256, 128}, 4, 4, 1, tm, d_cycles);
+    run("pair   N=256 + TMA + transform", 1, {256}, 6, 4, 1, tm, d_cycles);
+    run("single N=256 + TMA", 0, {256}, 1, 0, 1, tm, d_cycles);
+  }
+  return 0;
+}
