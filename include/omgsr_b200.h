@@ -43,6 +43,7 @@ extern "C" {
 #define OMGSR_OUT_F32 1      /* store fp32 instead of bf16 */
 #define OMGSR_B_MN_MAJOR 2   /* batched GEMM: B operand given as [K, N] (row-major V), not [N, K] */
 #define OMGSR_CONV_NO_HALO 4     /* conv2d: force the generic implicit-GEMM kernel (testing / A-B timing) */
+#define OMGSR_RES_F32 8      /* GEMMs: `res` is fp32 (with OMGSR_OUT_F32: an fp32 residual stream, N % 32 == 0) */
 
 int omgsr_version(void);
 const char* omgsr_last_error(void);
@@ -177,10 +178,11 @@ int omgsr_groupnorm_combine(const float* sums, const float* pixels, int entries,
  * gamma + (row / rows_per_batch) * gb_stride (gb_stride = 0: shared affine; >0: per-image AdaLN modulation,
  * caller passes g = 1 + scale, b = shift). gamma/beta may be null (no affine). Input row r lives at
  * x + r*ldx, or at x + (r / rows_per_batch)*x_batch_stride + (r % rows_per_batch)*ldx when x_batch_stride > 0
- * (a token range of a longer joint sequence); the output is dense [rows, C]. ldx = 0 means C.
+ * (a token range of a longer joint sequence); the output is dense bf16 [rows, C]. ldx = 0 means C. x is bf16, or fp32
+ * when x_f32 (the FLUX engine keeps its residual stream in fp32).
  * (UNet BasicTransformerBlock norms, eps 1e-5; FLUX AdaLayerNormZero / Continuous, eps 1e-6) */
-int omgsr_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C, float eps,
-                    long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch_stride,
+int omgsr_layernorm(const void* x, int x_f32, void* y, const float* gamma, const float* beta, long long rows, int C,
+                    float eps, long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch_stride,
                     void* stream);
 /* softmax over rows of fp32 scores: P[r, j] = softmax_j(scale * S[r, j]) for j < n, P[r, j] = 0 for
  * n <= j < n_pad. */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libomgsr_b200.so")
 
 ACT_NONE, ACT_SILU, ACT_GELU_ERF, ACT_GELU_TANH, ACT_GEGLU = 0, 1, 2, 3, 4
-OUT_F32, B_MN_MAJOR, CONV_NO_HALO = 1, 2, 4
+OUT_F32, B_MN_MAJOR, CONV_NO_HALO, RES_F32 = 1, 2, 4, 8
 
 # every symbol include/omgsr_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
@@ -343,8 +343,11 @@ def groupnorm_combine(sums, pixels, n_img, C, groups=32, raw=False):
 
 
 def layernorm(x, gamma=None, beta=None, eps=1e-5, rows_per_batch=0, gb_stride=0, out=None):
-    """x: dense [..., C] or a 3-D view [B, rows, C] with free row / batch strides; output dense."""
-    _cuda_bf16(x, "x"); _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta")
+    """x: dense [..., C] or a 3-D view [B, rows, C] with free row / batch strides (bf16, or fp32 for an fp32 residual
+    stream); output dense bf16."""
+    if not (x.is_cuda and x.dtype in (torch.bfloat16, torch.float32)):
+        raise TypeError(f"x must be a CUDA bf16 / fp32 tensor (got {x.device}, {x.dtype})")
+    _cuda_f32(gamma, "gamma"); _cuda_f32(beta, "beta")
     C = x.shape[-1]
     rows = x.numel() // C
     ldx, xbs = C, 0
@@ -356,7 +359,8 @@ def layernorm(x, gamma=None, beta=None, eps=1e-5, rows_per_batch=0, gb_stride=0,
         assert rows_per_batch == x.shape[1]
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    rc = _lib.omgsr_layernorm(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ll(rows), _i(C), _f(eps),
+    rc = _lib.omgsr_layernorm(_ptr(x), _i(int(x.dtype == torch.float32)), _ptr(out), _ptr(gamma), _ptr(beta), _ll(rows),
+                              _i(C), _f(eps),
                               _ll(rows_per_batch), _ll(gb_stride), _ll(ldx), _ll(xbs), _stream())
     _check(rc, "omgsr_layernorm")
     return out
@@ -400,8 +404,13 @@ def gemm_batched(a, w, bias=None, res=None, gate=None, act=ACT_NONE, act_cols=No
         out = torch.empty((B, M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     assert out.stride(2) == 1 and out.shape[:2] == (B, M)
     ldr = rb = 0
+    res_f32 = False
     if res is not None:
-        _cuda_bf16(res, "res")
+        if res.dtype == torch.float32:  # fp32 residual stream: out must be fp32 too
+            assert res.is_cuda and out.dtype == torch.float32, "an fp32 residual needs an fp32 output"
+            res_f32 = True
+        else:
+            _cuda_bf16(res, "res")
         assert res.stride(2) == 1
         ldr, rb = res.stride(1), res.stride(0)
     gld = 0
@@ -412,7 +421,8 @@ def gemm_batched(a, w, bias=None, res=None, gate=None, act=ACT_NONE, act_cols=No
     rc = _lib.omgsr_gemm_batched_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(res), _ptr(gate), _ptr(out), _i(B), _i(M),
                                       _i(N), _i(K), _ll(a.stride(1)), _ll(a.stride(0)), _ll(out.stride(1)),
                                       _ll(out.stride(0)), _ll(ldr), _ll(rb), _ll(gld), _i(act), _i(c0), _i(c1),
-                                      _i(OUT_F32 if out.dtype == torch.float32 else 0), _i(force_bn), _stream())
+                                      _i((OUT_F32 if out.dtype == torch.float32 else 0) | (RES_F32 if res_f32 else 0)),
+                                      _i(force_bn), _stream())
     _check(rc, "omgsr_gemm_batched_bf16")
     return out
 

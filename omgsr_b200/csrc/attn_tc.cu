@@ -47,7 +47,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   using C = AttnCfg<D>;
   constexpr int BN = C::kBN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + C::kQBytes;  // [stage][K | V]
   uint8_t* sP = sKV + C::kStages * (C::kKBytes + C::kVBytes);
@@ -302,7 +302,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   using C = Attn2Cfg<D>;
   constexpr int BN = C::kBN, PB = C::kPBuf;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
   uint8_t* sQ = smem;                                   // [group][panel][128 rows x 128 B]
   uint8_t* sKV = sQ + C::kQBytes;                       // [stage][K | V]
   uint8_t* sP = sKV + C::kStages * C::kStageBytes;      // [group][buf]

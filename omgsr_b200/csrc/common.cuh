@@ -36,8 +36,8 @@ int sm_count();  // of the CURRENT device
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): *done_mask has one bit per device
 int ensure_smem_attr(const void* func, int bytes, unsigned long long* done_mask, const char* what);
 // deterministic GroupNorm statistics (epilogue.cuh gn_flush / glue.cu gn_finalize_kernel): slots per image in the
-// scratch buffer = 4 epilogue warps x the largest grid any persistent kernel launches
-inline int gn_slots_per_image() { return sm_count() * 4; }
+// scratch buffer = up to 8 epilogue warps per CTA x the largest grid any persistent kernel launches
+inline int gn_slots_per_image() { return sm_count() * 8; }
 // out[b][i] = sum over (launch l, slot s) of scratch[((l * B + b) * slots + s) * n + i], in a fixed order
 int launch_gn_finalize(const float* scratch, int launches, int B, int slots, int n, float* out, cudaStream_t st);
 
@@ -132,6 +132,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
+  }
+}
+
+// Waiters with slack (producers waiting for a free slot, epilogue warps waiting for a whole tile of MMAs, transform warps a
+// few rows ahead of the tensor core): a failed probe is followed by a short nanosleep, so the spinning warp stops
+// competing for its scheduler's issue slots with the warps that are doing the work. ncu on the row-shared halo kernel:
+// one such loop alone issued 57 M warp-instructions per launch (try_wait returned after ~25 cycles each time), on
+// schedulers that also host the epilogue and transform warps. The MMA issuer keeps the tight mbar_wait.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) __trap();
   }
 }
 

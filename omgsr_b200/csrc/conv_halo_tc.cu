@@ -66,7 +66,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const HaloParams p) {
   using C = HaloCfg<BN, TM>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::kAStages * C::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::kBStages * C::kBBytes);
@@ -189,14 +189,14 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b = m / p.tiles_y;
       const int x = tx * 128 + row;
       if (p.gn_sums && b != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
         gn_b = b;
       }
       // residual rows of this thread's TM pixels: pulled into L2 now, then loaded one 32-channel chunk ahead of use
       EpiArgs e;
       e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
       e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
-      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32;
+      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32; e.res_f32 = 0;
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
       uint4 rr[4] = {};
@@ -230,7 +230,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (C::kAccSets == 2) { if (++set == 2) { set = 0; sph ^= 1; } }
       else { sph ^= 1; }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -269,7 +269,7 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   using C = Halo2Cfg<TM>;
   constexpr int BN = 128;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::kAStages * C::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::kBStages * C::kBBytes);
@@ -489,14 +489,14 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int b = dummy ? 0 : m / p.tiles_y;
       const int x = tx * 128 + row;
       if (p.gn_sums && !dummy && b != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
         gn_b = b;
       }
       // residual rows of this thread's TM pixels: pulled into L2 now, then loaded one 32-channel chunk ahead of use
       EpiArgs e;
       e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
       e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
-      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32;
+      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32; e.res_f32 = 0;
       float gn_part[16];
       e.gn_part = p.gn_sums ? gn_part : nullptr;
       uint4 rr[4] = {};
@@ -533,7 +533,7 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if (++set == 2) { set = 0; sph ^= 1; }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -542,6 +542,353 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-shared CTA-pair kernel (round 2; the default for 16 < Cout <= 128).
+//
+// scripts/mma_probe.cu measured what bounds the kernel above: a tcgen05.mma of M = 128 rows per CTA costs ~127-141
+// cycles whatever N <= 128 is and ~174 cycles at N = 256, i.e. an N = 128 instruction stream cannot exceed ~62 % of the
+// N = 256 rate - exactly where conv_halo_tc2_kernel sat (profiles/r02/mma_probe*.txt). A 3x3 convolution with 128
+// output channels still has N = 256 instructions in it: for a fixed tap column s, output row t with tap row r reads
+// input row rho = t + r, so (t, r) and (t + 1, r - 1) read the SAME A operand. With the two accumulators of a TM = 2
+// tile adjacent in TMEM, one instruction
+//     D[256 px pair, 256] (+)= A[row rho, shifted by s] x [ W(r = rho, s) | W(r = rho - 1, s) ]^T
+// feeds both. Per (64-channel chunk, s) the six N = 128 instructions become N = 128, 256, 256, 128 over input rows
+// 0..3: 2.33-2.40 k instead of 3.04-3.38 k cycles on the probe, and a third fewer A reads.
+//   * cta_group::2 splits the B rows of an instruction between the CTAs, so for the N = 256 instructions CTA 0 holds
+//     all 128 rows of W(rho, s) (-> accumulator t0, columns 0..127) and CTA 1 all of W(rho - 1, s) (-> t1); for the
+//     N = 128 leftovers (rho = 0 -> t0, rho = TM + R - 2 -> t1) each CTA holds its 64-row half as before.
+//   * an input ROW is the pipeline stage: stage rho = one halo row (17 KB slot, 1024-byte aligned so it is its own
+//     swizzle domain) + the S weight units that multiply it (S x 16 KB or S x 8 KB), at FIXED shared-memory offsets.
+//     Loop order chunk -> row -> s; ONE tcgen05.commit per row releases both (the probe: a commit behind short
+//     instructions costs 60-120 cycles, so per-unit commits ate the gain), and the stage is refilled with the same row of
+//     the next chunk / tile, i.e. operands are requested ~3 rows (5-6 k cycles) ahead of their use. Rows and weights have
+//     their own producer warps. Row 1 is visited first: its N = 256 instruction initialises BOTH accumulators.
+// Epilogue, statistics and the transform arithmetic are those of conv_halo_tc2_kernel.
+// ------------------------------------------------------------------------------------------------
+struct HaloRsCfg {
+  static constexpr int TM = 2;
+  static constexpr int kRowBytes = 17 * 1024;  // 130 px x 128 B = 16640 B, padded to a multiple of 1024
+  static constexpr int kMaxRows = 4;           // TM + R - 1 input rows per tile
+  static constexpr int kBBytes = 144 * 1024;   // R = S = 3: 24 + 48 + 48 + 24 KB of weight units per chunk
+  static constexpr int kBarBytes = 512;
+  // + statistics partial sums (8 epilogue warps x 64 floats) + bias slices (8 x 128 floats)
+  static constexpr int kSmemBytes = kMaxRows * kRowBytes + kBBytes + 1024 + kBarBytes + 2048 + 32 * 128;
+};
+
+// input rows of one chunk in visiting order: 1 first (see above), then 0, 2, 3, ...
+__device__ __forceinline__ int rs_row(int i) { return i == 0 ? 1 : (i == 1 ? 0 : i); }
+// byte offset of row rho's weight units inside the B region: leftover rows hold S x 8 KB, shared rows S x 16 KB
+__device__ __forceinline__ int rs_boff(int rho, int R, int S) {
+  // rows before rho: row 0 (leftover) and rows 1 .. rho - 1 (shared, as long as they are <= R - 1)
+  if (rho == 0) return 0;
+  const int shared_before = (rho - 1 < R - 1) ? rho - 1 : R - 1;
+  return S * 8192 + shared_before * S * 16384 + (rho - 1 - shared_before) * S * 8192;
+}
+
+template <bool XF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XF ? 480 : 352, 1)
+conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB128,
+                    const __grid_constant__ CUtensorMap tmB64, const HaloParams p) {
+  using C = HaloRsCfg;
+  constexpr int BN = 128, TM = C::TM, NS = C::kMaxRows;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NS * C::kRowBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::kBBytes);
+  uint64_t* a_full = bars;                // [NS] XF: per CTA (own bytes); else leader's (2 arrivals)
+  uint64_t* a_ready = a_full + NS;        // [NS] XF: leader's, 8 arrivals (4 transform warps x 2 CTAs)
+  uint64_t* b_full = a_ready + NS;        // [NS] leader's (2 arrivals)
+  uint64_t* empty = b_full + NS;          // [NS] per CTA: one multicast commit per row frees the row AND its weights
+  uint64_t* acc_full = empty + NS;        // [2] per CTA
+  uint64_t* acc_empty = acc_full + 2;     // [2] leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB128);
+    tma_prefetch_desc(&tmB64);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&a_full[i], XF ? 1 : 2);
+      mbar_init(&a_ready[i], 8);
+      mbar_init(&b_full[i], 2);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int halo_tiles = p.tiles_x * p.tiles_y * p.B;
+  const int total_pairs = (halo_tiles + 1) >> 1;   // n_tiles == 1 (Cout <= 128)
+  const int n_rows = TM + p.R - 1;                 // input rows per tile (<= NS)
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int row_bytes = p.pw * 128;
+  // warps: 0 row producer, 1 MMA issuer, 2..5 epilogue of accumulator row t0, 6..9 epilogue of t1 (two epilogue warps
+  // per scheduler: with one, every TMEM / residual-load latency was exposed and the residual + statistics variants were
+  // epilogue-bound at 1.7 ms), 10 weight producer, XF: 11..14 input transform
+  constexpr int kBWarp = 10;
+
+  // every role walks the same (tile pair, chunk, row) sequence; stage rho is used once per chunk, so the parity of a
+  // stage's barriers is the parity of the running chunk count
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= input-row producer =================
+      uint32_t ph = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        int m = 2 * pt + static_cast<int>(rank);
+        const bool dummy = m >= halo_tiles;
+        const int tx = m % p.tiles_x; m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int b = dummy ? p.B : m / p.tiles_y;
+        for (int c = 0; c < p.chunks; ++c, ph ^= 1) {
+          for (int i = 0; i < n_rows; ++i) {
+            const int rho = rs_row(i);
+            mbar_wait_relaxed(&empty[rho], ph ^ 1);
+            if (XF) {  // own barrier: this CTA's transform warps consume the row first
+              mbar_expect_tx(&a_full[rho], row_bytes);
+              tma_load_5d(sA + rho * C::kRowBytes, &tmA, &a_full[rho], c * 64, tx * 128 - p.pad_l, ty * TM - p.pad_t + rho, b, 0);
+            } else {
+              if (rank == 0) mbar_expect_tx(&a_full[rho], 2 * row_bytes);
+              else mbar_arrive_remote(&a_full[rho], 0);
+              tma2_load_5d(sA + rho * C::kRowBytes, &tmA, &a_full[rho], c * 64, tx * 128 - p.pad_l, ty * TM - p.pad_t + rho, b, 0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kBWarp) {
+    if (lane == 0) {
+      // ================= weight-unit producer =================
+      uint32_t ph = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        for (int c = 0; c < p.chunks; ++c, ph ^= 1) {
+          for (int i = 0; i < n_rows; ++i) {
+            const int rho = rs_row(i);
+            // weight units of this input row: both accumulators (N = 256: this CTA supplies all 128 rows of ITS tap
+            // row) or one (N = 128: this CTA supplies its 64-row half)
+            const bool both = rho >= 1 && rho <= p.R - 1;
+            const int r_mine = both ? rho - static_cast<int>(rank) : (rho == 0 ? 0 : p.R - 1);
+            const int unit = both ? 16384 : 8192;
+            uint8_t* dst = sB + rs_boff(rho, p.R, p.S);
+            mbar_wait_relaxed(&empty[rho], ph ^ 1);
+            if (rank == 0) mbar_expect_tx(&b_full[rho], 2 * p.S * unit);
+            else mbar_arrive_remote(&b_full[rho], 0);
+            for (int sx = 0; sx < p.S; ++sx) {
+              const int kcol = (r_mine * p.S + sx) * p.Cin + c * 64;
+              if (both) tma2_load_4d(dst + sx * unit, &tmB128, &b_full[rho], kcol, 0, 0, 0);
+              else tma2_load_4d(dst + sx * unit, &tmB64, &b_full[rho], kcol, static_cast<int>(rank) * 64, 0, 0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      // ================= MMA issuer =================
+      const uint32_t idesc256 = umma_idesc_bf16(256, 256, 0, 0), idesc128 = umma_idesc_bf16(256, 128, 0, 0);
+      int set = 0;
+      uint32_t ph = 0, sph = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        mbar_wait(&acc_empty[set], sph ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + set * (TM * BN);
+        uint32_t first = 1;  // the first instruction of a tile (row 1: N = 256) initialises both accumulators
+        for (int c = 0; c < p.chunks; ++c, ph ^= 1) {
+          for (int i = 0; i < n_rows; ++i) {
+            const int rho = rs_row(i);
+            if (XF) mbar_wait(&a_ready[rho], ph);
+            else mbar_wait(&a_full[rho], ph);
+            mbar_wait(&b_full[rho], ph);
+            tc_fence_after();
+            const uint32_t a_row = smem_u32(sA + rho * C::kRowBytes);
+            const bool both = rho >= 1 && rho <= p.R - 1;
+            const uint32_t d = both ? acc0 : (rho == 0 ? acc0 : acc0 + (TM - 1) * BN);
+            const uint32_t idesc = both ? idesc256 : idesc128;
+            const uint32_t b_row = smem_u32(sB + rs_boff(rho, p.R, p.S));
+            const uint32_t unit = both ? 16384u : 8192u;
+            for (int sx = 0; sx < p.S; ++sx) {
+              const uint32_t b_addr = b_row + sx * unit;
+              const uint32_t a_addr = a_row + static_cast<uint32_t>(sx * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (p.debug & 4) continue;  // timing-only ablation (OMGSR_HALO_DEBUG): no MMAs, results invalid
+                tc_mma2_ss(d, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024),
+                           idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+            tc_commit2_mc(&empty[rho]);  // the row and its weight units are free once everything issued so far retires
+          }
+        }
+        tc_commit2_mc(&acc_full[set]);
+        if (++set == 2) { set = 0; sph ^= 1; }
+      }
+    }
+  } else if (XF && warp >= 11) {
+    // ================= input transform (warps 11..14): GroupNorm + SiLU on each halo row, in place =================
+    const int tid = threadIdx.x - 352;  // 0..127
+    const int j = tid & 7;              // 16-byte unit (8 channels) of a 128-byte pixel row: fixed per thread
+    const int p0 = tid >> 3;            // first pixel of this thread in a row; then every 16th (<= 9 per row)
+    uint32_t ph = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      int m = 2 * pt + static_cast<int>(rank);
+      const bool dummy = m >= halo_tiles;
+      const int tx = m % p.tiles_x; m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int b = dummy ? 0 : m / p.tiles_y;
+      const int x0 = tx * 128 - p.pad_l, y0 = ty * TM - p.pad_t;
+      for (int c = 0; c < p.chunks; ++c, ph ^= 1) {
+        float ca[8], cb[8];
+        if (!dummy) {
+          const float4* cf = reinterpret_cast<const float4*>(p.gn_in + static_cast<long long>(b) * p.Cin + c * 64 + j * 8);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(cf + q);
+            ca[2 * q] = v.x; cb[2 * q] = v.y; ca[2 * q + 1] = v.z; cb[2 * q + 1] = v.w;
+          }
+        }
+        for (int i = 0; i < n_rows; ++i) {
+          const int rho = rs_row(i);
+          const int yy = y0 + rho;
+          mbar_wait_relaxed(&a_full[rho], ph, 32);
+          // rows / pixels outside the image: TMA wrote zeros = the conv padding, which must stay zero
+          if (!dummy && yy >= 0 && yy < p.IH) {
+            uint8_t* row = sA + rho * C::kRowBytes;
+            // ALL of this thread's units of the row (<= 9) are in flight at once: loads first, then the math, then the
+            // stores. One transform warp per scheduler has nothing else to hide LDS / MUFU latency behind (three
+            // units in flight: 2.1 k cycles per row, slower than the row's MMAs).
+            uint4 v[9];
+            bool on[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const int pi = p0 + 16 * q;
+              const int xx = x0 + pi;
+              on[q] = pi < p.pw && xx >= 0 && xx < p.IW;
+              if (on[q]) v[q] = *reinterpret_cast<const uint4*>(row + pi * 128 + ((j ^ (pi & 7)) << 4));
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              float f[8];
+              const float2 f0 = unpack_bf16x2(v[q].x), f1 = unpack_bf16x2(v[q].y), f2 = unpack_bf16x2(v[q].z),
+                           f3 = unpack_bf16x2(v[q].w);
+              f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = silu_f(fmaf(f[e], ca[e], cb[e]));
+              v[q].x = pack_bf16x2(f[0], f[1]); v[q].y = pack_bf16x2(f[2], f[3]);
+              v[q].z = pack_bf16x2(f[4], f[5]); v[q].w = pack_bf16x2(f[6], f[7]);
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const int pi = p0 + 16 * q;
+              if (on[q]) *reinterpret_cast<uint4*>(row + pi * 128 + ((j ^ (pi & 7)) << 4)) = v[q];
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) {
+            // plain / relaxed arrives: the row is only ever read by THIS CTA's tensor core, and fence.proxy.async has
+            // already made the writes visible to it (a .release.cluster arrive compiles to MEMBAR.ALL.GPU)
+            if (rank == 0) mbar_arrive(&a_ready[rho]); else mbar_arrive_remote_relaxed(&a_ready[rho], 0);
+          }
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ================= epilogue: warps 2..5 drain accumulator row t0, warps 6..9 row t1 =================
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int ew = t * 4 + quarter;       // epilogue warp index inside the CTA: statistics slot / bias slice
+    const int row = quarter * 32 + lane;
+    int set = 0;
+    uint32_t sph = 0;
+    float* my_gn = gn_acc + ew * 64;
+    float* my_bias = gn_acc + 8 * 64 + ew * BN;
+    if (p.bias) stage_bias<BN>(my_bias, p.bias, 0, p.Cout, lane);
+    const int epi_mode = epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
+    const int gn_n = p.gn_groups * 2;
+    int gn_b = -1;
+    if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      int m = 2 * pt + static_cast<int>(rank);
+      const bool dummy = m >= halo_tiles;
+      const int tx = m % p.tiles_x; m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int b = dummy ? 0 : m / p.tiles_y;
+      const int x = tx * 128 + row, y = ty * TM + t;
+      if (p.gn_sums && !dummy && b != gn_b) {
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 8 + ew, p.gn_slots), lane);
+        gn_b = b;
+      }
+      EpiArgs e;
+      e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
+      e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
+      e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32; e.res_f32 = 0;
+      float gn_part[16];
+      e.gn_part = p.gn_sums ? gn_part : nullptr;
+      const bool valid = !dummy && (x < p.W) && (y < p.H) && !(p.debug & 1);
+      uint4 rr[4] = {};
+      e.res_row = (p.res && !dummy) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+      if (e.res_row) {  // this thread's residual row: pulled into L2 now, first chunk loaded before the accumulator wait
+        prefetch_res_row(e, 0, BN, valid);
+        load_res32(rr, e, 0, valid);
+      }
+      e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+      mbar_wait_relaxed(&acc_full[set], sph);
+      tc_fence_after();
+      if (!(p.debug & 2)) {  // (timing-only ablation: no epilogue)
+        const uint32_t t_row = tmem_base + set * (TM * BN) + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+        epilogue_row_m<false>(epi_mode, t_row, BN, 0, 0, 0, valid, e, nullptr, 0, false, p.bias ? my_bias : nullptr, rr,
+                              my_gn, p.gn_cpg, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&acc_empty[set]);
+        else mbar_arrive_remote(&acc_empty[set], 0);
+      }
+      if (++set == 2) { set = 0; sph ^= 1; }
+    }
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 8 + ew, p.gn_slots), lane);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// 0: conv_halo_tc2_kernel (every instruction N = 128), 1: conv_halo_rs_kernel (row-shared N = 256 instructions)
+int g_halo_row_shared = 1;
+
+template <bool XF>
+static int launch_halo_rs(const CUtensorMap& tmA, const CUtensorMap& tmB128, const CUtensorMap& tmB64,
+                          const HaloParams& p, cudaStream_t st) {
+  using C = HaloRsCfg;
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_rs_kernel<XF>), C::kSmemBytes, &attr_done,
+                                "conv_halo_rs")) return rc;
+  const long long halo_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B;
+  const long long pairs = (halo_tiles + 1) / 2;
+  const int max_clusters = sm_count() / 2;
+  const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
+  g_trace_variant = XF ? "halo_rowshared128_gn" : "halo_rowshared128";
+  conv_halo_rs_kernel<XF><<<2 * clusters, XF ? 480 : 352, C::kSmemBytes, st>>>(tmA, tmB128, tmB64, p);
+  return check_launch("conv_halo_rs_kernel");
 }
 
 int g_halo_2cta = 1;
@@ -630,10 +977,24 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   rc = make_tmap_bf16(&tmB, w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (thin) return launch_halo<16, TM>(tmA, tmB, p, st);
-  if (gn_in) {
-    if (!pair) return set_error(OMGSR_ERR_SHAPE, "conv_halo: the fused input GroupNorm needs the CTA-pair halo kernel (16 < Cout <= 128, >= 2 tiles)");
-    return launch_halo2<TM, true>(tmA, tmB, p, st);
+  if (gn_in && !pair)
+    return set_error(OMGSR_ERR_SHAPE, "conv_halo: the fused input GroupNorm needs the CTA-pair halo kernel (16 < Cout <= 128, >= 2 tiles)");
+  static const bool rs_off = getenv("OMGSR_HALO_ROW_SHARED") && atoi(getenv("OMGSR_HALO_ROW_SHARED")) == 0;  // A/B timing
+  if (pair && g_halo_row_shared && !rs_off && R >= 2) {
+    // row-shared schedule: one input ROW per A load, weight units of 128 rows (N = 256 instructions) or 64 rows
+    CUtensorMap tmRow, tmB128, tmB64;
+    uint32_t rbox[5] = {64, static_cast<uint32_t>(p.pw), 1, 1, 1};
+    rc = make_tmap_bf16(&tmRow, x, 5, dims, strides, rbox, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    uint32_t wb128[4] = {64, 128, 1, 1}, wb64[4] = {64, 64, 1, 1};
+    rc = make_tmap_bf16(&tmB128, w, 4, wd, ws, wb128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmB64, w, 4, wd, ws, wb64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (gn_in) return launch_halo_rs<true>(tmRow, tmB128, tmB64, p, st);
+    return launch_halo_rs<false>(tmRow, tmB128, tmB64, p, st);
   }
+  if (gn_in) return launch_halo2<TM, true>(tmA, tmB, p, st);
   if (pair) return launch_halo2<TM, false>(tmA, tmB, p, st);
   return launch_halo<128, TM>(tmA, tmB, p, st);
 }

@@ -23,6 +23,7 @@ struct EpiArgs {
   int out_f32;
   int vec32;       // bf16 output rows are 32-byte aligned at every 16-channel granule pair: one 256-bit store each
   int res_vec32;   // same for the residual rows: 256-bit loads
+  int res_f32;     // res_row points at fp32 data (fp32 residual stream: EPI_F32S / EPI_F32S_GATE only)
   float* gn_part;  // optional: 16 per-thread partials of this 32-column chunk, (sum, sumsq) per 4 channels, filled
                    // by epilogue_store32 for the fused GroupNorm statistics (see gn_chunk_accumulate)
 };
@@ -248,8 +249,10 @@ __device__ __forceinline__ void epilogue_store32_t(float (&f)[32], int cv, int o
 }
 
 // option set -> specialisation id (0 = generic). Computed once per thread, warp-uniform.
-enum : int { EPI_GENERIC = 0, EPI_PLAIN, EPI_RES, EPI_GN, EPI_RES_GN, EPI_GELU_TANH, EPI_GATE_RES, EPI_SILU };
-__device__ __forceinline__ int epilogue_mode(int act, bool gate, bool res, bool out_f32, bool gn) {
+enum : int { EPI_GENERIC = 0, EPI_PLAIN, EPI_RES, EPI_GN, EPI_RES_GN, EPI_GELU_TANH, EPI_GATE_RES, EPI_SILU,
+              EPI_F32S, EPI_F32S_GATE };
+__device__ __forceinline__ int epilogue_mode(int act, bool gate, bool res, bool out_f32, bool gn, bool res_f32 = false) {
+  if (res_f32) return gate ? EPI_F32S_GATE : EPI_F32S;  // host side guarantees: out_f32, res, no activation, no gn
   if (out_f32) return EPI_GENERIC;
   if (act == OMGSR_ACT_NONE || act == OMGSR_ACT_GEGLU) {  // GEGLU: the kernels fold the gate half before the store
     if (gate) return (res && !gn) ? EPI_GATE_RES : EPI_GENERIC;
@@ -323,13 +326,13 @@ __device__ __forceinline__ void gn_chunk_accumulate(float (&part)[16], int cpg, 
 }
 
 // Deterministic statistics: each epilogue warp owns ONE slot per image in a scratch buffer laid out
-// [image][slot = CTA * 4 + warp][groups * 2] and writes its partial sums there with plain stores (a warp leaves an image
+// [image][slot = CTA * (epilogue warps per CTA: 4 or 8) + warp][groups * 2] and writes its partial sums there with plain stores (a warp leaves an image
 // at most once: the persistent tile loops visit the images in increasing order). Slots nobody writes stay zero (the
 // host zeroes the scratch), and gn_finalize_kernel (glue.cu) adds the slots of an image in a fixed order. The first
 // version used fp32 atomicAdd into one [groups][2] cell per image: the arrival order changed from run to run and with
 // it the rounding (1-3 dB of PSNR noise on the amplifying random-init nets).
-__device__ __forceinline__ float* gn_slot(float* scratch, int image, int n, int quarter, int slots) {
-  return scratch + (static_cast<long long>(image) * slots + blockIdx.x * 4 + quarter) * n;  // slots >= gridDim.x * 4
+__device__ __forceinline__ float* gn_slot(float* scratch, int image, int n, int slot, int slots) {
+  return scratch + (static_cast<long long>(image) * slots + slot) * n;  // slot = CTA * warps-per-CTA + warp < slots
 }
 __device__ __forceinline__ void gn_flush(float* acc, int n, float* slot, int lane) {
   __syncwarp();
@@ -417,6 +420,61 @@ __device__ __forceinline__ void epilogue_row(uint32_t t_row, int n_cols, int gat
   e.gn_part = gn_keep;
 }
 
+// fp32 residual stream (FLUX DiT): out = res + gate * (acc + bias), residual and output both fp32 rows. The DiT adds
+// 2 x 57 gated updates to one stream; rounding the stream to bf16 after each of them was the largest single error term
+// of the full-size FLUX parity test (DiT output 2.2e-2 max-relative vs the fp32 oracle). The residual of the next
+// chunk is loaded before the current one is consumed; n_cols % 32 == 0.
+__device__ __forceinline__ void st_global_f32x8(float* p, const float (&f)[32], int o) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(f[o]), "f"(f[o + 1]),
+               "f"(f[o + 2]), "f"(f[o + 3]), "f"(f[o + 4]), "f"(f[o + 5]), "f"(f[o + 6]), "f"(f[o + 7])
+               : "memory");
+}
+template <bool GATE>
+__device__ __forceinline__ void epilogue_row_f32stream(uint32_t t_row, int n_cols, int oc0, bool valid, const EpiArgs& e,
+                                                       const float* bias_s) {
+  const float* res = reinterpret_cast<const float*>(e.res_row);
+  float* out = static_cast<float*>(e.out) + e.o_off;
+  float4 rn[8];
+  auto load = [&](int oc) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      rn[q] = valid ? *reinterpret_cast<const float4*>(res + oc + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  load(oc0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < n_cols; c0 += 32) {
+    uint32_t v[32];
+    float f[32];
+    tmem_ld32(t_row + c0, v);
+    float4 rc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rc[q] = rn[q];
+    if (c0 + 32 < n_cols) load(oc0 + c0 + 32);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (bias_s) add_bias32_s(f, bias_s + c0);
+    const int oc = oc0 + c0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (GATE) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(e.gate_row + oc + 4 * q));
+        f[4 * q] *= g.x; f[4 * q + 1] *= g.y; f[4 * q + 2] *= g.z; f[4 * q + 3] *= g.w;
+      }
+      f[4 * q] += rc[q].x; f[4 * q + 1] += rc[q].y; f[4 * q + 2] += rc[q].z; f[4 * q + 3] += rc[q].w;
+    }
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_global_f32x8(out + oc + 8 * q, f, 8 * q);
+    }
+  }
+}
+
+// element offset -> residual row pointer for either residual type (EpiArgs carries it as a bf16 pointer)
+__device__ __forceinline__ const bf16* res_row_ptr(const bf16* res, long long off, int res_f32) {
+  return res_f32 ? reinterpret_cast<const bf16*>(reinterpret_cast<const float*>(res) + off) : res + off;
+}
+
 // run-time option set -> specialised row routine (once per accumulator row, outside the chunk loop)
 template <bool GEGLU>
 __device__ __forceinline__ void epilogue_row_m(int mode, uint32_t t_row, int n_cols, int gate_off, int cv0, int oc0,
@@ -429,6 +487,11 @@ __device__ __forceinline__ void epilogue_row_m(int mode, uint32_t t_row, int n_c
   if (GEGLU) {  // only the plain and the generic set occur with GEGLU
     if (mode == EPI_PLAIN) OMGSR_EPI_ROW(EPI_PLAIN);
     else OMGSR_EPI_ROW(EPI_GENERIC);
+    return;
+  }
+  if (mode == EPI_F32S || mode == EPI_F32S_GATE) {
+    if (mode == EPI_F32S_GATE) epilogue_row_f32stream<true>(t_row, n_cols, oc0, valid, e, bias_s);
+    else epilogue_row_f32stream<false>(t_row, n_cols, oc0, valid, e, bias_s);
     return;
   }
   switch (mode) {

@@ -53,6 +53,7 @@ struct ConvGemmParams {
   int act;             // OMGSR_ACT_*
   int out_f32;
   int out_vec32, res_vec32;  // output / residual rows allow 256-bit accesses (see epilogue.cuh)
+  int res_f32;               // the residual is fp32 (fp32 residual stream, together with out_f32)
   int a_bytes;         // bytes one A box delivers (tb may be clamped to B)
   float* gn_sums;      // optional fused GroupNorm statistics of the output: [B][groups][2]
   int gn_cpg, gn_groups, gn_slots;  // gn_sums: scratch [image][gn_slots][groups * 2], see gn_flush (epilogue.cuh)
@@ -94,7 +95,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operand tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
   uint64_t* full_bar = bars;                        // [kStages]
   uint64_t* empty_bar = bars + C::kStages;          // [kStages]
@@ -242,7 +243,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* my_gn = gn_acc + quarter * 64;
     float* my_bias = gn_acc + 256 + quarter * BN;
     int bias_tile = -1;
-    const int epi_mode = epilogue_mode(p.act, p.gate != nullptr, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
+    const int epi_mode = epilogue_mode(p.act, p.gate != nullptr, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr,
+                                       p.res_f32 != 0);
     const int gn_n = p.gn_groups * 2;  // <= 64: the slice holds every group of one image, whatever the n_tile
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
@@ -258,7 +260,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.bias && next_n != bias_tile) bias_prefetch<BN>(bias_nx, p.bias, next_n * BN, p.Cout, lane);
       const int x = t.tx * tw + xl, y = t.ty * th + yl, b = t.tbi * tb + bl;
       if (p.gn_sums && t.tbi != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
         gn_b = t.tbi;
       }
       const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
@@ -266,7 +268,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       e.bias = p.bias;
       e.out = p.out;
       e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
-      e.res_row = p.res ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+      e.res_row = p.res ? res_row_ptr(p.res, b * p.r_sb + y * p.r_sy + x * p.r_sx, p.res_f32) : nullptr;
+      e.res_f32 = p.res_f32;
       const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : b) : 0;
       e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
       e.Cout = p.Cout; e.cout_out = cout_out; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
@@ -275,8 +278,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       e.gn_part = p.gn_sums ? gn_part : nullptr;
 
       uint4 rr[4] = {};
-      prefetch_res_row(e, t.n_tile * out_bn, out_bn, valid);
-      load_res32(rr, e, t.n_tile * out_bn, valid);
+      if (!p.res_f32) {
+        prefetch_res_row(e, t.n_tile * out_bn, out_bn, valid);
+        load_res32(rr, e, t.n_tile * out_bn, valid);
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -296,7 +301,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bias_tile = next_n;
       }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -330,7 +335,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const ConvGemmParams p) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
   uint64_t* full_bar = bars;                        // [kStages]  (the leader's are the live ones)
   uint64_t* empty_bar = bars + C::kStages;          // [kStages]  per CTA
@@ -447,7 +452,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     float* my_gn = gn_acc + quarter * 64;
     float* my_bias = gn_acc + 256 + quarter * BN;
     int bias_tile = -1;
-    const int epi_mode = epilogue_mode(p.act, p.gate != nullptr, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
+    const int epi_mode = epilogue_mode(p.act, p.gate != nullptr, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr,
+                                       p.res_f32 != 0);
     const int gn_n = p.gn_groups * 2;
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
@@ -466,7 +472,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, tbi = m / (p.tiles_x * p.tiles_y);
       const int x = tx * tw + xl, y = ty * th + yl, b = tbi * tb + bl;
       if (p.gn_sums && !dummy && tbi != gn_b) {
-        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
         gn_b = tbi;
       }
       const bool valid = !dummy && (x < p.W) && (y < p.H) && (b < p.B);
@@ -474,7 +480,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       e.bias = p.bias;
       e.out = p.out;
       e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
-      e.res_row = (p.res && valid) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+      e.res_row = (p.res && valid) ? res_row_ptr(p.res, b * p.r_sb + y * p.r_sy + x * p.r_sx, p.res_f32) : nullptr;
+      e.res_f32 = p.res_f32;
       const int gate_b = p.gate ? (p.gate_rows > 0 ? x / p.gate_rows : min(b, p.B - 1)) : 0;
       e.gate_row = p.gate ? p.gate + static_cast<long long>(gate_b) * p.gate_ld : nullptr;
       e.Cout = p.Cout; e.cout_out = geglu ? p.Cout / 2 : p.Cout; e.act = p.act; e.act_c0 = p.act_c0; e.act_c1 = p.act_c1;
@@ -483,8 +490,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       e.gn_part = p.gn_sums ? gn_part : nullptr;
 
       uint4 rr[4] = {};
-      prefetch_res_row(e, n_tile * out_bn, out_bn, valid);
-      load_res32(rr, e, n_tile * out_bn, valid);
+      if (!p.res_f32) {
+        prefetch_res_row(e, n_tile * out_bn, out_bn, valid);
+        load_res32(rr, e, n_tile * out_bn, valid);
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -507,7 +516,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         bias_tile = next_n;
       }
     }
-    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, quarter, p.gn_slots), lane);
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 4 + quarter, p.gn_slots), lane);
   }
 
   tc_fence_before();
@@ -591,7 +600,7 @@ struct ConvDesc {
   int Cin, Cout, R, S, stride2, pad_t, pad_l;
   long long x_sx, x_sy, x_sb;  // input element strides per x / y / b (stride-1 path)
   long long o_sx, o_sy, o_sb, r_sx, r_sy, r_sb;
-  int act, gate_rows, force_bn, out_f32;
+  int act, gate_rows, force_bn, out_f32, res_f32;
   long long gate_ld; int act_c0, act_c1;
   float* gn_sums; int gn_groups;
   const float* gn_in;  // optional [B][Cin][2] input GroupNorm coefficients (+SiLU), halo pair kernel only
@@ -664,6 +673,15 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   p.gate = d.gate; p.gate_rows = d.gate_rows; p.act = d.act; p.out_f32 = d.out_f32;
   p.out_vec32 = !d.out_f32 && (reinterpret_cast<uintptr_t>(d.y) % 32 == 0) && ((d.o_sx | d.o_sy | d.o_sb) % 16 == 0);
   p.res_vec32 = d.res && (reinterpret_cast<uintptr_t>(d.res) % 32 == 0) && ((d.r_sx | d.r_sy | d.r_sb) % 16 == 0);
+  p.res_f32 = 0;
+  if (d.res_f32) {
+    // fp32 residual stream: out = res + gate * (acc + bias) with fp32 res / out rows (epilogue_row_f32stream)
+    if (!d.res || !d.out_f32 || d.act != OMGSR_ACT_NONE || d.gn_sums || (d.Cout % 32) ||
+        (reinterpret_cast<uintptr_t>(d.res) % 32) || (reinterpret_cast<uintptr_t>(d.y) % 32))
+      return set_error(OMGSR_ERR_SHAPE, "conv_gemm: OMGSR_RES_F32 needs OMGSR_OUT_F32, a residual, no activation, "
+                                        "N %% 32 == 0 and 32-byte aligned rows (N=%d)", d.Cout);
+    p.res_f32 = 1;
+  }
   p.gate_ld = d.gate_ld > 0 ? d.gate_ld : (geglu ? d.Cout / 2 : d.Cout);
   p.act_c0 = d.act_c1 > d.act_c0 ? d.act_c0 : 0; p.act_c1 = d.act_c1 > d.act_c0 ? d.act_c1 : 0x7fffffff;
   p.a_bytes = kBK * 2 * tw * th * tb_box;
@@ -794,6 +812,7 @@ extern "C" int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias,
   d.o_sx = ldd; d.o_sy = 0; d.o_sb = 0; d.r_sx = ldr; d.r_sy = 0; d.r_sb = 0;
   d.act = act; d.gate_rows = gate ? gate_rows : 0; d.force_bn = force_bn; d.w_ld = K;
   d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
+  d.res_f32 = (flags & OMGSR_RES_F32) ? 1 : 0;
   d.flat = 1;
   return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
 }
@@ -813,6 +832,7 @@ extern "C" int omgsr_gemm_batched_bf16(const void* A, const void* Wt, const floa
   d.act = act; d.gate_rows = 0; d.force_bn = force_bn; d.w_ld = K; d.gate_ld = gate_ld;
   d.act_c0 = act_c0; d.act_c1 = act_c1;
   d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
+  d.res_f32 = (flags & OMGSR_RES_F32) ? 1 : 0;
   d.flat = 1;  // 128-row tiles never straddle two batch entries
   return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
 }

@@ -238,8 +238,15 @@ __global__ void gn_combine_kernel(const float* __restrict__ sums, const float* _
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row; the row is cached in registers (C <= 4096).
 // ------------------------------------------------------------------------------------------------
-template <int VPL>  // 8-element vectors per lane
-__global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+// 8 consecutive input elements as floats: bf16 rows (16 bytes) or fp32 rows (the FLUX fp32 residual stream, 32 bytes)
+__device__ __forceinline__ void ld8_stream(const bf16* p, float (&f)[8]) { unpack8(ld_stream(p), f); }
+__device__ __forceinline__ void ld8_stream(const float* p, float (&f)[8]) {
+  const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(p)), b = ld_stream_f4(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <int VPL, typename TIn>  // 8-element vectors per lane
+__global__ void layernorm_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, long long rows, int C, float eps,
                                  long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch) {
   const int lane = threadIdx.x & 31;
@@ -248,16 +255,16 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
   const int nvec = C / 8;
   for (long long row = warp_global; row < rows; row += nwarps) {
     // input rows may be batch-strided (a token range inside a longer joint sequence); output is dense
-    const bf16* xr = (rows_per_batch > 0 && x_batch > 0)
-                         ? x + (row / rows_per_batch) * x_batch + (row % rows_per_batch) * ldx
-                         : x + row * ldx;
+    const TIn* xr = (rows_per_batch > 0 && x_batch > 0)
+                        ? x + (row / rows_per_batch) * x_batch + (row % rows_per_batch) * ldx
+                        : x + row * ldx;
     float f[VPL][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        unpack8(ld_stream(xr + v * 8), f[i]);
+        ld8_stream(xr + v * 8, f[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += f[i][j];
       }
@@ -770,8 +777,8 @@ extern "C" int omgsr_groupnorm_combine(const float* sums, const float* pixels, i
   return check_launch("gn_combine_kernel");
 }
 
-extern "C" int omgsr_layernorm(const void* x, void* y, const float* gamma, const float* beta, long long rows, int C,
-                               float eps, long long rows_per_batch, long long gb_stride, long long ldx,
+extern "C" int omgsr_layernorm(const void* x, int x_f32, void* y, const float* gamma, const float* beta, long long rows,
+                               int C, float eps, long long rows_per_batch, long long gb_stride, long long ldx,
                                long long x_batch_stride, void* stream) {
   if (C % 8 || C > 4096) return set_error(OMGSR_ERR_SHAPE, "layernorm: C=%d", C);
   if (ldx <= 0) ldx = C;
@@ -782,11 +789,16 @@ extern "C" int omgsr_layernorm(const void* x, void* y, const float* gamma, const
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
   const int vpl = (C / 8 + 31) / 32;
-  const bf16* xi = static_cast<const bf16*>(x);
   bf16* yo = static_cast<bf16*>(y);
-#define LN_CASE(V)                                                                                               \
-  layernorm_kernel<V><<<grid, threads, 0, st>>>(xi, yo, gamma, beta, rows, C, eps, rows_per_batch, gb_stride, ldx,   \
-                                                x_batch_stride)
+#define LN_CASE(V)                                                                                                  \
+  do {                                                                                                              \
+    if (x_f32)                                                                                                      \
+      layernorm_kernel<V, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), yo, gamma, beta, rows, C,  \
+                                                           eps, rows_per_batch, gb_stride, ldx, x_batch_stride);    \
+    else                                                                                                            \
+      layernorm_kernel<V, bf16><<<grid, threads, 0, st>>>(static_cast<const bf16*>(x), yo, gamma, beta, rows, C,    \
+                                                          eps, rows_per_batch, gb_stride, ldx, x_batch_stride);     \
+  } while (0)
   if (vpl <= 1) LN_CASE(1);
   else if (vpl <= 2) LN_CASE(2);
   else if (vpl <= 4) LN_CASE(4);

@@ -31,6 +31,9 @@ struct ProbeParams {
   int iters;       // pattern repetitions (each instruction is issued 4x: the K = 64 block)
   int xf_warps;    // extra warps doing LDS / FMA / tanh / STS on a 64 KB region (0 = none)
   int tma;         // 1: a producer thread streams 16 KB boxes into a 4-deep ring (not consumed)
+  int commit_each; // 1: tcgen05.commit (multicast in pair mode) to a dummy barrier after EVERY pattern element (4 MMAs)
+  int d_mode;      // 0: the 4 K-steps of a pattern element hit one accumulator; 1: consecutive instructions alternate
+                   //    between two accumulators (independent chains); 2: every instruction of the run hits ONE accumulator
   long long* cycles;  // [gridDim.x]
 };
 
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
   uint8_t* sA = smem;                 // 80 KB: A views
   uint8_t* sB = smem + 80 * 1024;     // 48 KB: B blocks
   uint8_t* sX = smem + 128 * 1024;    // 64 KB: transform / TMA scratch
-  __shared__ uint64_t done_bar, ring_bar[4];
+  __shared__ uint64_t done_bar, ring_bar[4], dummy_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = p.pair ? cluster_ctarank() : 0;
@@ -50,6 +53,7 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
     reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i * 2654435761u >> 20 & 0x00ff00ffu);  // small bf16 values
   if (threadIdx.x == 0) {
     mbar_init(&done_bar, 1);
+    mbar_init(&dummy_bar, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&ring_bar[i], 1);
     fence_barrier_init();
   }
@@ -77,14 +81,16 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
           const uint32_t idesc = umma_idesc_bf16(p.pair ? 256 : 128, N, 0, 0);
           const uint32_t a_addr = a0 + view * 128;
           if (++view >= p.a_views) view = 0;
-          const uint32_t d = tmem_base + ((j & 1) ? 256 : 0);
+          const uint32_t d0 = tmem_base + ((p.d_mode != 2 && (j & 1)) ? 256 : 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = umma_desc_sw128(b0 + (j & 3) * 4096 + k * 32, 16, 1024);
+            const uint32_t d = (p.d_mode == 1) ? tmem_base + ((k & 1) ? 256 : 0) : d0;
             if (p.pair) tc_mma2_ss(d, da, db, idesc, 1);
             else tc_mma_ss(d, da, db, idesc, 1);
           }
+          if (p.commit_each) { if (p.pair) tc_commit2_mc(&dummy_bar); else tc_commit(&dummy_bar); }
         }
         if ((it & 63) == 63) {  // bound the number of uncommitted instructions like a real pipeline does
           if (p.pair) tc_commit2_mc(&done_bar); else tc_commit(&done_bar);
@@ -150,8 +156,10 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
 }
 
 static double run(const char* name, int pair, std::initializer_list<int> pat, int a_views, int xf, int tma,
-                  const CUtensorMap& tm, long long* d_cycles) {
+                  const CUtensorMap& tm, long long* d_cycles, int d_mode = 0, int commit_each = 0) {
   ProbeParams p{};
+  p.d_mode = d_mode;
+  p.commit_each = commit_each;
   p.pair = pair; p.a_views = a_views; p.iters = 4096; p.xf_warps = xf; p.tma = tma; p.cycles = d_cycles;
   int j = 0;
   double nominal = 0;  // tensor-pipe cycles of one pattern at full rate: N / 2 per K = 16 instruction, 4 per block
@@ -165,7 +173,7 @@ static double run(const char* name, int pair, std::initializer_list<int> pat, in
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = pair ? 1 : 0;
   cudaEventRecord(e0);
   cudaError_t err = cudaLaunchKernelEx(&cfg, probe_kernel, tm, p);
   cudaEventRecord(e1);
@@ -181,8 +189,8 @@ static double run(const char* name, int pair, std::initializer_list<int> pat, in
   double sum = 0; int cnt = 0;
   for (long long c : h) if (c > 0) { sum += c; ++cnt; }
   const double cyc = sum / cnt / p.iters;
-  printf("%-46s a_views=%d xf=%d tma=%d : %7.1f cycles / pattern (nominal %5.0f) -> tensor pipe %5.1f %%   [%.2f ms]\n", name,
-         a_views, xf, tma, cyc, nominal, 100.0 * nominal / cyc, ms);
+  printf("%-46s a_views=%d xf=%d tma=%d d=%d : %7.1f cycles / pattern (nominal %5.0f) -> tensor pipe %5.1f %%   [%.2f ms]\n", name,
+         a_views, xf, tma, d_mode, cyc, nominal, 100.0 * nominal / cyc, ms);
   return cyc;
 }
 
@@ -208,6 +216,16 @@ int main() {
     run("pair   N=256 shifted views", 1, {256}, 6, 0, 0, tm, d_cycles);
     run("pair   mix 128,256,256,128", 1, {128, 256, 256, 128}, 4, 0, 0, tm, d_cycles);
     run("single mix 128,256,256,128", 0, {128, 256, 256, 128}, 4, 0, 0, tm, d_cycles);
+    run("pair   N=256 alternating accumulators", 1, {256}, 1, 0, 0, tm, d_cycles, 1);
+    run("pair   N=128 alternating accumulators", 1, {128}, 1, 0, 0, tm, d_cycles, 1);
+    run("pair   N=64  alternating accumulators", 1, {64}, 1, 0, 0, tm, d_cycles, 1);
+    run("pair   N=128,128 two accumulators per 4", 1, {128, 128}, 2, 0, 0, tm, d_cycles, 0);
+    run("pair   N=256,256 two accumulators per 4", 1, {256, 256}, 2, 0, 0, tm, d_cycles, 0);
+    run("pair   mix, alternating accumulators", 1, {128, 256, 256, 128}, 4, 0, 0, tm, d_cycles, 1);
+    run("pair   mix, one accumulator", 1, {128, 256, 256, 128}, 4, 0, 0, tm, d_cycles, 2);
+    run("pair   mix, commit after every 4 MMAs", 1, {128, 256, 256, 128}, 4, 0, 0, tm, d_cycles, 0, 1);
+    run("pair   N=128,128 commit after every 4 MMAs", 1, {128, 128}, 2, 0, 0, tm, d_cycles, 0, 1);
+    run("pair   N=256,256 commit after every 4 MMAs", 1, {256, 256}, 2, 0, 0, tm, d_cycles, 0, 1);
     run("pair   N=128 + TMA", 1, {128}, 6, 0, 1, tm, d_cycles);
     run("pair   N=128 + transform", 1, {128}, 6, 4, 0, tm, d_cycles);
     run("pair   N=128 + TMA + transform", 1, {128}, 6, 4, 1, tm, d_cycles);
