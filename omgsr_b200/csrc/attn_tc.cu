@@ -98,7 +98,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
         uint8_t* sK = sKV + stage * (C::kKBytes + C::kVBytes);
         uint8_t* sV = sK + C::kKBytes;
         mbar_expect_tx(&k_full[stage], C::kKBytes);
@@ -358,7 +358,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
         uint8_t* sK = sKV + stage * C::kStageBytes;
         uint8_t* sV = sK + C::kKBytes;
         mbar_expect_tx(&k_full[stage], C::kKBytes);

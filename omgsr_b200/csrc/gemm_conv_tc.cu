@@ -164,7 +164,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               c4 = b0;
             }
             for (int kc = 0; kc < p.kc_per_tap; ++kc, ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * C::kStageBytes;
               uint8_t* sb = sa + C::kABytes;
               mbar_expect_tx(&full_bar[stage], p.a_bytes + C::kBBytes);
@@ -282,7 +282,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         prefetch_res_row(e, t.n_tile * out_bn, out_bn, valid);
         load_res32(rr, e, t.n_tile * out_bn, valid);
       }
-      mbar_wait(&acc_full[acc], acc_phase);
+      mbar_wait_relaxed(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
       const float* bias_s = p.bias ? my_bias : nullptr;
@@ -400,7 +400,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               cbase = px * p.pair_off; c1 = x0 + ((dx - px) >> 1); c2 = py; c3 = y0 + ((dy - py) >> 1); c4 = b0;
             }
             for (int kc = 0; kc < p.kc_per_tap; ++kc, ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * C::kStageBytes;
               uint8_t* sb = sa + C::kABytes;
               if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (p.a_bytes + C::kBBytes));
@@ -494,7 +494,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         prefetch_res_row(e, n_tile * out_bn, out_bn, valid);
         load_res32(rr, e, n_tile * out_bn, valid);
       }
-      mbar_wait(&acc_full[acc], acc_phase);
+      mbar_wait_relaxed(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
       const float* bias_s = p.bias ? my_bias : nullptr;

@@ -31,6 +31,7 @@ struct ProbeParams {
   int iters;       // pattern repetitions (each instruction is issued 4x: the K = 64 block)
   int xf_warps;    // extra warps doing LDS / FMA / tanh / STS on a 64 KB region (0 = none)
   int tma;         // 1: a producer thread streams 16 KB boxes into a 4-deep ring (not consumed)
+  int a_tmem;      // single-CTA only: the A operand comes from TMEM (tcgen05.mma [d], [a_tmem], b_desc)
   int commit_each; // 1: tcgen05.commit (multicast in pair mode) to a dummy barrier after EVERY pattern element (4 MMAs)
   int d_mode;      // 0: the 4 K-steps of a pattern element hit one accumulator; 1: consecutive instructions alternate
                    //    between two accumulators (independent chains); 2: every instruction of the run hits ONE accumulator
@@ -39,6 +40,7 @@ struct ProbeParams {
 
 constexpr int kSmem = 200 * 1024;
 
+template <bool PAIR>
 __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ CUtensorMap tm, const ProbeParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -48,7 +50,8 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
   __shared__ uint64_t done_bar, ring_bar[4], dummy_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = p.pair ? cluster_ctarank() : 0;
+  uint32_t rank = 0;
+  if constexpr (PAIR) rank = cluster_ctarank();
   for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i * 2654435761u >> 20 & 0x00ff00ffu);  // small bf16 values
   if (threadIdx.x == 0) {
@@ -59,11 +62,11 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
   }
   fence_proxy_async_smem();
   if (warp == 1) {
-    if (p.pair) { tmem_alloc2(&tmem_slot, 512); tmem_relinquish2(); }
+    if constexpr (PAIR) { tmem_alloc2(&tmem_slot, 512); tmem_relinquish2(); }
     else { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  if (p.pair) cluster_sync_all(); else __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   __shared__ volatile int stop;
@@ -71,36 +74,37 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
   __syncthreads();
 
   if (warp == 0 && lane == 0) {
-    if (!p.pair || rank == 0) {
+    if (!PAIR || rank == 0) {
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       long long t0 = clock64();
       int view = 0;
       for (int it = 0; it < p.iters; ++it) {
         for (int j = 0; j < 8 && p.pattern[j]; ++j) {
           const int N = p.pattern[j];
-          const uint32_t idesc = umma_idesc_bf16(p.pair ? 256 : 128, N, 0, 0);
+          const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, N, 0, 0);
           const uint32_t a_addr = a0 + view * 128;
           if (++view >= p.a_views) view = 0;
-          const uint32_t d0 = tmem_base + ((p.d_mode != 2 && (j & 1)) ? 256 : 0);
+          const uint32_t d0 = tmem_base + ((p.d_mode != 2 && (j & 1) && !p.a_tmem) ? 256 : 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = umma_desc_sw128(b0 + (j & 3) * 4096 + k * 32, 16, 1024);
             const uint32_t d = (p.d_mode == 1) ? tmem_base + ((k & 1) ? 256 : 0) : d0;
-            if (p.pair) tc_mma2_ss(d, da, db, idesc, 1);
+            if constexpr (PAIR) tc_mma2_ss(d, da, db, idesc, 1);
+            else if (p.a_tmem) tc_mma_ts(d, tmem_base + 448 + k * 8, db, idesc, 1);  // A operand from TMEM (8 columns / K-step)
             else tc_mma_ss(d, da, db, idesc, 1);
           }
-          if (p.commit_each) { if (p.pair) tc_commit2_mc(&dummy_bar); else tc_commit(&dummy_bar); }
+          if (p.commit_each) { if constexpr (PAIR) tc_commit2_mc(&dummy_bar); else tc_commit(&dummy_bar); }
         }
         if ((it & 63) == 63) {  // bound the number of uncommitted instructions like a real pipeline does
-          if (p.pair) tc_commit2_mc(&done_bar); else tc_commit(&done_bar);
+          if constexpr (PAIR) tc_commit2_mc(&done_bar); else tc_commit(&done_bar);
           mbar_wait(&done_bar, (it >> 6) & 1);
         }
       }
       long long t1 = clock64();
       p.cycles[blockIdx.x] = t1 - t0;
       stop = 1;
-      if (p.pair) {  // tell the peer CTA (its interference warps keep running while the leader issues)
+      if constexpr (PAIR) {  // tell the peer CTA (its interference warps keep running while the leader issues)
         uint32_t remote;
         asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(remote) : "r"(smem_u32(const_cast<int*>(&stop))));
         asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(1) : "memory");
@@ -148,16 +152,17 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
   }
   __syncthreads();
   tc_fence_before();
-  if (p.pair) cluster_sync_all(); else __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (p.pair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
 static double run(const char* name, int pair, std::initializer_list<int> pat, int a_views, int xf, int tma,
-                  const CUtensorMap& tm, long long* d_cycles, int d_mode = 0, int commit_each = 0) {
+                  const CUtensorMap& tm, long long* d_cycles, int d_mode = 0, int commit_each = 0, int a_tmem = 0) {
   ProbeParams p{};
+  p.a_tmem = a_tmem;
   p.d_mode = d_mode;
   p.commit_each = commit_each;
   p.pair = pair; p.a_views = a_views; p.iters = 4096; p.xf_warps = xf; p.tma = tma; p.cycles = d_cycles;
@@ -165,7 +170,8 @@ static double run(const char* name, int pair, std::initializer_list<int> pat, in
   double nominal = 0;  // tensor-pipe cycles of one pattern at full rate: N / 2 per K = 16 instruction, 4 per block
   for (int n : pat) { p.pattern[j++] = n; nominal += 4 * n / 2.0; }
   cudaMemset(d_cycles, 0, 148 * sizeof(long long));
-  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaFuncSetAttribute(probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaFuncSetAttribute(probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaLaunchConfig_t cfg{};
@@ -175,7 +181,9 @@ static double run(const char* name, int pair, std::initializer_list<int> pat, in
   attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = pair ? 1 : 0;
   cudaEventRecord(e0);
-  cudaError_t err = cudaLaunchKernelEx(&cfg, probe_kernel, tm, p);
+  cudaError_t err = cudaSuccess;
+  if (pair) err = cudaLaunchKernelEx(&cfg, probe_kernel<true>, tm, p);
+  else { probe_kernel<false><<<148, 256, kSmem>>>(tm, p); err = cudaGetLastError(); }
   cudaEventRecord(e1);
   cudaError_t err2 = cudaDeviceSynchronize();
   if (err != cudaSuccess || err2 != cudaSuccess) {
@@ -209,6 +217,13 @@ int main() {
     run("single N=256", 0, {256}, 1, 0, 0, tm, d_cycles);
     run("single N=128", 0, {128}, 1, 0, 0, tm, d_cycles);
     run("single N=64", 0, {64}, 1, 0, 0, tm, d_cycles);
+    run("single N=256,256 two accumulators", 0, {256, 256}, 2, 0, 0, tm, d_cycles);
+    run("single N=128,128 two accumulators", 0, {128, 128}, 2, 0, 0, tm, d_cycles);
+    run("single N=64,64 two accumulators", 0, {64, 64}, 2, 0, 0, tm, d_cycles);
+    run("single N=256 A from TMEM", 0, {256, 256}, 2, 0, 0, tm, d_cycles, 0, 0, 1);
+    run("single N=128 A from TMEM", 0, {128, 128}, 2, 0, 0, tm, d_cycles, 0, 0, 1);
+    run("single N=64  A from TMEM", 0, {64, 64}, 2, 0, 0, tm, d_cycles, 0, 0, 1);
+    run("single N=128 + commit each", 0, {128, 128}, 2, 0, 0, tm, d_cycles, 0, 1);
     run("pair   N=256", 1, {256}, 1, 0, 0, tm, d_cycles);
     run("pair   N=128", 1, {128}, 1, 0, 0, tm, d_cycles);
     run("pair   N=64", 1, {64}, 1, 0, 0, tm, d_cycles);
