@@ -101,8 +101,9 @@ int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out
                           long long k_batch, long long v_row, long long v_head, long long v_batch, long long o_row,
                           long long o_head, long long o_batch, float scale, void* stream);
 
-/* A-B timing switch for the two attention kernels (1 = always the single-tile kernel). Test/bench use only. */
-int omgsr_flash_attn_set_variant(int force_v1);
+/* A-B timing switch for the attention kernels: 0 = automatic, 1 = always the single-tile kernel, 2 = the 64-key
+ * ping-pong kernel instead of the 128-key one. Test/bench use only. */
+int omgsr_flash_attn_set_variant(int variant);
 
 /* NHWC implicit-GEMM convolution, ksize in {1,3}, stride in {1,2}; `upsample2x` fuses a nearest 2x
  * upsample in front of a 3x3/p1 conv (weights must be packed by pack_upsample_weight: 4 x [Cout, 4*Cin]).

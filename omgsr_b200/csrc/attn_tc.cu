@@ -549,6 +549,330 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ================================================================================================================
+// v3 (round 2): 128 keys per block, single-buffered S and P, ping-pong order on the tensor pipe.
+//
+// scripts/mma_probe.cu (profiles/r02/mma_probe4_single_cta_tmemA.txt): a cta_group::1 tcgen05.mma costs ~154 cycles for
+// ANY N <= 128 (A from shared memory or from TMEM alike) and ~172 at N = 256. v2 issues S = Q K^T with N = 64 keys: per
+// 128 keys and 256 query rows its S instructions cost 2 x 2 x 8 x 154 = 4.9 k cycles for 2.5 k cycles of math, which is
+// why the FLUX attention sat at 34 % tensor-pipe activity whatever the softmax warps did. With 128 keys per block the
+// same S costs 2.5 k cycles (PV is unchanged: its N is the head dimension): 7.4 k -> 4.9 k cycles per 128 keys.
+//   * TMEM: S_a @0, S_b @128 (128 fp32 columns each, ONE buffer per group), O_a @256, O_b @384.
+//   * tensor-pipe order per block j:  PV_a(j), S_a(j+1), PV_b(j), S_b(j+1).  Group a exponentiates block j while
+//     the pipe runs PV_b(j-1) and S_b(j), group b while it runs PV_a(j) and S_a(j+1): each group has a window of two
+//     instruction groups (~2.5 k cycles) for 128 x 128 exponentials on four warps, so neither S nor P needs a second
+//     buffer (a double-buffered P alone would be 128 KB of shared memory at d = 128).
+//   * K and V tiles (128 keys each) travel through ONE ring in consumption order K0 V0 K1 V1 ... (3 slots of 32 KB at
+//     d = 128: live at any time are V(j), K(j+1) and the tile in flight).
+//   * softmax: the whole 128-score row of a thread is read once (2 x tcgen05.ld.x64) and kept in registers; stale-maximum
+//     scheme, lazy O rescale and the d = 64 ones-column row sums are those of v2.
+// ================================================================================================================
+template <int D>
+struct Attn3Cfg {
+  static constexpr int kBN = 128;
+  static constexpr int kSlots = (D == 64) ? 4 : 3;
+  static constexpr int kQBytes = 2 * 128 * D * 2;
+  static constexpr int kTileBytes = kBN * D * 2;         // one K or V tile
+  static constexpr int kPBytes = 128 * kBN * 2;          // P of one group: two 64-key panels of [128 rows x 128 B]
+  static constexpr bool kOnesCol = (D == 64);
+  static constexpr int kOnesBytes = kOnesCol ? kBN * 128 : 0;
+  static constexpr int kSmemBytes = kQBytes + kSlots * kTileBytes + 2 * kPBytes + kOnesBytes + 1024 + 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(320, 1)
+flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = Attn3Cfg<D>;
+  constexpr int BN = C::kBN, NS = C::kSlots;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                             // [group][d panel][128 rows x 128 B]
+  uint8_t* sKV = sQ + C::kQBytes;                 // [slot][d panel][128 keys x 128 B]
+  uint8_t* sP = sKV + NS * C::kTileBytes;         // [group][key panel][128 rows x 128 B]
+  uint8_t* sOnes = sP + 2 * C::kPBytes;           // [128 keys x 128 B] of bf16 1.0 (d = 64 only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::kOnesBytes);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* kv_full = q_full + 1;       // [NS]
+  uint64_t* kv_empty = kv_full + NS;    // [NS]
+  uint64_t* s_full = kv_empty + NS;     // [2 groups]
+  uint64_t* p_full = s_full + 2;        // [2]
+  uint64_t* pv_done = p_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 128); mbar_init(&pv_done[g], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (C::kOnesCol) {
+    for (int i = threadIdx.x; i < C::kOnesBytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: Q (both groups) once, then K0 V0 K1 V1 ... through the ring ----
+      mbar_expect_tx(q_full, C::kQBytes);
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sQ + (g * (D / 64) + pnl) * (128 * 128), &tmQ, q_full, pnl * 64, m0 + g * 128, h, b);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < 2 * nblk; ++t) {
+        mbar_wait_relaxed(&kv_empty[slot], phase ^ 1);
+        uint8_t* dst = sKV + slot * C::kTileBytes;
+        mbar_expect_tx(&kv_full[slot], C::kTileBytes);
+        const CUtensorMap* tm = (t & 1) ? &tmV : &tmK;
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(dst + pnl * (BN * 128), tm, &kv_full[slot], pnl * 64, (t >> 1) * BN, h, b);
+        if (++slot == NS) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, C::kOnesCol ? D + 16 : D, 0, 1);
+      auto tile_addr = [&](int t) { return smem_u32(sKV + (t % NS) * C::kTileBytes); };
+      auto wait_tile = [&](int t) { mbar_wait(&kv_full[t % NS], (t / NS) & 1); tc_fence_after(); };
+      auto free_tile = [&](int t) { tc_commit(&kv_empty[t % NS]); };
+      auto issue_s = [&](int g, int t) {
+        const uint32_t aQ = smem_u32(sQ + g * (D / 64) * (128 * 128));
+        const uint32_t aK = tile_addr(t);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
+          tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
+        }
+        tc_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, int t, int j) {
+        const uint32_t aP = smem_u32(sP + g * C::kPBytes);
+        const uint32_t aV = tile_addr(t);
+        // second 64-wide N atom: the next d panel (d = 128) or the all-ones panel (d = 64)
+        const uint32_t lbo = C::kOnesCol ? smem_u32(sOnes) - aV : BN * 128;
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc_sw128(aV + kk * 2048, lbo, 1024);
+          tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
+        }
+        tc_commit(&pv_done[g]);
+      };
+      mbar_wait(q_full, 0);
+      wait_tile(0);
+      issue_s(0, 0);
+      issue_s(1, 0);
+      free_tile(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int tV = 2 * j + 1, tK = 2 * j + 2;
+        const bool more = j + 1 < nblk;
+        mbar_wait(&p_full[0], j & 1);   // group a consumed S_a(j) and wrote P_a(j)
+        wait_tile(tV);
+        issue_pv(0, tV, j);
+        if (more) { wait_tile(tK); issue_s(0, tK); }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, tV, j);
+        free_tile(tV);
+        if (more) { issue_s(1, tK); free_tile(tK); }
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + g * 128 + lane_off, tO = tmem_base + 256 + g * 128 + lane_off;
+    uint8_t* p_row = sP + g * C::kPBytes + row * 128;
+    float m_stale = 0.f, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      // the row's 128 scores: the low half stays in registers, the high half is scanned for the maximum in two 32-column
+      // pieces and re-read from TMEM for its exponentials (a thread may hold 168 registers with ten warps per CTA:
+      // the full row spilled)
+      const int n_valid = min(BN, p.N - j * BN);
+      uint32_t sv[64];
+      tmem_ld64(tS, sv);
+      tmem_wait_ld();
+      if (n_valid < 64) {  // ragged last block only: mask the keys that do not exist
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= n_valid) sv[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]);
+#pragma unroll
+      for (int i = 2; i < 64; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+      }
+#pragma unroll
+      for (int c0 = 64; c0 < 128; c0 += 32) {
+        uint32_t hv[32];
+        tmem_ld32(tS + c0, hv);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          if (c0 + i < n_valid) mx0 = fmaxf(mx0, __uint_as_float(hv[i]));
+          if (c0 + i + 1 < n_valid) mx1 = fmaxf(mx1, __uint_as_float(hv[i + 1]));
+        }
+      }
+      const float mx = fmaxf(mx0, mx1);
+      if (j == 0) {
+        m_stale = mx;
+      } else {
+        // P_g and O_g belong to PV_g(j - 1) until it has retired
+        mbar_wait(&pv_done[g], (j - 1) & 1);
+        tc_fence_after();
+        const bool need = (mx - m_stale) * p.scale_log2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
+#pragma unroll
+          for (int c0 = 0; c0 < (C::kOnesCol ? D + 32 : D); c0 += 32) {  // + the row-sum column(s) at D
+            uint32_t v[32];
+            tmem_ld32(tO + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tO + c0, v);
+          }
+          tmem_wait_st();
+          l_run *= alpha;
+          if (need) m_stale = mx;
+        }
+      }
+      const float mb = m_stale * p.scale_log2;
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) {  // the high 64 scores again
+          tmem_ld64(tS + 64, sv);
+          tmem_wait_ld();
+          if (n_valid < BN) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (64 + i >= n_valid) sv[i] = 0xff800000u;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float pr[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pr[i] = exp2f(fmaf(__uint_as_float(sv[q * 8 + i]), p.scale_log2, -mb));  // exp2(-inf) = 0
+          if (!C::kOnesCol) {
+            ls0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
+            ls1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
+          }
+          uint4 u;
+          u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
+          u.z = pack_bf16x2(pr[4], pr[5]); u.w = pack_bf16x2(pr[6], pr[7]);
+          *reinterpret_cast<uint4*>(p_row + half * (128 * 128) + ((q ^ (row & 7)) << 4)) = u;
+        }
+      }
+      l_run += ls0 + ls1;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[g]);
+    }
+    // epilogue: O / l
+    mbar_wait(&pv_done[g], (nblk - 1) & 1);
+    tc_fence_after();
+    const int m = m0 + g * 128 + row;
+    if (C::kOnesCol) {  // l = the ones column of O
+      uint32_t lv[16];
+      tmem_ld16(tO + D, lv);
+      tmem_wait_ld();
+      l_run = __uint_as_float(lv[0]);
+    }
+    const float inv = 1.0f / l_run;
+    bf16* o = p.out + static_cast<long long>(b) * p.o_batch + static_cast<long long>(m) * p.o_row +
+              static_cast<long long>(h) * p.o_head;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tO + c0, v);
+      tmem_wait_ld();
+      if (m < p.M) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv, __uint_as_float(v[q * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv, __uint_as_float(v[q * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv, __uint_as_float(v[q * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv, __uint_as_float(v[q * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + c0 + q * 8) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D>
+static int launch_attn3(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
+                        const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
+                        cudaStream_t st) {
+  using C = Attn3Cfg<D>;
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&flash_attn3_kernel<D>), C::kSmemBytes, &attr_done, "flash_attn3")) return rc;
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t eb = 2;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(M), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t str[3] = {qs[0] * eb, qs[1] * eb, qs[2] * eb};
+    uint32_t box[4] = {64, 128, 1, 1};
+    int rc = make_tmap_bf16(&tmQ, q, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint32_t box[4] = {64, static_cast<uint32_t>(C::kBN), 1, 1};
+    uint64_t strk[3] = {ks[0] * eb, ks[1] * eb, ks[2] * eb};
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, strk, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    uint64_t strv[3] = {vs[0] * eb, vs[1] * eb, vs[2] * eb};
+    rc = make_tmap_bf16(&tmV, v, 4, dims, strv, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.M = M; p.N = N; p.H = H; p.B = B;
+  p.o_row = os[0]; p.o_head = os[1]; p.o_batch = os[2];
+  p.out = static_cast<bf16*>(out);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((M + 255) / 256, H, B);
+  flash_attn3_kernel<D><<<grid, 320, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  return check_launch("flash_attn3_kernel");
+}
+
 template <int D>
 static int launch_attn2(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
                         const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
@@ -625,9 +949,11 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
 
 using namespace omgsr;
 
-static int g_attn_force_v1 = 0;
-/* bring-up / A-B timing switch: 1 = always use the single-tile kernel */
-extern "C" int omgsr_flash_attn_set_variant(int force_v1) { g_attn_force_v1 = force_v1; return OMGSR_OK; }
+#include <cstdlib>
+static int g_attn_variant = getenv("OMGSR_ATTN_VARIANT") ? atoi(getenv("OMGSR_ATTN_VARIANT")) : 0;
+/* bring-up / A-B timing switch: 0 = automatic, 1 = always the single-tile kernel, 2 = the 64-key ping-pong kernel (v2)
+ * wherever the 128-key kernel (v3) would be chosen */
+extern "C" int omgsr_flash_attn_set_variant(int variant) { g_attn_variant = variant; return OMGSR_OK; }
 
 extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int M,
                                      int N, int D, long long q_row, long long q_head, long long q_batch,
@@ -647,7 +973,12 @@ extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // long query sequences: ping-pong kernel (2 x 128 rows per CTA, O in TMEM); short ones (M <= 128, e.g. the 8x8
   // UNet level) keep the 128-row kernel so half of every CTA is not padding.
-  const bool v2 = (M > 128) && !(g_attn_force_v1);
+  const bool v2 = (M > 128) && g_attn_variant != 1;
+  // long key sequences: 128 keys per block (v3: every S instruction is N = 128, half the instruction count of v2)
+  if (v2 && N >= 128 && g_attn_variant != 2) {
+    if (D == 64) return launch_attn3<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+    if (D == 128) return launch_attn3<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+  }
   if (v2) {
     if (D == 64) return launch_attn2<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
     if (D == 128) return launch_attn2<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
