@@ -168,7 +168,7 @@ class OMGSR_F_Infer(torch.nn.Module):
         wts = torch.outer(torch.tensor(ys, dtype=torch.float64), torch.tensor(xs, dtype=torch.float64))
         return torch.tile(wts.to(self.device), (nbatches, 16, 1, 1))
 
-    def _dit(self, packed, prompt_embeds, pooled_prompt_embeds, text_ids, latent_image_ids):
+    def _dit(self, packed, prompt_embeds, pooled_prompt_embeds, text_ids, latent_image_ids, seq_parallel=None):
         bsz = packed.shape[0]
         guidance_vec = torch.full((bsz,), self.guidance_scale, dtype=torch.float32)  # host: constant per run
         return self.flux_transformer(
@@ -180,6 +180,7 @@ class OMGSR_F_Infer(torch.nn.Module):
             txt_ids=text_ids,
             img_ids=latent_image_ids,
             return_dict=False,
+            **({"seq_parallel": seq_parallel} if seq_parallel is not None else {}),
         )[0]
 
     def _decode_latent(self, lq_latent_f32_or_bf16):
@@ -218,7 +219,16 @@ class OMGSR_F_Infer(torch.nn.Module):
         if D.tile_parallel():  # single large image on several GPUs: each rank runs the DiT on its share of the tiles
             if pe.shape[0] != 1:
                 raise RuntimeError("tile-parallel mode expects one shared prompt")
-            pred = D.tile_parallel_forward(lambda t: self._dit(t, pe, pp, text_ids, latent_image_ids), packed)
+            # tiles that fill a wave go one per rank; the left-over ones (9 tiles on 8 GPUs: the ninth) are computed by
+            # all ranks together through the engine's sequence-parallel forward instead of costing another wave
+            import torch.distributed as tdist
+            world, rank = tdist.get_world_size(), tdist.get_rank()
+            n_tok = packed.shape[1] + pe.shape[1]
+            fn_all = None
+            if n_tok % world == 0 and (nt * B) % world:
+                fn_all = lambda t: self._dit(t, pe, pp, text_ids, latent_image_ids, seq_parallel=(rank, world))
+            pred = D.tile_parallel_forward(lambda t: self._dit(t, pe, pp, text_ids, latent_image_ids), packed,
+                                           fn_all=fn_all)
         else:
             pred = self._dit(packed, pe, pp, text_ids, latent_image_ids)  # [nt*B, (T/2)^2, 4C] bf16
         T2 = tile_size // 2

@@ -129,6 +129,7 @@ class VAEHook:
         scale = 8 if self.is_decoder else 1
         oh, ow = (height * 8, width * 8) if self.is_decoder else (height // 8, width // 8)
         result = torch.zeros((N, outs[0].shape[1], oh, ow), device=z.device, dtype=torch.float32)
+        regions = {}
         for out, ids in zip(outs, members):
             if shadow:
                 break  # this rank only kept the collectives in step; it owns no output region
@@ -136,7 +137,14 @@ class VAEHook:
                 tile = out[k * N:(k + 1) * N]
                 m = self.crop_margins(in_boxes[i], out_boxes[i], self.is_decoder)
                 ob = out_boxes[i]
-                result[:, :, ob[2]:ob[3], ob[0]:ob[1]] = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]]
+                crop = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]]
+                if tp:
+                    regions[i] = crop
+                else:
+                    result[:, :, ob[2]:ob[3], ob[0]:ob[1]] = crop
         if tp:
-            torch.distributed.all_reduce(result)  # output regions are disjoint: the sum is the stitched image
+            # the output regions are disjoint: gather them (each tile's valid region travels once) instead of summing
+            # whole zero-filled images over the ranks
+            boxes = [(ob[2], ob[3], ob[0], ob[1]) for ob in out_boxes]
+            _dist.gather_tile_regions(result, regions, boxes)
         return result

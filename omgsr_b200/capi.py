@@ -571,12 +571,29 @@ def flash_attn(q, k, v, scale, out=None):
     return out
 
 
-def attention_materialised(q, k, v, scale):
-    """softmax(scale q k^T) v through the batched tcgen05 GEMMs + row softmax (fp32 scores in HBM)."""
+def attention_materialised(q, k, v, scale, max_score_bytes=2 << 30):
+    """softmax(scale q k^T) v through the batched tcgen05 GEMMs + row softmax, for head sizes the fused kernels do not
+    serve (the VAE mid block: one head, d = 512). The fp32 scores go through HBM, but only `max_score_bytes` of them at
+    a time: query rows are processed in chunks (rows are independent under softmax), so a 65 536-token untiled 2048^2
+    image needs 2 GB of scratch instead of 17 GB per image, and the chunk that was just written is re-read out of L2 /
+    HBM while still hot.
+    (A fused d = 512 kernel was designed and rejected on the measured instruction costs, DESIGN.md §4: the 128 x 512 fp32
+    O tile alone fills TMEM, so O must be split over two passes that each recompute S = Q K^T with 32 K-steps of
+    N <= 128 instructions at ~154 cycles: ~12.6 k cycles per 128 x 128 block against ~7 k for the two N = 256 GEMMs.)"""
+    B, M, H, _ = q.shape
     n = k.shape[1]
-    s = bgemm_qk(q, k)
-    p = softmax_rows(s, n, scale)
-    return bgemm_pv(p, v)
+    n_pad = (n + 63) // 64 * 64
+    rows = max(128, (max_score_bytes // (4 * n_pad * B * H)) // 128 * 128)
+    if rows >= M:
+        s = bgemm_qk(q, k)
+        p = softmax_rows(s, n, scale)
+        return bgemm_pv(p, v)
+    out = torch.empty((B, M, H, v.shape[3]), device=q.device, dtype=torch.bfloat16)
+    for m0 in range(0, M, rows):
+        qc = q[:, m0:m0 + rows]
+        p = softmax_rows(bgemm_qk(qc, k), n, scale)
+        bgemm_pv(p, v, out=out[:, m0:m0 + rows])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

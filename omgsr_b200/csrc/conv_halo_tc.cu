@@ -653,20 +653,6 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tx = m % p.tiles_x; m /= p.tiles_x;
         const int ty = m % p.tiles_y;
         const int b = dummy ? p.B : m / p.tiles_y;
-        {
-          // the NEXT tile's rows -> L2 now: with four row stages and three phases per row (load, transform, MMAs) a row
-          // is requested only ~3 rows ahead of its MMAs, less than an HBM round trip under load (ncu: the transform
-          // warps' wait for a_full was the largest single stall); from L2 the same request arrives in time
-          int mn = 2 * (pt + num_clusters) + static_cast<int>(rank);
-          if (mn < halo_tiles && !(p.debug & 8)) {  // (OMGSR_HALO_DEBUG bit 8: A/B switch, results unaffected)
-            const int ntx = mn % p.tiles_x; mn /= p.tiles_x;
-            const int nty = mn % p.tiles_y;
-            const int nb = mn / p.tiles_y;
-            for (int c = 0; c < p.chunks; ++c)
-              for (int i = 0; i < n_rows; ++i)
-                tma_prefetch_5d(&tmA, c * 64, ntx * 128 - p.pad_l, nty * TM - p.pad_t + i, nb, 0);
-          }
-        }
         for (int c = 0; c < p.chunks; ++c, ph ^= 1) {
           for (int i = 0; i < n_rows; ++i) {
             const int rho = rs_row(i);

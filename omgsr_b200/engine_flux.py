@@ -195,6 +195,26 @@ class B200FluxTransformer(torch.nn.Module):
                                "(latent_image_ids must match the packed latent grid)")
         mod = self._conditioning(timestep, guidance, pooled_projections, B, dev)
 
+        # ---- sequence-parallel mode (one forward spread over several GPUs; BASELINE config 5: the latent tile that is
+        # left over after the other tiles went one per GPU). Rank r owns rows [lo, hi) of the joint [text ; image]
+        # sequence for everything that is row-wise (LayerNorm, every linear layer, the gated residuals: 80 % of the
+        # FLOPs); per block ONE collective, an all-gather of the local K | V rows (2 x 3072 x S / W bf16 per rank),
+        # gives every rank the whole K / V for the attention of its own query rows. No other data crosses NVLink.
+        sp = kw.get("seq_parallel")
+        if sp is not None:
+            import torch.distributed as dist
+            sp_rank, sp_world = sp
+            if S % sp_world:
+                raise ValueError(f"sequence-parallel FLUX forward: {S} tokens do not split over {sp_world} ranks")
+            n_loc = S // sp_world
+            lo = sp_rank * n_loc
+        else:
+            n_loc, lo = S, 0
+        hi = lo + n_loc
+        nt = max(min(hi, Tt) - min(lo, Tt), 0)  # local text rows come first, then the local image rows
+        ni = n_loc - nt
+        i0 = lo + nt - Tt                        # first local image token (index into x_in)
+
         def mvec(key, chunk):
             o = self.mod_off[key] + chunk * d
             return mod[:, o:o + d]
@@ -204,53 +224,80 @@ class B200FluxTransformer(torch.nn.Module):
             gsc, gsh = mvec(key, c_scale), mvec(key, c_shift)
             return capi.layernorm(x3, gsc, gsh, eps=1e-6, rows_per_batch=x3.shape[1], gb_stride=mod.stride(0))
 
+        def all_kv(local):
+            """[B, n_loc, 2d] K | V rows of this rank -> [B, S, 2d] of all ranks (identity without sequence parallelism)."""
+            if sp is None:
+                return local
+            buf = local.contiguous()
+            full = torch.empty((sp_world,) + tuple(buf.shape), device=dev, dtype=bf)
+            dist.all_gather_into_tensor(full, buf)
+            return full.permute(1, 0, 2, 3).reshape(B, S, 2 * d)
+
         # joint residual stream [B, S, d], text rows first, kept in FP32: 2 x 57 gated updates land on it, and rounding it
         # to bf16 after each one was the largest error term against the fp32 reference (full-size DiT output 2.2e-2
         # max-relative with a bf16 stream). LayerNorm reads it as fp32, the gated-residual GEMM epilogues add in fp32.
-        h = torch.empty((B, S, d), device=dev, dtype=torch.float32)
-        capi.gemm_batched(ctx, self.c_emb[0], self.c_emb[1], out=h[:, :Tt])
-        capi.gemm_batched(x_in, self.x_emb[0], self.x_emb[1], out=h[:, Tt:])
+        h = torch.empty((B, n_loc, d), device=dev, dtype=torch.float32)
+        hc, hx = h[:, :nt], h[:, nt:]
+        if nt:
+            capi.gemm_batched(ctx[:, lo:lo + nt], self.c_emb[0], self.c_emb[1], out=hc)
+        if ni:
+            capi.gemm_batched(x_in[:, i0:i0 + ni], self.x_emb[0], self.x_emb[1], out=hx)
         scale = 1.0 / math.sqrt(cfg.head_dim)
-        qkv = torch.empty((B, S, 3 * d), device=dev, dtype=bf)
-        att = torch.empty((B, S, d), device=dev, dtype=bf)
-        hx, hc = h[:, Tt:], h[:, :Tt]
+        qkv = torch.empty((B, n_loc, 3 * d), device=dev, dtype=bf)
+        att = torch.empty((B, n_loc, d), device=dev, dtype=bf)
         for i, blk in enumerate(self.double):
             kx, kc = ("d", i, "x"), ("d", i, "c")
             # chunks: 0 shift_msa, 1 scale_msa, 2 gate_msa, 3 shift_mlp, 4 scale_mlp, 5 gate_mlp
-            xn = ln_mod(hx, kx, 1, 0)
-            cn = ln_mod(hc, kc, 1, 0)
-            capi.gemm_batched(cn, blk.cwqkv, blk.cbqkv, out=qkv[:, :Tt])
-            capi.gemm_batched(xn, blk.wqkv, blk.bqkv, out=qkv[:, Tt:])
-            capi.rmsnorm_rope_(qkv[:, :Tt], blk.cnqk, cos, sin, 2 * H, H, pos_offset=0)
-            capi.rmsnorm_rope_(qkv[:, Tt:], blk.nqk, cos, sin, 2 * H, H, pos_offset=Tt)
-            q, k, v = (qkv[..., j * d:(j + 1) * d].unflatten(-1, (H, 128)) for j in range(3))
+            if nt:
+                cn = ln_mod(hc, kc, 1, 0)
+                capi.gemm_batched(cn, blk.cwqkv, blk.cbqkv, out=qkv[:, :nt])
+                capi.rmsnorm_rope_(qkv[:, :nt], blk.cnqk, cos, sin, 2 * H, H, pos_offset=lo)
+            if ni:
+                xn = ln_mod(hx, kx, 1, 0)
+                capi.gemm_batched(xn, blk.wqkv, blk.bqkv, out=qkv[:, nt:])
+                capi.rmsnorm_rope_(qkv[:, nt:], blk.nqk, cos, sin, 2 * H, H, pos_offset=lo + nt)
+            kvf = all_kv(qkv[..., d:])
+            q = qkv[..., :d].unflatten(-1, (H, 128))
+            k, v = (kvf[..., j * d:(j + 1) * d].unflatten(-1, (H, 128)) for j in range(2))
             capi.flash_attn(q, k, v, scale, out=att.unflatten(-1, (H, 128)))
-            capi.gemm_batched(att[:, Tt:], blk.wo, blk.bo, res=hx, gate=mvec(kx, 2), out=hx)
-            capi.gemm_batched(att[:, :Tt], blk.cwo, blk.cbo, res=hc, gate=mvec(kc, 2), out=hc)
-            xn = ln_mod(hx, kx, 4, 3)
-            f = capi.gemm_batched(xn, blk.ff1, blk.ff1b, act=capi.ACT_GELU_TANH)
-            capi.gemm_batched(f, blk.ff2, blk.ff2b, res=hx, gate=mvec(kx, 5), out=hx)
-            cn = ln_mod(hc, kc, 4, 3)
-            f = capi.gemm_batched(cn, blk.cff1, blk.cff1b, act=capi.ACT_GELU_TANH)
-            capi.gemm_batched(f, blk.cff2, blk.cff2b, res=hc, gate=mvec(kc, 5), out=hc)
+            if ni:
+                capi.gemm_batched(att[:, nt:], blk.wo, blk.bo, res=hx, gate=mvec(kx, 2), out=hx)
+                xn = ln_mod(hx, kx, 4, 3)
+                f = capi.gemm_batched(xn, blk.ff1, blk.ff1b, act=capi.ACT_GELU_TANH)
+                capi.gemm_batched(f, blk.ff2, blk.ff2b, res=hx, gate=mvec(kx, 5), out=hx)
+            if nt:
+                capi.gemm_batched(att[:, :nt], blk.cwo, blk.cbo, res=hc, gate=mvec(kc, 2), out=hc)
+                cn = ln_mod(hc, kc, 4, 3)
+                f = capi.gemm_batched(cn, blk.cff1, blk.cff1b, act=capi.ACT_GELU_TANH)
+                capi.gemm_batched(f, blk.cff2, blk.cff2b, res=hc, gate=mvec(kc, 5), out=hc)
         # ---- single blocks on the joint stream ----
         dm = cfg.mlp_ratio * d
-        wide = torch.empty((B, S, 3 * d + dm), device=dev, dtype=bf) if self.single else None
+        wide = torch.empty((B, n_loc, 3 * d + dm), device=dev, dtype=bf) if self.single else None
         for i, blk in enumerate(self.single):
             ks = ("s", i)
             hn = ln_mod(h, ks, 1, 0)
             # columns [q | gelu(mlp) | k | v]
             capi.gemm_batched(hn, blk.w1, blk.b1, act=capi.ACT_GELU_TANH, act_cols=(d, d + dm), out=wide)
-            capi.rmsnorm_rope_(wide[..., :d], blk.nq, cos, sin, H, H, pos_offset=0)
-            capi.rmsnorm_rope_(wide[..., d + dm:2 * d + dm], blk.nk, cos, sin, H, H, pos_offset=0)
+            capi.rmsnorm_rope_(wide[..., :d], blk.nq, cos, sin, H, H, pos_offset=lo)
+            capi.rmsnorm_rope_(wide[..., d + dm:2 * d + dm], blk.nk, cos, sin, H, H, pos_offset=lo)
             q = wide[..., :d].unflatten(-1, (H, 128))
-            k = wide[..., d + dm:2 * d + dm].unflatten(-1, (H, 128))
-            v = wide[..., 2 * d + dm:].unflatten(-1, (H, 128))
+            kvf = all_kv(wide[..., d + dm:])
+            k, v = (kvf[..., j * d:(j + 1) * d].unflatten(-1, (H, 128)) for j in range(2))
             capi.flash_attn(q, k, v, scale, out=q)  # attention output overwrites the dead q slot
             capi.gemm_batched(wide[..., :d + dm], blk.w2, blk.b2, res=h, gate=mvec(ks, 2), out=h)
-        xo = capi.layernorm(h[:, Tt:], mvec(("out",), 0), mvec(("out",), 1), eps=1e-6,
-                            rows_per_batch=T, gb_stride=mod.stride(0))
-        out = capi.gemm_batched(xo, self.proj_out[0], self.proj_out[1]).to(self._dtype)
+        if sp is None:
+            xo = capi.layernorm(h[:, Tt:], mvec(("out",), 0), mvec(("out",), 1), eps=1e-6,
+                                rows_per_batch=T, gb_stride=mod.stride(0))
+            out = capi.gemm_batched(xo, self.proj_out[0], self.proj_out[1]).to(self._dtype)
+        else:
+            # output head on every local row (the few text rows of the first rank are dropped after the gather: equal
+            # shard sizes keep the collective a plain all-gather)
+            xo = capi.layernorm(h, mvec(("out",), 0), mvec(("out",), 1), eps=1e-6, rows_per_batch=n_loc,
+                                gb_stride=mod.stride(0))
+            loc = capi.gemm_batched(xo, self.proj_out[0], self.proj_out[1]).contiguous()
+            full = torch.empty((sp_world,) + tuple(loc.shape), device=dev, dtype=loc.dtype)
+            dist.all_gather_into_tensor(full, loc)
+            out = full.permute(1, 0, 2, 3).reshape(B, S, -1)[:, Tt:].contiguous().to(self._dtype)
         if return_dict:
             return SimpleNamespace(sample=out)
         return (out,)

@@ -82,6 +82,29 @@ def _worker_gn(rank, world, port, out):
     batch = torch.arange(9, dtype=torch.float32).reshape(9, 1) * 10
     got = D.tile_parallel_forward(lambda t: t + 1, batch)
     ok = ok and torch.equal(got, batch + 1)
+    # 9 tiles on 2 ranks with a cooperative form for the left-over tile (the sequence-parallel FLUX forward stands
+    # behind fn_all on the GPU): 8 tiles in 4 full waves, the ninth computed by both ranks together
+    calls = {"fn": 0, "all": 0}
+
+    def fn(t):
+        calls["fn"] += t.shape[0]
+        return t * 2
+
+    def fn_all(t):  # each rank handles half of the row, one all-gather puts it together (what the engine does with K|V)
+        calls["all"] += 1
+        half = t.shape[1] // world
+        part = (t[:, rank * half:(rank + 1) * half] * 2).contiguous()
+        return D.all_gather_batch(part).permute(1, 0, 2).reshape(t.shape[0], -1)
+
+    batch2 = torch.arange(9 * 4, dtype=torch.float32).reshape(9, 4)
+    got2 = D.tile_parallel_forward(fn, batch2, fn_all=fn_all)
+    ok = ok and torch.equal(got2, batch2 * 2) and calls == {"fn": 4, "all": 1} and D.plan_tile_waves(9, 8) == (8, 1)
+    # stitched tiled result: disjoint regions gathered, not all-reduced
+    boxes = [(0, 3, 0, 5), (0, 3, 5, 8), (3, 8, 0, 5), (3, 8, 5, 8), (8, 9, 0, 8)]   # (y0, y1, x0, x1): ragged sizes
+    want = torch.arange(2 * 3 * 9 * 8, dtype=torch.float32).reshape(2, 3, 9, 8)
+    mine = {i: want[:, :, b[0]:b[1], b[2]:b[3]].clone() for i, b in enumerate(boxes) if i % world == rank}
+    res = D.gather_tile_regions(torch.zeros_like(want), mine, boxes)
+    ok = ok and torch.equal(res, want)
     if rank == 0:
         out.put(bool(ok))
     torch.distributed.destroy_process_group()

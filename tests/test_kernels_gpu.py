@@ -242,6 +242,22 @@ def test_attention_materialised(capi, B, Hh, M, N, D):
     assert report(f"bgemm pv (MN-major V) {B},{Hh},{M},{N},{D}", o, ops.attention(q, k, v, scale), 2e-2)[0]
 
 
+def test_attention_materialised_query_chunks(capi):
+    """the d = 512 path bounds its fp32 score scratch by chunking over query rows: same bits as the one-shot form."""
+    from oracle import ops
+    g = _g(4242)
+    B, Hh, M, N, D = 2, 1, 1000, 1990, 512
+    q = bf16r(torch.randn(B, M, Hh, D, generator=g))
+    k = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    v = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    qc, kc, vc = q.cuda().bfloat16(), k.cuda().bfloat16(), v.cuda().bfloat16()
+    scale = 1.0 / math.sqrt(D)
+    whole = capi.attention_materialised(qc, kc, vc, scale)
+    chunked = capi.attention_materialised(qc, kc, vc, scale, max_score_bytes=4 * 2048 * B * 256)  # 256-row chunks
+    assert torch.equal(whole, chunked)
+    assert report("materialised attention d=512", whole, ops.attention(q, k, v, scale), 2e-2)[0]
+
+
 @pytest.mark.parametrize("B,Hh,M,N,D", [(1, 1, 128, 128, 64), (2, 5, 256, 384, 64), (2, 5, 1024, 77, 64),
                                          (1, 2, 200, 300, 64), (1, 10, 64, 64, 64), (1, 2, 4096, 4096, 64),
                                          (1, 1, 128, 64, 128), (1, 3, 256, 320, 128), (1, 2, 4608, 4608, 128)])
