@@ -707,80 +707,66 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tS = tmem_base + g * 128 + lane_off, tO = tmem_base + 256 + g * 128 + lane_off;
     uint8_t* p_row = sP + g * C::kPBytes + row * 128;
     float m_stale = 0.f, l_run = 0.f;
+    float pend_alpha = 1.0f;  // rescale decided at the end of the previous block (see flash_attn4_kernel)
+    bool pend = false;
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
-      // the row's 128 scores: the low half stays in registers, the high half is scanned for the maximum in two 32-column
-      // pieces and re-read from TMEM for its exponentials (a thread may hold 168 registers with ten warps per CTA:
-      // the full row spilled)
       const int n_valid = min(BN, p.N - j * BN);
-      uint32_t sv[64];
-      tmem_ld64(tS, sv);
-      tmem_wait_ld();
-      if (n_valid < 64) {  // ragged last block only: mask the keys that do not exist
+      if (j == 0) {  // the first block fixes the reference maximum: one extra scan of its scores
+        float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= n_valid) sv[i] = 0xff800000u;  // -inf
-      }
-      float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]);
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t hv[32];
+          tmem_ld32(tS + c0, hv);
+          tmem_wait_ld();
 #pragma unroll
-      for (int i = 2; i < 64; i += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
-      }
-#pragma unroll
-      for (int c0 = 64; c0 < 128; c0 += 32) {
-        uint32_t hv[32];
-        tmem_ld32(tS + c0, hv);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          if (c0 + i < n_valid) mx0 = fmaxf(mx0, __uint_as_float(hv[i]));
-          if (c0 + i + 1 < n_valid) mx1 = fmaxf(mx1, __uint_as_float(hv[i + 1]));
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(hv[i]));
         }
-      }
-      const float mx = fmaxf(mx0, mx1);
-      if (j == 0) {
         m_stale = mx;
       } else {
         // P_g and O_g belong to PV_g(j - 1) until it has retired
         mbar_wait(&pv_done[g], (j - 1) & 1);
         tc_fence_after();
-        const bool need = (mx - m_stale) * p.scale_log2 > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
+        if (__any_sync(0xffffffffu, pend)) {  // O rows are thread-local here: a warp rescales on its own
 #pragma unroll
           for (int c0 = 0; c0 < (C::kOnesCol ? D + 32 : D); c0 += 32) {  // + the row-sum column(s) at D
             uint32_t v[32];
             tmem_ld32(tO + c0, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * pend_alpha);
             tmem_st32(tO + c0, v);
           }
           tmem_wait_st();
-          l_run *= alpha;
-          if (need) m_stale = mx;
+          l_run *= pend_alpha;
         }
       }
+      // ONE pass over the row (flash_attn4_kernel has the argument): exponentials against the stale maximum, the true
+      // maximum tracked on the side decides whether the NEXT block starts from a new reference
       const float mb = m_stale * p.scale_log2;
-      float ls0 = 0.f, ls1 = 0.f;
+      float ls0 = 0.f, ls1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (half == 1) {  // the high 64 scores again
-          tmem_ld64(tS + 64, sv);
-          tmem_wait_ld();
-          if (n_valid < BN) {
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t sv[32];
+        tmem_ld32(tS + c0, sv);
+        tmem_wait_ld();
+        if (n_valid < BN) {  // ragged last block only
 #pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (64 + i >= n_valid) sv[i] = 0xff800000u;
-          }
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i >= n_valid) sv[i] = 0xff800000u;  // -inf
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           float pr[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pr[i] = exp2f(fmaf(__uint_as_float(sv[q * 8 + i]), p.scale_log2, -mb));  // exp2(-inf) = 0
+          for (int i = 0; i < 8; i += 2) {
+            const float s0 = __uint_as_float(sv[q * 8 + i]), s1 = __uint_as_float(sv[q * 8 + i + 1]);
+            pr[i] = exp2f(fmaf(s0, p.scale_log2, -mb));  // exp2(-inf) = 0
+            pr[i + 1] = exp2f(fmaf(s1, p.scale_log2, -mb));
+            mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
+          }
           if (!C::kOnesCol) {
             ls0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
             ls1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
@@ -788,13 +774,18 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           uint4 u;
           u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
           u.z = pack_bf16x2(pr[4], pr[5]); u.w = pack_bf16x2(pr[6], pr[7]);
-          *reinterpret_cast<uint4*>(p_row + half * (128 * 128) + ((q ^ (row & 7)) << 4)) = u;
+          const int ch = (c0 >> 3) + q;  // 16-byte chunk of the 256-byte row: two 64-key panels
+          *reinterpret_cast<uint4*>(p_row + (ch >> 3) * (128 * 128) + (((ch & 7) ^ (row & 7)) << 4)) = u;
         }
       }
       l_run += ls0 + ls1;
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&p_full[g]);
+      const float mx = fmaxf(mx0, mx1);
+      pend = (mx - m_stale) * p.scale_log2 > 8.0f;
+      pend_alpha = pend ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
+      if (pend) m_stale = mx;
     }
     // epilogue: O / l
     mbar_wait(&pv_done[g], (nblk - 1) & 1);
@@ -871,6 +862,352 @@ static int launch_attn3(const void* q, const void* k, const void* v, void* out, 
   dim3 grid((M + 255) / 256, H, B);
   flash_attn3_kernel<D><<<grid, 320, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
   return check_launch("flash_attn3_kernel");
+}
+
+// ================================================================================================================
+// v4 (round 2, d = 128): v3 with the PV product TRANSPOSED so that it, too, is made of N = 256 instructions.
+//
+// In v3 every PV instruction is N = d = 128 at ~154 cycles for 128 query rows x 16 keys. Here the accumulator is
+// O^T [d = 128 lanes, 256 query columns (both groups)]: A = V^T (the V tile read as an MN-major A operand), B = P of
+// BOTH groups ([256 query rows, 16 keys], K-major: the two groups' P tiles are adjacent in shared memory), one N = 256
+// instruction at ~172 cycles per 16 keys serves 256 query rows. Per 128 keys and 256 query rows: S 2 x 8 x 154 +
+// PV^T 8 x 172 = 3.8 k cycles against v3's 4.9 k (mma_probe figures).
+//   * TMEM: S_a @0, S_b @128 (single buffers), O^T @256 (256 columns: group a's query rows are columns 0..127).
+//   * tensor-pipe order: S_a(j+1), S_b(j+1), PV^T(j). A group reads its S, exponentiates into REGISTERS (bf16-packed,
+//     64 registers), releases S at once (s_free) so that the next S can be issued, and stores P only when PV^T(j-1) has
+//     retired (pv_done): no second P buffer (there is no shared memory for one: Q 64 + K/V ring 96 + P 64 KB).
+//   * lazy rescale per group: O^T columns belong to ONE group, so a group rescales its own 128 columns (each warp its
+//     lane quarter) with the per-row factors passed through shared memory; the "does any row of the group need it"
+//     vote is a named-barrier reduction of the group's 128 threads.
+//   * epilogue: O^T / l is transposed through shared memory (the dead Q tile of the group) and leaves as coalesced
+//     256-byte rows.
+// ================================================================================================================
+struct Attn4Cfg {
+  static constexpr int D = 128;
+  static constexpr int kBN = 128;
+  static constexpr int kSlots = 3;
+  static constexpr int kQBytes = 2 * 128 * D * 2;
+  static constexpr int kTileBytes = kBN * D * 2;
+  static constexpr int kPBytes = 2 * 256 * 128;      // [key panel][group][128 rows x 128 B]
+  static constexpr int kMiscBytes = 256 + 2 * 128 * 4;  // barriers, alpha[2][128] (reused for 1 / l in the epilogue)
+  static constexpr int kSmemBytes = kQBytes + kSlots * kTileBytes + kPBytes + kMiscBytes + 1024;
+};
+
+__device__ __forceinline__ bool group_any(int barrier_id, bool pred) {  // OR over the 128 threads of a softmax group
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "bar.red.or.pred p, %1, 128, q;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(out)
+      : "r"(barrier_id), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return out != 0;
+}
+__device__ __forceinline__ void group_sync(int barrier_id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(barrier_id) : "memory");
+}
+
+__global__ void __launch_bounds__(320, 1)
+flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = Attn4Cfg;
+  constexpr int D = C::D, BN = C::kBN, NS = C::kSlots;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                             // [group][d panel][128 rows x 128 B]; epilogue: transposed O tile
+  uint8_t* sKV = sQ + C::kQBytes;                 // [slot][d panel][128 keys x 128 B]
+  uint8_t* sP = sKV + NS * C::kTileBytes;         // [key panel][group][128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::kPBytes);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* kv_full = q_full + 1;       // [NS]
+  uint64_t* kv_empty = kv_full + NS;    // [NS]
+  uint64_t* s_full = kv_empty + NS;     // [2]
+  uint64_t* s_free = s_full + 2;        // [2] 128 arrivals: the group holds its scores in registers
+  uint64_t* p_full = s_free + 2;        // [2] 128 arrivals
+  uint64_t* pv_done = p_full + 2;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  float* s_alpha = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 128); mbar_init(&p_full[g], 128); }
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: Q once, then the K / V tiles in consumption order K0 | K1 V0 | K2 V1 | ... ----
+      mbar_expect_tx(q_full, C::kQBytes);
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sQ + (g * (D / 64) + pnl) * (128 * 128), &tmQ, q_full, pnl * 64, m0 + g * 128, h, b);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto load = [&](const CUtensorMap* tm, int blk) {
+        mbar_wait_relaxed(&kv_empty[slot], phase ^ 1);
+        uint8_t* dst = sKV + slot * C::kTileBytes;
+        mbar_expect_tx(&kv_full[slot], C::kTileBytes);
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(dst + pnl * (BN * 128), tm, &kv_full[slot], pnl * 64, blk * BN, h, b);
+        if (++slot == NS) { slot = 0; phase ^= 1; }
+      };
+      load(&tmK, 0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) load(&tmK, j + 1);
+        load(&tmV, j);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 256, 1, 0);  // A = V^T (MN-major), B = P (K-major), N = 256 rows
+      int slot = 0;     // ring position of the next tile to consume (same order as the producer)
+      uint32_t phase = 0;
+      auto next_tile = [&]() {
+        mbar_wait(&kv_full[slot], phase);
+        tc_fence_after();
+        const int s0 = slot;
+        if (++slot == NS) { slot = 0; phase ^= 1; }
+        return s0;
+      };
+      auto issue_s = [&](int g, int s0) {
+        const uint32_t aQ = smem_u32(sQ + g * (D / 64) * (128 * 128));
+        const uint32_t aK = smem_u32(sKV + s0 * C::kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
+          tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
+        }
+        tc_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      {
+        const int s0 = next_tile();  // K(0)
+        issue_s(0, s0);
+        issue_s(1, s0);
+        tc_commit(&kv_empty[s0]);
+      }
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {
+          const int s0 = next_tile();  // K(j + 1)
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&s_free[g], j & 1);  // group g holds S_g(j) in registers: its TMEM columns may be overwritten
+            tc_fence_after();
+            issue_s(g, s0);
+          }
+          tc_commit(&kv_empty[s0]);
+        }
+        const int sv = next_tile();    // V(j)
+        mbar_wait(&p_full[0], j & 1);
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + sv * C::kTileBytes);
+        const uint32_t aP = smem_u32(sP);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          // A = V^T: 64-wide d atoms are BN*128 bytes apart (LBO), 8-key groups 1024 B apart (SBO)
+          const uint64_t da = umma_desc_sw128(aV + kk * 2048, BN * 128, 1024);
+          const uint64_t db = umma_desc_sw128(aP + (kk >> 2) * (256 * 128) + (kk & 3) * 32, 16, 1024);
+          tc_mma_ss(tmem_base + 256, da, db, idesc_o, (j | kk) != 0);
+        }
+        tc_commit(pv_done);
+        tc_commit(&kv_empty[sv]);
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // softmax role: query row of the group; O^T role: d index (TMEM lane)
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + g * 128 + lane_off;
+    const uint32_t tOT = tmem_base + 256 + g * 128 + lane_off;  // this group's 128 query columns, my 32 d lanes
+    uint8_t* p_row = sP + g * (128 * 128) + row * 128;
+    float* alpha_g = s_alpha + g * 128;
+    float m_stale = 0.f, l_run = 0.f;
+    float pend_alpha = 1.0f;   // rescale decided at the end of the previous block, applied once PV^T of that block retired
+    bool pend_any = false;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      const int n_valid = min(BN, p.N - j * BN);
+      if (j == 0) {  // the first block fixes the reference maximum: one extra scan of its scores
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t hv[32];
+          tmem_ld32(tS + c0, hv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(hv[i]));
+        }
+        m_stale = mx;
+      }
+      // ONE pass over the row: exponentials against the stale maximum straight into bf16-packed registers, the true
+      // maximum of the raw scores is tracked on the side and only decides whether the NEXT block starts from a new
+      // reference (p <= 2^(max - stale): bounded by the score range, far inside fp32 / bf16 range, and rescaled
+      // away one block later). 4.5 instead of 7.4 issued instructions per score: with two softmax warps per scheduler
+      // the instruction stream of this loop, not the tensor pipe, set the pace of the first version of this kernel.
+      const float mb = m_stale * p.scale_log2;
+      uint32_t pk[64];
+      float ls0 = 0.f, ls1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t sv[32];
+        tmem_ld32(tS + c0, sv);
+        tmem_wait_ld();
+        if (c0 == 96) {  // the whole row has left TMEM: the next S may overwrite it
+          tc_fence_before();
+          mbar_arrive(&s_free[g]);
+        }
+        if (n_valid < BN) {  // ragged last block only
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i >= n_valid) sv[i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
+          const float e0 = exp2f(fmaf(s0, p.scale_log2, -mb));  // exp2(-inf) = 0
+          const float e1 = exp2f(fmaf(s1, p.scale_log2, -mb));
+          ls0 += e0; ls1 += e1;
+          mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
+          pk[(c0 + i) >> 1] = pack_bf16x2(e0, e1);
+        }
+      }
+      // the P tile (and O^T) belong to PV^T(j - 1) until it has retired
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (pend_any) {  // rescale this group's 128 columns of O^T (everything up to block j - 1) to the new reference
+        group_sync(1 + g);  // every row's factor is in shared memory
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tOT + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha_g[c0 + i]);
+          tmem_st32(tOT + c0, v);
+        }
+        tmem_wait_st();
+        l_run *= pend_alpha;
+      }
+      l_run += ls0 + ls1;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        uint4 u = make_uint4(pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        *reinterpret_cast<uint4*>(p_row + (q >> 3) * (256 * 128) + (((q & 7) ^ (row & 7)) << 4)) = u;
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[g]);
+      // does the next block start from a new reference maximum? (the vote also orders this block's reads of alpha_g
+      // before the next writes)
+      const float mx = fmaxf(mx0, mx1);
+      const bool need = (mx - m_stale) * p.scale_log2 > 8.0f;
+      pend_alpha = need ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
+      if (need) m_stale = mx;
+      pend_any = (j + 1 < nblk) && group_any(1 + g, need);
+      if (pend_any) alpha_g[row] = pend_alpha;
+    }
+    // a rescale decided in the last block never happened: l and O^T are both still in the old reference
+    // ---- epilogue: O^T / l -> shared memory (transposed) -> coalesced rows ----
+    mbar_wait(pv_done, (nblk - 1) & 1);
+    tc_fence_after();
+    float* invl_g = alpha_g;  // the rescale factors are dead now
+    invl_g[row] = 1.0f / l_run;
+    group_sync(1 + g);
+    bf16* tile = reinterpret_cast<bf16*>(sQ + g * (2 * 128 * 128));  // [128 query rows][128 d], the group's dead Q tile
+#pragma unroll
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tOT + c0, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        tile[(c0 + i) * 128 + row] = __float2bfloat16(__uint_as_float(v[i]) * invl_g[c0 + i]);
+    }
+    tc_fence_before();
+    group_sync(1 + g);
+    const int tid = (warp - 2 - 4 * g) * 32 + lane;  // 0..127 inside the group
+    for (int idx = tid; idx < 128 * 16; idx += 128) {
+      const int r = idx >> 4, ch = idx & 15;
+      const int m = m0 + g * 128 + r;
+      if (m < p.M) {
+        bf16* o = p.out + static_cast<long long>(b) * p.o_batch + static_cast<long long>(m) * p.o_row +
+                  static_cast<long long>(h) * p.o_head;
+        *reinterpret_cast<uint4*>(o + ch * 8) = *reinterpret_cast<const uint4*>(tile + r * 128 + ch * 8);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attn4(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
+                        const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
+                        cudaStream_t st) {
+  using C = Attn4Cfg;
+  constexpr int D = 128;
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&flash_attn4_kernel), C::kSmemBytes, &attr_done, "flash_attn4")) return rc;
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t eb = 2;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(M), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t str[3] = {qs[0] * eb, qs[1] * eb, qs[2] * eb};
+    uint32_t box[4] = {64, 128, 1, 1};
+    int rc = make_tmap_bf16(&tmQ, q, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint32_t box[4] = {64, static_cast<uint32_t>(C::kBN), 1, 1};
+    uint64_t strk[3] = {ks[0] * eb, ks[1] * eb, ks[2] * eb};
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, strk, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    uint64_t strv[3] = {vs[0] * eb, vs[1] * eb, vs[2] * eb};
+    rc = make_tmap_bf16(&tmV, v, 4, dims, strv, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.M = M; p.N = N; p.H = H; p.B = B;
+  p.o_row = os[0]; p.o_head = os[1]; p.o_batch = os[2];
+  p.out = static_cast<bf16*>(out);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((M + 255) / 256, H, B);
+  flash_attn4_kernel<<<grid, 320, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  return check_launch("flash_attn4_kernel");
 }
 
 template <int D>
@@ -952,7 +1289,8 @@ using namespace omgsr;
 #include <cstdlib>
 static int g_attn_variant = getenv("OMGSR_ATTN_VARIANT") ? atoi(getenv("OMGSR_ATTN_VARIANT")) : 0;
 /* bring-up / A-B timing switch: 0 = automatic, 1 = always the single-tile kernel, 2 = the 64-key ping-pong kernel (v2)
- * wherever the 128-key kernel (v3) would be chosen */
+ * wherever a 128-key kernel would be chosen, 3 = v3 (128 keys, O in natural layout) also at d = 128 where v4
+ * (transposed O, N = 256 PV instructions) is the default */
 extern "C" int omgsr_flash_attn_set_variant(int variant) { g_attn_variant = variant; return OMGSR_OK; }
 
 extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int M,
@@ -977,6 +1315,8 @@ extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v
   // long key sequences: 128 keys per block (v3: every S instruction is N = 128, half the instruction count of v2)
   if (v2 && N >= 128 && g_attn_variant != 2) {
     if (D == 64) return launch_attn3<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+    if (D == 128 && g_attn_variant != 3 && o_head == 128)  // (v4's coalesced row store assumes head-contiguous output)
+      return launch_attn4(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
     if (D == 128) return launch_attn3<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
   }
   if (v2) {

@@ -757,7 +757,8 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 v = __ldg(cf + q);
-            ca[2 * q] = v.x; cb[2 * q] = v.y; ca[2 * q + 1] = v.z; cb[2 * q + 1] = v.w;
+            // halved: silu(a x + b) = h + h tanh(h) with h = (a / 2) x + b / 2
+            ca[2 * q] = 0.5f * v.x; cb[2 * q] = 0.5f * v.y; ca[2 * q + 1] = 0.5f * v.z; cb[2 * q + 1] = 0.5f * v.w;
           }
         }
         for (int i = 0; i < n_rows; ++i) {
@@ -786,7 +787,7 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            f3 = unpack_bf16x2(v[q].w);
               f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = silu_f(fmaf(f[e], ca[e], cb[e]));
+              for (int e = 0; e < 8; ++e) f[e] = silu_half(fmaf(f[e], ca[e], cb[e]));
               v[q].x = pack_bf16x2(f[0], f[1]); v[q].y = pack_bf16x2(f[2], f[3]);
               v[q].z = pack_bf16x2(f[4], f[5]); v[q].w = pack_bf16x2(f[6], f[7]);
             }

@@ -177,7 +177,11 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
   float ca[8], cb[8];
   const float2* cf = coef + static_cast<long long>(b) * C + v * 8;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { const float2 t = __ldg(cf + j); ca[j] = t.x; cb[j] = t.y; }
+  for (int j = 0; j < 8; ++j) {
+    const float2 t = __ldg(cf + j);
+    ca[j] = SILU ? 0.5f * t.x : t.x;  // SiLU: halved affine, silu(2h) = h + h tanh(h)
+    cb[j] = SILU ? 0.5f * t.y : t.y;
+  }
   const bf16* xb = x + static_cast<long long>(b) * HW * ldx + v * 8;
   bf16* yb = y + static_cast<long long>(b) * HW * ldy + v * 8;
   const long long step = static_cast<long long>(blocks_per_img) * rows_per_iter;
@@ -194,7 +198,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float o = fmaf(f[j], ca[j], cb[j]);
-        f[j] = SILU ? silu_f(o) : o;
+        f[j] = SILU ? silu_half(o) : o;
       }
       *reinterpret_cast<uint4*>(yb + (r + i * step) * ldy) = pack8(f);
     }
@@ -205,7 +209,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float o0 = fmaf(f0[j], ca[j], cb[j]);
-      f0[j] = SILU ? silu_f(o0) : o0;
+      f0[j] = SILU ? silu_half(o0) : o0;
     }
     *reinterpret_cast<uint4*>(yb + r * ldy) = pack8(f0);
   }

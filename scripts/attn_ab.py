@@ -20,9 +20,9 @@ for name, (B, H, M, N, D) in (("FLUX joint", (4, 24, 4608, 4608, 128)), ("UNet 6
     o = torch.empty_like(q)
     fl = 4.0 * B * H * M * N * D
     res = []
-    for variant in (2, 0):
+    for variant, nm in ((2, "v2"), (3, "v3"), (0, "auto (v4 at d=128)")):
         capi.lib().omgsr_flash_attn_set_variant(variant)
         ms = timeit(lambda: capi.flash_attn(q, k, v, D ** -0.5, out=o))
-        res.append(f"{'v3' if variant == 0 else 'v2'} {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s")
+        res.append(f"{nm} {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s")
     capi.lib().omgsr_flash_attn_set_variant(0)
     print(f"{name:18s} B={B} H={H} M={M} N={N} d={D}: " + " | ".join(res), flush=True)

@@ -31,6 +31,7 @@ struct ProbeParams {
   int iters;       // pattern repetitions (each instruction is issued 4x: the K = 64 block)
   int xf_warps;    // extra warps doing LDS / FMA / tanh / STS on a 64 KB region (0 = none)
   int tma;         // 1: a producer thread streams 16 KB boxes into a 4-deep ring (not consumed)
+  int a_mn, b_mn;  // operand majors: 1 = MN-major (transposed) A / B, as the attention kernels use for V
   int a_tmem;      // single-CTA only: the A operand comes from TMEM (tcgen05.mma [d], [a_tmem], b_desc)
   int commit_each; // 1: tcgen05.commit (multicast in pair mode) to a dummy barrier after EVERY pattern element (4 MMAs)
   int d_mode;      // 0: the 4 K-steps of a pattern element hit one accumulator; 1: consecutive instructions alternate
@@ -81,14 +82,15 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
       for (int it = 0; it < p.iters; ++it) {
         for (int j = 0; j < 8 && p.pattern[j]; ++j) {
           const int N = p.pattern[j];
-          const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, N, 0, 0);
+          const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, N, p.a_mn, p.b_mn);
           const uint32_t a_addr = a0 + view * 128;
           if (++view >= p.a_views) view = 0;
           const uint32_t d0 = tmem_base + ((p.d_mode != 2 && (j & 1) && !p.a_tmem) ? 256 : 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b0 + (j & 3) * 4096 + k * 32, 16, 1024);
+            const uint64_t da = p.a_mn ? umma_desc_sw128(a_addr + k * 2048, 16384, 1024) : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = p.b_mn ? umma_desc_sw128(b0 + k * 2048, 16384, 1024)
+                                       : umma_desc_sw128(b0 + (j & 3) * 4096 + k * 32, 16, 1024);
             const uint32_t d = (p.d_mode == 1) ? tmem_base + ((k & 1) ? 256 : 0) : d0;
             if constexpr (PAIR) tc_mma2_ss(d, da, db, idesc, 1);
             else if (p.a_tmem) tc_mma_ts(d, tmem_base + 448 + k * 8, db, idesc, 1);  // A operand from TMEM (8 columns / K-step)
@@ -160,8 +162,10 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
 }
 
 static double run(const char* name, int pair, std::initializer_list<int> pat, int a_views, int xf, int tma,
-                  const CUtensorMap& tm, long long* d_cycles, int d_mode = 0, int commit_each = 0, int a_tmem = 0) {
+                  const CUtensorMap& tm, long long* d_cycles, int d_mode = 0, int commit_each = 0, int a_tmem = 0,
+                  int a_mn = 0, int b_mn = 0) {
   ProbeParams p{};
+  p.a_mn = a_mn; p.b_mn = b_mn;
   p.a_tmem = a_tmem;
   p.d_mode = d_mode;
   p.commit_each = commit_each;
@@ -224,6 +228,10 @@ int main() {
     run("single N=128 A from TMEM", 0, {128, 128}, 2, 0, 0, tm, d_cycles, 0, 0, 1);
     run("single N=64  A from TMEM", 0, {64, 64}, 2, 0, 0, tm, d_cycles, 0, 0, 1);
     run("single N=128 + commit each", 0, {128, 128}, 2, 0, 0, tm, d_cycles, 0, 1);
+    run("single N=256 A MN-major (V^T as A)", 0, {256, 256}, 1, 0, 0, tm, d_cycles, 0, 0, 0, 1, 0);
+    run("single N=128 A MN-major", 0, {128, 128}, 1, 0, 0, tm, d_cycles, 0, 0, 0, 1, 0);
+    run("single N=128 B MN-major (V as B)", 0, {128, 128}, 1, 0, 0, tm, d_cycles, 0, 0, 0, 0, 1);
+    run("single N=256 B MN-major", 0, {256, 256}, 1, 0, 0, tm, d_cycles, 0, 0, 0, 0, 1);
     run("pair   N=256", 1, {256}, 1, 0, 0, tm, d_cycles);
     run("pair   N=128", 1, {128}, 1, 0, 0, tm, d_cycles);
     run("pair   N=64", 1, {64}, 1, 0, 0, tm, d_cycles);

@@ -290,7 +290,20 @@ def test_flash_attention_variants_agree(capi):
     finally:
         capi.lib().omgsr_flash_attn_set_variant(0)
     assert report("flash v1 (single tile)", o1, ref, 2e-2)[0]
-    assert report("flash v2 (ping-pong)", o2, ref, 2e-2)[0]
+    assert report("flash auto (d=128: v4, transposed O)", o2, ref, 2e-2)[0]
+    for variant, name in ((2, "v2 (64-key ping-pong)"), (3, "v3 (128 keys)")):
+        capi.lib().omgsr_flash_attn_set_variant(variant)
+        try:
+            ov = capi.flash_attn(qc, kc, vc, 0.25)
+        finally:
+            capi.lib().omgsr_flash_attn_set_variant(0)
+        assert report("flash " + name, ov, ref, 2e-2)[0]
+    # growing maxima along the key axis force the lazy O rescale (v4: per-group column rescale of O^T) in every block
+    ramp = torch.linspace(0.0, 6.0, N)[None, :, None, None]
+    k2 = bf16r(k * 0.2 + ramp * torch.sign(q.mean(dim=1, keepdim=True)))
+    ref2 = ops.attention(q, k2, v, 0.25)
+    o4 = capi.flash_attn(qc, k2.cuda().bfloat16(), vc, 0.25)
+    assert report("flash v4 with rescales", o4, ref2, 2e-2)[0]
 
 
 def test_flash_attention_fused_qkv_layout(capi):
