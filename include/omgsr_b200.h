@@ -64,6 +64,19 @@ int omgsr_gemm_bf16(const void* A, const void* Wt, const float* bias, const void
                     long long M, int N, int K, long long lda, long long ldd, long long ldr, int act, int gate_rows,
                     int flags, int force_bn, void* stream);
 
+/* Row-batched projection whose q / k head columns leave the epilogue RMS-normalised and rotated: for output columns in
+ * [q0, q1) (weight wq[128]) and [k0, k1) (weight wk[128]), per 128-column head
+ *     y = rope(x / sqrt(mean(x^2) + eps) * w),  rope: (y[2i], y[2i+1]) -> (y[2i] c - y[2i+1] s, y[2i+1] c + y[2i] s)
+ * with c = cos_t[pos, :], s = sin_t[pos, :] ([positions, 128] fp32, frequencies repeated twice) and pos = pos_offset + m
+ * (row m of every batch entry); all other columns get +bias and the activation on [act_c0, act_c1) as in
+ * omgsr_gemm_batched_bf16. Replaces the Linear -> RMSNorm -> apply_rotary_emb chain of diffusers' FLUX attention
+ * processors (reached from infer/omgsr_f_infer_model.py:191-200): the fused q|k|v projections of the double blocks and the
+ * q|mlp|k|v projection of the single blocks. N % 128 == 0, ranges multiples of 128, bf16 output rows 32-byte aligned. */
+int omgsr_gemm_rope_bf16(const void* A, const void* Wt, const float* bias, void* D, int batch, int M, int N, int K,
+                         long long lda, long long a_batch, long long ldd, long long d_batch, int act, int act_c0,
+                         int act_c1, const float* wq, const float* wk, int q0, int q1, int k0, int k1,
+                         const float* cos_t, const float* sin_t, int pos_offset, float eps, int force_bn, void* stream);
+
 /* 1: route the 256-wide GEMMs / convolutions to the CTA-pair kernel (tcgen05 cta_group::2, M = 256 per cluster of
  * two CTAs, each CTA streaming half of the weight tile); 0: single-CTA kernel. Process-wide switch. */
 int omgsr_set_gemm_2cta(int on);

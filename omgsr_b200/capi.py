@@ -19,7 +19,7 @@ OUT_F32, B_MN_MAJOR, CONV_NO_HALO, RES_F32 = 1, 2, 4, 8
 SYMBOLS = [
     "omgsr_version", "omgsr_last_error", "omgsr_destroy", "omgsr_launch_count", "omgsr_last_variant",
     "omgsr_gn_scratch_floats",
-    "omgsr_gemm_bf16", "omgsr_gemm_batched_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
+    "omgsr_gemm_bf16", "omgsr_gemm_batched_bf16", "omgsr_gemm_rope_bf16", "omgsr_bgemm_bf16", "omgsr_conv2d_nhwc_bf16",
     "omgsr_conv_in_nchw", "omgsr_conv_out_nchw", "omgsr_im2col3x3_nchw",
     "omgsr_groupnorm_stats", "omgsr_groupnorm_apply", "omgsr_groupnorm_combine", "omgsr_layernorm", "omgsr_softmax_rows",
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
@@ -424,6 +424,30 @@ def gemm_batched(a, w, bias=None, res=None, gate=None, act=ACT_NONE, act_cols=No
                                       _i((OUT_F32 if out.dtype == torch.float32 else 0) | (RES_F32 if res_f32 else 0)),
                                       _i(force_bn), _stream())
     _check(rc, "omgsr_gemm_batched_bf16")
+    return out
+
+
+def gemm_rope(a, w, bias, wq, wk, q_cols, k_cols, cos_t, sin_t, pos_offset=0, eps=1e-6, act=ACT_NONE, act_cols=None,
+              out=None, force_bn=0):
+    """out[b, m, :] = a[b, m, :] @ w^T + bias with per-head RMSNorm (weights wq / wk, fp32 [128]) + RoPE applied to the
+    head columns q_cols = (q0, q1) and k_cols = (k0, k1) in the GEMM epilogue; position of row m = pos_offset + m."""
+    _cuda_bf16(a, "a"); _cuda_bf16(w, "w"); _cuda_f32(bias, "bias")
+    for t, nm in ((wq, "wq"), (wk, "wk"), (cos_t, "cos"), (sin_t, "sin")):
+        _cuda_f32(t, nm)
+        assert t.is_contiguous()
+    B, M, K = a.shape
+    N = w.shape[0]
+    assert a.stride(2) == 1 and w.is_contiguous() and w.shape[1] == K and cos_t.shape[0] >= pos_offset + M
+    if out is None:
+        out = torch.empty((B, M, N), device=a.device, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.stride(2) == 1 and out.shape[:2] == (B, M)
+    c0, c1 = act_cols if act_cols is not None else (0, 0)
+    rc = _lib.omgsr_gemm_rope_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), _i(B), _i(M), _i(N), _i(K),
+                                   _ll(a.stride(1)), _ll(a.stride(0)), _ll(out.stride(1)), _ll(out.stride(0)), _i(act),
+                                   _i(c0), _i(c1), _ptr(wq), _ptr(wk), _i(q_cols[0]), _i(q_cols[1]), _i(k_cols[0]),
+                                   _i(k_cols[1]), _ptr(cos_t), _ptr(sin_t), _i(pos_offset), _f(eps), _i(force_bn),
+                                   _stream())
+    _check(rc, "omgsr_gemm_rope_bf16")
     return out
 
 

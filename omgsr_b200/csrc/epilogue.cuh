@@ -475,6 +475,79 @@ __device__ __forceinline__ const bf16* res_row_ptr(const bf16* res, long long of
   return res_f32 ? reinterpret_cast<const bf16*>(reinterpret_cast<const float*>(res) + off) : res + off;
 }
 
+// ---- FLUX q / k heads: per-head RMSNorm + RoPE applied to the fp32 accumulator -------------------------------
+// (diffusers: q = to_q(x); q = RMSNorm_128(q) * w; q = apply_rope(q) inside the attention processor that
+// infer/omgsr_f_infer_model.py:191-200 reaches.) A thread owns one token row, a head is 128 consecutive accumulator
+// columns of that row, so the mean square is thread-local: pass 1 reads the head from TMEM for the sum of squares,
+// pass 2 reads it again, scales, rotates pairs (x0, x1) -> (x0 c - x1 s, x1 c + x0 s) and stores bf16. Round 1 ran this
+// as a separate in-place kernel over the bf16 projection (114 launches and 450 MB of HBM traffic each per F-1024
+// step); fused, the rounding to bf16 happens once, after the rotation.
+struct RopeArgs {
+  const float* wq;     // [128] RMSNorm weight of the q heads
+  const float* wk;     // [128] of the k heads
+  const float* cos_t;  // [positions, 128] (each frequency repeated twice), null = no rope mode
+  const float* sin_t;
+  int q0, q1, k0, k1;  // accumulator column ranges (multiples of 128) holding q / k heads
+  int pos_offset;      // position of row 0 of every batch entry
+  float eps;
+};
+
+__device__ __forceinline__ void epilogue_head_rope(uint32_t t_head, const float* bias_s, const float* __restrict__ w,
+                                                   const float* __restrict__ cs, const float* __restrict__ sn,
+                                                   bf16* orow, bool valid, float eps) {
+  float ssq = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    float f[32];
+    tmem_ld32(t_head + c0, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (bias_s) add_bias32_s(f, bias_s + c0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ssq = fmaf(f[j], f[j], ssq);
+  }
+  const float rs = rsqrtf(ssq * (1.0f / 128.f) + eps);
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    float f[32];
+    tmem_ld32(t_head + c0, v);
+    float4 cc[8], ss[8];
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        cc[q] = __ldg(reinterpret_cast<const float4*>(cs + c0) + q);
+        ss[q] = __ldg(reinterpret_cast<const float4*>(sn + c0) + q);
+      }
+    }
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (bias_s) add_bias32_s(f, bias_s + c0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c0) + q);
+      f[4 * q + 0] *= rs * wv.x; f[4 * q + 1] *= rs * wv.y; f[4 * q + 2] *= rs * wv.z; f[4 * q + 3] *= rs * wv.w;
+    }
+    if (valid) {
+      uint4 o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 c0v = cc[2 * q], c1v = cc[2 * q + 1], s0v = ss[2 * q], s1v = ss[2 * q + 1];
+        const float* x = f + 8 * q;
+        o[q].x = pack_bf16x2(x[0] * c0v.x - x[1] * s0v.x, x[1] * c0v.y + x[0] * s0v.y);
+        o[q].y = pack_bf16x2(x[2] * c0v.z - x[3] * s0v.z, x[3] * c0v.w + x[2] * s0v.w);
+        o[q].z = pack_bf16x2(x[4] * c1v.x - x[5] * s1v.x, x[5] * c1v.y + x[4] * s1v.y);
+        o[q].w = pack_bf16x2(x[6] * c1v.z - x[7] * s1v.z, x[7] * c1v.w + x[6] * s1v.w);
+      }
+      st_global_256(orow + c0, o[0], o[1]);
+      st_global_256(orow + c0 + 16, o[2], o[3]);
+    }
+  }
+}
+
 // run-time option set -> specialised row routine (once per accumulator row, outside the chunk loop)
 template <bool GEGLU>
 __device__ __forceinline__ void epilogue_row_m(int mode, uint32_t t_row, int n_cols, int gate_off, int cv0, int oc0,

@@ -55,6 +55,7 @@ struct ConvGemmParams {
   int out_vec32, res_vec32;  // output / residual rows allow 256-bit accesses (see epilogue.cuh)
   int res_f32;               // the residual is fp32 (fp32 residual stream, together with out_f32)
   int a_bytes;         // bytes one A box delivers (tb may be clamped to B)
+  RopeArgs rope;       // rope.cos_t != null: q / k head columns get RMSNorm + RoPE in the epilogue (FLUX projections)
   float* gn_sums;      // optional fused GroupNorm statistics of the output: [B][groups][2]
   int gn_cpg, gn_groups, gn_slots;  // gn_sums: scratch [image][gn_slots][groups * 2], see gn_flush (epilogue.cuh)
 };
@@ -86,6 +87,28 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const ConvGemmParams&
   t.ty = (m / p.tiles_x) % p.tiles_y;
   t.tbi = m / (p.tiles_x * p.tiles_y);
   return t;
+}
+
+// accumulator row of a rope-mode GEMM: head by head (128 columns), q / k heads through epilogue_head_rope, the other
+// columns (v, the single blocks' MLP half) through the ordinary specialised routine
+template <int BN>
+__device__ __forceinline__ void epilogue_row_rope(const ConvGemmParams& p, int epi_mode, uint32_t t_row, int n_tile, int x,
+                                                  bool valid, EpiArgs& e, const float* bias_s, uint4 (&rr)[4], int lane) {
+  static_assert(BN % 128 == 0 || BN < 128, "rope mode needs whole heads per tile");
+  const long long pos = p.rope.pos_offset + x;
+#pragma unroll 1
+  for (int hh = 0; hh < BN / 128; ++hh) {
+    const int cv = n_tile * BN + hh * 128;
+    const bool is_q = cv >= p.rope.q0 && cv < p.rope.q1, is_k = cv >= p.rope.k0 && cv < p.rope.k1;
+    if (is_q || is_k) {
+      epilogue_head_rope(t_row + hh * 128, bias_s ? bias_s + hh * 128 : nullptr, is_q ? p.rope.wq : p.rope.wk,
+                         p.rope.cos_t + pos * 128, p.rope.sin_t + pos * 128,
+                         static_cast<bf16*>(e.out) + e.o_off + cv, valid, p.rope.eps);
+    } else {
+      epilogue_row_m<false>(epi_mode, t_row + hh * 128, 128, 0, cv, cv, valid, e, nullptr, 0, false,
+                            bias_s ? bias_s + hh * 128 : nullptr, rr, nullptr, 0, lane);
+    }
+  }
 }
 
 template <int BN>
@@ -286,7 +309,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
       const float* bias_s = p.bias ? my_bias : nullptr;
-      if (geglu)
+      if (p.rope.cos_t) {
+        if constexpr (BN % 128 == 0) epilogue_row_rope<BN>(p, epi_mode, t_row, t.n_tile, x, valid, e, bias_s, rr, lane);
+      } else if (geglu)
         epilogue_row_m<true>(epi_mode, t_row, out_bn, BN / 2, t.n_tile * BN, t.n_tile * out_bn, valid, e, nullptr, 0,
                              false, bias_s, rr, my_gn, p.gn_cpg, lane);
       else
@@ -498,7 +523,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
       const float* bias_s = p.bias ? my_bias : nullptr;
-      if (geglu)
+      if (p.rope.cos_t) {
+        if constexpr (BN % 128 == 0) epilogue_row_rope<BN>(p, epi_mode, t_row, n_tile, x, valid, e, bias_s, rr, lane);
+      } else if (geglu)
         epilogue_row_m<true>(epi_mode, t_row, out_bn, BN / 2, n_tile * BN, n_tile * out_bn, valid, e, nullptr, 0,
                              false, bias_s, rr, my_gn, p.gn_cpg, lane);
       else
@@ -604,6 +631,7 @@ struct ConvDesc {
   long long gate_ld; int act_c0, act_c1;
   float* gn_sums; int gn_groups;
   const float* gn_in;  // optional [B][Cin][2] input GroupNorm coefficients (+SiLU), halo pair kernel only
+  RopeArgs rope;       // rope.cos_t != null: RMSNorm + RoPE on the q / k head columns (plain GEMMs only)
   long long w_ld;  // elements per weight row (R*S*Cin)
   // batched B operand (attention)
   int b_batched, b_mn_major, flat;
@@ -685,6 +713,14 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   p.gate_ld = d.gate_ld > 0 ? d.gate_ld : (geglu ? d.Cout / 2 : d.Cout);
   p.act_c0 = d.act_c1 > d.act_c0 ? d.act_c0 : 0; p.act_c1 = d.act_c1 > d.act_c0 ? d.act_c1 : 0x7fffffff;
   p.a_bytes = kBK * 2 * tw * th * tb_box;
+  p.rope = d.rope;
+  if (d.rope.cos_t) {
+    if (!d.flat || d.out_f32 || d.res || d.gate || d.gn_sums || geglu || d.b_batched || (d.Cout % 128) ||
+        ((d.rope.q0 | d.rope.q1 | d.rope.k0 | d.rope.k1) % 128) || !d.rope.wq || !d.rope.wk || !d.rope.sin_t)
+      return set_error(OMGSR_ERR_SHAPE, "gemm_rope: plain bf16 GEMM with N %% 128 == 0 and head-aligned q / k ranges only");
+    if ((reinterpret_cast<uintptr_t>(d.y) % 32) || (d.o_sx % 16) || (d.o_sb % 16))
+      return set_error(OMGSR_ERR_ALIGN, "gemm_rope: output rows must be 32-byte aligned");
+  }
   p.gn_sums = nullptr; p.gn_cpg = 0; p.gn_groups = 0;
   if (d.gn_sums) {
     // fused statistics need: bf16 output, one image per tile, 8-channel store granules that map to whole groups
@@ -696,7 +732,8 @@ static int run_conv_gemm_impl(const ConvDesc& d, cudaStream_t st) {
   }
 
   const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_b;
-  const int bn = pick_bn(d.Cout, m_tiles, d.force_bn, geglu, d.b_mn_major, g_use_2cta && !d.b_batched);
+  int bn = pick_bn(d.Cout, m_tiles, d.force_bn, geglu, d.b_mn_major, g_use_2cta && !d.b_batched);
+  if (d.rope.cos_t && bn != 256 && bn != 128) bn = (d.Cout % 256 == 0) ? 256 : 128;  // whole 128-column heads per tile
   if (bn != 256 && bn != 160 && bn != 128 && bn != 64) return set_error(OMGSR_ERR_SHAPE, "conv_gemm: BN=%d", bn);
   if (geglu && ((bn % 64) || (d.Cout % bn)))
     return set_error(OMGSR_ERR_SHAPE, "conv_gemm: GEGLU needs Cout %% BN == 0 and BN %% 64 == 0");
@@ -834,6 +871,27 @@ extern "C" int omgsr_gemm_batched_bf16(const void* A, const void* Wt, const floa
   d.out_f32 = (flags & OMGSR_OUT_F32) ? 1 : 0;
   d.res_f32 = (flags & OMGSR_RES_F32) ? 1 : 0;
   d.flat = 1;  // 128-row tiles never straddle two batch entries
+  return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int omgsr_gemm_rope_bf16(const void* A, const void* Wt, const float* bias, void* D, int batch, int M, int N,
+                                    int K, long long lda, long long a_batch, long long ldd, long long d_batch, int act,
+                                    int act_c0, int act_c1, const float* wq, const float* wk, int q0, int q1, int k0,
+                                    int k1, const float* cos_t, const float* sin_t, int pos_offset, float eps,
+                                    int force_bn, void* stream) {
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) return set_error(OMGSR_ERR_SHAPE, "gemm_rope: empty problem");
+  if (!cos_t || !sin_t || !wq || !wk) return set_error(OMGSR_ERR_SHAPE, "gemm_rope: tables and norm weights are required");
+  if (q0 < 0 || q1 > N || k0 < 0 || k1 > N || q1 < q0 || k1 < k0) return set_error(OMGSR_ERR_SHAPE, "gemm_rope: column ranges");
+  ConvDesc d{};
+  d.x = A; d.w = Wt; d.bias = bias; d.y = D;
+  d.B = batch; d.H = 1; d.W = M; d.IH = 1; d.IW = M;
+  d.Cin = K; d.Cout = N; d.R = 1; d.S = 1;
+  d.x_sx = lda; d.x_sy = lda * M; d.x_sb = a_batch;
+  d.o_sx = ldd; d.o_sy = 0; d.o_sb = d_batch;
+  d.act = act; d.force_bn = force_bn; d.w_ld = K; d.act_c0 = act_c0; d.act_c1 = act_c1;
+  d.flat = 1;
+  d.rope.wq = wq; d.rope.wk = wk; d.rope.cos_t = cos_t; d.rope.sin_t = sin_t;
+  d.rope.q0 = q0; d.rope.q1 = q1; d.rope.k0 = k0; d.rope.k1 = k1; d.rope.pos_offset = pos_offset; d.rope.eps = eps;
   return run_conv_gemm(d, static_cast<cudaStream_t>(stream));
 }
 

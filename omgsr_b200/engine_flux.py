@@ -12,7 +12,7 @@ B200-first choices
     attention reads q/k/v in place (strided TMA views) and the double->single block transition needs no
     concat; q|k|v (double blocks) and q|mlp|k|v (single blocks) are single fused GEMMs, the attention
     output overwrites the dead q slot so proj_out of the single blocks reads [attn | gelu(mlp)] contiguously.
-  * per-head RMSNorm + RoPE run in place on the fused projection (one launch for q and k).
+  * per-head RMSNorm + RoPE of q and k run inside the epilogue of the fused projection GEMM (omgsr_gemm_rope_bf16).
   * gate * (.) + residual and GELU-tanh are GEMM epilogues; LayerNorm + modulation is one kernel.
 """
 import math
@@ -250,12 +250,13 @@ class B200FluxTransformer(torch.nn.Module):
             # chunks: 0 shift_msa, 1 scale_msa, 2 gate_msa, 3 shift_mlp, 4 scale_mlp, 5 gate_mlp
             if nt:
                 cn = ln_mod(hc, kc, 1, 0)
-                capi.gemm_batched(cn, blk.cwqkv, blk.cbqkv, out=qkv[:, :nt])
-                capi.rmsnorm_rope_(qkv[:, :nt], blk.cnqk, cos, sin, 2 * H, H, pos_offset=lo)
+                # q | k | v projection with the per-head RMSNorm + RoPE of q and k applied in the GEMM epilogue
+                capi.gemm_rope(cn, blk.cwqkv, blk.cbqkv, blk.cnqk[0], blk.cnqk[1], (0, d), (d, 2 * d), cos, sin,
+                               pos_offset=lo, out=qkv[:, :nt])
             if ni:
                 xn = ln_mod(hx, kx, 1, 0)
-                capi.gemm_batched(xn, blk.wqkv, blk.bqkv, out=qkv[:, nt:])
-                capi.rmsnorm_rope_(qkv[:, nt:], blk.nqk, cos, sin, 2 * H, H, pos_offset=lo + nt)
+                capi.gemm_rope(xn, blk.wqkv, blk.bqkv, blk.nqk[0], blk.nqk[1], (0, d), (d, 2 * d), cos, sin,
+                               pos_offset=lo + nt, out=qkv[:, nt:])
             kvf = all_kv(qkv[..., d:])
             q = qkv[..., :d].unflatten(-1, (H, 128))
             k, v = (kvf[..., j * d:(j + 1) * d].unflatten(-1, (H, 128)) for j in range(2))
@@ -277,9 +278,8 @@ class B200FluxTransformer(torch.nn.Module):
             ks = ("s", i)
             hn = ln_mod(h, ks, 1, 0)
             # columns [q | gelu(mlp) | k | v]
-            capi.gemm_batched(hn, blk.w1, blk.b1, act=capi.ACT_GELU_TANH, act_cols=(d, d + dm), out=wide)
-            capi.rmsnorm_rope_(wide[..., :d], blk.nq, cos, sin, H, H, pos_offset=lo)
-            capi.rmsnorm_rope_(wide[..., d + dm:2 * d + dm], blk.nk, cos, sin, H, H, pos_offset=lo)
+            capi.gemm_rope(hn, blk.w1, blk.b1, blk.nq[0], blk.nk[0], (0, d), (d + dm, 2 * d + dm), cos, sin, pos_offset=lo,
+                           act=capi.ACT_GELU_TANH, act_cols=(d, d + dm), out=wide)
             q = wide[..., :d].unflatten(-1, (H, 128))
             kvf = all_kv(wide[..., d + dm:])
             k, v = (kvf[..., j * d:(j + 1) * d].unflatten(-1, (H, 128)) for j in range(2))

@@ -242,6 +242,50 @@ def test_attention_materialised(capi, B, Hh, M, N, D):
     assert report(f"bgemm pv (MN-major V) {B},{Hh},{M},{N},{D}", o, ops.attention(q, k, v, scale), 2e-2)[0]
 
 
+def test_gemm_rope_epilogue(capi):
+    """fused q|mlp|k|v projection with RMSNorm + RoPE of the q / k heads in the GEMM epilogue (FLUX single-block layout)
+    against fp32 torch, and against the unfused pair (GEMM, then the in-place rmsnorm_rope kernel)."""
+    import torch.nn.functional as F
+    g = _g(777)
+    B, M, K, Hh = 2, 300, 256, 2
+    d, dm = Hh * 128, 384
+    N = 3 * d + dm                                   # [q | mlp | k | v]
+    a = bf16r(torch.randn(B, M, K, generator=g))
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, generator=g) * 0.1
+    wq, wk = 1 + 0.1 * torch.randn(128, generator=g), 1 + 0.1 * torch.randn(128, generator=g)
+    pos0 = 5
+    ang = torch.rand(pos0 + M, 64, generator=g) * 6.28
+    cos_t = ang.cos().repeat_interleave(2, dim=1).contiguous()
+    sin_t = ang.sin().repeat_interleave(2, dim=1).contiguous()
+    y = F.linear(a, w, bias)                          # fp32 reference
+
+    def head_ref(x, wn):                              # x [B, M, heads, 128]
+        xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * wn
+        x2 = xn.reshape(*xn.shape[:-1], 64, 2)
+        rot = torch.stack([-x2[..., 1], x2[..., 0]], -1).flatten(-2)
+        c, s_ = cos_t[pos0:pos0 + M][None, :, None], sin_t[pos0:pos0 + M][None, :, None]
+        return xn * c + rot * s_
+
+    ref = y.clone()
+    ref[..., :d] = head_ref(y[..., :d].reshape(B, M, Hh, 128), wq).reshape(B, M, d)
+    ref[..., d + dm:2 * d + dm] = head_ref(y[..., d + dm:2 * d + dm].reshape(B, M, Hh, 128), wk).reshape(B, M, d)
+    ref[..., d:d + dm] = F.gelu(y[..., d:d + dm], approximate="tanh")
+    ac, wc, bc = a.cuda().bfloat16(), w.cuda().bfloat16(), bias.cuda()
+    args = (wq.cuda(), wk.cuda(), (0, d), (d + dm, 2 * d + dm), cos_t.cuda(), sin_t.cuda())
+    got = capi.gemm_rope(ac, wc, bc, *args, pos_offset=pos0, act=capi.ACT_GELU_TANH, act_cols=(d, d + dm))
+    assert report("gemm + rmsnorm + rope epilogue", got, ref, 1e-2)[0]
+    # the unfused pair of round 1
+    un = capi.gemm_batched(ac, wc, bc, act=capi.ACT_GELU_TANH, act_cols=(d, d + dm))
+    capi.rmsnorm_rope_(un[..., :d], wq.cuda().reshape(1, 128), cos_t.cuda(), sin_t.cuda(), Hh, Hh, pos_offset=pos0)
+    capi.rmsnorm_rope_(un[..., d + dm:2 * d + dm], wk.cuda().reshape(1, 128), cos_t.cuda(), sin_t.cuda(), Hh, Hh, pos_offset=pos0)
+    assert report("fused vs unfused", got, un.float(), 1.5e-2)[0]
+    # into a strided destination (rows of a wider joint buffer), BN = 128 path (N = 128 * 11 is not a multiple of 256)
+    wide = torch.zeros(B, M + 7, N + 64, device="cuda", dtype=torch.bfloat16)
+    capi.gemm_rope(ac, wc, bc, *args, pos_offset=pos0, act=capi.ACT_GELU_TANH, act_cols=(d, d + dm), out=wide[:, 7:, :N])
+    assert torch.equal(wide[:, 7:, :N], got) and float(wide[:, :7].abs().max()) == 0.0
+
+
 def test_attention_materialised_query_chunks(capi):
     """the d = 512 path bounds its fp32 score scratch by chunking over query rows: same bits as the one-shot form."""
     from oracle import ops
