@@ -426,8 +426,11 @@ def bench_f1024(ctx, args, with_baselines=True):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/r02/)
-HALO_GN_TRAFFIC = 2.1099e9   # conv_halo (GroupNorm+SiLU -> 3x3 128->128 @512^2 x16): profiles/r01/ncu_halo_pair128_gn.txt
-F_GEMM_TRAFFIC = None        # filled from profiles/r02/ncu_f_gemm.txt once captured
+HALO_GN_TRAFFIC = 2.1905e9   # conv_halo_rs_kernel<1> (GroupNorm+SiLU -> 3x3 128->128 @512^2 x16): 1.1508 GB read + 1.0397 GB
+                             # written, profiles/r02/ncu_r02_halo_rs_gn.txt (algorithmic: input + output = 2 x 1.0737 GB)
+F_GEMM_TRAFFIC = 2.2646e9    # conv_gemm_tc2_kernel<256> (18432 x 12288 x 3072 + GELU): 1.8222 GB read + 0.4425 GB written,
+                             # profiles/r02/ncu_r02_f_gemm_3072_12288.txt (algorithmic A + W + D = 0.642 GB; the 75 MB weight
+                             # matrix is re-streamed per 256-row tile pair and only partly stays in L2)
 
 
 def f_kernel_roofline(capi, dev, B, peak_tflops, how):
@@ -468,7 +471,7 @@ def f_kernel_roofline(capi, dev, B, peak_tflops, how):
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
             "traffic": F_GEMM_TRAFFIC if B == 4 else None, "traffic_unit": "bytes/launch",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms,
-            "attention": {"kernel": "flash_attn2_kernel<128> (joint attention, 24 heads x 4608 tokens, batch %d)" % B,
+            "attention": {"kernel": "flash_attn4_kernel (joint attention, 24 heads x 4608 tokens, d = 128, batch %d)" % B,
                           "achieved": ach_a, "frac": ach_a / peak_tflops, "ms_per_launch": ms_a}}
 
 
@@ -553,41 +556,66 @@ def bench_s512(ctx, args):
     return line
 
 
-def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
-    """the launch class that dominates the step: the VAE's GroupNorm+SiLU -> 3x3 conv 128->128 at 512x512 (11 launches
-    per step, 1.24 TFLOP each at batch 16), served by the input-halo tcgen05 kernel with the normalisation applied to
-    the operand tile in shared memory. Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W."""
-    from omgsr_b200.pack import pack_conv_weight
-    C, H = 128, 512
-    x = torch.randn(B, H, H, C, device=dev, dtype=torch.bfloat16)
-    w = pack_conv_weight(torch.randn(C, C, 3, 3) / 34.0).to(dev)
-    b = torch.zeros(C, device=dev)
-    coef = capi.groupnorm_coef(capi.groupnorm_stats(x, 32), torch.ones(C, device=dev), torch.zeros(C, device=dev), B,
-                               H * H, 32, 1e-6)
-    out = torch.empty_like(x)
-    # the burst peak is a cold-start figure: let the board leave the power-capped state of the timed steps first
-    torch.cuda.synchronize()
-    time.sleep(3.0)
+PAIR256_TRAFFIC = 1.0465e9   # conv_gemm_tc2_kernel<256> (3x3 256->256 @256^2 x16): 0.5431 GB read + 0.5034 GB written,
+                             # profiles/r01/ncu_gemm_pair256.txt (algorithmic input + output = 2 x 0.5369 GB)
+
+
+def _time_launch(fn, n=10):
     for _ in range(3):
-        capi.conv2d_gn(x, coef, w, b, out=out)
+        fn()
     torch.cuda.synchronize()
-    n = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
-        capi.conv2d_gn(x, coef, w, b, out=out)
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    flops = 2.0 * C * C * 9 * B * H * H
-    ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_halo (GroupNorm+SiLU -> 3x3, 128->128 ch, 512x512, batch %d): %s"
-                                         % (B, capi.last_conv_variant()),
-            "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this very launch from one `ncu --set full` capture;
-            # algorithmic input + output = 2 x 1.0737 GB
-            "traffic": HALO_GN_TRAFFIC if (B, C, H) == (16, 128, 512) else None, "traffic_unit": "bytes/launch",
-            "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
+    return e0.elapsed_time(e1) / n
+
+
+def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
+    """Roofline of the step's dominant kernel, timed live on its launch stream.
+
+    By share of the step (ncu launch list, profiles/r02/launches_s512_b16_r02_summary.txt) the dominant KERNEL is
+    conv_gemm_tc2_kernel<256> (CTA-pair implicit-GEMM conv / GEMM, N = 256 tiles: 34 % of the step, 82 launches), probed
+    on its largest recurring shape, the VAE's 3x3 256->256 convolution at 256x256 (0.62 TFLOP per launch at batch 16).
+    Second by share (25 %, 14 launches) and the kernel round 1's verdict asked to lift is the 128-channel input-halo
+    convolution with the GroupNorm + SiLU of its input fused into the operand path (conv_halo_rs_kernel<1>, the largest
+    single layer shape of the step: 1.24 TFLOP per launch): reported next to it as `second`.
+    Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W in both cases."""
+    from omgsr_b200.pack import pack_conv_weight
+    # the burst peak is a cold-start figure: let the board leave the power-capped state of the timed steps first
+    torch.cuda.synchronize()
+    time.sleep(3.0)
+    out = {}
+    for key, C, H in (("pair256", 256, 256), ("halo", 128, 512)):
+        x = torch.randn(B, H, H, C, device=dev, dtype=torch.bfloat16)
+        w = pack_conv_weight(torch.randn(C, C, 3, 3) / (3.0 * C ** 0.5)).to(dev)
+        b = torch.zeros(C, device=dev)
+        y = torch.empty_like(x)
+        if key == "halo":
+            coef = capi.groupnorm_coef(capi.groupnorm_stats(x, 32), torch.ones(C, device=dev),
+                                       torch.zeros(C, device=dev), B, H * H, 32, 1e-6)
+            ms = _time_launch(lambda: capi.conv2d_gn(x, coef, w, b, out=y))
+            label = "GroupNorm+SiLU -> 3x3, 128->128 ch, 512x512"
+            traffic = HALO_GN_TRAFFIC if (B, C, H) == (16, 128, 512) else None
+        else:
+            ms = _time_launch(lambda: capi.conv2d(x, w, b, out=y))
+            label = "3x3, 256->256 ch, 256x256"
+            traffic = PAIR256_TRAFFIC if (B, C, H) == (16, 256, 256) else None
+        flops = 2.0 * C * C * 9 * B * H * H
+        ach = flops / (ms * 1e-3) / 1e12
+        out[key] = {"bound": "tensor", "kernel": f"{capi.last_conv_variant()} ({label}, batch {B})", "achieved": ach,
+                    "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this very launch from one `ncu --set full` capture
+                    "traffic": traffic, "traffic_unit": "bytes/launch",
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
+        del x, y
+    roof = out["pair256"]
+    roof["share_of_step"] = "34 % (conv_gemm_tc2_kernel<256>, profiles/r02/launches_s512_b16_r02_summary.txt)"
+    roof["second"] = out["halo"]
+    roof["second"]["share_of_step"] = "25 % (conv_halo_rs_kernel<1>)"
+    return roof
 
 
 def bench_c5(ctx, args):

@@ -887,7 +887,7 @@ static int launch_halo_rs(const CUtensorMap& tmA, const CUtensorMap& tmB128, con
   const long long pairs = (halo_tiles + 1) / 2;
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
-  g_trace_variant = XF ? "halo_rowshared128_gn" : "halo_rowshared128";
+  g_trace_variant = XF ? "conv_halo_rs_kernel<1>" : "conv_halo_rs_kernel<0>";
   conv_halo_rs_kernel<XF><<<2 * clusters, XF ? 480 : 352, C::kSmemBytes, st>>>(tmA, tmB128, tmB64, p);
   return check_launch("conv_halo_rs_kernel");
 }
@@ -904,7 +904,7 @@ static int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ha
   const long long pairs = (halo_tiles + 1) / 2;
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
-  g_trace_variant = XF ? "halo_pair128_gn" : "halo_pair128";
+  g_trace_variant = XF ? "conv_halo_tc2_kernel<2,true>" : "conv_halo_tc2_kernel<2,false>";
   conv_halo_tc2_kernel<TM, XF><<<2 * clusters, XF ? 320 : 192, C::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_halo_tc2_kernel");
 }
@@ -917,7 +917,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
                                 "conv_halo_tc")) return rc;
   const long long total = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles;
   const int grid = total < sm_count() ? static_cast<int>(total) : sm_count();
-  g_trace_variant = "halo_single128";
+  g_trace_variant = BN == 16 ? "conv_halo_tc_kernel<16,2>" : "conv_halo_tc_kernel<128,2>";
   conv_halo_tc_kernel<BN, TM><<<grid, 192, C::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_halo_tc_kernel");
 }

@@ -566,7 +566,7 @@ static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   const long long pairs = static_cast<long long>((m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
-  g_trace_variant = BN == 256 ? "pair256" : BN == 160 ? "pair160" : "pair128";
+  g_trace_variant = BN == 256 ? "conv_gemm_tc2_kernel<256>" : BN == 160 ? "conv_gemm_tc2_kernel<160>" : "conv_gemm_tc2_kernel<128>";
   conv_gemm_tc2_kernel<BN><<<2 * clusters, kThreads, Cfg2<BN>::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_gemm_tc2_kernel");
 }
@@ -587,7 +587,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
   if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_gemm_tc_kernel<BN>), C::kSmemBytes, &attr_done, "conv_gemm")) return rc;
   const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  g_trace_variant = BN == 256 ? "single256" : BN == 160 ? "single160" : BN == 128 ? "single128" : "single64";
+  g_trace_variant = BN == 256 ? "conv_gemm_tc_kernel<256>" : BN == 160 ? "conv_gemm_tc_kernel<160>" : BN == 128 ? "conv_gemm_tc_kernel<128>" : "conv_gemm_tc_kernel<64>";
   conv_gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmB, p);
   return check_launch("conv_gemm_tc_kernel");
 }
