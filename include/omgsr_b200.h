@@ -81,6 +81,11 @@ int omgsr_gemm_rope_bf16(const void* A, const void* Wt, const float* bias, void*
  * two CTAs, each CTA streaming half of the weight tile); 0: single-CTA kernel. Process-wide switch. */
 int omgsr_set_gemm_2cta(int on);
 
+/* Schedule of the 3x3 input-halo convolution (16 < Cout <= 128): -1 automatic (rolling input rows, each loaded and
+ * GroupNorm-transformed once, for the fused input GroupNorm variants; row-shared 2-row tiles otherwise), 0 never the
+ * rolling-row kernel, 1 the rolling-row kernel for every eligible convolution. Test / A-B timing only. */
+int omgsr_set_halo_rolling(int mode);
+
 /* Row-batched linear layer: D[b, m, :] = epi(A[b, m, :] * Wt^T) for b < batch, with independent batch strides
  * for A / D / res (tokens of one image may live inside a longer joint [text; image] sequence), a per-batch
  * gate vector gate[b * gate_ld + n], and the activation restricted to output columns [act_c0, act_c1)

@@ -25,7 +25,7 @@ SYMBOLS = [
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
-    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta",
+    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta", "omgsr_set_halo_rolling",
     "omgsr_groupnorm_coef", "omgsr_conv2d_gn_nhwc_bf16",
     "omgsr_resample_coeffs", "omgsr_resize_u8_workspace", "omgsr_resize_u8", "omgsr_u8_to_input", "omgsr_output_to_u8",
 ]

@@ -549,6 +549,9 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// one-pass softmax (v3 / v4): a block whose row sum exceeds this moves the row's reference exponent up by log2(sum)
+constexpr float kAttnRebase = 1024.0f;
+
 // ================================================================================================================
 // v3 (round 2): 128 keys per block, single-buffered S and P, ping-pong order on the tensor pipe.
 //
@@ -706,14 +709,14 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tS = tmem_base + g * 128 + lane_off, tO = tmem_base + 256 + g * 128 + lane_off;
     uint8_t* p_row = sP + g * C::kPBytes + row * 128;
-    float m_stale = 0.f, l_run = 0.f;
-    float pend_alpha = 1.0f;  // rescale decided at the end of the previous block (see flash_attn4_kernel)
+    float mb = 0.f, l_run = 0.f;  // mb: the row's reference exponent (log2 units), see flash_attn4_kernel
+    float pend_alpha = 1.0f;      // rescale decided at the end of the previous block
     bool pend = false;
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
       const int n_valid = min(BN, p.N - j * BN);
-      if (j == 0) {  // the first block fixes the reference maximum: one extra scan of its scores
+      if (j == 0) {  // the first block fixes the reference: one extra scan of its scores for the maximum
         float mx = -INFINITY;
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -724,7 +727,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < 32; ++i)
             if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(hv[i]));
         }
-        m_stale = mx;
+        mb = mx * p.scale_log2;
       } else {
         // P_g and O_g belong to PV_g(j - 1) until it has retired
         mbar_wait(&pv_done[g], (j - 1) & 1);
@@ -743,10 +746,10 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           l_run *= pend_alpha;
         }
       }
-      // ONE pass over the row (flash_attn4_kernel has the argument): exponentials against the stale maximum, the true
-      // maximum tracked on the side decides whether the NEXT block starts from a new reference
-      const float mb = m_stale * p.scale_log2;
-      float ls0 = 0.f, ls1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+      // ONE pass over the row (flash_attn4_kernel has the argument): exponentials against the running reference; the
+      // block's row sum decides whether the NEXT block starts from a new one
+      const float nmb = -mb;
+      float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t sv[32];
@@ -762,14 +765,11 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float pr[8];
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
-            const float s0 = __uint_as_float(sv[q * 8 + i]), s1 = __uint_as_float(sv[q * 8 + i + 1]);
-            pr[i] = exp2f(fmaf(s0, p.scale_log2, -mb));  // exp2(-inf) = 0
-            pr[i + 1] = exp2f(fmaf(s1, p.scale_log2, -mb));
-            mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
-          }
-          if (!C::kOnesCol) {
-            ls0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
-            ls1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
+            float t0, t1;
+            ffma2(t0, t1, __uint_as_float(sv[q * 8 + i]), __uint_as_float(sv[q * 8 + i + 1]), p.scale_log2, nmb);
+            pr[i] = exp2f(t0);  // exp2(-inf) = 0
+            pr[i + 1] = exp2f(t1);
+            fadd2(ls0, ls1, pr[i], pr[i + 1]);
           }
           uint4 u;
           u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
@@ -778,14 +778,15 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           *reinterpret_cast<uint4*>(p_row + (ch >> 3) * (128 * 128) + (((ch & 7) ^ (row & 7)) << 4)) = u;
         }
       }
-      l_run += ls0 + ls1;
+      const float ls = ls0 + ls1;
+      l_run += ls;
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&p_full[g]);
-      const float mx = fmaxf(mx0, mx1);
-      pend = (mx - m_stale) * p.scale_log2 > 8.0f;
-      pend_alpha = pend ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
-      if (pend) m_stale = mx;
+      pend = ls > kAttnRebase;
+      const float lg = pend ? log2f(ls) : 0.f;
+      pend_alpha = exp2f(-lg);
+      mb += lg;
     }
     // epilogue: O / l
     mbar_wait(&pv_done[g], (nblk - 1) & 1);
@@ -1046,14 +1047,14 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tOT = tmem_base + 256 + g * 128 + lane_off;  // this group's 128 query columns, my 32 d lanes
     uint8_t* p_row = sP + g * (128 * 128) + row * 128;
     float* alpha_g = s_alpha + g * 128;
-    float m_stale = 0.f, l_run = 0.f;
+    float mb = 0.f, l_run = 0.f;  // mb: the row's reference exponent (log2 units); p = 2^(s * scale_log2 - mb)
     float pend_alpha = 1.0f;   // rescale decided at the end of the previous block, applied once PV^T of that block retired
     bool pend_any = false;
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
       const int n_valid = min(BN, p.N - j * BN);
-      if (j == 0) {  // the first block fixes the reference maximum: one extra scan of its scores
+      if (j == 0) {  // the first block fixes the reference at its maximum: one extra scan of its scores
         float mx = -INFINITY;
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -1064,16 +1065,20 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < 32; ++i)
             if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(hv[i]));
         }
-        m_stale = mx;
+        mb = mx * p.scale_log2;
       }
-      // ONE pass over the row: exponentials against the stale maximum straight into bf16-packed registers, the true
-      // maximum of the raw scores is tracked on the side and only decides whether the NEXT block starts from a new
-      // reference (p <= 2^(max - stale): bounded by the score range, far inside fp32 / bf16 range, and rescaled
-      // away one block later). 4.5 instead of 7.4 issued instructions per score: with two softmax warps per scheduler
-      // the instruction stream of this loop, not the tensor pipe, set the pace of the first version of this kernel.
-      const float mb = m_stale * p.scale_log2;
+      // ONE pass over the row: exponentials against the running reference straight into bf16-packed registers. The
+      // reference need not be the row maximum: any value within a bounded distance of it keeps p inside fp32 / bf16
+      // range, and l and O carry the same factor, which cancels in O / l. So the maximum is not tracked at all; the
+      // block's row SUM (needed anyway) is the trigger: sum <= 2^10 bounds every p of the block by 2^10; a larger sum
+      // moves the reference up by log2(sum) for the NEXT block (then that block's p would have summed to 1, its largest
+      // lying in [1/128, 1]) and l / O^T are rescaled by 1 / sum one block later. Per pair of scores: FFMA2, 2 MUFU.EX2,
+      // FADD2, one bf16x2 pack = 2.5 issued instructions per score (4.5 with the maximum tracked in scalar fp32, 7.4 in
+      // the two-pass form): with two softmax warps per scheduler the instruction stream of this loop, not the tensor
+      // pipe, set the pace of the earlier versions of this kernel.
+      const float nmb = -mb;
       uint32_t pk[64];
-      float ls0 = 0.f, ls1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+      float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t sv[32];
@@ -1090,11 +1095,11 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
-          const float e0 = exp2f(fmaf(s0, p.scale_log2, -mb));  // exp2(-inf) = 0
-          const float e1 = exp2f(fmaf(s1, p.scale_log2, -mb));
-          ls0 += e0; ls1 += e1;
-          mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
+          float e0, e1;
+          ffma2(e0, e1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), p.scale_log2, nmb);
+          e0 = exp2f(e0);  // exp2(-inf) = 0
+          e1 = exp2f(e1);
+          fadd2(ls0, ls1, e0, e1);
           pk[(c0 + i) >> 1] = pack_bf16x2(e0, e1);
         }
       }
@@ -1117,7 +1122,8 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_wait_st();
         l_run *= pend_alpha;
       }
-      l_run += ls0 + ls1;
+      const float ls = ls0 + ls1;
+      l_run += ls;
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         uint4 u = make_uint4(pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
@@ -1126,12 +1132,12 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&p_full[g]);
-      // does the next block start from a new reference maximum? (the vote also orders this block's reads of alpha_g
-      // before the next writes)
-      const float mx = fmaxf(mx0, mx1);
-      const bool need = (mx - m_stale) * p.scale_log2 > 8.0f;
-      pend_alpha = need ? exp2f((m_stale - mx) * p.scale_log2) : 1.0f;
-      if (need) m_stale = mx;
+      // does the next block start from a new reference? (the vote also orders this block's reads of alpha_g before
+      // the next writes)
+      const bool need = ls > kAttnRebase;
+      const float lg = need ? log2f(ls) : 0.f;
+      pend_alpha = exp2f(-lg);
+      mb += lg;
       pend_any = (j + 1 < nblk) && group_any(1 + g, need);
       if (pend_any) alpha_g[row] = pend_alpha;
     }

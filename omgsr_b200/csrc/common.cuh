@@ -67,10 +67,33 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes' worth of fp32 arithmetic. ptxas keeps the pairs in
+// aligned register pairs (tcgen05.ld results are consecutive registers), so the mov.b64 packs cost nothing.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {  // d = a * b + c
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmov.b64 c, {%5, %5};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void ffma2p(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {  // d += a
+  asm("{\n\t.reg .b64 a, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 d, {%0, %1};\n\t"
+      "add.rn.f32x2 d, d, a;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+
 // x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE MUFU op (tanh.approx.f32) instead of two (ex2 + rcp). The streaming
 // GroupNorm+SiLU pass spends 2 MUFU ops per element otherwise (537 M elements per 512^2 x 16 tensor = 0.25 ms of the
 // 16-per-clock MUFU pipe under a 0.33 ms memory floor). tanh.approx is good to ~2^-11: |error| <= |h| * 5e-4, below
 // the bf16 rounding of the stored result except in the far negative tail, where the exact value is ~0 anyway.
+__device__ __forceinline__ float tanh_approx(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return t;
+}
 __device__ __forceinline__ float silu_f(float x) {
   const float h = 0.5f * x;
   float t;

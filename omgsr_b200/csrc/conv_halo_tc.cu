@@ -787,7 +787,11 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            f3 = unpack_bf16x2(v[q].w);
               f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = silu_half(fmaf(f[e], ca[e], cb[e]));
+              for (int e = 0; e < 8; e += 2) {  // packed fp32 pairs: h = (a / 2) x + b / 2, y = h + h tanh(h)
+                float h0, h1;
+                ffma2p(h0, h1, f[e], f[e + 1], ca[e], ca[e + 1], cb[e], cb[e + 1]);
+                ffma2p(f[e], f[e + 1], h0, h1, tanh_approx(h0), tanh_approx(h1), h0, h1);
+              }
               v[q].x = pack_bf16x2(f[0], f[1]); v[q].y = pack_bf16x2(f[2], f[3]);
               v[q].z = pack_bf16x2(f[4], f[5]); v[q].w = pack_bf16x2(f[6], f[7]);
             }
@@ -871,6 +875,390 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rolling-row kernel (round 2, 3x3 only): conv_halo_rs_kernel loads (and, with the fused input GroupNorm, TRANSFORMS)
+// 4 input rows per 2 output rows, i.e. every input row twice; the transform pipeline alone takes 0.80 ms of the 0.9 ms
+// of MMAs on the 512^2 x 16 layer (profiles/r02/halo_rowshared_ablation_v3_8epi.txt) and the two stages do not overlap
+// perfectly through 4 row slots. Here a CTA pair walks DOWN a pair of 128-pixel column strips: each input row is loaded
+// and transformed ONCE and feeds the three output rows it touches (tap rows 2, 1, 0 of outputs y-1, y, y+1).
+//   * TMEM: a ring of four 128-column accumulators; output n (running count) lives in slot n & 3. Three are being
+//     accumulated while the fourth is drained. The epilogue ZEROES a slot after reading it, so every MMA accumulates
+//     (enable-input-d = 1) and an N = 256 instruction may cover ANY two adjacent slots - also a fresh one next to an
+//     old one (one instruction has one accumulate flag). Per input row, chunk and tap column: one N = 256 + one N = 128
+//     instruction, the same 315 cycles per three row-taps as the row-shared schedule.
+//   * unit of the pipeline = (input row, 64-channel chunk): A ring of four 17 KB rows, B ring of two 72 KB weight sets
+//     (pair units 3 x 16 KB: this CTA's 128 rows of ITS tap row; single units 3 x 8 KB: its 64-row half), one
+//     tcgen05.commit per unit frees both.
+//   * work split: the B * ceil(tiles_x / 2) * H pair-rows are cut into one contiguous range per cluster (a range crosses
+//     at most a few strip boundaries; each segment costs two extra input rows), so all clusters finish together.
+//   * epilogue: warps 2..5 drain columns 0..63 of every output row, warps 6..9 columns 64..127 (a slot must be free
+//     again one row-step, ~7.5 k cycles, after it completes).
+// ------------------------------------------------------------------------------------------------
+struct HaloRrCfg {
+  static constexpr int kRowBytes = 17 * 1024;
+  static constexpr int kASlots = 4;
+  static constexpr int kBSlotBytes = 72 * 1024;
+  static constexpr int kBSlots = 2;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kASlots * kRowBytes + kBSlots * kBSlotBytes + 1024 + kBarBytes + 2048 + 32 * 128;
+};
+
+// the MMAs of one input row (step i of a segment of L output rows whose first output has running index n0): up to two
+// ops, a pair (N = 256 over slots lo, lo + 1) and / or singles (N = 128)
+struct RrPlan {
+  int n_ops;
+  int pair[2];   // 1: N = 256
+  int slot[2];   // first TMEM slot
+  int tap0[2];   // tap row of the (first) accumulator
+  int tap1[2];   // pair: tap row of the second accumulator
+  int boff[2];   // byte offset of the op's weight units inside the B slot
+};
+__device__ __forceinline__ RrPlan rr_plan(int i, int L, uint32_t n0) {
+  RrPlan pl;
+  const int lo = i - 2 > 0 ? i - 2 : 0, hi = i < L - 1 ? i : L - 1;
+  const int cnt = hi - lo + 1;
+  const int s_lo = static_cast<int>((n0 + lo) & 3u);
+  auto set = [&](int k, int is_pair, int o, int boff) {
+    pl.pair[k] = is_pair; pl.slot[k] = static_cast<int>((n0 + o) & 3u); pl.tap0[k] = i - o; pl.tap1[k] = i - o - 1;
+    pl.boff[k] = boff;
+  };
+  if (cnt == 3) {
+    pl.n_ops = 2;
+    if (s_lo != 3) { set(0, 1, lo, 0); set(1, 0, hi, 3 * 16384); }
+    else { set(0, 0, lo, 3 * 16384); set(1, 1, lo + 1, 0); }
+  } else if (cnt == 2) {
+    if (s_lo != 3) { pl.n_ops = 1; set(0, 1, lo, 0); }
+    else { pl.n_ops = 2; set(0, 0, lo, 0); set(1, 0, hi, 3 * 8192); }
+  } else {
+    pl.n_ops = 1; set(0, 0, lo, 0);
+  }
+  return pl;
+}
+
+template <bool XF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XF ? 480 : 352, 1)
+conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB128,
+                    const __grid_constant__ CUtensorMap tmB64, const HaloParams p) {
+  using C = HaloRrCfg;
+  constexpr int BN = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset, not a cast: keeps the shared address space (LDS / STS)
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::kASlots * C::kRowBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::kBSlots * C::kBSlotBytes);
+  uint64_t* a_full = bars;                // [4] XF: per CTA (own bytes); else leader's (2 arrivals)
+  uint64_t* a_ready = a_full + 4;         // [4] XF: leader's, 8 arrivals (4 transform warps x 2 CTAs)
+  uint64_t* b_full = a_ready + 4;         // [2] leader's (2 arrivals)
+  uint64_t* empty = b_full + 2;           // [4] per CTA, per unit (u & 3): one multicast commit per unit
+  uint64_t* acc_full = empty + 4;         // [4] per CTA
+  uint64_t* acc_empty = acc_full + 4;     // [4] leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB128);
+    tma_prefetch_desc(&tmB64);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&a_full[i], XF ? 1 : 2);
+      mbar_init(&a_ready[i], 8);
+      mbar_init(&empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 16);
+    }
+    for (int i = 0; i < 2; ++i) mbar_init(&b_full[i], 2);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2 && warp < 10) {  // all four accumulators start at zero (every MMA accumulates)
+    const uint32_t z[32] = {};
+    const uint32_t t0 = tmem_base + ((warp - 2) >> 2) * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < 256; c0 += 32) tmem_st32(t0 + c0, z);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+
+  // this cluster's contiguous range of pair-rows: pair-strip q = (image, pair of 128-pixel strips), H rows each
+  const int xp = (p.tiles_x + 1) >> 1;
+  const long long G = static_cast<long long>(p.B) * xp * p.H;  // < 2^31 (host check)
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int g_begin = static_cast<int>(G * cluster_id / num_clusters), g_end = static_cast<int>(G * (cluster_id + 1) / num_clusters);
+  const int row_bytes = p.pw * 128;
+  constexpr int kBWarp = 10;
+  // segment decode shared by all roles
+  auto segment = [&](int g, int& b, int& tx, bool& dummy, int& ya, int& L) {
+    const int q = g / p.H;
+    ya = g - q * p.H;
+    L = min(p.H - ya, g_end - g);
+    b = q / xp;
+    tx = 2 * (q - b * xp) + static_cast<int>(rank);
+    dummy = tx >= p.tiles_x;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= input-row producer =================
+      uint32_t u = 0;
+      for (int g = g_begin; g < g_end;) {
+        int b, tx, ya, L; bool dummy;
+        segment(g, b, tx, dummy, ya, L);
+        if (dummy) b = p.B;  // out of range: TMA fills zeros
+        for (int i = 0; i < L + 2; ++i) {
+          for (int c = 0; c < p.chunks; ++c, ++u) {
+            const int slot = u & 3;
+            mbar_wait_relaxed(&empty[slot], ((u >> 2) & 1) ^ 1);
+            uint8_t* dst = sA + slot * C::kRowBytes;
+            if (XF) {  // own barrier: this CTA's transform warps consume the row first
+              mbar_expect_tx(&a_full[slot], row_bytes);
+              tma_load_5d(dst, &tmA, &a_full[slot], c * 64, tx * 128 - p.pad_l, ya - p.pad_t + i, b, 0);
+            } else {
+              if (rank == 0) mbar_expect_tx(&a_full[slot], 2 * row_bytes);
+              else mbar_arrive_remote(&a_full[slot], 0);
+              tma2_load_5d(dst, &tmA, &a_full[slot], c * 64, tx * 128 - p.pad_l, ya - p.pad_t + i, b, 0);
+            }
+          }
+        }
+        g += L;
+      }
+    }
+  } else if (warp == kBWarp) {
+    if (lane == 0) {
+      // ================= weight-unit producer =================
+      uint32_t u = 0, n0 = 0;
+      for (int g = g_begin; g < g_end;) {
+        int b, tx, ya, L; bool dummy;
+        segment(g, b, tx, dummy, ya, L);
+        for (int i = 0; i < L + 2; ++i) {
+          const RrPlan pl = rr_plan(i, L, n0);
+          int bytes = 0;
+          for (int k = 0; k < pl.n_ops; ++k) bytes += pl.pair[k] ? 3 * 16384 : 3 * 8192;
+          for (int c = 0; c < p.chunks; ++c, ++u) {
+            uint8_t* dst = sB + (u & 1) * C::kBSlotBytes;
+            if (u >= 2) mbar_wait_relaxed(&empty[(u - 2) & 3], ((u - 2) >> 2) & 1);
+            if (rank == 0) mbar_expect_tx(&b_full[u & 1], 2 * bytes);
+            else mbar_arrive_remote(&b_full[u & 1], 0);
+            for (int k = 0; k < pl.n_ops; ++k) {
+              const int r_mine = pl.pair[k] ? (rank == 0 ? pl.tap0[k] : pl.tap1[k]) : pl.tap0[k];
+              for (int sx = 0; sx < 3; ++sx) {
+                const int kcol = (r_mine * 3 + sx) * p.Cin + c * 64;
+                if (pl.pair[k]) tma2_load_4d(dst + pl.boff[k] + sx * 16384, &tmB128, &b_full[u & 1], kcol, 0, 0, 0);
+                else tma2_load_4d(dst + pl.boff[k] + sx * 8192, &tmB64, &b_full[u & 1], kcol, static_cast<int>(rank) * 64, 0, 0);
+              }
+            }
+          }
+        }
+        g += L; n0 += L;
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      // ================= MMA issuer =================
+      const uint32_t idesc256 = umma_idesc_bf16(256, 256, 0, 0), idesc128 = umma_idesc_bf16(256, 128, 0, 0);
+      uint32_t u = 0, n0 = 0;
+      for (int g = g_begin; g < g_end;) {
+        int b, tx, ya, L; bool dummy;
+        segment(g, b, tx, dummy, ya, L);
+        for (int i = 0; i < L + 2; ++i) {
+          if (i < L) {  // output i starts in this step: its slot must have been drained (and zeroed)
+            const uint32_t n = n0 + i;
+            mbar_wait(&acc_empty[n & 3], ((n >> 2) & 1) ^ 1);
+          }
+          const RrPlan pl = rr_plan(i, L, n0);
+          for (int c = 0; c < p.chunks; ++c, ++u) {
+            const int slot = u & 3;
+            if (XF) mbar_wait(&a_ready[slot], (u >> 2) & 1);
+            else mbar_wait(&a_full[slot], (u >> 2) & 1);
+            mbar_wait(&b_full[u & 1], (u >> 1) & 1);
+            tc_fence_after();
+            const uint32_t a_row = smem_u32(sA + slot * C::kRowBytes);
+            const uint32_t b_base = smem_u32(sB + (u & 1) * C::kBSlotBytes);
+            for (int sx = 0; sx < 3; ++sx) {
+              const uint32_t a_addr = a_row + static_cast<uint32_t>(sx * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (p.debug & 4) continue;  // timing-only ablation (OMGSR_HALO_DEBUG): no MMAs, results invalid
+                const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+                for (int o = 0; o < pl.n_ops; ++o) {
+                  const uint32_t b_addr = b_base + pl.boff[o] + sx * (pl.pair[o] ? 16384u : 8192u) + k * 32;
+                  tc_mma2_ss(tmem_base + pl.slot[o] * BN, da, umma_desc_sw128(b_addr, 16, 1024),
+                             pl.pair[o] ? idesc256 : idesc128, 1u);
+                }
+              }
+            }
+            tc_commit2_mc(&empty[slot]);  // the row and its weight units are free once everything issued so far retires
+          }
+          if (i >= 2) tc_commit2_mc(&acc_full[(n0 + i - 2) & 3]);  // output i - 2 has received its three tap rows
+        }
+        g += L; n0 += L;
+      }
+    }
+  } else if (XF && warp >= 11) {
+    // ================= input transform (warps 11..14): GroupNorm + SiLU on each halo row, in place =================
+    const int tid = threadIdx.x - 352;  // 0..127
+    const int j = tid & 7;              // 16-byte unit (8 channels) of a 128-byte pixel row: fixed per thread
+    const int p0 = tid >> 3;            // first pixel of this thread in a row; then every 16th (<= 9 per row)
+    uint32_t u = 0;
+    for (int g = g_begin; g < g_end;) {
+      int b, tx, ya, L; bool dummy;
+      segment(g, b, tx, dummy, ya, L);
+      const int x0 = tx * 128 - p.pad_l;
+      for (int i = 0; i < L + 2; ++i) {
+        const int yy = ya - p.pad_t + i;
+        for (int c = 0; c < p.chunks; ++c, ++u) {
+          const int slot = u & 3;
+          float ca[8], cb[8];
+          const bool live = !dummy && yy >= 0 && yy < p.IH;
+          if (live) {
+            const float4* cf = reinterpret_cast<const float4*>(p.gn_in + static_cast<long long>(b) * p.Cin + c * 64 + j * 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 v = __ldg(cf + q);
+              // halved: silu(a x + b) = h + h tanh(h) with h = (a / 2) x + b / 2
+              ca[2 * q] = 0.5f * v.x; cb[2 * q] = 0.5f * v.y; ca[2 * q + 1] = 0.5f * v.z; cb[2 * q + 1] = 0.5f * v.w;
+            }
+          }
+          mbar_wait_relaxed(&a_full[slot], (u >> 2) & 1, 32);
+          // rows / pixels outside the image: TMA wrote zeros = the conv padding, which must stay zero
+          if (live) {
+            uint8_t* row = sA + slot * C::kRowBytes;
+            uint4 v[9];
+            bool on[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const int pi = p0 + 16 * q;
+              const int xx = x0 + pi;
+              on[q] = pi < p.pw && xx >= 0 && xx < p.IW;
+              if (on[q]) v[q] = *reinterpret_cast<const uint4*>(row + pi * 128 + ((j ^ (pi & 7)) << 4));
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              float f[8];
+              const float2 f0 = unpack_bf16x2(v[q].x), f1 = unpack_bf16x2(v[q].y), f2 = unpack_bf16x2(v[q].z),
+                           f3 = unpack_bf16x2(v[q].w);
+              f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {  // packed fp32 pairs: h = (a / 2) x + b / 2, y = h + h tanh(h)
+                float h0, h1;
+                ffma2p(h0, h1, f[e], f[e + 1], ca[e], ca[e + 1], cb[e], cb[e + 1]);
+                ffma2p(f[e], f[e + 1], h0, h1, tanh_approx(h0), tanh_approx(h1), h0, h1);
+              }
+              v[q].x = pack_bf16x2(f[0], f[1]); v[q].y = pack_bf16x2(f[2], f[3]);
+              v[q].z = pack_bf16x2(f[4], f[5]); v[q].w = pack_bf16x2(f[6], f[7]);
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const int pi = p0 + 16 * q;
+              if (on[q]) *reinterpret_cast<uint4*>(row + pi * 128 + ((j ^ (pi & 7)) << 4)) = v[q];
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&a_ready[slot]); else mbar_arrive_remote_relaxed(&a_ready[slot], 0);
+          }
+        }
+      }
+      g += L;
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ================= epilogue: warps 2..5 drain columns 0..63 of every output row, warps 6..9 columns 64..127 =====
+    const int half = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int ew = half * 4 + quarter;    // epilogue warp index inside the CTA: statistics slot / bias slice
+    const int row = quarter * 32 + lane;
+    const int c_off = half * 64;
+    float* my_gn = gn_acc + ew * 64;
+    float* my_bias = gn_acc + 8 * 64 + ew * BN;
+    if (p.bias) stage_bias<BN>(my_bias, p.bias, 0, p.Cout, lane);
+    const int epi_mode = epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
+    const int gn_n = p.gn_groups * 2;
+    int gn_b = -1;
+    if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
+    const uint32_t zeros[32] = {};
+    uint32_t n = 0;
+    for (int g = g_begin; g < g_end;) {
+      int b, tx, ya, L; bool dummy;
+      segment(g, b, tx, dummy, ya, L);
+      if (p.gn_sums && !dummy && b != gn_b) {
+        if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 8 + ew, p.gn_slots), lane);
+        gn_b = b;
+      }
+      const int x = tx * 128 + row;
+      for (int o = 0; o < L; ++o, ++n) {
+        const int y = ya + o;
+        EpiArgs e;
+        e.bias = p.bias; e.gate_row = nullptr; e.out = p.out;
+        e.Cout = p.Cout; e.cout_out = p.Cout; e.act = p.act; e.act_c0 = 0; e.act_c1 = 0x7fffffff;
+        e.out_f32 = p.out_f32; e.vec32 = p.out_vec32; e.res_vec32 = p.res_vec32; e.res_f32 = 0;
+        float gn_part[16];
+        e.gn_part = p.gn_sums ? gn_part : nullptr;
+        const bool valid = !dummy && (x < p.W) && !(p.debug & 1);
+        uint4 rr[4] = {};
+        e.res_row = (p.res && !dummy) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+        if (e.res_row) {  // this thread's residual row: pulled into L2 now, first chunk loaded before the accumulator wait
+          prefetch_res_row(e, c_off, 64, valid);
+          load_res32(rr, e, c_off, valid);
+        }
+        e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
+        const int slot = n & 3;
+        mbar_wait_relaxed(&acc_full[slot], (n >> 2) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + slot * BN + c_off + (static_cast<uint32_t>(quarter * 32) << 16);
+        if (!(p.debug & 2)) {  // (timing-only ablation: no epilogue)
+          epilogue_row_m<false>(epi_mode, t_row, 64, 0, c_off, c_off, valid, e, nullptr, 0, false,
+                                p.bias ? my_bias + c_off : nullptr, rr, my_gn, p.gn_cpg, lane);
+        }
+        tmem_st32(t_row, zeros);
+        tmem_st32(t_row + 32, zeros);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&acc_empty[slot]);
+          else mbar_arrive_remote(&acc_empty[slot], 0);
+        }
+      }
+      g += L;
+    }
+    if (p.gn_sums && gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 8 + ew, p.gn_slots), lane);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// conv_halo_rr_kernel where it applies (3x3, a long enough share of output rows per cluster): -1 automatic (the fused
+// input GroupNorm variants), 0 never, 1 every eligible convolution. OMGSR_HALO_ROLLING / omgsr_set_halo_rolling.
+int g_halo_rolling = getenv("OMGSR_HALO_ROLLING") ? atoi(getenv("OMGSR_HALO_ROLLING")) : 0;  // off until measured
+
+template <bool XF>
+static int launch_halo_rr(const CUtensorMap& tmA, const CUtensorMap& tmB128, const CUtensorMap& tmB64,
+                          const HaloParams& p, int clusters, cudaStream_t st) {
+  using C = HaloRrCfg;
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_rr_kernel<XF>), C::kSmemBytes, &attr_done,
+                                "conv_halo_rr")) return rc;
+  g_trace_variant = XF ? "conv_halo_rr_kernel<1>" : "conv_halo_rr_kernel<0>";
+  conv_halo_rr_kernel<XF><<<2 * clusters, XF ? 480 : 352, C::kSmemBytes, st>>>(tmA, tmB128, tmB64, p);
+  return check_launch("conv_halo_rr_kernel");
 }
 
 // 0: conv_halo_tc2_kernel (every instruction N = 128), 1: conv_halo_rs_kernel (row-shared N = 256 instructions)
@@ -992,6 +1380,16 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
     if (rc) return rc;
     rc = make_tmap_bf16(&tmB64, w, 4, wd, ws, wb64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    // rolling rows: every input row loaded / transformed once; worth it when a cluster's share of output rows is long
+    // against the two extra input rows per segment
+    const long long pair_rows = static_cast<long long>(B) * ((p.tiles_x + 1) / 2) * OH;
+    const int max_clusters = sm_count() / 2;
+    const bool rr_fit = R == 3 && S == 3 && pair_rows >= static_cast<long long>(max_clusters) * 48 && pair_rows < 0x7fffffffLL;
+    const bool rr_on = g_halo_rolling >= 0 ? g_halo_rolling != 0 : gn_in != nullptr;
+    if (rr_fit && rr_on) {
+      if (gn_in) return launch_halo_rr<true>(tmRow, tmB128, tmB64, p, max_clusters, st);
+      return launch_halo_rr<false>(tmRow, tmB128, tmB64, p, max_clusters, st);
+    }
     if (gn_in) return launch_halo_rs<true>(tmRow, tmB128, tmB64, p, st);
     return launch_halo_rs<false>(tmRow, tmB128, tmB64, p, st);
   }
@@ -1001,3 +1399,5 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
 }
 
 }  // namespace omgsr
+
+extern "C" int omgsr_set_halo_rolling(int mode) { omgsr::g_halo_rolling = mode; return OMGSR_OK; }

@@ -350,6 +350,38 @@ def test_flash_attention_variants_agree(capi):
     assert report("flash v4 with rescales", o4, ref2, 2e-2)[0]
 
 
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("shape", ["ramp", "spike"])
+def test_flash_attention_reference_rebase(capi, D, variant, shape):
+    """One-pass softmax of v3 / v4: the row's reference exponent moves when a block's row sum exceeds 2^10.
+    'ramp': scores grow along the key axis, so the reference moves in most blocks; 'spike': a few keys in a late
+    block score up to ~40 (log2 units) above everything before them (p ~ 2^40 for one block, rescaled away in the next).
+    Envelope of the one-pass form (stated in attn_tc.cu): within ONE 128-key block a row's scaled scores may exceed the
+    running reference by < 127 log2 units (88 nats); the 64-key kernel (variant 2) has no such limit."""
+    from oracle import ops
+    g = _g(7 + D)
+    B, M, N, Hh = 1, 384, 1024, 2
+    q = bf16r(torch.randn(B, M, Hh, D, generator=g))
+    k = bf16r(torch.randn(B, N, Hh, D, generator=g) * 0.3)
+    v = bf16r(torch.randn(B, N, Hh, D, generator=g))
+    qdir = q.mean(dim=1, keepdim=True)
+    qdir = qdir / qdir.norm(dim=-1, keepdim=True)
+    if shape == "ramp":
+        k = bf16r(k + torch.linspace(0.0, 8.0, N)[None, :, None, None] * torch.sign(qdir))
+    else:
+        k[:, 700:704] = bf16r(k[:, 700:704] + 8.0 * torch.sign(qdir))   # |q . sign| <~ 3.5 sqrt(D): jumps of <~ 40 (log2 units)
+    scale = D ** -0.5
+    ref = ops.attention(q, k, v, scale)
+    capi.lib().omgsr_flash_attn_set_variant(variant)
+    try:
+        o = capi.flash_attn(q.cuda().bfloat16(), k.cuda().bfloat16(), v.cuda().bfloat16(), scale)
+    finally:
+        capi.lib().omgsr_flash_attn_set_variant(0)
+    assert torch.isfinite(o.float()).all()
+    assert report(f"flash d={D} variant={variant} {shape}", o, ref, 2e-2)[0]
+
+
 def test_flash_attention_fused_qkv_layout(capi):
     """q/k/v as column slices of one fused [B, T, 3*H*D] projection output (strided views)."""
     from oracle import ops
@@ -636,6 +668,74 @@ def test_groupnorm_combine_zero_weight_entries(capi):
     zero = torch.zeros_like(pix)  # a rank that holds ONLY shadows: all-zero numerators, not NaN
     num, wsum = capi.groupnorm_combine(sums, zero, n_img, C, raw=True)
     assert float(num.abs().max()) == 0.0 and float(wsum.abs().max()) == 0.0
+
+
+ROLLING_CASES = [
+    # B, H, W, Cin, Cout: B * ceil(ceil(W / 128) / 2) * H >= 74 * 48 pair-rows -> conv_halo_rr_kernel is eligible
+    (2, 900, 384, 128, 128),    # three strips: the pair's second CTA idles on a dummy strip; H not a multiple of anything
+    (4, 1024, 200, 128, 128),   # ragged x
+    (4, 1000, 256, 64, 128),    # one K chunk: the A / B rings advance one unit per input row
+    (2, 930, 500, 192, 64),     # three K chunks, thin Cout (zero-filled weight rows, masked stores)
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", ROLLING_CASES)
+@pytest.mark.parametrize("variant", ["plain", "res_stats", "gn_in", "gn_in_res_stats"])
+def test_conv_halo_rolling_rows(capi, B, H, W, Cin, Cout, variant):
+    """conv_halo_rr_kernel (each input row loaded / transformed once, four-slot accumulator ring) against the
+    row-shared kernel on the same problem (bit-identical sums are not expected: the tap order differs) and against the
+    fp32 oracle on a row band that includes a segment boundary, the image top and the image bottom."""
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight
+    g = _g(B * 13 + H + W + Cin + Cout)
+    x = bf16r(torch.randn(B, H, W, Cin, generator=g) * 1.5 + 0.3)
+    gamma, beta = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.2
+    w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+    b = torch.randn(Cout, generator=g)
+    with_res = "res" in variant
+    with_stats = "stats" in variant and Cout % 32 == 0 and Cout // 32 in (4, 8, 16)
+    with_gn = variant.startswith("gn_in")
+    r = bf16r(torch.randn(B, H, W, Cout, generator=g)) if with_res else None
+    xc, wc, bc = x.cuda().bfloat16(), pack_conv_weight(w).cuda(), b.cuda()
+    rc = r.cuda().bfloat16() if with_res else None
+    coef = None
+    if with_gn:
+        st = capi.groupnorm_stats(xc, 32)
+        coef = capi.groupnorm_coef(st, gamma.cuda(), beta.cuda(), B, H * W, 32, 1e-6)
+
+    def run(mode):
+        capi.lib().omgsr_set_halo_rolling(mode)
+        try:
+            so = torch.empty(B, 32, 2, device="cuda") if with_stats else None
+            if with_gn:
+                y = capi.conv2d_gn(xc, coef, wc, bc, res=rc, gn_stats=so)
+            else:
+                y = capi.conv2d(xc, wc, bc, res=rc, gn_stats=so, cout=Cout)
+            torch.cuda.synchronize()
+            return y, so, capi.last_conv_variant()
+        finally:
+            capi.lib().omgsr_set_halo_rolling(-1)
+
+    y_rr, s_rr, name_rr = run(1)
+    y_rs, s_rs, name_rs = run(0)
+    assert "conv_halo_rr_kernel" in name_rr and "conv_halo_rr_kernel" not in name_rs, (name_rr, name_rs)
+    assert report(f"rolling vs row-shared [{variant}]", y_rr, y_rs.float().cpu(), 4e-3)[0]
+    if with_stats:
+        assert report("output statistics, rolling vs row-shared", s_rr, s_rs.cpu(), 1e-3)[0]
+        f32 = y_rr.float()
+        s_ref = torch.stack([f32.reshape(B, H * W, 32, Cout // 32).sum((1, 3)),
+                             (f32 * f32).reshape(B, H * W, 32, Cout // 32).sum((1, 3))], -1)
+        assert report("output statistics vs the stored tensor", s_rr, s_ref.cpu(), 1e-3)[0]
+    # fp32 oracle on bands of rows (image top, bottom, and around the first cluster boundary G / 74)
+    xin = bf16r(torch.nn.functional.silu(ops.groupnorm_nhwc(x, gamma, beta, 32, 1e-6))) if with_gn else x
+    xp = ((W + 127) // 128 + 1) // 2
+    cut = (B * xp * H // 74) % H
+    for y0, y1 in ((0, 6), (H - 6, H), (max(cut - 4, 0), min(cut + 4, H))):
+        lo, hi = max(y0 - 1, 0), min(y1 + 1, H)
+        band = ops.conv2d_nhwc(xin[:, lo:hi], w, b)[:, y0 - lo:y0 - lo + (y1 - y0)]
+        if with_res:
+            band = band + r[:, y0:y1]
+        assert report(f"rolling rows {y0}..{y1} vs oracle [{variant}]", y_rr[:, y0:y1], band)[0]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(2, 8, 128, 64, 128, False), (1, 33, 200, 128, 128, True),
