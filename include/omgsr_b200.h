@@ -83,7 +83,8 @@ int omgsr_set_gemm_2cta(int on);
 
 /* Schedule of the 3x3 input-halo convolution (16 < Cout <= 128): -1 automatic (rolling input rows, each loaded and
  * GroupNorm-transformed once, for the fused input GroupNorm variants; row-shared 2-row tiles otherwise), 0 never the
- * rolling-row kernel, 1 the rolling-row kernel for every eligible convolution. Test / A-B timing only. */
+ * rolling-row kernel, 1 the rolling-row kernel for every eligible convolution, -2 back to the start-up default
+ * (OMGSR_HALO_ROLLING). Test / A-B timing only. */
 int omgsr_set_halo_rolling(int mode);
 
 /* Row-batched linear layer: D[b, m, :] = epi(A[b, m, :] * Wt^T) for b < batch, with independent batch strides

@@ -61,7 +61,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* o_full = s_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
   const int m0 = blockIdx.x * C::kBM, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.N + BN - 1) / BN;
 
@@ -87,7 +87,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -113,7 +113,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
       // ---- MMA issuer ----
       const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);  // S = Q K^T : both K-major
       const uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);   // O = P V   : V is MN-major ([kv, d])
@@ -125,14 +126,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (C::kBM * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
-          tc_mma_ss(tS, da, db, idesc_s, kk != 0);
+          if (leader) tc_mma_ss(tS, da, db, idesc_s, kk != 0);
         }
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_s(0);
-      tc_commit(s_full);
+      if (leader) tc_commit(s_full);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
@@ -145,18 +146,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const uint64_t da = umma_desc_sw128(aP + (kk >> 2) * (C::kBM * 128) + (kk & 3) * 32, 16, 1024);
           // MN-major V: 64-wide d atoms are BN*128 bytes apart (LBO), 8-row kv groups 1024 B apart (SBO)
           const uint64_t db = umma_desc_sw128(aV + kk * 2048, BN * 128, 1024);
-          tc_mma_ss(tO, da, db, idesc_o, kk != 0);
+          if (leader) tc_mma_ss(tO, da, db, idesc_o, kk != 0);
         }
-        tc_commit(o_full);
+        if (leader) tc_commit(o_full);
         const int nstage = (stage + 1 == C::kStages) ? 0 : stage + 1;
         const uint32_t nphase = (stage + 1 == C::kStages) ? (phase ^ 1) : phase;
         if (j + 1 < nblk) {
           mbar_wait(&k_full[nstage], nphase);
           tc_fence_after();
           issue_s(nstage);
-          tc_commit(s_full);
+          if (leader) tc_commit(s_full);
         }
-        tc_commit(&kv_empty[stage]);  // K_j and V_j are free once everything issued so far retires
+        if (leader) tc_commit(&kv_empty[stage]);  // K_j and V_j are free once everything issued so far retires
         stage = nstage;
         phase = nphase;
       }
@@ -317,7 +318,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* pv_done = p_full + 2 * PB;       // [2][PB]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2 * PB);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
   const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.N + BN - 1) / BN;
 
@@ -346,7 +347,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -373,7 +374,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
       const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, C::kOnesCol ? D + 16 : D, 0, 1);
       // S_g(j) goes to buffer j & 1 of group g: the scores of block j + 1 are issued BEFORE waiting for the
@@ -388,9 +390,9 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
-          tc_mma_ss(tmem_base + g * 128 + buf * BN, da, db, idesc_s, kk != 0);
+          if (leader) tc_mma_ss(tmem_base + g * 128 + buf * BN, da, db, idesc_s, kk != 0);
         }
-        tc_commit(&s_full[g * 2 + buf]);
+        if (leader) tc_commit(&s_full[g * 2 + buf]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -424,11 +426,11 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // second 64-wide N atom: the next d panel (d = 128) or the all-ones panel (d = 64)
             const uint32_t lbo = C::kOnesCol ? smem_u32(sOnes) - aV : BN * 128;
             const uint64_t db = umma_desc_sw128(aV + kk * 2048, lbo, 1024);
-            tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
+            if (leader) tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
           }
-          tc_commit(&pv_done[g * PB + pb]);
+          if (leader) tc_commit(&pv_done[g * PB + pb]);
         }
-        tc_commit(&kv_empty[stage]);
+        if (leader) tc_commit(&kv_empty[stage]);
         stage = nstage;
         phase = nphase;
       }
@@ -603,7 +605,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* pv_done = p_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
   const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.N + BN - 1) / BN;
 
@@ -628,7 +630,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -652,13 +654,14 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
       // ---- MMA issuer ----
       const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, C::kOnesCol ? D + 16 : D, 0, 1);
       auto tile_addr = [&](int t) { return smem_u32(sKV + (t % NS) * C::kTileBytes); };
       auto wait_tile = [&](int t) { mbar_wait(&kv_full[t % NS], (t / NS) & 1); tc_fence_after(); };
-      auto free_tile = [&](int t) { tc_commit(&kv_empty[t % NS]); };
+      auto free_tile = [&](int t) { if (leader) tc_commit(&kv_empty[t % NS]); };
       auto issue_s = [&](int g, int t) {
         const uint32_t aQ = smem_u32(sQ + g * (D / 64) * (128 * 128));
         const uint32_t aK = tile_addr(t);
@@ -666,9 +669,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
-          tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
+          if (leader) tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
         }
-        tc_commit(&s_full[g]);
+        if (leader) tc_commit(&s_full[g]);
       };
       auto issue_pv = [&](int g, int t, int j) {
         const uint32_t aP = smem_u32(sP + g * C::kPBytes);
@@ -679,9 +682,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int kk = 0; kk < BN / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(aP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t db = umma_desc_sw128(aV + kk * 2048, lbo, 1024);
-          tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
+          if (leader) tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
         }
-        tc_commit(&pv_done[g]);
+        if (leader) tc_commit(&pv_done[g]);
       };
       mbar_wait(q_full, 0);
       wait_tile(0);
@@ -931,7 +934,7 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
   float* s_alpha = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][128]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
   const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.N + BN - 1) / BN;
 
@@ -952,7 +955,7 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -980,7 +983,8 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
       // ---- MMA issuer ----
       const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, 256, 1, 0);  // A = V^T (MN-major), B = P (K-major), N = 256 rows
@@ -1000,16 +1004,16 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
-          tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
+          if (leader) tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
         }
-        tc_commit(&s_full[g]);
+        if (leader) tc_commit(&s_full[g]);
       };
       mbar_wait(q_full, 0);
       {
         const int s0 = next_tile();  // K(0)
         issue_s(0, s0);
         issue_s(1, s0);
-        tc_commit(&kv_empty[s0]);
+        if (leader) tc_commit(&kv_empty[s0]);
       }
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) {
@@ -1019,7 +1023,7 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tc_fence_after();
             issue_s(g, s0);
           }
-          tc_commit(&kv_empty[s0]);
+          if (leader) tc_commit(&kv_empty[s0]);
         }
         const int sv = next_tile();    // V(j)
         mbar_wait(&p_full[0], j & 1);
@@ -1032,10 +1036,10 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           // A = V^T: 64-wide d atoms are BN*128 bytes apart (LBO), 8-key groups 1024 B apart (SBO)
           const uint64_t da = umma_desc_sw128(aV + kk * 2048, BN * 128, 1024);
           const uint64_t db = umma_desc_sw128(aP + (kk >> 2) * (256 * 128) + (kk & 3) * 32, 16, 1024);
-          tc_mma_ss(tmem_base + 256, da, db, idesc_o, (j | kk) != 0);
+          if (leader) tc_mma_ss(tmem_base + 256, da, db, idesc_o, (j | kk) != 0);
         }
-        tc_commit(pv_done);
-        tc_commit(&kv_empty[sv]);
+        if (leader) tc_commit(pv_done);
+        if (leader) tc_commit(&kv_empty[sv]);
       }
     }
   } else {

@@ -67,6 +67,11 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// register re-split between warpgroups (all four warps of a warpgroup execute it; .inc blocks until another warpgroup's
+// .dec has returned the registers)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes' worth of fp32 arithmetic. ptxas keeps the pairs in
 // aligned register pairs (tcgen05.ld results are consecutive registers), so the mov.b64 packs cost nothing.
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {  // d = a * b + c

@@ -79,7 +79,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [4 warps][64]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -95,7 +95,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int total_tiles = p.tiles_x * p.tiles_y * p.B * p.n_tiles;
   const int taps = p.R * p.S;
@@ -125,8 +125,12 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32), desc_lo = static_cast<uint32_t>(desc0);
+      const bool no_mma = (p.debug & 4) != 0;
       int as = 0, bs = 0, set = 0;
       uint32_t aph = 0, bph = 0, sph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -142,25 +146,26 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int s = 0; s < p.S; ++s, ++tap) {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
-              const uint32_t b_addr = smem_u32(sB + bs * C::kBBytes);
+              const uint32_t b_lo = desc_lo | (smem_u32(sB + bs * C::kBBytes) >> 4);
+              const uint32_t a_lo = desc_lo | ((a_base + static_cast<uint32_t>((r * p.pw + s) * 128)) >> 4);
+              const uint32_t a_row = static_cast<uint32_t>(p.pw * 8);  // one halo row down, in 16-byte units
+              if (leader && !no_mma) {
 #pragma unroll
-              for (int t = 0; t < TM; ++t) {
-                const uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
+                for (int t = 0; t < TM; ++t) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (p.debug & 4) continue;
-                  tc_mma_ss(acc0 + t * BN, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                            umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (c | tap | k) != 0);
+                  for (int k = 0; k < 4; ++k)
+                    tc_mma_ss(acc0 + t * BN, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + t * a_row + 2 * k),
+                              (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (c | tap | k) != 0);
                 }
               }
-              tc_commit(&b_empty[bs]);
+              if (leader) tc_commit(&b_empty[bs]);
               if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
             }
           }
-          tc_commit(&a_empty[as]);
+          if (leader) tc_commit(&a_empty[as]);
           if (++as == C::kAStages) { as = 0; aph ^= 1; }
         }
-        tc_commit(&acc_full[set]);
+        if (leader) tc_commit(&acc_full[set]);
         if (C::kAccSets == 2) { if (++set == 2) { set = 0; sph ^= 1; } }
         else { sph ^= 1; }
       }
@@ -283,7 +288,7 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2 * C::kAStages);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
   const uint32_t rank = cluster_ctarank();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -305,7 +310,7 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int halo_tiles = p.tiles_x * p.tiles_y * p.B;
   const int total_pairs = (halo_tiles + 1) >> 1;   // n_tiles == 1 (Cout <= 128)
@@ -344,8 +349,12 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {  // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
       const uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32), desc_lo = static_cast<uint32_t>(desc0);
+      const bool no_mma = (p.debug & 4) != 0;
       int as = 0, bs = 0, set = 0;
       uint32_t aph = 0, bph = 0, sph = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
@@ -365,25 +374,26 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int s = 0; s < p.S; ++s, ++tap) {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
-              const uint32_t b_addr = smem_u32(sB + bs * C::kBBytes);
+              const uint32_t b_lo = desc_lo | (smem_u32(sB + bs * C::kBBytes) >> 4);
+              const uint32_t a_lo = desc_lo | ((a_base + static_cast<uint32_t>((r * p.pw + s) * 128)) >> 4);
+              const uint32_t a_row = static_cast<uint32_t>(p.pw * 8);  // one halo row down, in 16-byte units
+              if (leader && !no_mma) {
 #pragma unroll
-              for (int t = 0; t < TM; ++t) {
-                const uint32_t a_addr = a_base + static_cast<uint32_t>(((t + r) * p.pw + s) * 128);
+                for (int t = 0; t < TM; ++t) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (p.debug & 4) continue;
-                  tc_mma2_ss(acc0 + t * BN, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                             umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (c | tap | k) != 0);
+                  for (int k = 0; k < 4; ++k)
+                    tc_mma2_ss(acc0 + t * BN, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + t * a_row + 2 * k),
+                               (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (c | tap | k) != 0);
                 }
               }
-              tc_commit2_mc(&b_empty[bs]);
+              if (leader) tc_commit2_mc(&b_empty[bs]);
               if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
             }
           }
-          tc_commit2_mc(&a_empty[as]);
+          if (leader) tc_commit2_mc(&a_empty[as]);
           if (++as == C::kAStages) { as = 0; aph ^= 1; }
         }
-        tc_commit2_mc(&acc_full[set]);
+        if (leader) tc_commit2_mc(&acc_full[set]);
         if (++set == 2) { set = 0; sph ^= 1; }
       }
     }
@@ -607,7 +617,7 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
   const uint32_t rank = cluster_ctarank();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -629,7 +639,7 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int halo_tiles = p.tiles_x * p.tiles_y * p.B;
   const int total_pairs = (halo_tiles + 1) >> 1;   // n_tiles == 1 (Cout <= 128)
@@ -696,9 +706,14 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       // ================= MMA issuer =================
+      // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
       const uint32_t idesc256 = umma_idesc_bf16(256, 256, 0, 0), idesc128 = umma_idesc_bf16(256, 128, 0, 0);
+      const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32), desc_lo = static_cast<uint32_t>(desc0);
+      const bool no_mma = (p.debug & 4) != 0;  // timing-only ablation (OMGSR_HALO_DEBUG): no MMAs, results invalid
       int set = 0;
       uint32_t ph = 0, sph = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
@@ -720,20 +735,20 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t b_row = smem_u32(sB + rs_boff(rho, p.R, p.S));
             const uint32_t unit = both ? 16384u : 8192u;
             for (int sx = 0; sx < p.S; ++sx) {
-              const uint32_t b_addr = b_row + sx * unit;
-              const uint32_t a_addr = a_row + static_cast<uint32_t>(sx * 128);
+              const uint32_t b_lo = desc_lo | ((b_row + sx * unit) >> 4);
+              const uint32_t a_lo = desc_lo | ((a_row + static_cast<uint32_t>(sx * 128)) >> 4);
+              if (leader && !no_mma) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (p.debug & 4) continue;  // timing-only ablation (OMGSR_HALO_DEBUG): no MMAs, results invalid
-                tc_mma2_ss(d, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024),
-                           idesc, first ? 0u : 1u);
-                first = 0;
+                for (int k = 0; k < 4; ++k)
+                  tc_mma2_ss(d, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k),
+                             (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (first && k == 0) ? 0u : 1u);
               }
+              first = 0;
             }
-            tc_commit2_mc(&empty[rho]);  // the row and its weight units are free once everything issued so far retires
+            if (leader) tc_commit2_mc(&empty[rho]);  // the row and its weight units are free once everything issued so far retires
           }
         }
-        tc_commit2_mc(&acc_full[set]);
+        if (leader) tc_commit2_mc(&acc_full[set]);
         if (++set == 2) { set = 0; sph ^= 1; }
       }
     }
@@ -893,8 +908,9 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //     tcgen05.commit per unit frees both.
 //   * work split: the B * ceil(tiles_x / 2) * H pair-rows are cut into one contiguous range per cluster (a range crosses
 //     at most a few strip boundaries; each segment costs two extra input rows), so all clusters finish together.
-//   * epilogue: warps 2..5 drain columns 0..63 of every output row, warps 6..9 columns 64..127 (a slot must be free
-//     again one row-step, ~7.5 k cycles, after it completes).
+//   * epilogue: warps 4..7 take columns 0..63 of every output row, warps 8..11 columns 64..127. A slot must be free
+//     again ONE row-step (~6.5 k cycles) after it completes, so a warp copies its 64 columns to registers, zeroes
+//     them and returns the slot before it does any arithmetic or stores.
 // ------------------------------------------------------------------------------------------------
 struct HaloRrCfg {
   static constexpr int kRowBytes = 17 * 1024;
@@ -937,8 +953,11 @@ __device__ __forceinline__ RrPlan rr_plan(int i, int L, uint32_t n0) {
   return pl;
 }
 
-template <bool XF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XF ? 480 : 352, 1)
+// MODE: the epilogue option set (EPI_*), a template parameter so that ONE epilogue body is compiled in: with the
+// run-time switch the kernel had 11 k instructions (7.9 k of them epilogue) and 'no instruction' was the top stall reason
+// of every role, the MMA issuer included (ncu, profiles/r02/ncu_halo_rr_gn_res_v1.txt).
+template <bool XF, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XF ? 512 : 384, 1)
 conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB128,
                     const __grid_constant__ CUtensorMap tmB64, const HaloParams p) {
   using C = HaloRrCfg;
@@ -957,7 +976,9 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps the MMA
+  // issuer's address arithmetic in uniform registers (see the MMA issuer below)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -980,10 +1001,15 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2 && warp < 10) {  // all four accumulators start at zero (every MMA accumulates)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // warps: 0 row producer, 1 MMA issuer, 2 weight producer, 3 idle | 4..11 epilogue | XF: 12..15 input transform.
+  // One role class per warpgroup so that the register file can be re-split (XF: 512 threads start at 128 registers;
+  // the epilogue holds 64 accumulator columns + residual + statistics partials and spilled at that cap).
+  // (the setmaxnreg of each class is the first instruction of its branch below: ptxas sizes a region by the
+  // setmaxnreg that dominates it)
+  if (warp >= 4 && warp < 12) {  // all four accumulators start at zero (every MMA accumulates)
     const uint32_t z[32] = {};
-    const uint32_t t0 = tmem_base + ((warp - 2) >> 2) * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t t0 = tmem_base + ((warp - 4) >> 2) * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 #pragma unroll
     for (int c0 = 0; c0 < 256; c0 += 32) tmem_st32(t0 + c0, z);
     tmem_wait_st();
@@ -998,7 +1024,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int g_begin = static_cast<int>(G * cluster_id / num_clusters), g_end = static_cast<int>(G * (cluster_id + 1) / num_clusters);
   const int row_bytes = p.pw * 128;
-  constexpr int kBWarp = 10;
+  constexpr int kBWarp = 2;
   // segment decode shared by all roles
   auto segment = [&](int g, int& b, int& tx, bool& dummy, int& ya, int& L) {
     const int q = g / p.H;
@@ -1009,6 +1035,8 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     dummy = tx >= p.tiles_x;
   };
 
+  if (warp < 4) {
+  if (XF) setmaxnreg_dec<56>();
   if (warp == 0) {
     if (lane == 0) {
       // ================= input-row producer =================
@@ -1065,9 +1093,21 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       // ================= MMA issuer =================
+      // The WHOLE warp runs the loop on warp-uniform values and one elected lane issues. Issuing from a divergent
+      // single-lane branch (all kernels of round 1 did) makes every MMA operand thread-private to the compiler: each
+      // tcgen05.mma then sits in an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY sequence, ~20 dependent instructions =
+      // 130-170 cycles per MMA - the "instruction cost floor" of profiles/r02/mma_probe*.txt was this loop, not the
+      // tensor pipe (profiles/r02/mma_probe6_lean.txt: 64 cycles per N = 128 instruction, 128 per N = 256 = 99.5 %).
+      const bool leader = elect_one();
       const uint32_t idesc256 = umma_idesc_bf16(256, 256, 0, 0), idesc128 = umma_idesc_bf16(256, 128, 0, 0);
+      // shared-memory descriptors (128B swizzle, LBO 16, SBO 1024): only the start-address field [0, 14) of the low
+      // word changes, so the issue loop adds to a 32-bit word instead of rebuilding two 64-bit descriptors per MMA
+      const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32), desc_lo = static_cast<uint32_t>(desc0);
+      auto dsc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
+      const bool no_mma = (p.debug & 4) != 0;  // timing-only ablation (OMGSR_HALO_DEBUG): no MMAs, results invalid
       uint32_t u = 0, n0 = 0;
       for (int g = g_begin; g < g_end;) {
         int b, tx, ya, L; bool dummy;
@@ -1078,44 +1118,75 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&acc_empty[n & 3], ((n >> 2) & 1) ^ 1);
           }
           const RrPlan pl = rr_plan(i, L, n0);
+          const uint32_t d0 = tmem_base + pl.slot[0] * BN, id0 = pl.pair[0] ? idesc256 : idesc128;
+          const uint32_t bs0 = pl.pair[0] ? 1024u : 512u;  // weight unit of the next tap column, >> 4
+          const bool two = pl.n_ops > 1;
+          const uint32_t d1 = tmem_base + pl.slot[1] * BN, id1 = pl.pair[1] ? idesc256 : idesc128;
+          const uint32_t bs1 = pl.pair[1] ? 1024u : 512u;
           for (int c = 0; c < p.chunks; ++c, ++u) {
             const int slot = u & 3;
-            if (XF) mbar_wait(&a_ready[slot], (u >> 2) & 1);
-            else mbar_wait(&a_full[slot], (u >> 2) & 1);
-            mbar_wait(&b_full[u & 1], (u >> 1) & 1);
+            if (p.debug & 8) {  // A/B: back-off waits in the issuer
+              mbar_wait_relaxed(XF ? &a_ready[slot] : &a_full[slot], (u >> 2) & 1, 32);
+              mbar_wait_relaxed(&b_full[u & 1], (u >> 1) & 1, 32);
+            } else {
+              if (XF) mbar_wait(&a_ready[slot], (u >> 2) & 1);
+              else mbar_wait(&a_full[slot], (u >> 2) & 1);
+              mbar_wait(&b_full[u & 1], (u >> 1) & 1);
+            }
             tc_fence_after();
-            const uint32_t a_row = smem_u32(sA + slot * C::kRowBytes);
             const uint32_t b_base = smem_u32(sB + (u & 1) * C::kBSlotBytes);
-            for (int sx = 0; sx < 3; ++sx) {
-              const uint32_t a_addr = a_row + static_cast<uint32_t>(sx * 128);
+            uint32_t a_lo = desc_lo | (smem_u32(sA + slot * C::kRowBytes) >> 4);
+            uint32_t b0_lo = desc_lo | ((b_base + pl.boff[0]) >> 4), b1_lo = desc_lo | ((b_base + pl.boff[1]) >> 4);
+            if (!no_mma) {
+#pragma unroll 1
+              for (int sx = 0; sx < 3; ++sx) {  // tap column: the A view shifts by one pixel (128 B)
+                if (leader) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (p.debug & 4) continue;  // timing-only ablation (OMGSR_HALO_DEBUG): no MMAs, results invalid
-                const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-                for (int o = 0; o < pl.n_ops; ++o) {
-                  const uint32_t b_addr = b_base + pl.boff[o] + sx * (pl.pair[o] ? 16384u : 8192u) + k * 32;
-                  tc_mma2_ss(tmem_base + pl.slot[o] * BN, da, umma_desc_sw128(b_addr, 16, 1024),
-                             pl.pair[o] ? idesc256 : idesc128, 1u);
+                  for (int k = 0; k < 4; ++k) {
+                    tc_mma2_ss(d0, dsc(a_lo + 2 * k), dsc(b0_lo + 2 * k), id0, 1u);
+                    if (two) tc_mma2_ss(d1, dsc(a_lo + 2 * k), dsc(b1_lo + 2 * k), id1, 1u);
+                  }
                 }
+                a_lo += 8; b0_lo += bs0; b1_lo += bs1;
               }
             }
-            tc_commit2_mc(&empty[slot]);  // the row and its weight units are free once everything issued so far retires
+            if (leader) tc_commit2_mc(&empty[slot]);  // the row and its weight units are free once everything issued so far retires
           }
-          if (i >= 2) tc_commit2_mc(&acc_full[(n0 + i - 2) & 3]);  // output i - 2 has received its three tap rows
+          if (i >= 2 && leader) tc_commit2_mc(&acc_full[(n0 + i - 2) & 3]);  // output i - 2 has received its three tap rows
         }
         g += L; n0 += L;
       }
     }
-  } else if (XF && warp >= 11) {
-    // ================= input transform (warps 11..14): GroupNorm + SiLU on each halo row, in place =================
-    const int tid = threadIdx.x - 352;  // 0..127
+  }
+  } else if (XF && warp >= 12) {
+    setmaxnreg_dec<112>();
+    // ================= input transform (warps 12..15): GroupNorm + SiLU on each halo row, in place =================
+    const int tid = threadIdx.x - 384;  // 0..127
     const int j = tid & 7;              // 16-byte unit (8 channels) of a 128-byte pixel row: fixed per thread
     const int p0 = tid >> 3;            // first pixel of this thread in a row; then every 16th (<= 9 per row)
     uint32_t u = 0;
+    // (scale / 2, shift / 2) of this thread's 8 channels: both 64-channel chunks of the current image stay in
+    // registers when Cin <= 128 (a load per unit sat on the row's critical path: ncu long-scoreboard samples)
+    float ca0[8], cb0[8], ca1[8], cb1[8];
+    int coef_b = -1;
+    auto load_coef = [&](float (&a)[8], float (&bb)[8], int b, int c) {
+      const float4* cf = reinterpret_cast<const float4*>(p.gn_in + static_cast<long long>(b) * p.Cin + c * 64 + j * 8);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(cf + q);
+        // halved: silu(a x + b) = h + h tanh(h) with h = (a / 2) x + b / 2
+        a[2 * q] = 0.5f * v.x; bb[2 * q] = 0.5f * v.y; a[2 * q + 1] = 0.5f * v.z; bb[2 * q + 1] = 0.5f * v.w;
+      }
+    };
     for (int g = g_begin; g < g_end;) {
       int b, tx, ya, L; bool dummy;
       segment(g, b, tx, dummy, ya, L);
       const int x0 = tx * 128 - p.pad_l;
+      if (!dummy && b != coef_b && p.chunks <= 2) {
+        load_coef(ca0, cb0, b, 0);
+        if (p.chunks == 2) load_coef(ca1, cb1, b, 1);
+        coef_b = b;
+      }
       for (int i = 0; i < L + 2; ++i) {
         const int yy = ya - p.pad_t + i;
         for (int c = 0; c < p.chunks; ++c, ++u) {
@@ -1123,12 +1194,11 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float ca[8], cb[8];
           const bool live = !dummy && yy >= 0 && yy < p.IH;
           if (live) {
-            const float4* cf = reinterpret_cast<const float4*>(p.gn_in + static_cast<long long>(b) * p.Cin + c * 64 + j * 8);
+            if (p.chunks <= 2) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 v = __ldg(cf + q);
-              // halved: silu(a x + b) = h + h tanh(h) with h = (a / 2) x + b / 2
-              ca[2 * q] = 0.5f * v.x; cb[2 * q] = 0.5f * v.y; ca[2 * q + 1] = 0.5f * v.z; cb[2 * q + 1] = 0.5f * v.w;
+              for (int e = 0; e < 8; ++e) { ca[e] = c ? ca1[e] : ca0[e]; cb[e] = c ? cb1[e] : cb0[e]; }
+            } else {
+              load_coef(ca, cb, b, c);
             }
           }
           mbar_wait_relaxed(&a_full[slot], (u >> 2) & 1, 32);
@@ -1174,9 +1244,10 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       g += L;
     }
-  } else if (warp >= 2 && warp < 10) {
-    // ================= epilogue: warps 2..5 drain columns 0..63 of every output row, warps 6..9 columns 64..127 =====
-    const int half = (warp - 2) >> 2;
+  } else {
+    // ================= epilogue: warps 4..7 drain columns 0..63 of every output row, warps 8..11 columns 64..127 ====
+    if (XF) setmaxnreg_inc<168>();
+    const int half = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int ew = half * 4 + quarter;    // epilogue warp index inside the CTA: statistics slot / bias slice
     const int row = quarter * 32 + lane;
@@ -1184,7 +1255,6 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* my_gn = gn_acc + ew * 64;
     float* my_bias = gn_acc + 8 * 64 + ew * BN;
     if (p.bias) stage_bias<BN>(my_bias, p.bias, 0, p.Cout, lane);
-    const int epi_mode = epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr);
     const int gn_n = p.gn_groups * 2;
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
@@ -1207,21 +1277,23 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float gn_part[16];
         e.gn_part = p.gn_sums ? gn_part : nullptr;
         const bool valid = !dummy && (x < p.W) && !(p.debug & 1);
-        uint4 rr[4] = {};
+        uint4 rr0[4] = {}, rr1[4] = {};
         e.res_row = (p.res && !dummy) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
-        if (e.res_row) {  // this thread's residual row: pulled into L2 now, first chunk loaded before the accumulator wait
-          prefetch_res_row(e, c_off, 64, valid);
-          load_res32(rr, e, c_off, valid);
+        if (e.res_row) {  // this thread's 64 residual channels are in flight before the accumulator wait
+          load_res32(rr0, e, c_off, valid);
+          load_res32(rr1, e, c_off + 32, valid);
         }
         e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
         const int slot = n & 3;
         mbar_wait_relaxed(&acc_full[slot], (n >> 2) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + slot * BN + c_off + (static_cast<uint32_t>(quarter * 32) << 16);
-        if (!(p.debug & 2)) {  // (timing-only ablation: no epilogue)
-          epilogue_row_m<false>(epi_mode, t_row, 64, 0, c_off, c_off, valid, e, nullptr, 0, false,
-                                p.bias ? my_bias + c_off : nullptr, rr, my_gn, p.gn_cpg, lane);
-        }
+        // the slot is needed again ONE row-step after it completes: copy the 64 columns out, zero them and hand the
+        // slot back before any arithmetic (the bias / residual / store / statistics work then overlaps the next MMAs)
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_row, v0);
+        tmem_ld32(t_row + 32, v1);
+        tmem_wait_ld();
         tmem_st32(t_row, zeros);
         tmem_st32(t_row + 32, zeros);
         tmem_wait_st();
@@ -1230,6 +1302,10 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
           if (rank == 0) mbar_arrive(&acc_empty[slot]);
           else mbar_arrive_remote(&acc_empty[slot], 0);
+        }
+        if (!(p.debug & 2)) {  // (timing-only ablation: no epilogue)
+          epilogue_regs64<MODE>(v0, v1, c_off, c_off, valid, e, p.bias ? my_bias + c_off : nullptr, rr0, rr1, my_gn,
+                                p.gn_cpg, lane);
         }
       }
       g += L;
@@ -1245,20 +1321,34 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// conv_halo_rr_kernel where it applies (3x3, a long enough share of output rows per cluster): -1 automatic (the fused
-// input GroupNorm variants), 0 never, 1 every eligible convolution. OMGSR_HALO_ROLLING / omgsr_set_halo_rolling.
-int g_halo_rolling = getenv("OMGSR_HALO_ROLLING") ? atoi(getenv("OMGSR_HALO_ROLLING")) : 0;  // off until measured
+// conv_halo_rr_kernel where it applies (3x3, a long enough share of output rows per cluster): 1 every eligible
+// convolution (default: measured faster in all six epilogue / transform variants, profiles/r02/halo_rolling_ab.txt),
+// 0 never, -1 only the fused input GroupNorm variants. OMGSR_HALO_ROLLING / omgsr_set_halo_rolling.
+static const int g_halo_rolling_default = getenv("OMGSR_HALO_ROLLING") ? atoi(getenv("OMGSR_HALO_ROLLING")) : 1;
+int g_halo_rolling = g_halo_rolling_default;
+int halo_rolling_default() { return g_halo_rolling_default; }
 
+template <bool XF, int MODE>
+static int launch_halo_rr_m(const CUtensorMap& tmA, const CUtensorMap& tmB128, const CUtensorMap& tmB64,
+                            const HaloParams& p, int clusters, cudaStream_t st) {
+  using C = HaloRrCfg;
+  static unsigned long long attr_done = 0;  // one bit per device
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_rr_kernel<XF, MODE>), C::kSmemBytes, &attr_done,
+                                "conv_halo_rr")) return rc;
+  g_trace_variant = XF ? "conv_halo_rr_kernel<1>" : "conv_halo_rr_kernel<0>";
+  conv_halo_rr_kernel<XF, MODE><<<2 * clusters, XF ? 512 : 384, C::kSmemBytes, st>>>(tmA, tmB128, tmB64, p);
+  return check_launch("conv_halo_rr_kernel");
+}
 template <bool XF>
 static int launch_halo_rr(const CUtensorMap& tmA, const CUtensorMap& tmB128, const CUtensorMap& tmB64,
                           const HaloParams& p, int clusters, cudaStream_t st) {
-  using C = HaloRrCfg;
-  static unsigned long long attr_done = 0;  // one bit per device
-  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_rr_kernel<XF>), C::kSmemBytes, &attr_done,
-                                "conv_halo_rr")) return rc;
-  g_trace_variant = XF ? "conv_halo_rr_kernel<1>" : "conv_halo_rr_kernel<0>";
-  conv_halo_rr_kernel<XF><<<2 * clusters, XF ? 480 : 352, C::kSmemBytes, st>>>(tmA, tmB128, tmB64, p);
-  return check_launch("conv_halo_rr_kernel");
+  switch (epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr)) {
+    case EPI_PLAIN: return launch_halo_rr_m<XF, EPI_PLAIN>(tmA, tmB128, tmB64, p, clusters, st);
+    case EPI_RES: return launch_halo_rr_m<XF, EPI_RES>(tmA, tmB128, tmB64, p, clusters, st);
+    case EPI_GN: return launch_halo_rr_m<XF, EPI_GN>(tmA, tmB128, tmB64, p, clusters, st);
+    case EPI_RES_GN: return launch_halo_rr_m<XF, EPI_RES_GN>(tmA, tmB128, tmB64, p, clusters, st);
+    default: return launch_halo_rr_m<XF, EPI_GENERIC>(tmA, tmB128, tmB64, p, clusters, st);
+  }
 }
 
 // 0: conv_halo_tc2_kernel (every instruction N = 128), 1: conv_halo_rs_kernel (row-shared N = 256 instructions)
@@ -1400,4 +1490,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
 
 }  // namespace omgsr
 
-extern "C" int omgsr_set_halo_rolling(int mode) { omgsr::g_halo_rolling = mode; return OMGSR_OK; }
+extern "C" int omgsr_set_halo_rolling(int mode) {
+  omgsr::g_halo_rolling = mode < -1 ? omgsr::halo_rolling_default() : mode;  // < -1: back to the start-up default
+  return OMGSR_OK;
+}

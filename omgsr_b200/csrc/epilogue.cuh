@@ -251,7 +251,7 @@ __device__ __forceinline__ void epilogue_store32_t(float (&f)[32], int cv, int o
 // option set -> specialisation id (0 = generic). Computed once per thread, warp-uniform.
 enum : int { EPI_GENERIC = 0, EPI_PLAIN, EPI_RES, EPI_GN, EPI_RES_GN, EPI_GELU_TANH, EPI_GATE_RES, EPI_SILU,
               EPI_F32S, EPI_F32S_GATE };
-__device__ __forceinline__ int epilogue_mode(int act, bool gate, bool res, bool out_f32, bool gn, bool res_f32 = false) {
+__host__ __device__ __forceinline__ int epilogue_mode(int act, bool gate, bool res, bool out_f32, bool gn, bool res_f32 = false) {
   if (res_f32) return gate ? EPI_F32S_GATE : EPI_F32S;  // host side guarantees: out_f32, res, no activation, no gn
   if (out_f32) return EPI_GENERIC;
   if (act == OMGSR_ACT_NONE || act == OMGSR_ACT_GEGLU) {  // GEGLU: the kernels fold the gate half before the store
@@ -546,6 +546,32 @@ __device__ __forceinline__ void epilogue_head_rope(uint32_t t_head, const float*
       st_global_256(orow + c0 + 16, o[2], o[3]);
     }
   }
+}
+
+// 64 accumulator columns that are ALREADY in registers (the rolling-row convolution copies a row out of TMEM, frees the
+// TMEM slot at once and only then does the arithmetic and the stores): the chunk body of epilogue_row, twice. Both
+// 32-column halves of the residual row were loaded by the caller before it waited for the accumulator.
+template <int MODE>
+__device__ __forceinline__ void epilogue_regs64(const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cv0, int oc0,
+                                                bool valid, EpiArgs& e, const float* bias_s, const uint4 (&rr0)[4],
+                                                const uint4 (&rr1)[4], float* gn_slice, int gn_cpg, int lane) {
+  using T = EpiTraits<MODE>;
+  const bool has_gn = T::kGeneric ? (gn_slice != nullptr && e.gn_part != nullptr) : T::kGn;
+  float gn_part[16];
+  float* const gn_keep = e.gn_part;
+  e.gn_part = has_gn ? gn_part : nullptr;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c0 = 32 * h;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(h == 0 ? v0[j] : v1[j]);
+    if (bias_s) add_bias32_s(f, bias_s + c0);
+    if (T::kGeneric) epilogue_store32(f, cv0 + c0, oc0 + c0, valid, e, h == 0 ? rr0 : rr1);
+    else epilogue_store32_t<T::kAct, T::kGate, T::kRes, T::kGn>(f, cv0 + c0, oc0 + c0, valid, e, h == 0 ? rr0 : rr1);
+    if (has_gn) gn_chunk_accumulate(gn_part, gn_cpg, gn_slice + ((cv0 + c0) / gn_cpg) * 2, lane);
+  }
+  e.gn_part = gn_keep;
 }
 
 // run-time option set -> specialised row routine (once per accumulator row, outside the chunk loop)

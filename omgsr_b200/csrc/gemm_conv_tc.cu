@@ -127,7 +127,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [4 warps][64]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform to the compiler (see the MMA issuer)
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -150,7 +150,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
   const int num_kb = p.R * p.S * p.kc_per_tap;
@@ -209,8 +209,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // whole warp on warp-uniform values, one elected lane issues (conv_gemm_tc2_kernel has the argument)
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, p.b_mn_major);
+      const uint64_t da0 = umma_desc_sw128(0, 16, 1024);
+      // MN-major SW128 B: atoms of {64 n x 8 k}; LBO = next 64-wide N atom, SBO = next 8 k-rows
+      const uint64_t db0 = p.b_mn_major ? umma_desc_sw128(0, 64 * kBK * 2, 1024) : da0;
+      const uint32_t a_hi = static_cast<uint32_t>(da0 >> 32), a_lo0 = static_cast<uint32_t>(da0);
+      const uint32_t b_hi = static_cast<uint32_t>(db0 >> 32), b_lo0 = static_cast<uint32_t>(db0);
+      // advance 16 bf16 along K: K-major +32 B inside the swizzle atom (+2 in the addr >> 4 field); MN-major two
+      // 1024-byte row groups (+128)
+      const uint32_t b_step = p.b_mn_major ? 128u : 2u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -223,28 +233,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t sb = sa + C::kABytes;
-          const uint64_t da = umma_desc_sw128(sa, 16, 1024);
-          if (!p.b_mn_major) {
-            const uint64_t db = umma_desc_sw128(sb, 16, 1024);
+          const uint32_t a_lo = a_lo0 | (sa >> 4), b_lo = b_lo0 | ((sa + C::kABytes) >> 4);
+          if (leader) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              tc_mma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            }
-          } else {
-            // MN-major SW128: atoms of {64 n x 8 k}; LBO = next 64-wide N atom, SBO = next 8 k-rows
-            const uint64_t db = umma_desc_sw128(sb, 64 * kBK * 2, 1024);
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              // 16 k-rows = two 1024-byte row groups: +128 in the (addr >> 4) field
-              tc_mma_ss(d_tmem, da + 2 * k, db + 128 * k, idesc, (kb | k) != 0);
-            }
+            for (int k = 0; k < kBK / 16; ++k)
+              tc_mma_ss(d_tmem, (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2 * k),
+                        (static_cast<uint64_t>(b_hi) << 32) | (b_lo + b_step * k), idesc, (kb | k) != 0);
+            tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&acc_full[acc]);
+        if (leader) tc_commit(&acc_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -369,7 +368,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform to the compiler (see the MMA issuer)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
 
@@ -393,7 +392,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int m_pairs = (m_tiles + 1) >> 1;
@@ -439,8 +438,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
+      // The WHOLE warp runs this loop on warp-uniform values and one elected lane issues the MMAs and commits. Round 1
+      // issued from a divergent `lane == 0` branch: every operand was then thread-private to the compiler and each
+      // tcgen05.mma sat behind an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY sequence (~20 dependent instructions, 130-170
+      // cycles per MMA where the tensor pipe needs 128 for N = 256 and 64 for N = 128: profiles/r02/mma_probe6_lean.txt).
+      const bool leader = elect_one();
       const uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);  // only the start-address field of the low word changes
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32), desc_lo = static_cast<uint32_t>(desc0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -453,14 +459,17 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t da = umma_desc_sw128(sa, 16, 1024);
-          const uint64_t db = umma_desc_sw128(sa + C::kABytes, 16, 1024);
+          const uint32_t a_lo = desc_lo | (sa >> 4), b_lo = desc_lo | ((sa + C::kABytes) >> 4);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) tc_mma2_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          tc_commit2_mc(&empty_bar[stage]);
+            for (int k = 0; k < kBK / 16; ++k)
+              tc_mma2_ss(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k),
+                         (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (kb | k) != 0);
+            tc_commit2_mc(&empty_bar[stage]);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit2_mc(&acc_full[acc]);
+        if (leader) tc_commit2_mc(&acc_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -1,5 +1,5 @@
 """A/B timing of the 128-channel halo convolution: row-shared schedule (N = 256 instructions) vs the round-1 kernel.
-Run twice: OMGSR_HALO_ROW_SHARED=0|1 python scripts/halo_ab.py"""
+Run twice: OMGSR_HALO_ROW_SHARED=0|1 python scripts/halo_ab.py; OMGSR_HALO_ROLLING=0|1 selects the rolling-row kernel."""
 import os, sys, math
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -24,6 +24,7 @@ for name, fn in (("plain", lambda: capi.conv2d(x, w, b, out=out)),
                  ("+gn_stats", lambda: capi.conv2d(x, w, b, out=out, gn_stats=st)),
                  ("+res+gn_stats", lambda: capi.conv2d(x, w, b, res=res, out=out, gn_stats=st)),
                  ("gn_in", lambda: capi.conv2d_gn(x, coef, w, b, out=out)),
+                 ("gn_in+gn_stats", lambda: capi.conv2d_gn(x, coef, w, b, out=out, gn_stats=st)),
                  ("gn_in+res+gn_stats", lambda: capi.conv2d_gn(x, coef, w, b, res=res, out=out, gn_stats=st))):
     ms = timeit(fn)
     print(f"3x3 128->128 @512^2 x16 {name:20s} {capi.last_conv_variant():22s} {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s", flush=True)

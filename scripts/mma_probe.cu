@@ -161,6 +161,95 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const __grid_constant__ C
   }
 }
 
+// ---- lean issue loop: the whole warp executes it with warp-uniform values (descriptors advance by a 32-bit add in the
+// uniform datapath), one elected lane issues. probe_kernel issues from a divergent single-lane branch, where every MMA
+// operand goes through an ELECT / R2UR.BROADCAST sequence (~20 SASS instructions per MMA).
+template <bool PAIR>
+__global__ void __launch_bounds__(256, 1) probe_lean_kernel(const ProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  uint32_t rank = 0;
+  if constexpr (PAIR) rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i * 2654435761u >> 20 & 0x00ff00ffu);
+  if (threadIdx.x == 0) { mbar_init(&done_bar, 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  if (warp == 1) {
+    if constexpr (PAIR) { tmem_alloc2(&tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  if (warp == 0 && (!PAIR || rank == 0)) {
+    const bool leader = elect_one();
+    const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
+    const uint32_t hi = static_cast<uint32_t>(desc0 >> 32), lo = static_cast<uint32_t>(desc0);
+    auto dsc = [&](uint32_t l) { return (static_cast<uint64_t>(hi) << 32) | l; };
+    const uint32_t a_lo = lo | (smem_u32(smem) >> 4), b_lo = lo | (smem_u32(smem + 80 * 1024) >> 4);
+    const uint32_t id0 = umma_idesc_bf16(PAIR ? 256 : 128, p.pattern[0], 0, 0);
+    const uint32_t id1 = umma_idesc_bf16(PAIR ? 256 : 128, p.pattern[1] ? p.pattern[1] : p.pattern[0], 0, 0);
+    const long long t0 = clock64();
+    for (int it = 0; it < p.iters; ++it) {
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if constexpr (PAIR) tc_mma2_ss(tmem_base, dsc(a_lo + 2 * k), dsc(b_lo + 2 * k), id0, 1);
+          else tc_mma_ss(tmem_base, dsc(a_lo + 2 * k), dsc(b_lo + 2 * k), id0, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if constexpr (PAIR) tc_mma2_ss(tmem_base + 256, dsc(a_lo + 8 + 2 * k), dsc(b_lo + 256 + 2 * k), id1, 1);
+          else tc_mma_ss(tmem_base + 256, dsc(a_lo + 8 + 2 * k), dsc(b_lo + 256 + 2 * k), id1, 1);
+        }
+      }
+      if ((it & 63) == 63) {
+        if (leader) { if constexpr (PAIR) tc_commit2_mc(&done_bar); else tc_commit(&done_bar); }
+        mbar_wait(&done_bar, (it >> 6) & 1);
+      }
+    }
+    const long long t1 = clock64();
+    if (leader) p.cycles[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  tc_fence_before();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static void run_lean(const char* name, int pair, int n0, int n1, long long* d_cycles) {
+  ProbeParams p{};
+  p.iters = 4096; p.cycles = d_cycles; p.pattern[0] = n0; p.pattern[1] = n1;
+  cudaMemset(d_cycles, 0, 148 * sizeof(long long));
+  cudaFuncSetAttribute(probe_lean_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaFuncSetAttribute(probe_lean_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(148); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = kSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = pair ? 1 : 0;
+  cudaError_t err = cudaSuccess;
+  if (pair) err = cudaLaunchKernelEx(&cfg, probe_lean_kernel<true>, p);
+  else { probe_lean_kernel<false><<<148, 256, kSmem>>>(p); err = cudaGetLastError(); }
+  cudaError_t err2 = cudaDeviceSynchronize();
+  if (err != cudaSuccess || err2 != cudaSuccess) { printf("%-46s FAILED: %s / %s\n", name, cudaGetErrorString(err), cudaGetErrorString(err2)); return; }
+  std::vector<long long> h(148);
+  cudaMemcpy(h.data(), d_cycles, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double sum = 0; int cnt = 0;
+  for (long long c : h) if (c > 0) { sum += c; ++cnt; }
+  const double per_instr = sum / cnt / p.iters / 8.0;
+  const double nominal = (n0 + (n1 ? n1 : n0)) / 2.0 / 2.0;  // N / 2 cycles per K = 16 instruction at full rate
+  printf("LEAN %-40s : %6.1f cycles / instruction (nominal %5.1f) -> tensor pipe %5.1f %%\n", name, per_instr, nominal, 100.0 * nominal / per_instr);
+}
+
 static double run(const char* name, int pair, std::initializer_list<int> pat, int a_views, int xf, int tma,
                   const CUtensorMap& tm, long long* d_cycles, int d_mode = 0, int commit_each = 0, int a_tmem = 0,
                   int a_mn = 0, int b_mn = 0) {
@@ -217,6 +306,21 @@ int main() {
   uint64_t str[1] = {128};
   uint32_t box[2] = {64, 128};
   if (make_tmap_bf16(&tm, gbuf, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("tensor map failed\n"); return 1; }
+  if (getenv("PROBE_LEAN")) {
+    for (int rep = 0; rep < 2; ++rep) {
+      for (int n : {256, 192, 160, 128, 96, 80, 64, 32, 16}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "single N=%d", n); run_lean(nm, 0, n, 0, d_cycles);
+        snprintf(nm, sizeof nm, "pair   N=%d", n); run_lean(nm, 1, n, 0, d_cycles);
+      }
+      run_lean("pair   N=256 / N=128 alternating blocks", 1, 256, 128, d_cycles);
+      run_lean("single N=256 / N=128 alternating blocks", 0, 256, 128, d_cycles);
+      run("(old issue loop) pair   N=128", 1, {128}, 1, 0, 0, tm, d_cycles);
+      run("(old issue loop) single N=128", 0, {128}, 1, 0, 0, tm, d_cycles);
+      run("(old issue loop) single N=64", 0, {64}, 1, 0, 0, tm, d_cycles);
+    }
+    return 0;
+  }
   for (int rep = 0; rep < 2; ++rep) {  // first round warms the clocks
     run("single N=256", 0, {256}, 1, 0, 0, tm, d_cycles);
     run("single N=128", 0, {128}, 1, 0, 0, tm, d_cycles);

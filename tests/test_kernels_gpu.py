@@ -714,12 +714,12 @@ def test_conv_halo_rolling_rows(capi, B, H, W, Cin, Cout, variant):
             torch.cuda.synchronize()
             return y, so, capi.last_conv_variant()
         finally:
-            capi.lib().omgsr_set_halo_rolling(-1)
+            capi.lib().omgsr_set_halo_rolling(-2)
 
     y_rr, s_rr, name_rr = run(1)
     y_rs, s_rs, name_rs = run(0)
     assert "conv_halo_rr_kernel" in name_rr and "conv_halo_rr_kernel" not in name_rs, (name_rr, name_rs)
-    assert report(f"rolling vs row-shared [{variant}]", y_rr, y_rs.float().cpu(), 4e-3)[0]
+    assert report(f"rolling vs row-shared [{variant}]", y_rr, y_rs.float().cpu(), 8e-3)[0]   # two bf16 steps at the largest value
     if with_stats:
         assert report("output statistics, rolling vs row-shared", s_rr, s_rs.cpu(), 1e-3)[0]
         f32 = y_rr.float()
