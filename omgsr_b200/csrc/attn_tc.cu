@@ -1298,9 +1298,12 @@ using namespace omgsr;
 
 #include <cstdlib>
 static int g_attn_variant = getenv("OMGSR_ATTN_VARIANT") ? atoi(getenv("OMGSR_ATTN_VARIANT")) : 0;
-/* bring-up / A-B timing switch: 0 = automatic, 1 = always the single-tile kernel, 2 = the 64-key ping-pong kernel (v2)
- * wherever a 128-key kernel would be chosen, 3 = v3 (128 keys, O in natural layout) also at d = 128 where v4
- * (transposed O, N = 256 PV instructions) is the default */
+/* bring-up / A-B timing switch: 0 = automatic (v3: 128 keys, O in natural layout), 1 = always the single-tile kernel,
+ * 2 = the 64-key ping-pong kernel (v2) wherever a 128-key kernel would be chosen, 3 = v3 explicitly, 4 = v4 (transposed
+ * O, N = 256 PV instructions) at d = 128. v4 was the default while every kernel issued MMAs from a single-lane branch
+ * (N = 128 instructions then cost 154 cycles, N = 256 172); with the warp-uniform issue loop an N = 128 instruction
+ * costs its 64 tensor-pipe cycles and v3 is the faster one (0.895 vs 0.977 ms on the FLUX shape,
+ * profiles/r02/attn_lean_issue.txt). */
 extern "C" int omgsr_flash_attn_set_variant(int variant) { g_attn_variant = variant; return OMGSR_OK; }
 
 extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int M,
@@ -1325,7 +1328,7 @@ extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v
   // long key sequences: 128 keys per block (v3: every S instruction is N = 128, half the instruction count of v2)
   if (v2 && N >= 128 && g_attn_variant != 2) {
     if (D == 64) return launch_attn3<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
-    if (D == 128 && g_attn_variant != 3 && o_head == 128)  // (v4's coalesced row store assumes head-contiguous output)
+    if (D == 128 && g_attn_variant == 4 && o_head == 128)  // (v4's coalesced row store assumes head-contiguous output)
       return launch_attn4(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
     if (D == 128) return launch_attn3<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
   }

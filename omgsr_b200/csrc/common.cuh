@@ -72,6 +72,21 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// 16-byte shared-memory accesses through a 32-bit shared-window address: LDS.128 / STS.128 with an immediate offset (a
+// generic pointer into dynamic shared memory costs an S2R + LEA per access in a role branch that the compiler cannot
+// prove uniform)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes' worth of fp32 arithmetic. ptxas keeps the pairs in
 // aligned register pairs (tcgen05.ld results are consecutive registers), so the mov.b64 packs cost nothing.
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {  // d = a * b + c

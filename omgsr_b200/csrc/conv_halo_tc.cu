@@ -903,9 +903,11 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //     (enable-input-d = 1) and an N = 256 instruction may cover ANY two adjacent slots - also a fresh one next to an
 //     old one (one instruction has one accumulate flag). Per input row, chunk and tap column: one N = 256 + one N = 128
 //     instruction, the same 315 cycles per three row-taps as the row-shared schedule.
-//   * unit of the pipeline = (input row, 64-channel chunk): A ring of four 17 KB rows, B ring of two 72 KB weight sets
-//     (pair units 3 x 16 KB: this CTA's 128 rows of ITS tap row; single units 3 x 8 KB: its 64-row half), one
-//     tcgen05.commit per unit frees both.
+//   * unit of the pipeline = (input row, 64-channel chunk): A ring of seven 17 KB rows (the rows come from DRAM and, with
+//     the input transform, pass through a second stage before the MMAs: with four slots the issuer waited on the
+//     transform and the transform on TMA, ncu profiles/r02/ncu_r02_halo_rr_gn_lean.txt). The weights of a unit arrive
+//     per tap column: B ring of four 24 KB stages (pair unit 16 KB: this CTA's 128 rows of ITS tap row; single unit
+//     8 KB: its 64-row half); one tcgen05.commit per B stage and one per unit (A slot).
 //   * work split: the B * ceil(tiles_x / 2) * H pair-rows are cut into one contiguous range per cluster (a range crosses
 //     at most a few strip boundaries; each segment costs two extra input rows), so all clusters finish together.
 //   * epilogue: warps 4..7 take columns 0..63 of every output row, warps 8..11 columns 64..127. A slot must be free
@@ -914,11 +916,12 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 struct HaloRrCfg {
   static constexpr int kRowBytes = 17 * 1024;
-  static constexpr int kASlots = 4;
-  static constexpr int kBSlotBytes = 72 * 1024;
-  static constexpr int kBSlots = 2;
+  static constexpr int kASlots = 7;             // (input row, chunk) units in flight: the rows come from DRAM
+  static constexpr int kBSlotBytes = 24 * 1024; // weight units of ONE tap column of a unit: 16 KB pair + 8 KB single
+  static constexpr int kBSlots = 4;
   static constexpr int kBarBytes = 512;
-  static constexpr int kSmemBytes = kASlots * kRowBytes + kBSlots * kBSlotBytes + 1024 + kBarBytes + 2048 + 32 * 128;
+  // + statistics partials (8 warps x 64 floats) + bias slices (8 x 128 floats) + input GroupNorm coefficient table (2 KB)
+  static constexpr int kSmemBytes = kASlots * kRowBytes + kBSlots * kBSlotBytes + 1024 + kBarBytes + 2048 + 32 * 128 + 2048;
 };
 
 // the MMAs of one input row (step i of a segment of L output rows whose first output has running index n0): up to two
@@ -929,7 +932,7 @@ struct RrPlan {
   int slot[2];   // first TMEM slot
   int tap0[2];   // tap row of the (first) accumulator
   int tap1[2];   // pair: tap row of the second accumulator
-  int boff[2];   // byte offset of the op's weight units inside the B slot
+  int boff[2];   // byte offset of the op's weight unit inside a B stage (one tap column)
 };
 __device__ __forceinline__ RrPlan rr_plan(int i, int L, uint32_t n0) {
   RrPlan pl;
@@ -942,11 +945,11 @@ __device__ __forceinline__ RrPlan rr_plan(int i, int L, uint32_t n0) {
   };
   if (cnt == 3) {
     pl.n_ops = 2;
-    if (s_lo != 3) { set(0, 1, lo, 0); set(1, 0, hi, 3 * 16384); }
-    else { set(0, 0, lo, 3 * 16384); set(1, 1, lo + 1, 0); }
+    if (s_lo != 3) { set(0, 1, lo, 0); set(1, 0, hi, 16384); }
+    else { set(0, 0, lo, 16384); set(1, 1, lo + 1, 0); }
   } else if (cnt == 2) {
     if (s_lo != 3) { pl.n_ops = 1; set(0, 1, lo, 0); }
-    else { pl.n_ops = 2; set(0, 0, lo, 0); set(1, 0, hi, 3 * 8192); }
+    else { pl.n_ops = 2; set(0, 0, lo, 0); set(1, 0, hi, 8192); }
   } else {
     pl.n_ops = 1; set(0, 0, lo, 0);
   }
@@ -967,11 +970,13 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::kASlots * C::kRowBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::kBSlots * C::kBSlotBytes);
-  uint64_t* a_full = bars;                // [4] XF: per CTA (own bytes); else leader's (2 arrivals)
-  uint64_t* a_ready = a_full + 4;         // [4] XF: leader's, 8 arrivals (4 transform warps x 2 CTAs)
-  uint64_t* b_full = a_ready + 4;         // [2] leader's (2 arrivals)
-  uint64_t* empty = b_full + 2;           // [4] per CTA, per unit (u & 3): one multicast commit per unit
-  uint64_t* acc_full = empty + 4;         // [4] per CTA
+  constexpr int NA = C::kASlots, NB = C::kBSlots;
+  uint64_t* a_full = bars;                // [NA] XF: per CTA (own bytes); else leader's (2 arrivals)
+  uint64_t* a_ready = a_full + NA;        // [NA] XF: leader's, 8 arrivals (4 transform warps x 2 CTAs)
+  uint64_t* a_empty = a_ready + NA;       // [NA] per CTA: one multicast commit per unit
+  uint64_t* b_full = a_empty + NA;        // [NB] leader's (2 arrivals)
+  uint64_t* b_empty = b_full + NB;        // [NB] per CTA: one multicast commit per tap column
+  uint64_t* acc_full = b_empty + NB;      // [4] per CTA
   uint64_t* acc_empty = acc_full + 4;     // [4] leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   float* gn_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);
@@ -984,14 +989,13 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB128);
     tma_prefetch_desc(&tmB64);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NA; ++i) {
       mbar_init(&a_full[i], XF ? 1 : 2);
       mbar_init(&a_ready[i], 8);
-      mbar_init(&empty[i], 1);
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 16);
+      mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&b_full[i], 2);
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 2); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1040,15 +1044,15 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ================= input-row producer =================
-      uint32_t u = 0;
+      int slot = 0;
+      uint32_t ph = 0;
       for (int g = g_begin; g < g_end;) {
         int b, tx, ya, L; bool dummy;
         segment(g, b, tx, dummy, ya, L);
         if (dummy) b = p.B;  // out of range: TMA fills zeros
         for (int i = 0; i < L + 2; ++i) {
-          for (int c = 0; c < p.chunks; ++c, ++u) {
-            const int slot = u & 3;
-            mbar_wait_relaxed(&empty[slot], ((u >> 2) & 1) ^ 1);
+          for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait_relaxed(&a_empty[slot], ph ^ 1);
             uint8_t* dst = sA + slot * C::kRowBytes;
             if (XF) {  // own barrier: this CTA's transform warps consume the row first
               mbar_expect_tx(&a_full[slot], row_bytes);
@@ -1058,6 +1062,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               else mbar_arrive_remote(&a_full[slot], 0);
               tma2_load_5d(dst, &tmA, &a_full[slot], c * 64, tx * 128 - p.pad_l, ya - p.pad_t + i, b, 0);
             }
+            if (++slot == NA) { slot = 0; ph ^= 1; }
           }
         }
         g += L;
@@ -1066,26 +1071,29 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == kBWarp) {
     if (lane == 0) {
       // ================= weight-unit producer =================
-      uint32_t u = 0, n0 = 0;
+      uint32_t n0 = 0;
+      int bs = 0;
+      uint32_t bph = 0;
       for (int g = g_begin; g < g_end;) {
         int b, tx, ya, L; bool dummy;
         segment(g, b, tx, dummy, ya, L);
         for (int i = 0; i < L + 2; ++i) {
           const RrPlan pl = rr_plan(i, L, n0);
           int bytes = 0;
-          for (int k = 0; k < pl.n_ops; ++k) bytes += pl.pair[k] ? 3 * 16384 : 3 * 8192;
-          for (int c = 0; c < p.chunks; ++c, ++u) {
-            uint8_t* dst = sB + (u & 1) * C::kBSlotBytes;
-            if (u >= 2) mbar_wait_relaxed(&empty[(u - 2) & 3], ((u - 2) >> 2) & 1);
-            if (rank == 0) mbar_expect_tx(&b_full[u & 1], 2 * bytes);
-            else mbar_arrive_remote(&b_full[u & 1], 0);
-            for (int k = 0; k < pl.n_ops; ++k) {
-              const int r_mine = pl.pair[k] ? (rank == 0 ? pl.tap0[k] : pl.tap1[k]) : pl.tap0[k];
-              for (int sx = 0; sx < 3; ++sx) {
+          for (int k = 0; k < pl.n_ops; ++k) bytes += pl.pair[k] ? 16384 : 8192;
+          for (int c = 0; c < p.chunks; ++c) {
+            for (int sx = 0; sx < 3; ++sx) {
+              uint8_t* dst = sB + bs * C::kBSlotBytes;
+              mbar_wait_relaxed(&b_empty[bs], bph ^ 1);
+              if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * bytes);
+              else mbar_arrive_remote(&b_full[bs], 0);
+              for (int k = 0; k < pl.n_ops; ++k) {
+                const int r_mine = pl.pair[k] ? (rank == 0 ? pl.tap0[k] : pl.tap1[k]) : pl.tap0[k];
                 const int kcol = (r_mine * 3 + sx) * p.Cin + c * 64;
-                if (pl.pair[k]) tma2_load_4d(dst + pl.boff[k] + sx * 16384, &tmB128, &b_full[u & 1], kcol, 0, 0, 0);
-                else tma2_load_4d(dst + pl.boff[k] + sx * 8192, &tmB64, &b_full[u & 1], kcol, static_cast<int>(rank) * 64, 0, 0);
+                if (pl.pair[k]) tma2_load_4d(dst + pl.boff[k], &tmB128, &b_full[bs], kcol, 0, 0, 0);
+                else tma2_load_4d(dst + pl.boff[k], &tmB64, &b_full[bs], kcol, static_cast<int>(rank) * 64, 0, 0);
               }
+              if (++bs == NB) { bs = 0; bph ^= 1; }
             }
           }
         }
@@ -1108,7 +1116,9 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32), desc_lo = static_cast<uint32_t>(desc0);
       auto dsc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
       const bool no_mma = (p.debug & 4) != 0;  // timing-only ablation (OMGSR_HALO_DEBUG): no MMAs, results invalid
-      uint32_t u = 0, n0 = 0;
+      uint32_t n0 = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       for (int g = g_begin; g < g_end;) {
         int b, tx, ya, L; bool dummy;
         segment(g, b, tx, dummy, ya, L);
@@ -1119,38 +1129,33 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           const RrPlan pl = rr_plan(i, L, n0);
           const uint32_t d0 = tmem_base + pl.slot[0] * BN, id0 = pl.pair[0] ? idesc256 : idesc128;
-          const uint32_t bs0 = pl.pair[0] ? 1024u : 512u;  // weight unit of the next tap column, >> 4
           const bool two = pl.n_ops > 1;
           const uint32_t d1 = tmem_base + pl.slot[1] * BN, id1 = pl.pair[1] ? idesc256 : idesc128;
-          const uint32_t bs1 = pl.pair[1] ? 1024u : 512u;
-          for (int c = 0; c < p.chunks; ++c, ++u) {
-            const int slot = u & 3;
-            if (p.debug & 8) {  // A/B: back-off waits in the issuer
-              mbar_wait_relaxed(XF ? &a_ready[slot] : &a_full[slot], (u >> 2) & 1, 32);
-              mbar_wait_relaxed(&b_full[u & 1], (u >> 1) & 1, 32);
-            } else {
-              if (XF) mbar_wait(&a_ready[slot], (u >> 2) & 1);
-              else mbar_wait(&a_full[slot], (u >> 2) & 1);
-              mbar_wait(&b_full[u & 1], (u >> 1) & 1);
-            }
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(sB + (u & 1) * C::kBSlotBytes);
-            uint32_t a_lo = desc_lo | (smem_u32(sA + slot * C::kRowBytes) >> 4);
-            uint32_t b0_lo = desc_lo | ((b_base + pl.boff[0]) >> 4), b1_lo = desc_lo | ((b_base + pl.boff[1]) >> 4);
-            if (!no_mma) {
+          for (int c = 0; c < p.chunks; ++c) {
+            if (XF) mbar_wait(&a_ready[as], aph);
+            else mbar_wait(&a_full[as], aph);
+            uint32_t a_lo = desc_lo | (smem_u32(sA + as * C::kRowBytes) >> 4);
 #pragma unroll 1
-              for (int sx = 0; sx < 3; ++sx) {  // tap column: the A view shifts by one pixel (128 B)
-                if (leader) {
+            for (int sx = 0; sx < 3; ++sx) {  // tap column: the A view shifts by one pixel (128 B)
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t b_base = smem_u32(sB + bs * C::kBSlotBytes);
+              const uint32_t b0_lo = desc_lo | ((b_base + pl.boff[0]) >> 4), b1_lo = desc_lo | ((b_base + pl.boff[1]) >> 4);
+              if (leader) {
+                if (!no_mma) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     tc_mma2_ss(d0, dsc(a_lo + 2 * k), dsc(b0_lo + 2 * k), id0, 1u);
                     if (two) tc_mma2_ss(d1, dsc(a_lo + 2 * k), dsc(b1_lo + 2 * k), id1, 1u);
                   }
                 }
-                a_lo += 8; b0_lo += bs0; b1_lo += bs1;
+                tc_commit2_mc(&b_empty[bs]);
               }
+              a_lo += 8;
+              if (++bs == NB) { bs = 0; bph ^= 1; }
             }
-            if (leader) tc_commit2_mc(&empty[slot]);  // the row and its weight units are free once everything issued so far retires
+            if (leader) tc_commit2_mc(&a_empty[as]);  // the row is free once everything issued so far retires
+            if (++as == NA) { as = 0; aph ^= 1; }
           }
           if (i >= 2 && leader) tc_commit2_mc(&acc_full[(n0 + i - 2) & 3]);  // output i - 2 has received its three tap rows
         }
@@ -1161,78 +1166,86 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (XF && warp >= 12) {
     setmaxnreg_dec<112>();
     // ================= input transform (warps 12..15): GroupNorm + SiLU on each halo row, in place =================
+    // One warp per scheduler, so the schedule inside the warp matters (the first version ran at 0.15 IPC, fully
+    // busy, and set the pace of the kernel: ncu profiles/r02/ncu_r02_halo_rr_gn_lean.txt). Per unit a thread owns
+    // 9 x 16 bytes (8 channels of pixels p0, p0 + 16, ...): fixed swizzle term, so the addresses are one base plus
+    // immediates; three 16-byte units at a time go through three PHASES (24 affine results, 24 tanh, 24 outputs) so
+    // that the MUFU latencies overlap; the coefficients of the image come from a 1 KB table in shared memory.
     const int tid = threadIdx.x - 384;  // 0..127
     const int j = tid & 7;              // 16-byte unit (8 channels) of a 128-byte pixel row: fixed per thread
     const int p0 = tid >> 3;            // first pixel of this thread in a row; then every 16th (<= 9 per row)
-    uint32_t u = 0;
-    // (scale / 2, shift / 2) of this thread's 8 channels: both 64-channel chunks of the current image stay in
-    // registers when Cin <= 128 (a load per unit sat on the row's critical path: ncu long-scoreboard samples)
-    float ca0[8], cb0[8], ca1[8], cb1[8];
+    const uint32_t off0 = static_cast<uint32_t>(p0 * 128 + ((j ^ (p0 & 7)) << 4));
+    float* coef_tab = gn_acc + 8 * 64 + 8 * BN;  // scale / 2 [256] then shift / 2 [256] (separate arrays: the packed
+    const uint32_t coef_s = smem_u32(coef_tab);  // fp32 FMAs want (scale, scale) and (shift, shift) register pairs)
+    int slot = 0;
+    uint32_t ph = 0;
     int coef_b = -1;
-    auto load_coef = [&](float (&a)[8], float (&bb)[8], int b, int c) {
-      const float4* cf = reinterpret_cast<const float4*>(p.gn_in + static_cast<long long>(b) * p.Cin + c * 64 + j * 8);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = __ldg(cf + q);
-        // halved: silu(a x + b) = h + h tanh(h) with h = (a / 2) x + b / 2
-        a[2 * q] = 0.5f * v.x; bb[2 * q] = 0.5f * v.y; a[2 * q + 1] = 0.5f * v.z; bb[2 * q + 1] = 0.5f * v.w;
-      }
-    };
     for (int g = g_begin; g < g_end;) {
       int b, tx, ya, L; bool dummy;
       segment(g, b, tx, dummy, ya, L);
       const int x0 = tx * 128 - p.pad_l;
-      if (!dummy && b != coef_b && p.chunks <= 2) {
-        load_coef(ca0, cb0, b, 0);
-        if (p.chunks == 2) load_coef(ca1, cb1, b, 1);
+      uint32_t onmask = 0;  // this thread's pixels that lie inside the image (the others are conv padding: stay zero)
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const int pi = p0 + 16 * q, xx = x0 + pi;
+        if (pi < p.pw && xx >= 0 && xx < p.IW) onmask |= 1u << q;
+      }
+      if (!dummy && b != coef_b) {  // (warp-uniform per CTA: all four transform warps take this branch together)
+        named_bar_sync(3, 128);  // nobody still reads the previous image's table
+        for (int ch = tid; ch < p.Cin; ch += 128) {
+          const float2 v = __ldg(p.gn_in + static_cast<long long>(b) * p.Cin + ch);
+          // halved: silu(a x + b) = h + h tanh(h) with h = (a / 2) x + b / 2
+          coef_tab[ch] = 0.5f * v.x;
+          coef_tab[256 + ch] = 0.5f * v.y;
+        }
+        named_bar_sync(3, 128);
         coef_b = b;
       }
       for (int i = 0; i < L + 2; ++i) {
         const int yy = ya - p.pad_t + i;
-        for (int c = 0; c < p.chunks; ++c, ++u) {
-          const int slot = u & 3;
+        const bool live = !dummy && yy >= 0 && yy < p.IH;
+        for (int c = 0; c < p.chunks; ++c) {
           float ca[8], cb[8];
-          const bool live = !dummy && yy >= 0 && yy < p.IH;
           if (live) {
-            if (p.chunks <= 2) {
+            const uint32_t ct = coef_s + static_cast<uint32_t>((c * 64 + j * 8) * 4);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { ca[e] = c ? ca1[e] : ca0[e]; cb[e] = c ? cb1[e] : cb0[e]; }
-            } else {
-              load_coef(ca, cb, b, c);
+            for (int q = 0; q < 2; ++q) {
+              const uint4 va = lds128(ct + q * 16), vb = lds128(ct + 1024 + q * 16);
+              ca[4 * q] = __uint_as_float(va.x); ca[4 * q + 1] = __uint_as_float(va.y);
+              ca[4 * q + 2] = __uint_as_float(va.z); ca[4 * q + 3] = __uint_as_float(va.w);
+              cb[4 * q] = __uint_as_float(vb.x); cb[4 * q + 1] = __uint_as_float(vb.y);
+              cb[4 * q + 2] = __uint_as_float(vb.z); cb[4 * q + 3] = __uint_as_float(vb.w);
             }
           }
-          mbar_wait_relaxed(&a_full[slot], (u >> 2) & 1, 32);
-          // rows / pixels outside the image: TMA wrote zeros = the conv padding, which must stay zero
+          mbar_wait_relaxed(&a_full[slot], ph, 32);
           if (live) {
-            uint8_t* row = sA + slot * C::kRowBytes;
-            uint4 v[9];
-            bool on[9];
+            const uint32_t row_s = smem_u32(sA + slot * C::kRowBytes) + off0;
 #pragma unroll
-            for (int q = 0; q < 9; ++q) {
-              const int pi = p0 + 16 * q;
-              const int xx = x0 + pi;
-              on[q] = pi < p.pw && xx >= 0 && xx < p.IW;
-              if (on[q]) v[q] = *reinterpret_cast<const uint4*>(row + pi * 128 + ((j ^ (pi & 7)) << 4));
-            }
+            for (int qb = 0; qb < 9; qb += 3) {
+              uint4 v[3];
+              float h[24], th[24];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) {
-              float f[8];
-              const float2 f0 = unpack_bf16x2(v[q].x), f1 = unpack_bf16x2(v[q].y), f2 = unpack_bf16x2(v[q].z),
-                           f3 = unpack_bf16x2(v[q].w);
-              f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
+              for (int t = 0; t < 3; ++t) v[t] = lds128(row_s + (qb + t) * 2048);  // (past the row for q = 8: harmless)
 #pragma unroll
-              for (int e = 0; e < 8; e += 2) {  // packed fp32 pairs: h = (a / 2) x + b / 2, y = h + h tanh(h)
-                float h0, h1;
-                ffma2p(h0, h1, f[e], f[e + 1], ca[e], ca[e + 1], cb[e], cb[e + 1]);
-                ffma2p(f[e], f[e + 1], h0, h1, tanh_approx(h0), tanh_approx(h1), h0, h1);
+              for (int t = 0; t < 3; ++t) {
+                const float2 f0 = unpack_bf16x2(v[t].x), f1 = unpack_bf16x2(v[t].y), f2 = unpack_bf16x2(v[t].z),
+                             f3 = unpack_bf16x2(v[t].w);
+                ffma2p(h[t * 8 + 0], h[t * 8 + 1], f0.x, f0.y, ca[0], ca[1], cb[0], cb[1]);
+                ffma2p(h[t * 8 + 2], h[t * 8 + 3], f1.x, f1.y, ca[2], ca[3], cb[2], cb[3]);
+                ffma2p(h[t * 8 + 4], h[t * 8 + 5], f2.x, f2.y, ca[4], ca[5], cb[4], cb[5]);
+                ffma2p(h[t * 8 + 6], h[t * 8 + 7], f3.x, f3.y, ca[6], ca[7], cb[6], cb[7]);
               }
-              v[q].x = pack_bf16x2(f[0], f[1]); v[q].y = pack_bf16x2(f[2], f[3]);
-              v[q].z = pack_bf16x2(f[4], f[5]); v[q].w = pack_bf16x2(f[6], f[7]);
-            }
 #pragma unroll
-            for (int q = 0; q < 9; ++q) {
-              const int pi = p0 + 16 * q;
-              if (on[q]) *reinterpret_cast<uint4*>(row + pi * 128 + ((j ^ (pi & 7)) << 4)) = v[q];
+              for (int e = 0; e < 24; ++e) th[e] = tanh_approx(h[e]);
+#pragma unroll
+              for (int e = 0; e < 24; e += 2) ffma2p(h[e], h[e + 1], h[e], h[e + 1], th[e], th[e + 1], h[e], h[e + 1]);
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+                uint4 o;
+                o.x = pack_bf16x2(h[t * 8 + 0], h[t * 8 + 1]); o.y = pack_bf16x2(h[t * 8 + 2], h[t * 8 + 3]);
+                o.z = pack_bf16x2(h[t * 8 + 4], h[t * 8 + 5]); o.w = pack_bf16x2(h[t * 8 + 6], h[t * 8 + 7]);
+                if ((onmask >> (qb + t)) & 1u) sts128(row_s + (qb + t) * 2048, o);
+              }
             }
           }
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -1240,6 +1253,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0) {
             if (rank == 0) mbar_arrive(&a_ready[slot]); else mbar_arrive_remote_relaxed(&a_ready[slot], 0);
           }
+          if (++slot == NA) { slot = 0; ph ^= 1; }
         }
       }
       g += L;
@@ -1474,7 +1488,8 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
     // against the two extra input rows per segment
     const long long pair_rows = static_cast<long long>(B) * ((p.tiles_x + 1) / 2) * OH;
     const int max_clusters = sm_count() / 2;
-    const bool rr_fit = R == 3 && S == 3 && pair_rows >= static_cast<long long>(max_clusters) * 48 && pair_rows < 0x7fffffffLL;
+    const bool rr_fit = R == 3 && S == 3 && pair_rows >= static_cast<long long>(max_clusters) * 48 && pair_rows < 0x7fffffffLL &&
+                        Cin <= 256;  // (the input-GroupNorm coefficient table in shared memory holds 256 channels)
     const bool rr_on = g_halo_rolling >= 0 ? g_halo_rolling != 0 : gn_in != nullptr;
     if (rr_fit && rr_on) {
       if (gn_in) return launch_halo_rr<true>(tmRow, tmB128, tmB64, p, max_clusters, st);
