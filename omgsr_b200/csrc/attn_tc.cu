@@ -88,6 +88,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -348,6 +350,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -631,6 +635,8 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -864,7 +870,7 @@ static int launch_attn3(const void* q, const void* k, const void* v, void* out, 
   p.out = static_cast<bf16*>(out);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((M + 255) / 256, H, B);
-  flash_attn3_kernel<D><<<grid, 320, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  launch_pdl(flash_attn3_kernel<D>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
   return check_launch("flash_attn3_kernel");
 }
 
@@ -956,6 +962,8 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1216,7 +1224,7 @@ static int launch_attn4(const void* q, const void* k, const void* v, void* out, 
   p.out = static_cast<bf16*>(out);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((M + 255) / 256, H, B);
-  flash_attn4_kernel<<<grid, 320, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  launch_pdl(flash_attn4_kernel, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
   return check_launch("flash_attn4_kernel");
 }
 
@@ -1252,7 +1260,7 @@ static int launch_attn2(const void* q, const void* k, const void* v, void* out, 
   p.out = static_cast<bf16*>(out);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((M + 255) / 256, H, B);
-  flash_attn2_kernel<D><<<grid, 320, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  launch_pdl(flash_attn2_kernel<D>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
   return check_launch("flash_attn2_kernel");
 }
 
@@ -1288,7 +1296,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   p.out = static_cast<bf16*>(out);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((M + C::kBM - 1) / C::kBM, H, B);
-  flash_attn_kernel<D><<<grid, 192, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  launch_pdl(flash_attn_kernel<D>, dim3(grid), dim3(192), C::kSmemBytes, st, tmQ, tmK, tmV, p);
   return check_launch("flash_attn_kernel");
 }
 

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // C-ABI plumbing: error state, tensor-map encoding through the runtime-resolved driver entry point,
 // device properties, launch counter.
 #include "common.cuh"
@@ -8,6 +9,7 @@
 #include <cudaTypedefs.h>
 
 namespace omgsr {
+int g_pdl = getenv("OMGSR_PDL") ? atoi(getenv("OMGSR_PDL")) : 1;
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};

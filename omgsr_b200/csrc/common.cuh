@@ -72,6 +72,27 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// ---- programmatic dependent launch -------------------------------------------------------------------------------
+// A step is 650-800 dependent launches. Every kernel below calls pdl_launch_dependents() first (the NEXT kernel of the
+// stream may then be scheduled as soon as this kernel's CTAs have all started, i.e. its CTAs take over an SM the moment
+// ours exit and run their prologue - barrier init, TMEM allocation, descriptor prefetch - under our tail) and
+// pdl_wait() before its first global-memory access (returns once every kernel it depends on has COMPLETED and its
+// writes are visible; immediately if the kernel was launched without the attribute). Only kernels that call pdl_wait()
+// are launched through launch_pdl(): a kernel with the attribute that did not wait would also un-order its successors.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+extern int g_pdl;  // capi.cu: 1 unless OMGSR_PDL=0
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in check_launch()
+}
+
 // 16-byte shared-memory accesses through a 32-bit shared-window address: LDS.128 / STS.128 with an immediate offset (a
 // generic pointer into dynamic shared memory costs an S2R + LEA per access in a role branch that the compiler cannot
 // prove uniform)

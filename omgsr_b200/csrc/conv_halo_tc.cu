@@ -96,6 +96,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   const int total_tiles = p.tiles_x * p.tiles_y * p.B * p.n_tiles;
   const int taps = p.R * p.S;
@@ -311,6 +313,8 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   const int halo_tiles = p.tiles_x * p.tiles_y * p.B;
   const int total_pairs = (halo_tiles + 1) >> 1;   // n_tiles == 1 (Cout <= 128)
@@ -640,6 +644,8 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   const int halo_tiles = p.tiles_x * p.tiles_y * p.B;
   const int total_pairs = (halo_tiles + 1) >> 1;   // n_tiles == 1 (Cout <= 128)
@@ -1021,6 +1027,8 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   // this cluster's contiguous range of pair-rows: pair-strip q = (image, pair of 128-pixel strips), H rows each
   const int xp = (p.tiles_x + 1) >> 1;
@@ -1296,6 +1304,9 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (e.res_row) {  // this thread's 64 residual channels are in flight before the accumulator wait
           load_res32(rr0, e, c_off, valid);
           load_res32(rr1, e, c_off + 32, valid);
+          // the residual comes from DRAM: pull the NEXT row's 128-byte line of this thread into L2 now (the first use of
+          // rr0 was the largest long-scoreboard stall of the epilogue, ncu profiles/r02/ncu_r02_halo_rr_gn_res_final.txt)
+          if (valid && o + 1 < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.res_row + p.r_sy + c_off));
         }
         e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
         const int slot = n & 3;
@@ -1350,7 +1361,7 @@ static int launch_halo_rr_m(const CUtensorMap& tmA, const CUtensorMap& tmB128, c
   if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_rr_kernel<XF, MODE>), C::kSmemBytes, &attr_done,
                                 "conv_halo_rr")) return rc;
   g_trace_variant = XF ? "conv_halo_rr_kernel<1>" : "conv_halo_rr_kernel<0>";
-  conv_halo_rr_kernel<XF, MODE><<<2 * clusters, XF ? 512 : 384, C::kSmemBytes, st>>>(tmA, tmB128, tmB64, p);
+  launch_pdl(conv_halo_rr_kernel<XF, MODE>, dim3(2 * clusters), dim3(XF ? 512 : 384), C::kSmemBytes, st, tmA, tmB128, tmB64, p);
   return check_launch("conv_halo_rr_kernel");
 }
 template <bool XF>
@@ -1380,7 +1391,7 @@ static int launch_halo_rs(const CUtensorMap& tmA, const CUtensorMap& tmB128, con
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
   g_trace_variant = XF ? "conv_halo_rs_kernel<1>" : "conv_halo_rs_kernel<0>";
-  conv_halo_rs_kernel<XF><<<2 * clusters, XF ? 480 : 352, C::kSmemBytes, st>>>(tmA, tmB128, tmB64, p);
+  launch_pdl(conv_halo_rs_kernel<XF>, dim3(2 * clusters), dim3(XF ? 480 : 352), C::kSmemBytes, st, tmA, tmB128, tmB64, p);
   return check_launch("conv_halo_rs_kernel");
 }
 
@@ -1397,7 +1408,7 @@ static int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ha
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
   g_trace_variant = XF ? "conv_halo_tc2_kernel<2,true>" : "conv_halo_tc2_kernel<2,false>";
-  conv_halo_tc2_kernel<TM, XF><<<2 * clusters, XF ? 320 : 192, C::kSmemBytes, st>>>(tmA, tmB, p);
+  launch_pdl(conv_halo_tc2_kernel<TM, XF>, dim3(2 * clusters), dim3(XF ? 320 : 192), C::kSmemBytes, st, tmA, tmB, p);
   return check_launch("conv_halo_tc2_kernel");
 }
 
@@ -1410,7 +1421,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
   const long long total = static_cast<long long>(p.tiles_x) * p.tiles_y * p.B * p.n_tiles;
   const int grid = total < sm_count() ? static_cast<int>(total) : sm_count();
   g_trace_variant = BN == 16 ? "conv_halo_tc_kernel<16,2>" : "conv_halo_tc_kernel<128,2>";
-  conv_halo_tc_kernel<BN, TM><<<grid, 192, C::kSmemBytes, st>>>(tmA, tmB, p);
+  launch_pdl(conv_halo_tc_kernel<BN, TM>, dim3(grid), dim3(192), C::kSmemBytes, st, tmA, tmB, p);
   return check_launch("conv_halo_tc_kernel");
 }
 

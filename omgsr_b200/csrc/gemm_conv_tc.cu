@@ -151,6 +151,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
   const int num_kb = p.R * p.S * p.kc_per_tap;
@@ -393,6 +395,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int m_pairs = (m_tiles + 1) >> 1;
@@ -576,7 +580,7 @@ static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   const int max_clusters = sm_count() / 2;
   const int clusters = pairs < max_clusters ? static_cast<int>(pairs) : max_clusters;
   g_trace_variant = BN == 256 ? "conv_gemm_tc2_kernel<256>" : BN == 160 ? "conv_gemm_tc2_kernel<160>" : "conv_gemm_tc2_kernel<128>";
-  conv_gemm_tc2_kernel<BN><<<2 * clusters, kThreads, Cfg2<BN>::kSmemBytes, st>>>(tmA, tmB, p);
+  launch_pdl(conv_gemm_tc2_kernel<BN>, dim3(2 * clusters), dim3(kThreads), Cfg2<BN>::kSmemBytes, st, tmA, tmB, p);
   return check_launch("conv_gemm_tc2_kernel");
 }
 
@@ -597,7 +601,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
   const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   g_trace_variant = BN == 256 ? "conv_gemm_tc_kernel<256>" : BN == 160 ? "conv_gemm_tc_kernel<160>" : BN == 128 ? "conv_gemm_tc_kernel<128>" : "conv_gemm_tc_kernel<64>";
-  conv_gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmB, p);
+  launch_pdl(conv_gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, tmA, tmB, p);
   return check_launch("conv_gemm_tc_kernel");
 }
 

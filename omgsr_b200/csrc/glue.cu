@@ -48,6 +48,8 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ scratch, long long HW,
                                 int C, int G, int vpr, int rows_per_iter, int blocks_per_img) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float tab[];  // [2][rows_per_iter][C]: per-(row lane, channel) sum / sum of squares
   const int b = blockIdx.x / blocks_per_img;
   const int blk = blockIdx.x % blocks_per_img;
@@ -101,6 +103,8 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
 // 20 us per call, 3 % of the S-512 step; 8 x more blocks and a quarter of the chain length bring it to ~3 us.)
 __global__ void gn_finalize_kernel(const float* __restrict__ scratch, int launches, int B, int slots, int n, int V,
                                    float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float part[];  // [P][V]
   const int b = blockIdx.x, v0 = blockIdx.y * V;
   const int P = blockDim.x / V;
@@ -133,7 +137,7 @@ int launch_gn_finalize(const float* scratch, int launches, int B, int slots, int
   if (n <= 0 || n > 1024 || (n & 1)) return set_error(OMGSR_ERR_SHAPE, "gn_finalize: 2 * groups = %d out of range", n);
   const int V = (n % 8 == 0) ? 8 : 2;
   const int threads = 512;
-  gn_finalize_kernel<<<dim3(B, n / V), threads, static_cast<size_t>(threads) * sizeof(float), st>>>(scratch, launches, B,
+  launch_pdl(gn_finalize_kernel, dim3(dim3(B, n / V)), dim3(threads), static_cast<size_t>(threads) * sizeof(float), st, scratch, launches, B,
                                                                                                   slots, n, V, out);
   return check_launch("gn_finalize_kernel");
 }
@@ -145,6 +149,8 @@ int launch_gn_finalize(const float* scratch, int launches, int B, int slots, int
 __global__ void gn_coef_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
                                const float* __restrict__ beta, float2* __restrict__ coef, int B, long long HW, int C,
                                int G, float eps, int stats_mode, int stats_mod) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
@@ -169,6 +175,8 @@ template <bool SILU>
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                 const float2* __restrict__ coef, long long HW, int C, int vpr, int rows_per_iter,
                                 int blocks_per_img) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / blocks_per_img;
   const int blk = blockIdx.x % blocks_per_img;
   if (threadIdx.x >= vpr * rows_per_iter) return;
@@ -220,6 +228,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
 // with w_e = pixels_e / sum of pixels over the tiles of image b.
 __global__ void gn_combine_kernel(const float* __restrict__ sums, const float* __restrict__ pixels, int entries,
                                   int n_img, int G, int cpg, float* __restrict__ out, float* __restrict__ wsum_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * G) return;
   const int b = i / G, g = i % G;
@@ -257,6 +267,8 @@ template <int VPL, typename TIn>  // 8-element vectors per lane
 __global__ void layernorm_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, long long rows, int C, float eps,
                                  long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -317,6 +329,8 @@ __global__ void layernorm_kernel(const TIn* __restrict__ x, bf16* __restrict__ y
 // ------------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s, bf16* __restrict__ P, long long ld_p,
                                     int n, int n_pad, float scale_log2e) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const float* s = S + blockIdx.x * ld_s;
   bf16* p = P + blockIdx.x * ld_p;
@@ -348,6 +362,8 @@ template <int V4>
 __global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* __restrict__ S, long long ld_s,
                                                                bf16* __restrict__ P, long long ld_p, int n, int n_pad,
                                                                float scale_log2e) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][8];
   const float4* s4 = reinterpret_cast<const float4*>(S + blockIdx.x * ld_s);
   uint2* p2 = reinterpret_cast<uint2*>(P + blockIdx.x * ld_p);
@@ -408,6 +424,8 @@ __global__ void rmsnorm_rope_kernel(bf16* __restrict__ x, long long ld, long lon
                                     const float* __restrict__ weight, const float* __restrict__ cos_t,
                                     const float* __restrict__ sin_t, long long rows_per_batch, int batch, int heads,
                                     int heads_per_w, int pos_offset, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -441,6 +459,8 @@ template <typename TIn>
 __global__ void conv_in_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                bf16* __restrict__ y, int B, int Cin, int H, int W, int Cout, int ks, long long ldy,
                                int cg, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pad = ks / 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -478,6 +498,8 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const float* __restric
 template <typename TIn>
 __global__ void im2col3x3_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, int Cin, int H, int W, int Kpad,
                                  long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunks = Kpad / 8;
   const int K = 9 * Cin;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -508,6 +530,8 @@ template <int COUT, typename TOut>
 __global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
                                 TOut* __restrict__ y, int B, int H, int W, int Cin, int clamp, long long ldx,
                                 long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float ws[];  // [COUT][9*Cin]
   const int K = 9 * Cin;
   for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) ws[i] = __bfloat162float(w[i]);
@@ -557,6 +581,8 @@ template <typename TOut>
 __global__ void posterior_kernel(const float* __restrict__ mom, long long ldm, const float* __restrict__ eps,
                                  TOut* __restrict__ z, int Cz, long long hw, long long total, float shift,
                                  float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long p = i % hw;
@@ -573,6 +599,8 @@ __global__ void posterior_kernel(const float* __restrict__ mom, long long ldm, c
 template <typename T>
 __global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, long long n,
                              float a, float b, float c) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v = a * static_cast<float>(x[i]) + c;
@@ -586,6 +614,8 @@ __global__ void x0_unscale_kernel(const TZ* __restrict__ z, const float* __restr
                                   bf16* __restrict__ out, const float* __restrict__ Wpq, const float* __restrict__ bpq,
                                   int Cz, long long hw, long long total_pix, float s1, float inv_s2, float inv_scale,
                                   float shift) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_pix;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / hw, p = i % hw;
@@ -610,6 +640,8 @@ __global__ void x0_unscale_kernel(const TZ* __restrict__ z, const float* __restr
 // FLUX 2x2 pack: tokens[b, (y/2)(w/2) + x/2, c*4 + dy*2 + dx] = z[b, c, y, x]
 __global__ void pack_kernel(const bf16* __restrict__ z, bf16* __restrict__ tok, int C, int h, int w, long long ld,
                             long long total, int unpack) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(i % w);
@@ -631,6 +663,8 @@ template <typename T>
 __global__ void tile_blend_kernel(const T* __restrict__ tiles, const float* __restrict__ wts,
                                   const int* __restrict__ ofs, int ntiles, float* __restrict__ out, int B, int C, int h,
                                   int w, int T_, long long total, BlendStrides st) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
@@ -652,6 +686,8 @@ __global__ void tile_blend_kernel(const T* __restrict__ tiles, const float* __re
 // layout changes through a 32x32 smem tile
 template <typename TIn>
 __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, int C, long long HW, long long ldy) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const long long p0 = blockIdx.x * 32LL;
@@ -671,6 +707,8 @@ __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, bf16* __restrict_
 template <typename TOut>
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, long long ldx, TOut* __restrict__ y, int C,
                                     long long HW, int clamp) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const long long p0 = blockIdx.x * 32LL;
@@ -728,7 +766,7 @@ extern "C" int omgsr_groupnorm_stats(const void* x, long long ldx, float* stats,
     return set_error(OMGSR_ERR_SHAPE, "groupnorm_stats: scratch needs %lld floats (omgsr_gn_scratch_floats), got %lld",
                      bpi * B * 2 * G, scratch ? scratch_floats : 0LL);
   const size_t smem = 2ull * rows_per_iter * C * sizeof(float);  // <= 32 KB
-  gn_stats_kernel<<<static_cast<unsigned>(bpi * B), threads, smem, st>>>(
+  launch_pdl(gn_stats_kernel, dim3(static_cast<unsigned>(bpi * B)), dim3(threads), smem, st, 
       static_cast<const bf16*>(x), ldx, scratch, HW, C, G, vpr, rows_per_iter, static_cast<int>(bpi));
   int rc = check_launch("gn_stats_kernel");
   if (rc) return rc;
@@ -744,7 +782,7 @@ extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long
   if (!coef_scratch) return set_error(OMGSR_ERR_SHAPE, "groupnorm_apply: coef_scratch (B*C float2) is required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float2* coef = static_cast<float2*>(coef_scratch);
-  gn_coef_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(stats, gamma, beta, coef, B, HW, C, G, eps, stats_mode, stats_mod);
+  launch_pdl(gn_coef_kernel, dim3((B * C + 255) / 256), dim3(256), 0, st, stats, gamma, beta, coef, B, HW, C, G, eps, stats_mode, stats_mod);
   int rc = check_launch("gn_coef_kernel");
   if (rc) return rc;
   const int vpr = C / 8;
@@ -757,10 +795,10 @@ extern "C" int omgsr_groupnorm_apply(const void* x, long long ldx, void* y, long
   if (bpi < 1) bpi = 1;
   const unsigned grid = static_cast<unsigned>(bpi * B);
   if (silu)
-    gn_apply_kernel<true><<<grid, threads, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, coef,
+    launch_pdl(gn_apply_kernel<true>, dim3(grid), dim3(threads), 0, st, static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, coef,
                                                     HW, C, vpr, rows_per_iter, static_cast<int>(bpi));
   else
-    gn_apply_kernel<false><<<grid, threads, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, coef,
+    launch_pdl(gn_apply_kernel<false>, dim3(grid), dim3(threads), 0, st, static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, coef,
                                                      HW, C, vpr, rows_per_iter, static_cast<int>(bpi));
   return check_launch("gn_apply_kernel");
 }
@@ -770,7 +808,7 @@ extern "C" int omgsr_groupnorm_coef(const float* stats, const float* gamma, cons
   if (C % 8 || C % G) return set_error(OMGSR_ERR_SHAPE, "groupnorm_coef: C=%d G=%d", C, G);
   if (stats_mode && stats_mod <= 0) return set_error(OMGSR_ERR_SHAPE, "groupnorm_coef: stats_mod must be > 0");
   if (!coef || (reinterpret_cast<uintptr_t>(coef) & 15)) return set_error(OMGSR_ERR_ALIGN, "groupnorm_coef: coef must be 16-byte aligned");
-  gn_coef_kernel<<<(B * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(gn_coef_kernel, dim3((B * C + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       stats, gamma, beta, static_cast<float2*>(coef), B, HW, C, G, eps, stats_mode, stats_mod);
   return check_launch("gn_coef_kernel");
 }
@@ -780,7 +818,7 @@ extern "C" int omgsr_groupnorm_combine(const float* sums, const float* pixels, i
   if (entries <= 0 || n_img <= 0 || entries % n_img || C % G)
     return set_error(OMGSR_ERR_SHAPE, "groupnorm_combine: entries=%d n_img=%d", entries, n_img);
   const int n = n_img * G;
-  gn_combine_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, pixels, entries, n_img, G,
+  launch_pdl(gn_combine_kernel, dim3((n + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), sums, pixels, entries, n_img, G,
                                                                                  C / G, out, wsum_out);
   return check_launch("gn_combine_kernel");
 }
@@ -801,10 +839,10 @@ extern "C" int omgsr_layernorm(const void* x, int x_f32, void* y, const float* g
 #define LN_CASE(V)                                                                                                  \
   do {                                                                                                              \
     if (x_f32)                                                                                                      \
-      layernorm_kernel<V, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), yo, gamma, beta, rows, C,  \
+      launch_pdl(layernorm_kernel<V, float>, dim3(grid), dim3(threads), 0, st, static_cast<const float*>(x), yo, gamma, beta, rows, C,  \
                                                            eps, rows_per_batch, gb_stride, ldx, x_batch_stride);    \
     else                                                                                                            \
-      layernorm_kernel<V, bf16><<<grid, threads, 0, st>>>(static_cast<const bf16*>(x), yo, gamma, beta, rows, C,    \
+      launch_pdl(layernorm_kernel<V, bf16>, dim3(grid), dim3(threads), 0, st, static_cast<const bf16*>(x), yo, gamma, beta, rows, C,    \
                                                           eps, rows_per_batch, gb_stride, ldx, x_batch_stride);     \
   } while (0)
   if (vpl <= 1) LN_CASE(1);
@@ -829,13 +867,13 @@ extern "C" int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long 
     const unsigned g = static_cast<unsigned>(rows);
     bf16* Pb = static_cast<bf16*>(P);
     const float sl = scale * 1.4426950408889634f;
-    if (n_pad <= 2048) softmax_rows_reg_kernel<2><<<g, 256, 0, st>>>(S, ld_s, Pb, ld_p, n, n_pad, sl);
-    else if (n_pad <= 4096) softmax_rows_reg_kernel<4><<<g, 256, 0, st>>>(S, ld_s, Pb, ld_p, n, n_pad, sl);
-    else softmax_rows_reg_kernel<8><<<g, 256, 0, st>>>(S, ld_s, Pb, ld_p, n, n_pad, sl);
+    if (n_pad <= 2048) launch_pdl(softmax_rows_reg_kernel<2>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
+    else if (n_pad <= 4096) launch_pdl(softmax_rows_reg_kernel<4>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
+    else launch_pdl(softmax_rows_reg_kernel<8>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
     return check_launch("softmax_rows_reg_kernel");
   }
   const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
       S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f);
   return check_launch("softmax_rows_kernel");
 }
@@ -845,7 +883,7 @@ extern "C" int omgsr_rmsnorm_rope(void* x, long long ld, long long batch_stride,
                                   int heads, int heads_per_weight, int pos_offset, float eps, void* stream) {
   if ((ld | batch_stride) % 4) return set_error(OMGSR_ERR_ALIGN, "rmsnorm_rope: strides %% 4");
   if (heads <= 0 || heads_per_weight <= 0) return set_error(OMGSR_ERR_SHAPE, "rmsnorm_rope: heads");
-  rmsnorm_rope_kernel<<<grid_for(rows_per_batch * batch * heads * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(rmsnorm_rope_kernel, dim3(grid_for(rows_per_batch * batch * heads * 32, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<bf16*>(x), ld, batch_stride, weight, cos_t, sin_t, rows_per_batch, batch, heads, heads_per_weight,
       pos_offset, eps);
   return check_launch("rmsnorm_rope_kernel");
@@ -859,11 +897,11 @@ extern "C" int omgsr_conv_in_nchw(const void* x, int x_f32, const float* w, cons
   const long long total = static_cast<long long>(B) * H * W * cg;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_f32)
-    conv_in_kernel<float><<<grid_for(total, 256) * 4, 256, 0, st>>>(static_cast<const float*>(x), w, bias,
+    launch_pdl(conv_in_kernel<float>, dim3(grid_for(total, 256) * 4), dim3(256), 0, st, static_cast<const float*>(x), w, bias,
                                                                    static_cast<bf16*>(y), B, Cin, H, W, Cout, ksize,
                                                                    ldy, cg, total);
   else
-    conv_in_kernel<bf16><<<grid_for(total, 256) * 4, 256, 0, st>>>(static_cast<const bf16*>(x), w, bias,
+    launch_pdl(conv_in_kernel<bf16>, dim3(grid_for(total, 256) * 4), dim3(256), 0, st, static_cast<const bf16*>(x), w, bias,
                                                                   static_cast<bf16*>(y), B, Cin, H, W, Cout, ksize,
                                                                   ldy, cg, total);
   return check_launch("conv_in_kernel");
@@ -875,10 +913,10 @@ extern "C" int omgsr_im2col3x3_nchw(const void* x, int x_f32, void* y, int B, in
   const long long total = static_cast<long long>(B) * H * W * (Kpad / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_f32)
-    im2col3x3_kernel<float><<<grid_for(total, 256) * 2, 256, 0, st>>>(static_cast<const float*>(x), static_cast<bf16*>(y),
+    launch_pdl(im2col3x3_kernel<float>, dim3(grid_for(total, 256) * 2), dim3(256), 0, st, static_cast<const float*>(x), static_cast<bf16*>(y),
                                                                       Cin, H, W, Kpad, total);
   else
-    im2col3x3_kernel<bf16><<<grid_for(total, 256) * 2, 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y),
+    launch_pdl(im2col3x3_kernel<bf16>, dim3(grid_for(total, 256) * 2), dim3(256), 0, st, static_cast<const bf16*>(x), static_cast<bf16*>(y),
                                                                      Cin, H, W, Kpad, total);
   return check_launch("im2col3x3_kernel");
 }
@@ -893,7 +931,7 @@ static int launch_conv_out(const void* x, const void* w, const float* bias, void
     if (e != cudaSuccess) return set_error(OMGSR_ERR_CUDA, "conv_out smem: %s", cudaGetErrorString(e));
   }
   const long long total = static_cast<long long>(B) * H * W;
-  conv_out_kernel<COUT, TOut><<<grid_for(total, 128), 128, smem, st>>>(
+  launch_pdl(conv_out_kernel<COUT, TOut>, dim3(grid_for(total, 128)), dim3(128), smem, st, 
       static_cast<const bf16*>(x), static_cast<const bf16*>(w), bias, static_cast<TOut*>(y), B, H, W, Cin, clamp, ldx,
       total);
   return check_launch("conv_out_kernel");
@@ -918,10 +956,10 @@ extern "C" int omgsr_posterior_sample(const float* moments, long long ldm, const
   const long long hw = static_cast<long long>(h) * w, total = hw * Cz * B;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (z_f32)
-    posterior_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(moments, ldm, eps, static_cast<float*>(z), Cz, hw,
+    launch_pdl(posterior_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, st, moments, ldm, eps, static_cast<float*>(z), Cz, hw,
                                                                   total, shift, scale);
   else
-    posterior_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(moments, ldm, eps, static_cast<bf16*>(z), Cz, hw,
+    launch_pdl(posterior_kernel<bf16>, dim3(grid_for(total, 256)), dim3(256), 0, st, moments, ldm, eps, static_cast<bf16*>(z), Cz, hw,
                                                                  total, shift, scale);
   return check_launch("posterior_kernel");
 }
@@ -930,10 +968,10 @@ extern "C" int omgsr_latent_axpby(const void* x, const void* y, void* out, int i
                                   float c, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_f32)
-    axpby_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(y),
+    launch_pdl(axpby_kernel<float>, dim3(grid_for(n, 256)), dim3(256), 0, st, static_cast<const float*>(x), static_cast<const float*>(y),
                                                           static_cast<float*>(out), n, a, b, c);
   else
-    axpby_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(y),
+    launch_pdl(axpby_kernel<bf16>, dim3(grid_for(n, 256)), dim3(256), 0, st, static_cast<const bf16*>(x), static_cast<const bf16*>(y),
                                                          static_cast<bf16*>(out), n, a, b, c);
   return check_launch("axpby_kernel");
 }
@@ -945,11 +983,11 @@ extern "C" int omgsr_x0_unscale(const void* z, int z_f32, const float* eps_hat, 
   const long long hw = static_cast<long long>(h) * w, total = hw * B;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (z_f32)
-    x0_unscale_kernel<float><<<grid_for(total, 128), 128, 0, st>>>(static_cast<const float*>(z), eps_hat, lde,
+    launch_pdl(x0_unscale_kernel<float>, dim3(grid_for(total, 128)), dim3(128), 0, st, static_cast<const float*>(z), eps_hat, lde,
                                                                    static_cast<bf16*>(out), Wpq, bpq, Cz, hw, total, s1,
                                                                    1.0f / s2, 1.0f / scale, shift);
   else
-    x0_unscale_kernel<bf16><<<grid_for(total, 128), 128, 0, st>>>(static_cast<const bf16*>(z), eps_hat, lde,
+    launch_pdl(x0_unscale_kernel<bf16>, dim3(grid_for(total, 128)), dim3(128), 0, st, static_cast<const bf16*>(z), eps_hat, lde,
                                                                   static_cast<bf16*>(out), Wpq, bpq, Cz, hw, total, s1,
                                                                   1.0f / s2, 1.0f / scale, shift);
   return check_launch("x0_unscale_kernel");
@@ -959,7 +997,7 @@ extern "C" int omgsr_pack_latents(const void* z, void* tokens, int B, int C, int
                                   void* stream) {
   if ((h | w) & 1) return set_error(OMGSR_ERR_SHAPE, "pack_latents: odd latent size");
   const long long total = static_cast<long long>(B) * C * h * w;
-  pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(pack_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const bf16*>(z), static_cast<bf16*>(tokens), C, h, w, ld_tok, total, 0);
   return check_launch("pack_kernel");
 }
@@ -967,7 +1005,7 @@ extern "C" int omgsr_unpack_latents(const void* tokens, void* z, int B, int C, i
                                     void* stream) {
   if ((h | w) & 1) return set_error(OMGSR_ERR_SHAPE, "unpack_latents: odd latent size");
   const long long total = static_cast<long long>(B) * C * h * w;
-  pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(pack_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const bf16*>(z), const_cast<bf16*>(static_cast<const bf16*>(tokens)), C, h, w, ld_tok, total, 1);
   return check_launch("pack_kernel");
 }
@@ -982,10 +1020,10 @@ extern "C" int omgsr_tile_blend(const void* tiles, int tiles_f32, const float* w
   bs.t_x = tile_strides[4];
   bs.o_b = out_strides[0]; bs.o_c = out_strides[1]; bs.o_y = out_strides[2]; bs.o_x = out_strides[3];
   if (tiles_f32)
-    tile_blend_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(tiles), weights,
+    launch_pdl(tile_blend_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, st, static_cast<const float*>(tiles), weights,
                                                                    ofs_xy_dev, ntiles, out, B, C, h, w, T, total, bs);
   else
-    tile_blend_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const bf16*>(tiles), weights, ofs_xy_dev,
+    launch_pdl(tile_blend_kernel<bf16>, dim3(grid_for(total, 256)), dim3(256), 0, st, static_cast<const bf16*>(tiles), weights, ofs_xy_dev,
                                                                   ntiles, out, B, C, h, w, T, total, bs);
   return check_launch("tile_blend_kernel");
 }
@@ -996,9 +1034,9 @@ extern "C" int omgsr_nchw_to_nhwc(const void* x, int x_f32, void* y, int B, int 
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_f32)
-    nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x), static_cast<bf16*>(y), C, HW, ldy);
+    launch_pdl(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(block), 0, st, static_cast<const float*>(x), static_cast<bf16*>(y), C, HW, ldy);
   else
-    nchw_to_nhwc_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), C, HW, ldy);
+    launch_pdl(nchw_to_nhwc_kernel<bf16>, dim3(grid), dim3(block), 0, st, static_cast<const bf16*>(x), static_cast<bf16*>(y), C, HW, ldy);
   return check_launch("nchw_to_nhwc_kernel");
 }
 extern "C" int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f32, int B, int C, int H, int W,
@@ -1007,10 +1045,10 @@ extern "C" int omgsr_nhwc_to_nchw(const void* x, long long ldx, void* y, int y_f
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (y_f32)
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<float*>(y), C, HW,
+    launch_pdl(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(block), 0, st, static_cast<const bf16*>(x), ldx, static_cast<float*>(y), C, HW,
                                                        clamp);
   else
-    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), C, HW,
+    launch_pdl(nhwc_to_nchw_kernel<bf16>, dim3(grid), dim3(block), 0, st, static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), C, HW,
                                                       clamp);
   return check_launch("nhwc_to_nchw_kernel");
 }
