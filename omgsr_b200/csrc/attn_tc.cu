@@ -555,6 +555,27 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// exp2 of a PAIR on the FMA pipe (no MUFU): round-to-nearest split t = r + f with the 1.5 * 2^23 trick, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, P is stored as bf16: 3.9e-3), 2^r added into the exponent
+// field. 2 FMNMX + 6 FFMA2 + 2 SHL + 2 IADD per pair against 2 MUFU.EX2, which occupy the 4-lane MUFU unit of the
+// scheduler for 16 cycles: the softmax of these kernels is MUFU-bound (128 exponentials per row and key block = 2048
+// MUFU cycles per 256 x 128 block, as much as its MMAs), so a fraction of the pairs goes this way.
+__device__ __forceinline__ void exp2_poly2(float& t0, float& t1) {
+  const float magic = 12582912.0f;  // 1.5 * 2^23
+  t0 = fmaxf(t0, -125.0f);
+  t1 = fmaxf(t1, -125.0f);
+  float i0, i1, r0, r1, f0, f1, p0, p1;
+  ffma2p(i0, i1, t0, t1, 1.0f, 1.0f, magic, magic);      // low mantissa bits = round(t)
+  ffma2p(r0, r1, i0, i1, 1.0f, 1.0f, -magic, -magic);    // round(t) as a float
+  ffma2p(f0, f1, r0, r1, -1.0f, -1.0f, t0, t1);          // f = t - round(t)
+  ffma2p(p0, p1, f0, f1, 0.0551716648f, 0.0551716648f, 0.2426111251f, 0.2426111251f);
+  ffma2p(p0, p1, p0, p1, f0, f1, 0.6932609677f, 0.6932609677f);
+  ffma2p(p0, p1, p0, p1, f0, f1, 0.9999280572f, 0.9999280572f);
+  t0 = __int_as_float(__float_as_int(p0) + (__float_as_int(i0) << 23));
+  t1 = __int_as_float(__float_as_int(p1) + (__float_as_int(i1) << 23));
+}
+
+constexpr int kAttnPolyDefault = 2;  // d = 64: 0.598 -> 0.538 ms, d = 128: 0.902 -> 0.888 ms (profiles/r02/attn_poly_exp2.txt)
 // one-pass softmax (v3 / v4): a block whose row sum exceeds this moves the row's reference exponent up by log2(sum)
 constexpr float kAttnRebase = 1024.0f;
 
@@ -588,7 +609,8 @@ struct Attn3Cfg {
   static constexpr int kSmemBytes = kQBytes + kSlots * kTileBytes + 2 * kPBytes + kOnesBytes + 1024 + 256;
 };
 
-template <int D>
+// PMASK: which of the 4 pairs of every 8 scores take exp2_poly2 instead of MUFU.EX2 (bit i = pair i)
+template <int D, int PMASK>
 __global__ void __launch_bounds__(320, 1)
 flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -776,8 +798,13 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < 8; i += 2) {
             float t0, t1;
             ffma2(t0, t1, __uint_as_float(sv[q * 8 + i]), __uint_as_float(sv[q * 8 + i + 1]), p.scale_log2, nmb);
-            pr[i] = exp2f(t0);  // exp2(-inf) = 0
-            pr[i + 1] = exp2f(t1);
+            if ((PMASK >> (i >> 1)) & 1) {
+              exp2_poly2(t0, t1);  // (-inf -> 2^-125: negligible against the row sum, and its V row is zero)
+              pr[i] = t0; pr[i + 1] = t1;
+            } else {
+              pr[i] = exp2f(t0);  // exp2(-inf) = 0
+              pr[i + 1] = exp2f(t1);
+            }
             fadd2(ls0, ls1, pr[i], pr[i + 1]);
           }
           uint4 u;
@@ -843,8 +870,13 @@ static int launch_attn3(const void* q, const void* k, const void* v, void* out, 
                         const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
                         cudaStream_t st) {
   using C = Attn3Cfg<D>;
-  static unsigned long long attr_done = 0;  // one bit per device
-  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&flash_attn3_kernel<D>), C::kSmemBytes, &attr_done, "flash_attn3")) return rc;
+  // fraction of the exponentials on the FMA pipe: 0 none, 1 one pair in four, 2 every other pair (OMGSR_ATTN_POLY)
+  static const int poly = getenv("OMGSR_ATTN_POLY") ? atoi(getenv("OMGSR_ATTN_POLY")) : kAttnPolyDefault;
+  static unsigned long long attr_done[3] = {0, 0, 0};  // one bit per device
+  const void* kfn = poly == 2 ? reinterpret_cast<const void*>(&flash_attn3_kernel<D, 0xA>)
+                  : poly == 1 ? reinterpret_cast<const void*>(&flash_attn3_kernel<D, 0x8>)
+                              : reinterpret_cast<const void*>(&flash_attn3_kernel<D, 0>);
+  if (int rc = ensure_smem_attr(kfn, C::kSmemBytes, &attr_done[poly == 2 ? 2 : (poly == 1 ? 1 : 0)], "flash_attn3")) return rc;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t eb = 2;
   {
@@ -870,7 +902,9 @@ static int launch_attn3(const void* q, const void* k, const void* v, void* out, 
   p.out = static_cast<bf16*>(out);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((M + 255) / 256, H, B);
-  launch_pdl(flash_attn3_kernel<D>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
+  if (poly == 2) launch_pdl(flash_attn3_kernel<D, 0xA>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
+  else if (poly == 1) launch_pdl(flash_attn3_kernel<D, 0x8>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
+  else launch_pdl(flash_attn3_kernel<D, 0>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
   return check_launch("flash_attn3_kernel");
 }
 

@@ -355,7 +355,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s,
     p[j] = __float2bfloat16(j < n ? exp2f((s[j] - m) * scale_log2e) * inv : 0.f);
 }
 
-// Register-resident variant for rows of up to 256 * 4 * V4 scores: the row is read from HBM exactly once (V4 float4
+// Register-resident variant for rows of up to 256 * 4 * V4 scores (V4 <= 32: 32768): the row is read from HBM exactly once (V4 float4
 // per thread, all in flight), reduced, exponentiated and written as bf16 (8-byte stores). The three-pass kernel above
 // ran at 1.3 TB/s on the VAE mid-block attention (4096 x 4096 scores per image).
 template <int V4>
@@ -863,13 +863,17 @@ extern "C" int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool vec_ok = (n_pad % 4 == 0) && (ld_s % 4 == 0) && (ld_p % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P) & 7) == 0);
-  if (vec_ok && n_pad >= 1024 && n_pad <= 8192) {
+  if (vec_ok && n_pad >= 1024 && n_pad <= 32768) {
     const unsigned g = static_cast<unsigned>(rows);
     bf16* Pb = static_cast<bf16*>(P);
     const float sl = scale * 1.4426950408889634f;
     if (n_pad <= 2048) launch_pdl(softmax_rows_reg_kernel<2>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
     else if (n_pad <= 4096) launch_pdl(softmax_rows_reg_kernel<4>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
-    else launch_pdl(softmax_rows_reg_kernel<8>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
+    else if (n_pad <= 8192) launch_pdl(softmax_rows_reg_kernel<8>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
+    // 1024^2 images: 16384 tokens in the VAE mid block (the three-pass kernel took 2 ms per launch there, 7x its
+    // HBM time; profiles/r02/launches_f1024_b4_r02_summary.txt)
+    else if (n_pad <= 16384) launch_pdl(softmax_rows_reg_kernel<16>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
+    else launch_pdl(softmax_rows_reg_kernel<32>, dim3(g), dim3(256), 0, st, S, ld_s, Pb, ld_p, n, n_pad, sl);
     return check_launch("softmax_rows_reg_kernel");
   }
   const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);

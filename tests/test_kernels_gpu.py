@@ -223,7 +223,9 @@ def test_conv_residual_silu_concat(capi):
                                          (1, 2, 200, 300, 64), (1, 1, 256, 256, 512), (1, 3, 256, 320, 128),
                                          # rows of >= 1024 scores: register-resident softmax (2 / 4 / 8 float4 per thread)
                                          (1, 1, 256, 1024, 512), (1, 1, 128, 1990, 64), (1, 1, 128, 4096, 512),
-                                         (1, 1, 128, 5000, 64)])
+                                         (1, 1, 128, 5000, 64),
+                                         # 16 / 32 float4 per thread (1024^2 image: 16384 tokens in the VAE mid block)
+                                         (1, 1, 128, 16384, 64), (1, 1, 128, 20000, 64)])
 def test_attention_materialised(capi, B, Hh, M, N, D):
     from oracle import ops
     g = _g(B + Hh + M + N + D)
