@@ -319,7 +319,20 @@ class _Ctx:
         import torch.distributed as dist
         self.dist = dist
         if self.ws > 1 and not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=self.dev)
+            # NCCL prints its version banner on STDOUT when the first communicator comes up: keep stdout to the one JSON
+            # line the driver parses (the banner goes to stderr instead)
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                t = torch.zeros(1, device=self.dev)
+                dist.all_reduce(t)
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         if self.ws > 1:
@@ -426,10 +439,10 @@ def bench_f1024(ctx, args, with_baselines=True):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/r02/)
-HALO_GN_TRAFFIC = 2.1905e9   # conv_halo_rs_kernel<1> (GroupNorm+SiLU -> 3x3 128->128 @512^2 x16): 1.1508 GB read + 1.0397 GB
-                             # written, profiles/r02/ncu_r02_halo_rs_gn.txt (algorithmic: input + output = 2 x 1.0737 GB)
-F_GEMM_TRAFFIC = 2.2646e9    # conv_gemm_tc2_kernel<256> (18432 x 12288 x 3072 + GELU): 1.8222 GB read + 0.4425 GB written,
-                             # profiles/r02/ncu_r02_f_gemm_3072_12288.txt (algorithmic A + W + D = 0.642 GB; the 75 MB weight
+HALO_GN_TRAFFIC = 2.1171e9   # conv_halo_rr_kernel<1> (GroupNorm+SiLU -> 3x3 128->128 @512^2 x16): 1.0882 GB read + 1.0289 GB
+                             # written, profiles/r02/ncu_r02_halo_rr_gn_final.txt (algorithmic: input + output = 2 x 1.0737 GB)
+F_GEMM_TRAFFIC = 2.4589e9    # conv_gemm_tc2_kernel<256> (18432 x 12288 x 3072 + GELU): 2.0158 GB read + 0.4431 GB written,
+                             # profiles/r02/ncu_r02b_f_gemm.txt (algorithmic A + W + D = 0.642 GB; the 75 MB weight
                              # matrix is re-streamed per 256-row tile pair and only partly stays in L2)
 
 
@@ -471,7 +484,7 @@ def f_kernel_roofline(capi, dev, B, peak_tflops, how):
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
             "traffic": F_GEMM_TRAFFIC if B == 4 else None, "traffic_unit": "bytes/launch",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms,
-            "attention": {"kernel": "flash_attn4_kernel (joint attention, 24 heads x 4608 tokens, d = 128, batch %d)" % B,
+            "attention": {"kernel": "flash_attn3_kernel<128> (joint attention, 24 heads x 4608 tokens, d = 128, batch %d)" % B,
                           "achieved": ach_a, "frac": ach_a / peak_tflops, "ms_per_launch": ms_a}}
 
 
@@ -556,8 +569,8 @@ def bench_s512(ctx, args):
     return line
 
 
-PAIR256_TRAFFIC = 1.0465e9   # conv_gemm_tc2_kernel<256> (3x3 256->256 @256^2 x16): 0.5431 GB read + 0.5034 GB written,
-                             # profiles/r01/ncu_gemm_pair256.txt (algorithmic input + output = 2 x 0.5369 GB)
+PAIR256_TRAFFIC = 1.0394e9   # conv_gemm_tc2_kernel<256> (3x3 256->256 @256^2 x16): 0.5382 GB read + 0.5012 GB written,
+                             # profiles/r02/ncu_r02b_conv256.txt (algorithmic input + output = 2 x 0.5369 GB)
 
 
 def _time_launch(fn, n=10):
@@ -576,12 +589,13 @@ def _time_launch(fn, n=10):
 def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
     """Roofline of the step's dominant kernel, timed live on its launch stream.
 
-    By share of the step (ncu launch list, profiles/r02/launches_s512_b16_r02_summary.txt) the dominant KERNEL is
-    conv_gemm_tc2_kernel<256> (CTA-pair implicit-GEMM conv / GEMM, N = 256 tiles: 34 % of the step, 82 launches), probed
+    By share of the step (ncu launch list, profiles/r02/launches_s512_b16_final_summary.txt) the dominant KERNEL is
+    conv_gemm_tc2_kernel<256> (CTA-pair implicit-GEMM conv / GEMM, N = 256 tiles: 40 % of the step, 82 launches), probed
     on its largest recurring shape, the VAE's 3x3 256->256 convolution at 256x256 (0.62 TFLOP per launch at batch 16).
-    Second by share (25 %, 14 launches) and the kernel round 1's verdict asked to lift is the 128-channel input-halo
-    convolution with the GroupNorm + SiLU of its input fused into the operand path (conv_halo_rs_kernel<1>, the largest
-    single layer shape of the step: 1.24 TFLOP per launch): reported next to it as `second`.
+    Second among the single layer shapes (18 %, 11 launches) and the kernel round 1's verdict asked to lift is the
+    128-channel input-halo convolution with the GroupNorm + SiLU of its input fused into the operand path (round 2:
+    conv_halo_rr_kernel<1>, rolling input rows; the largest single layer shape of the step: 1.24 TFLOP per launch):
+    reported next to it as `second`.
     Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W in both cases."""
     from omgsr_b200.pack import pack_conv_weight
     # the burst peak is a cold-start figure: let the board leave the power-capped state of the timed steps first
@@ -612,9 +626,9 @@ def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
         del x, y
     roof = out["pair256"]
-    roof["share_of_step"] = "34 % (conv_gemm_tc2_kernel<256>, profiles/r02/launches_s512_b16_r02_summary.txt)"
+    roof["share_of_step"] = "40 % (conv_gemm_tc2_kernel<256>, profiles/r02/launches_s512_b16_final_summary.txt)"
     roof["second"] = out["halo"]
-    roof["second"]["share_of_step"] = "25 % (conv_halo_rs_kernel<1>)"
+    roof["second"]["share_of_step"] = "18 % (conv_halo_rr_kernel<1, *>: fused input GroupNorm, 11 launches)"
     return roof
 
 
