@@ -209,6 +209,15 @@ int omgsr_layernorm(const void* x, int x_f32, void* y, const float* gamma, const
  * n <= j < n_pad. */
 int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int n_pad,
                        float scale, void* stream);
+/* The same with a causal mask (CLIP text encoders, transformers modeling_clip.py `_create_4d_causal_attention_mask`
+ * as used by `CLIPTextModel` in infer/infer_omgsr_s.py:19-45 and `FluxPipeline.encode_prompt`, infer_omgsr_f.py:36-43):
+ * rows are laid out [..., queries]; query i attends to keys 0..i, P[r, j] = 0 for j > i. */
+int omgsr_softmax_rows_causal(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int n_pad,
+                              float scale, int queries, void* stream);
+/* Token + position embedding of the text encoders (CLIPTextEmbeddings: token_embedding(ids) + position_embedding;
+ * pos may be null): out[r, :] = tok[ids[r], :] + pos[r % T, :], bf16 tables [vocab, C] / [T, C], int32 ids, C % 8 == 0. */
+int omgsr_embed_tokens(const int* ids, const void* tok, const void* pos, void* out, long long rows, int T, int C,
+                       int vocab, void* stream);
 /* FLUX q/k RMSNorm (per head, d = 128, learned weight, fp32 statistics) + rotary embedding, in place on
  * x[b, r, h, 128] = x + b*batch_stride + r*ld + h*128 (bf16). Heads [0, heads_per_weight) use weight[0],
  * the next heads_per_weight use weight[1], ... so q and k of a fused qkv row take one launch.

@@ -14,27 +14,36 @@ from infer.omgsr_s_infer_model import OMGSR_S_Infer  # noqa: E402
 
 
 def encode_prompt_clip(args):
-    """CLIP-H text encoding of the prompt (reference :19-45); needs the SD checkpoint's tokenizer/text_encoder."""
-    from transformers import AutoTokenizer, CLIPTextModel
-    tok = AutoTokenizer.from_pretrained(args.sd_path, subfolder="tokenizer")
-    enc = CLIPTextModel.from_pretrained(args.sd_path, subfolder="text_encoder").to(args.device, dtype=args.weight_dtype)
+    """CLIP-H text encoding of the prompt (reference :19-45): `CLIPTextModel(ids)[0]` through the sm_100a text engine
+    (omgsr_b200/engine_clip.py). Tokenisation is host string processing and stays with the checkpoint's own tokenizer;
+    without one (random:// weights, no tokenizer files offline) only the empty prompt can be tokenised here:
+    [BOS, EOS, pad...]."""
+    import omgsr_synth as syn
+    from omgsr_b200.engine_clip import build_clip_text
     prompts = args.prompt if isinstance(args.prompt, list) else [args.prompt]
     print(f"Current prompt: {prompts}")
-    with torch.no_grad():
-        embs = [enc(tok(p, max_length=tok.model_max_length, padding="max_length", truncation=True,
-                        return_tensors="pt").input_ids.to(enc.device))[0] for p in prompts]
-    del tok, enc
+    if args.sd_path.startswith("random://"):
+        enc = build_clip_text("random://clip_h?seed=1235" if "sd21" in args.sd_path else "random://clip_tiny?seed=1235",
+                              args.device)
+        if any(p for p in prompts):
+            raise ValueError("random:// checkpoints carry no tokenizer: only the empty prompt \"\" (the reference's "
+                             "default) can be encoded; pass --prompt_embeds for anything else")
+        ids = syn.empty_prompt_ids(enc.cfg).repeat(len(prompts), 1)
+    else:
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(args.sd_path, subfolder="tokenizer")
+        enc = build_clip_text(os.path.join(args.sd_path, "text_encoder"), args.device)
+        ids = torch.cat([tok(p, max_length=tok.model_max_length, padding="max_length", truncation=True,
+                             return_tensors="pt").input_ids for p in prompts])
+    embs, _ = enc(ids)
+    del enc
     torch.cuda.empty_cache()
-    return torch.concat(embs, dim=0)
+    return embs.to(dtype=args.weight_dtype)
 
 
 def main(args):
     if args.prompt_embeds:
         prompt_embeds = torch.load(args.prompt_embeds).to(args.device, dtype=args.weight_dtype)
-    elif args.sd_path.startswith("random://"):
-        g = torch.Generator().manual_seed(1235)
-        dim = 1024 if "sd21" in args.sd_path else 128
-        prompt_embeds = torch.randn(1, 77, dim, generator=g).to(args.device, dtype=args.weight_dtype)
     else:
         prompt_embeds = encode_prompt_clip(args)
     net_sr = OMGSR_S_Infer(sd_path=args.sd_path, lora_path=args.lora_path, mid_timestep=args.mid_timestep,

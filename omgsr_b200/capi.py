@@ -25,7 +25,7 @@ SYMBOLS = [
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
-    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta", "omgsr_set_halo_rolling",
+    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta", "omgsr_set_halo_rolling", "omgsr_softmax_rows_causal", "omgsr_embed_tokens",
     "omgsr_groupnorm_coef", "omgsr_conv2d_gn_nhwc_bf16",
     "omgsr_resample_coeffs", "omgsr_resize_u8_workspace", "omgsr_resize_u8", "omgsr_u8_to_input", "omgsr_output_to_u8",
 ]
@@ -366,17 +366,38 @@ def layernorm(x, gamma=None, beta=None, eps=1e-5, rows_per_batch=0, gb_stride=0,
     return out
 
 
-def softmax_rows(s, n, scale, out=None):
-    """s: fp32 [..., n_pad]; returns bf16 probabilities with columns >= n zeroed."""
+def softmax_rows(s, n, scale, out=None, causal=False):
+    """s: fp32 [..., M, n_pad]; returns bf16 probabilities with columns >= n zeroed. causal: query i (the second to
+    last axis) sees keys 0..i only."""
     _cuda_f32(s, "s")
     n_pad = s.shape[-1]
     rows = s.numel() // n_pad
     assert s.is_contiguous()
     if out is None:
         out = torch.empty(s.shape, device=s.device, dtype=torch.bfloat16)
+    if causal:
+        rc = _lib.omgsr_softmax_rows_causal(_ptr(s), _ll(n_pad), _ptr(out), _ll(n_pad), _ll(rows), _i(n), _i(n_pad),
+                                            _f(scale), _i(s.shape[-2]), _stream())
+        _check(rc, "omgsr_softmax_rows_causal")
+        return out
     rc = _lib.omgsr_softmax_rows(_ptr(s), _ll(n_pad), _ptr(out), _ll(n_pad), _ll(rows), _i(n), _i(n_pad), _f(scale),
                                  _stream())
     _check(rc, "omgsr_softmax_rows")
+    return out
+
+
+def embed_tokens(ids, tok, pos=None):
+    """ids: int32 [B, T]; tok: bf16 [vocab, C]; pos: bf16 [T, C] or None -> bf16 [B, T, C] = tok[ids] + pos."""
+    if not (ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous()):
+        raise TypeError("ids must be a contiguous CUDA int32 tensor")
+    _cuda_bf16(tok, "tok"); _cuda_bf16(pos, "pos")
+    assert tok.is_contiguous() and (pos is None or (pos.is_contiguous() and pos.shape[0] >= ids.shape[-1]))
+    B, T = ids.shape
+    C = tok.shape[1]
+    out = torch.empty((B, T, C), device=ids.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_embed_tokens(_ptr(ids), _ptr(tok), _ptr(pos), _ptr(out), _ll(B * T), _i(T), _i(C), _i(tok.shape[0]),
+                                 _stream())
+    _check(rc, "omgsr_embed_tokens")
     return out
 
 
@@ -601,9 +622,9 @@ def attention_materialised(q, k, v, scale, max_score_bytes=2 << 30):
     a time: query rows are processed in chunks (rows are independent under softmax), so a 65 536-token untiled 2048^2
     image needs 2 GB of scratch instead of 17 GB per image, and the chunk that was just written is re-read out of L2 /
     HBM while still hot.
-    (A fused d = 512 kernel was designed and rejected on the measured instruction costs, DESIGN.md §4: the 128 x 512 fp32
-    O tile alone fills TMEM, so O must be split over two passes that each recompute S = Q K^T with 32 K-steps of
-    N <= 128 instructions at ~154 cycles: ~12.6 k cycles per 128 x 128 block against ~7 k for the two N = 256 GEMMs.)"""
+    (A fused d = 512 kernel is not built, DESIGN.md §8: the 128 x 512 fp32 O tile alone fills TMEM, so O must be split
+    over two passes that each recompute S = Q K^T with 32 K-steps: ~6.1 k tensor cycles per 128 x 128 block against 4.1 k
+    for the two GEMMs here, whose remaining cost is the score round trip through HBM.)"""
     B, M, H, _ = q.shape
     n = k.shape[1]
     n_pad = (n + 63) // 64 * 64

@@ -328,12 +328,14 @@ __global__ void layernorm_kernel(const TIn* __restrict__ x, bf16* __restrict__ y
 // Row softmax of fp32 scores -> bf16 probabilities (one block per row, scores re-read from L2).
 // ------------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s, bf16* __restrict__ P, long long ld_p,
-                                    int n, int n_pad, float scale_log2e) {
+                                    int n, int n_pad, float scale_log2e, int causal_m) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[32];
   const float* s = S + blockIdx.x * ld_s;
   bf16* p = P + blockIdx.x * ld_p;
+  // causal (text encoders): rows are [.., M queries]; query i sees keys 0..i, the rest of the row is written as zeros
+  if (causal_m > 0) n = min(n, static_cast<int>(blockIdx.x % causal_m) + 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float m = -INFINITY;
   for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, s[j]);
@@ -878,8 +880,54 @@ extern "C" int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long 
   }
   const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);
   launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
-      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f);
+      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f, 0);
   return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int omgsr_softmax_rows_causal(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n,
+                                         int n_pad, float scale, int queries, void* stream) {
+  if (rows <= 0 || n <= 0 || n_pad < n || queries <= 0 || rows % queries)
+    return set_error(OMGSR_ERR_SHAPE, "softmax_rows_causal: rows=%lld n=%d queries=%d", rows, n, queries);
+  if (rows > 0x7fffffffLL) return set_error(OMGSR_ERR_SHAPE, "softmax_rows_causal: too many rows");
+  const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);
+  launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0, static_cast<cudaStream_t>(stream),
+      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f, queries);
+  return check_launch("softmax_rows_kernel(causal)");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Token + position embedding of the text encoders: out[r, :] = tok[ids[r], :] + pos[r % T, :] (fp32 add, bf16 out)
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_tokens_kernel(const int* __restrict__ ids, const bf16* __restrict__ tok, const bf16* __restrict__ pos,
+                                    bf16* __restrict__ out, long long rows, int T, int C, int vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // one 8-channel granule each
+  const int cg = C >> 3;
+  if (idx >= rows * cg) return;
+  const long long r = idx / cg;
+  const int c = static_cast<int>(idx - r * cg) * 8;
+  int id = ids[r];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const uint4 a = *reinterpret_cast<const uint4*>(tok + static_cast<long long>(id) * C + c);
+  uint4 o = a;
+  if (pos) {
+    const uint4 b = *reinterpret_cast<const uint4*>(pos + static_cast<long long>(r % T) * C + c);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+    const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+    o.x = pack_bf16x2(a0.x + b0.x, a0.y + b0.y); o.y = pack_bf16x2(a1.x + b1.x, a1.y + b1.y);
+    o.z = pack_bf16x2(a2.x + b2.x, a2.y + b2.y); o.w = pack_bf16x2(a3.x + b3.x, a3.y + b3.y);
+  }
+  *reinterpret_cast<uint4*>(out + r * C + c) = o;
+}
+
+extern "C" int omgsr_embed_tokens(const int* ids, const void* tok, const void* pos, void* out, long long rows, int T,
+                                  int C, int vocab, void* stream) {
+  if (rows <= 0 || T <= 0 || C <= 0 || (C % 8) || vocab <= 0) return set_error(OMGSR_ERR_SHAPE, "embed_tokens: rows=%lld T=%d C=%d", rows, T, C);
+  const long long total = rows * (C / 8);
+  launch_pdl(embed_tokens_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), ids,
+             static_cast<const bf16*>(tok), static_cast<const bf16*>(pos), static_cast<bf16*>(out), rows, T, C, vocab);
+  return check_launch("embed_tokens_kernel");
 }
 
 extern "C" int omgsr_rmsnorm_rope(void* x, long long ld, long long batch_stride, const float* weight,

@@ -1,0 +1,127 @@
+"""CLIP text tower (transformers' CLIPTextModel) driven through the sm_100a kernels.
+
+Replaces the text-conditioning step that runs once per process BEFORE the super-resolution path:
+
+    infer/infer_omgsr_s.py:19-45   CLIPTextModel(sd_path/text_encoder)(ids)[0]      -> prompt_embeds [1, 77, 1024]
+    infer/infer_omgsr_f.py:36-43   FluxPipeline.encode_prompt: CLIPTextModel(ids).pooler_output -> pooled [1, 768]
+                                    (its T5-XXL half is not built: drivers still take `--prompt_embeds` for it)
+
+Architecture per transformers models/clip/modeling_clip.py (restated and pinned in oracle/clip_text.py): token +
+position embedding, `num_layers` pre-LN blocks (causal self-attention, fc1 -> act -> fc2), final LayerNorm; pooled
+output = the row of the EOS token.
+
+B200-first choices
+  * q | k | v are one fused [3C, C] GEMM; the attention reads its output in place through strided views. 77 tokens
+    are a single 128-wide score tile per head: batched tcgen05 GEMM -> causal row softmax -> batched GEMM
+    (`omgsr_softmax_rows_causal`); the fused flash kernels have no mask and would be all padding here.
+  * fp32 residual stream; bias, residual add and the activation ride in the GEMM epilogues (erf GELU natively; quick_gelu(x) =
+    silu(1.702 x) / 1.702, so 1.702 is folded into fc1 and 1 / 1.702 into fc2 at load time and the SiLU epilogue serves).
+  * no tokenizer: ids arrive tokenized (`omgsr_synth.empty_prompt_ids` gives the reference's default prompt "").
+"""
+import json
+import os
+
+import torch
+
+from . import capi
+
+
+def _dev(t, device, dtype):
+    return t.detach().to(device=device, dtype=dtype).contiguous()
+
+
+class B200CLIPText:
+    def __init__(self, sd, cfg, device):
+        bf, f32 = torch.bfloat16, torch.float32
+        self.cfg, self.device = cfg, torch.device(device)
+        if cfg.hidden_size % (8 * cfg.num_heads) or cfg.hidden_act not in ("gelu", "quick_gelu"):
+            raise ValueError(f"unsupported CLIP text config: {cfg}")
+        g = lambda k, dt: _dev(sd[k], self.device, dt)
+        self.tok = g("text_model.embeddings.token_embedding.weight", bf)
+        self.pos = g("text_model.embeddings.position_embedding.weight", bf)
+        quick = cfg.hidden_act == "quick_gelu"
+        self.act = capi.ACT_SILU if quick else capi.ACT_GELU_ERF
+        s1, s2 = (1.702, 1.0 / 1.702) if quick else (1.0, 1.0)
+        self.layers = []
+        for i in range(cfg.num_layers):
+            b = f"text_model.encoder.layers.{i}"
+            qkv_w = torch.cat([sd[f"{b}.self_attn.{n}_proj.weight"].float() for n in "qkv"], 0)
+            qkv_b = torch.cat([sd[f"{b}.self_attn.{n}_proj.bias"].float() for n in "qkv"], 0)
+            self.layers.append(dict(
+                ln1=(g(b + ".layer_norm1.weight", f32), g(b + ".layer_norm1.bias", f32)),
+                ln2=(g(b + ".layer_norm2.weight", f32), g(b + ".layer_norm2.bias", f32)),
+                w_qkv=_dev(qkv_w, self.device, bf), b_qkv=_dev(qkv_b, self.device, f32),
+                w_o=g(b + ".self_attn.out_proj.weight", bf), b_o=g(b + ".self_attn.out_proj.bias", f32),
+                w1=_dev(sd[b + ".mlp.fc1.weight"].float() * s1, self.device, bf),
+                b1=_dev(sd[b + ".mlp.fc1.bias"].float() * s1, self.device, f32),
+                w2=_dev(sd[b + ".mlp.fc2.weight"].float() * s2, self.device, bf),
+                b2=g(b + ".mlp.fc2.bias", f32)))
+        self.ln_f = (g("text_model.final_layer_norm.weight", f32), g("text_model.final_layer_norm.bias", f32))
+
+    @torch.no_grad()
+    def forward(self, input_ids):
+        """input_ids: integer [B, T <= max_positions] (host or device). Returns (last_hidden_state [B, T, C] bf16,
+        pooler_output [B, C] bf16) like CLIPTextModel(...)[0] / .pooler_output."""
+        cfg = self.cfg
+        if input_ids.dim() != 2 or input_ids.shape[1] > cfg.max_positions:
+            raise ValueError(f"input_ids must be [B, T <= {cfg.max_positions}] (got {tuple(input_ids.shape)})")
+        ids = input_ids.to(self.device)
+        B, T = ids.shape
+        C, H = cfg.hidden_size, cfg.num_heads
+        D = C // H
+        with torch.cuda.device(self.device):
+            # fp32 residual stream (as in the FLUX engine): 2 x num_layers updates land on it; rounding it to bf16 after
+            # each left the 23-layer SD-2.1 tower at 1.9e-2 of the fp32 result, on the 2e-2 bar
+            x = capi.embed_tokens(ids.to(torch.int32).contiguous(), self.tok, self.pos).float()
+            for L in self.layers:
+                h = capi.layernorm(x, L["ln1"][0], L["ln1"][1], eps=cfg.layer_norm_eps).view(B * T, C)
+                qkv = capi.gemm(h, L["w_qkv"], L["b_qkv"]).view(B, T, 3, H, D)
+                s = capi.bgemm_qk(qkv[:, :, 0], qkv[:, :, 1])
+                p = capi.softmax_rows(s, T, D ** -0.5, causal=True)
+                a = capi.bgemm_pv(p, qkv[:, :, 2]).view(B, T, C)
+                x = capi.gemm_batched(a, L["w_o"], L["b_o"], res=x, out=x)
+                h = capi.layernorm(x, L["ln2"][0], L["ln2"][1], eps=cfg.layer_norm_eps).view(B * T, C)
+                h = capi.gemm(h, L["w1"], L["b1"], act=self.act).view(B, T, -1)
+                x = capi.gemm_batched(h, L["w2"], L["b2"], res=x, out=x)
+            x = capi.layernorm(x, self.ln_f[0], self.ln_f[1], eps=cfg.layer_norm_eps).view(B, T, C)
+            # pooled row: first EOS (argmax of ids for the legacy eos_token_id == 2 configs), modeling_clip.py
+            if cfg.eos_token_id == 2:
+                eos = ids.to(torch.int32).argmax(dim=-1)
+            else:
+                eos = (ids == cfg.eos_token_id).to(torch.int32).argmax(dim=-1)
+            pooled = x[torch.arange(B, device=self.device), eos]
+        return x, pooled
+
+    __call__ = forward
+
+
+def read_clip_text_folder(folder):
+    """`<sd_path>/text_encoder` of a diffusers checkpoint directory (config.json + *.safetensors, transformers'
+    CLIPTextModel key names) -> (state dict, ClipTextConfig). No transformers import: own safetensors reader."""
+    from omgsr_synth import ClipTextConfig
+    from .checkpoint import _load_folder
+    sd, c = _load_folder(folder)
+    cfg = ClipTextConfig(vocab_size=c.get("vocab_size", 49408), hidden_size=c.get("hidden_size", 1024),
+                         intermediate_size=c.get("intermediate_size", 4096), num_layers=c.get("num_hidden_layers", 23),
+                         num_heads=c.get("num_attention_heads", 16), max_positions=c.get("max_position_embeddings", 77),
+                         hidden_act=c.get("hidden_act", "gelu"), layer_norm_eps=c.get("layer_norm_eps", 1e-5),
+                         eos_token_id=c.get("eos_token_id", 49407), pad_token_id=c.get("pad_token_id", 0))
+    return sd, cfg
+
+
+def load_clip_text(folder, device):
+    sd, cfg = read_clip_text_folder(folder)
+    return B200CLIPText(sd, cfg, device)
+
+
+def build_clip_text(spec, device):
+    """`random://clip_h?seed=2` | `random://clip_l?seed=2` | a `text_encoder` checkpoint folder."""
+    if spec.startswith("random://"):
+        import omgsr_synth as syn
+        name, _, query = spec[len("random://"):].partition("?")
+        seed = int(dict(kv.split("=") for kv in query.split("&") if kv).get("seed", 0))
+        cfg = {"clip_h": syn.SD21_CLIP_H, "clip_l": syn.FLUX_CLIP_L, "clip_tiny": syn.TINY_CLIP}[name]
+        return B200CLIPText(syn.random_state_dict(syn.clip_text_shapes(cfg), seed=seed), cfg, device)
+    if not os.path.isdir(spec):
+        raise FileNotFoundError(spec)
+    return load_clip_text(spec, device)

@@ -7,6 +7,7 @@ SD-2.1 DDPM alphas. Lives outside `omgsr_b200/` so that `bench.py --impl referen
 same weights without importing the product package (which dlopen()s the CUDA library).
 LoRA targets: train/train_omgsr_s.py:61-72,89-100 and train/train_omgsr_f.py:155-169 of the reference.
 """
+import dataclasses
 import math
 from dataclasses import dataclass, field
 from typing import Dict, Tuple
@@ -249,6 +250,58 @@ def flux_shapes(cfg: FluxConfig) -> Dict[str, tuple]:
 # ------------------------------------------------------------------------------------------------
 # random init (synthetic weights: there is no network access for checkpoints)
 # ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class ClipTextConfig:
+    """Text tower of CLIP as transformers' CLIPTextModel builds it (key names `text_model.*`)."""
+    vocab_size: int = 49408
+    hidden_size: int = 1024
+    intermediate_size: int = 4096
+    num_layers: int = 23
+    num_heads: int = 16
+    max_positions: int = 77
+    hidden_act: str = "gelu"       # "gelu" (erf) | "quick_gelu" (x * sigmoid(1.702 x))
+    layer_norm_eps: float = 1e-5
+    eos_token_id: int = 49407
+    pad_token_id: int = 0          # SD-2.x tokenizer pads with "!" (id 0); the OpenAI CLIP-L tokenizer with EOS
+
+
+# stabilityai/stable-diffusion-2-1-base/text_encoder (OpenCLIP ViT-H/14 text tower without its last layer): the
+# `CLIPTextModel` of infer/infer_omgsr_s.py:19-45
+SD21_CLIP_H = ClipTextConfig()
+# openai/clip-vit-large-patch14 text tower: `text_encoder` of FluxPipeline.encode_prompt (infer_omgsr_f.py:36-43)
+FLUX_CLIP_L = ClipTextConfig(hidden_size=768, intermediate_size=3072, num_layers=12, num_heads=12,
+                             hidden_act="quick_gelu", pad_token_id=49407)
+TINY_CLIP = ClipTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2,
+                           eos_token_id=999, pad_token_id=0)
+TINY_CLIP_QUICK = ClipTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2,
+                                 hidden_act="quick_gelu", eos_token_id=999, pad_token_id=999)
+
+
+def clip_text_shapes(cfg: ClipTextConfig) -> Dict[str, tuple]:
+    sd = {}
+    C = cfg.hidden_size
+    sd["text_model.embeddings.token_embedding.weight"] = (cfg.vocab_size, C)
+    sd["text_model.embeddings.position_embedding.weight"] = (cfg.max_positions, C)
+    for i in range(cfg.num_layers):
+        b = f"text_model.encoder.layers.{i}"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            _lin(sd, f"{b}.self_attn.{n}", C, C)
+        _norm(sd, f"{b}.layer_norm1", C)
+        _lin(sd, f"{b}.mlp.fc1", C, cfg.intermediate_size)
+        _lin(sd, f"{b}.mlp.fc2", cfg.intermediate_size, C)
+        _norm(sd, f"{b}.layer_norm2", C)
+    _norm(sd, "text_model.final_layer_norm", C)
+    return sd
+
+
+def empty_prompt_ids(cfg: ClipTextConfig):
+    """Token ids of the empty prompt "" at max_length padding - the reference's default prompt
+    (infer_omgsr_s.py `--prompt ""`): [BOS, EOS, pad, pad, ...]. No tokenizer files exist offline; any other prompt
+    has to arrive tokenized."""
+    return torch.tensor([[49406 if cfg.vocab_size >= 49408 else cfg.vocab_size - 2, cfg.eos_token_id] +
+                         [cfg.pad_token_id] * (cfg.max_positions - 2)], dtype=torch.int64)
+
+
 def random_state_dict(shapes: Dict[str, tuple], seed: int, dtype=torch.float32, out_gain: Dict[str, float] = None,
                       device="cpu"):
     """Variance-preserving init: conv/linear weights ~ N(0, 1/fan_in), biases ~ N(0, 0.02^2), norm affine

@@ -120,3 +120,28 @@ def test_flux_checkpoint_and_adapter_dirs(tmp_path):
     assert all(torch.allclose(mv[k], ev[k], atol=1e-6) for k in ev)
     assert all(torch.allclose(mf[k], ef[k], atol=1e-6) for k in ef)
     assert sum(int(not torch.equal(mf[k], flux_sd[k])) for k in flux_sd) == len(flux_ad)
+
+
+def test_clip_text_checkpoint_folder_roundtrip(tmp_path):
+    """`<sd_path>/text_encoder` as diffusers writes it (config.json + model.safetensors with transformers' key names)
+    -> read_clip_text_folder: same tensors, config fields mapped (infer/infer_omgsr_s.py:19-22 loads exactly this
+    folder)."""
+    import json
+    import omgsr_synth as syn
+    from omgsr_b200.checkpoint import write_safetensors
+    cfg = syn.TINY_CLIP_QUICK
+    sd = syn.random_state_dict(syn.clip_text_shapes(cfg), seed=3)
+    folder = tmp_path / "text_encoder"
+    folder.mkdir()
+    write_safetensors(str(folder / "model.safetensors"), sd)
+    json.dump({"vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size,
+               "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+               "max_position_embeddings": cfg.max_positions, "hidden_act": cfg.hidden_act, "layer_norm_eps": 1e-5,
+               "eos_token_id": cfg.eos_token_id, "pad_token_id": cfg.pad_token_id}, open(folder / "config.json", "w"))
+    try:
+        from omgsr_b200.engine_clip import read_clip_text_folder
+    except ImportError as e:   # the product package needs its CUDA library to import
+        pytest.skip(str(e))
+    sd2, cfg2 = read_clip_text_folder(str(folder))
+    assert cfg2 == cfg
+    assert set(sd2) == set(sd) and all(torch.equal(sd2[k], sd[k]) for k in sd)

@@ -267,3 +267,37 @@ def test_reference_arm_does_not_load_the_cuda_library():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "BAD [] False" in r.stdout, r.stdout
+
+
+# ------------------------------------------------------------------------------------------------
+# text conditioning: the oracle's CLIP text tower against transformers' own CLIPTextModel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["TINY_CLIP", "TINY_CLIP_QUICK", "SD21_CLIP_H", "FLUX_CLIP_L"])
+def test_clip_text_oracle_matches_transformers(name):
+    """oracle/clip_text.py == transformers.CLIPTextModel on the same random weights (last hidden state and pooled
+    output), tiny configs and the full SD-2.1 (23 x 1024, gelu) / OpenAI CLIP-L (12 x 768, quick_gelu) towers; ids: the
+    empty prompt [BOS, EOS, pad...] and a random prompt with an early EOS."""
+    transformers = pytest.importorskip("transformers")
+    import omgsr_synth as syn
+    from oracle import clip_text
+    cfg = getattr(syn, name)
+    sd = syn.random_state_dict(syn.clip_text_shapes(cfg), seed=11)
+    hf_cfg = transformers.CLIPTextConfig(
+        vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+        num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads, max_position_embeddings=cfg.max_positions,
+        hidden_act=cfg.hidden_act, layer_norm_eps=cfg.layer_norm_eps, eos_token_id=cfg.eos_token_id,
+        pad_token_id=cfg.pad_token_id, bos_token_id=0)
+    model = transformers.CLIPTextModel(hf_cfg).eval()
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(5)
+    rnd = torch.randint(1, cfg.eos_token_id - 1, (1, cfg.max_positions), generator=g)
+    rnd[0, 9] = cfg.eos_token_id
+    rnd[0, 10:] = cfg.pad_token_id
+    ids = torch.cat([syn.empty_prompt_ids(cfg), rnd])
+    with torch.no_grad():
+        ref = model(input_ids=ids)
+        h, pooled = clip_text.clip_text_forward(sd, cfg, ids)
+    scale = float(ref.last_hidden_state.abs().max())
+    assert float((h - ref.last_hidden_state).abs().max()) <= 2e-5 * scale
+    assert float((pooled - ref.pooler_output).abs().max()) <= 2e-5 * scale
