@@ -218,6 +218,17 @@ int omgsr_softmax_rows_causal(const float* S, long long ld_s, void* P, long long
  * pos may be null): out[r, :] = tok[ids[r], :] + pos[r % T, :], bf16 tables [vocab, C] / [T, C], int32 ids, C % 8 == 0. */
 int omgsr_embed_tokens(const int* ids, const void* tok, const void* pos, void* out, long long rows, int T, int C,
                        int vocab, void* stream);
+/* Row softmax with an additive bias (T5Attention of `T5EncoderModel` in FluxPipeline.encode_prompt,
+ * infer_omgsr_f.py:36-43: softmax(q k^T + position_bias), no 1/sqrt(d)): P[r, j] = softmax_j(scale * S[r, j] +
+ * bias[(r % bias_rows) * ld_b + j]); bias fp32 [bias_rows = heads * queries, >= n]. */
+int omgsr_softmax_rows_bias(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int n_pad,
+                            float scale, const float* bias, long long bias_rows, long long ld_b, void* stream);
+/* T5LayerNorm: y[r, :] = x[r, :] * rsqrt(mean(x[r, :]^2) + eps) * weight (no mean subtraction, no bias); x bf16 or
+ * fp32 rows at pitch ldx (0 = C), y dense bf16. C % 8 == 0. */
+int omgsr_rmsnorm(const void* x, int x_f32, void* y, const float* weight, long long rows, int C, float eps,
+                  long long ldx, void* stream);
+/* out = a * b elementwise, dense bf16, n % 8 == 0 (T5DenseGatedActDense: gelu_new(wi_0 x) * wi_1 x). */
+int omgsr_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 /* FLUX q/k RMSNorm (per head, d = 128, learned weight, fp32 statistics) + rotary embedding, in place on
  * x[b, r, h, 128] = x + b*batch_stride + r*ld + h*128 (bf16). Heads [0, heads_per_weight) use weight[0],
  * the next heads_per_weight use weight[1], ... so q and k of a fused qkv row take one launch.

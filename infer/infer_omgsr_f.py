@@ -20,6 +20,40 @@ def _prepare_latent_image_ids(height, width, device, dtype):
     return ids.reshape(height * width, 3).to(device=device, dtype=dtype)
 
 
+def encode_prompt_flux(args):
+    """`FluxPipeline.encode_prompt(prompt, prompt_2=None)` (reference :36-48) through the sm_100a text engines:
+    pooled_prompt_embeds = CLIP-L(ids_77).pooler_output, prompt_embeds = T5-XXL encoder(ids_512)[0], text_ids = zeros.
+    Tokenisation is host string processing and stays with the checkpoint's own tokenizers; `random://` weights carry none,
+    so only the empty prompt (the reference's default) can be encoded there: CLIP [BOS, EOS, EOS...], T5 [EOS, pad...]."""
+    import omgsr_synth as syn
+    from omgsr_b200.engine_clip import build_clip_text
+    from omgsr_b200.engine_t5 import build_t5_encoder
+    if args.flux_path.startswith("random://"):
+        if args.prompt:
+            raise ValueError("random:// checkpoints carry no tokenizer: only the empty prompt \"\" can be encoded; "
+                             "pass --prompt_embeds for anything else")
+        full = "flux_dev" in args.flux_path
+        clip = build_clip_text("random://clip_l?seed=1235" if full else "random://clip_tiny_flux?seed=1235", args.device)
+        ids_clip = syn.empty_prompt_ids(clip.cfg)
+        t5 = build_t5_encoder("random://t5_xxl?seed=1236" if full else "random://t5_tiny_flux?seed=1236", args.device)
+        ids_t5 = syn.empty_prompt_ids_t5(t5.cfg, 512 if full else 32)
+    else:
+        from transformers import AutoTokenizer
+        tok1 = AutoTokenizer.from_pretrained(args.flux_path, subfolder="tokenizer")
+        tok2 = AutoTokenizer.from_pretrained(args.flux_path, subfolder="tokenizer_2")
+        clip = build_clip_text(os.path.join(args.flux_path, "text_encoder"), args.device)
+        t5 = build_t5_encoder(os.path.join(args.flux_path, "text_encoder_2"), args.device)
+        ids_clip = tok1(args.prompt, padding="max_length", max_length=tok1.model_max_length, truncation=True,
+                        return_tensors="pt").input_ids
+        ids_t5 = tok2(args.prompt, padding="max_length", max_length=512, truncation=True, return_tensors="pt").input_ids
+    _, pooled = clip(ids_clip)
+    del clip
+    prompt_embeds = t5(ids_t5)
+    del t5
+    torch.cuda.empty_cache()
+    return prompt_embeds, pooled, torch.zeros(prompt_embeds.shape[1], 3)
+
+
 def main(args):
     from infer.omgsr_f_infer_model import OMGSR_F_Infer
     omgsr = OMGSR_F_Infer(args.flux_path, args.lora_path, device=args.device, guidance_scale=args.guidance_scale,
@@ -27,19 +61,8 @@ def main(args):
     if args.prompt_embeds:
         pe = torch.load(args.prompt_embeds)
         prompt_embeds, pooled, text_ids = pe["prompt_embeds"], pe["pooled_prompt_embeds"], pe["text_ids"]
-    elif args.flux_path.startswith("random://"):
-        g = torch.Generator().manual_seed(1235)
-        full = "flux_dev" in args.flux_path
-        prompt_embeds = torch.randn(1, 512 if full else 32, 4096 if full else 256, generator=g)
-        pooled = torch.randn(1, 768 if full else 64, generator=g)
-        text_ids = torch.zeros(prompt_embeds.shape[1], 3)
     else:
-        from diffusers import FluxPipeline  # needs the real checkpoint + diffusers (reference :36-48)
-        pipe = FluxPipeline.from_pretrained(args.flux_path, transformer=None, vae=None, torch_dtype=args.weight_dtype).to("cuda")
-        with torch.no_grad():
-            prompt_embeds, pooled, text_ids = pipe.encode_prompt(args.prompt, prompt_2=None)
-        del pipe
-        torch.cuda.empty_cache()
+        prompt_embeds, pooled, text_ids = encode_prompt_flux(args)
     to = dict(device=args.device, dtype=args.weight_dtype)
     prompt_embeds, pooled, text_ids = prompt_embeds.to(**to), pooled.to(**to), text_ids.to(**to)
     grid = (args.process_size // 8) // 2

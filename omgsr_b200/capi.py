@@ -25,7 +25,7 @@ SYMBOLS = [
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
-    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta", "omgsr_set_halo_rolling", "omgsr_softmax_rows_causal", "omgsr_embed_tokens",
+    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta", "omgsr_set_halo_rolling", "omgsr_softmax_rows_causal", "omgsr_embed_tokens", "omgsr_softmax_rows_bias", "omgsr_rmsnorm", "omgsr_mul_bf16",
     "omgsr_groupnorm_coef", "omgsr_conv2d_gn_nhwc_bf16",
     "omgsr_resample_coeffs", "omgsr_resize_u8_workspace", "omgsr_resize_u8", "omgsr_u8_to_input", "omgsr_output_to_u8",
 ]
@@ -386,11 +386,51 @@ def softmax_rows(s, n, scale, out=None, causal=False):
     return out
 
 
+def softmax_rows_bias(s, n, scale, bias, out=None):
+    """s: fp32 [B, H, M, n_pad]; bias: fp32 [H, M, >= n] shared by the batch -> bf16 softmax(scale * s + bias)."""
+    _cuda_f32(s, "s"); _cuda_f32(bias, "bias")
+    assert s.is_contiguous() and bias.is_contiguous() and s.dim() == 4 and bias.shape[:2] == s.shape[1:3]
+    n_pad = s.shape[-1]
+    rows = s.numel() // n_pad
+    if out is None:
+        out = torch.empty(s.shape, device=s.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_softmax_rows_bias(_ptr(s), _ll(n_pad), _ptr(out), _ll(n_pad), _ll(rows), _i(n), _i(n_pad), _f(scale),
+                                      _ptr(bias), _ll(bias.shape[0] * bias.shape[1]), _ll(bias.shape[2]), _stream())
+    _check(rc, "omgsr_softmax_rows_bias")
+    return out
+
+
+def rmsnorm(x, weight, eps=1e-6, out=None):
+    """T5LayerNorm over the last dim of a dense bf16 / fp32 tensor -> dense bf16."""
+    if not (x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.is_contiguous()):
+        raise TypeError("x must be a contiguous CUDA bf16 / fp32 tensor")
+    _cuda_f32(weight, "weight")
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    rc = _lib.omgsr_rmsnorm(_ptr(x), _i(int(x.dtype == torch.float32)), _ptr(out), _ptr(weight), _ll(x.numel() // C),
+                            _i(C), _f(eps), _ll(C), _stream())
+    _check(rc, "omgsr_rmsnorm")
+    return out
+
+
+def mul(a, b, out=None):
+    _cuda_bf16(a, "a"); _cuda_bf16(b, "b")
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    if out is None:
+        out = torch.empty_like(a)
+    rc = _lib.omgsr_mul_bf16(_ptr(a), _ptr(b), _ptr(out), _ll(a.numel()), _stream())
+    _check(rc, "omgsr_mul_bf16")
+    return out
+
+
 def embed_tokens(ids, tok, pos=None):
     """ids: int32 [B, T]; tok: bf16 [vocab, C]; pos: bf16 [T, C] or None -> bf16 [B, T, C] = tok[ids] + pos."""
     if not (ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous()):
         raise TypeError("ids must be a contiguous CUDA int32 tensor")
-    _cuda_bf16(tok, "tok"); _cuda_bf16(pos, "pos")
+    _cuda_bf16(tok, "tok")
+    if pos is not None:
+        _cuda_bf16(pos, "pos")
     assert tok.is_contiguous() and (pos is None or (pos.is_contiguous() and pos.shape[0] >= ids.shape[-1]))
     B, T = ids.shape
     C = tok.shape[1]

@@ -266,7 +266,8 @@ __device__ __forceinline__ void ld8_stream(const float* p, float (&f)[8]) {
 template <int VPL, typename TIn>  // 8-element vectors per lane
 __global__ void layernorm_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, long long rows, int C, float eps,
-                                 long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch) {
+                                 long long rows_per_batch, long long gb_stride, long long ldx, long long x_batch,
+                                 int rms) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -289,7 +290,7 @@ __global__ void layernorm_kernel(const TIn* __restrict__ x, bf16* __restrict__ y
         for (int j = 0; j < 8; ++j) s += f[i][j];
       }
     }
-    const float mean = warp_sum(s) / C;
+    const float mean = rms ? 0.f : warp_sum(s) / C;  // rms (T5LayerNorm): no mean subtraction, variance about zero
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -328,17 +329,21 @@ __global__ void layernorm_kernel(const TIn* __restrict__ x, bf16* __restrict__ y
 // Row softmax of fp32 scores -> bf16 probabilities (one block per row, scores re-read from L2).
 // ------------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s, bf16* __restrict__ P, long long ld_p,
-                                    int n, int n_pad, float scale_log2e, int causal_m) {
+                                    int n, int n_pad, float scale_log2e, int causal_m, const float* __restrict__ bias,
+                                    long long bias_rows, long long ld_b) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[32];
   const float* s = S + blockIdx.x * ld_s;
   bf16* p = P + blockIdx.x * ld_p;
+  // additive bias (T5 relative position bias [heads * queries, keys], shared by the batch), in natural-log units
+  const float* bz = bias ? bias + (blockIdx.x % bias_rows) * ld_b : nullptr;
   // causal (text encoders): rows are [.., M queries]; query i sees keys 0..i, the rest of the row is written as zeros
   if (causal_m > 0) n = min(n, static_cast<int>(blockIdx.x % causal_m) + 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  auto val = [&](int j) { return bz ? fmaf(s[j], scale_log2e, bz[j] * 1.4426950408889634f) : s[j] * scale_log2e; };
   float m = -INFINITY;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, s[j]);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, val(j));
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
@@ -346,7 +351,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s,
   m = warp_max(m);
   __syncthreads();
   float sum = 0.f;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) sum += exp2f((s[j] - m) * scale_log2e);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sum += exp2f(val(j) - m);
   sum = warp_sum(sum);
   if (lane == 0) red[warp] = sum;
   __syncthreads();
@@ -354,7 +359,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long ld_s,
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
   for (int j = threadIdx.x; j < n_pad; j += blockDim.x)
-    p[j] = __float2bfloat16(j < n ? exp2f((s[j] - m) * scale_log2e) * inv : 0.f);
+    p[j] = __float2bfloat16(j < n ? exp2f(val(j) - m) * inv : 0.f);
 }
 
 // Register-resident variant for rows of up to 256 * 4 * V4 scores (V4 <= 32: 32768): the row is read from HBM exactly once (V4 float4
@@ -825,9 +830,22 @@ extern "C" int omgsr_groupnorm_combine(const float* sums, const float* pixels, i
   return check_launch("gn_combine_kernel");
 }
 
+static int layernorm_impl(const void* x, int x_f32, void* y, const float* gamma, const float* beta, long long rows, int C,
+                          float eps, long long rows_per_batch, long long gb_stride, long long ldx,
+                          long long x_batch_stride, int rms, void* stream);
 extern "C" int omgsr_layernorm(const void* x, int x_f32, void* y, const float* gamma, const float* beta, long long rows,
                                int C, float eps, long long rows_per_batch, long long gb_stride, long long ldx,
                                long long x_batch_stride, void* stream) {
+  return layernorm_impl(x, x_f32, y, gamma, beta, rows, C, eps, rows_per_batch, gb_stride, ldx, x_batch_stride, 0, stream);
+}
+/* T5LayerNorm: y = x * rsqrt(mean(x^2) + eps) * weight */
+extern "C" int omgsr_rmsnorm(const void* x, int x_f32, void* y, const float* weight, long long rows, int C, float eps,
+                             long long ldx, void* stream) {
+  return layernorm_impl(x, x_f32, y, weight, nullptr, rows, C, eps, 0, 0, ldx, 0, 1, stream);
+}
+static int layernorm_impl(const void* x, int x_f32, void* y, const float* gamma, const float* beta, long long rows, int C,
+                          float eps, long long rows_per_batch, long long gb_stride, long long ldx,
+                          long long x_batch_stride, int rms, void* stream) {
   if (C % 8 || C > 4096) return set_error(OMGSR_ERR_SHAPE, "layernorm: C=%d", C);
   if (ldx <= 0) ldx = C;
   if ((ldx | x_batch_stride) % 8) return set_error(OMGSR_ERR_ALIGN, "layernorm: strides %% 8");
@@ -842,10 +860,10 @@ extern "C" int omgsr_layernorm(const void* x, int x_f32, void* y, const float* g
   do {                                                                                                              \
     if (x_f32)                                                                                                      \
       launch_pdl(layernorm_kernel<V, float>, dim3(grid), dim3(threads), 0, st, static_cast<const float*>(x), yo, gamma, beta, rows, C,  \
-                                                           eps, rows_per_batch, gb_stride, ldx, x_batch_stride);    \
+                                                           eps, rows_per_batch, gb_stride, ldx, x_batch_stride, rms);    \
     else                                                                                                            \
       launch_pdl(layernorm_kernel<V, bf16>, dim3(grid), dim3(threads), 0, st, static_cast<const bf16*>(x), yo, gamma, beta, rows, C,    \
-                                                          eps, rows_per_batch, gb_stride, ldx, x_batch_stride);     \
+                                                          eps, rows_per_batch, gb_stride, ldx, x_batch_stride, rms);     \
   } while (0)
   if (vpl <= 1) LN_CASE(1);
   else if (vpl <= 2) LN_CASE(2);
@@ -880,7 +898,7 @@ extern "C" int omgsr_softmax_rows(const float* S, long long ld_s, void* P, long 
   }
   const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);
   launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
-      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f, 0);
+      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f, 0, static_cast<const float*>(nullptr), 1LL, 0LL);
   return check_launch("softmax_rows_kernel");
 }
 
@@ -891,8 +909,45 @@ extern "C" int omgsr_softmax_rows_causal(const float* S, long long ld_s, void* P
   if (rows > 0x7fffffffLL) return set_error(OMGSR_ERR_SHAPE, "softmax_rows_causal: too many rows");
   const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);
   launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0, static_cast<cudaStream_t>(stream),
-      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f, queries);
+      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f, queries, static_cast<const float*>(nullptr), 1LL, 0LL);
   return check_launch("softmax_rows_kernel(causal)");
+}
+
+extern "C" int omgsr_softmax_rows_bias(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n,
+                                       int n_pad, float scale, const float* bias, long long bias_rows, long long ld_b,
+                                       void* stream) {
+  if (rows <= 0 || n <= 0 || n_pad < n || !bias || bias_rows <= 0 || ld_b < n)
+    return set_error(OMGSR_ERR_SHAPE, "softmax_rows_bias: rows=%lld n=%d bias_rows=%lld", rows, n, bias_rows);
+  if (rows > 0x7fffffffLL) return set_error(OMGSR_ERR_SHAPE, "softmax_rows_bias: too many rows");
+  const int threads = n >= 2048 ? 256 : (n >= 512 ? 128 : 64);
+  launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0, static_cast<cudaStream_t>(stream),
+      S, ld_s, static_cast<bf16*>(P), ld_p, n, n_pad, scale * 1.4426950408889634f, 0, bias, bias_rows, ld_b);
+  return check_launch("softmax_rows_kernel(bias)");
+}
+
+// elementwise product of two dense bf16 tensors (T5 gated feed-forward: gelu_new(wi_0 x) * wi_1 x)
+__global__ void mul_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;  // grid_for caps the grid
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8; i += stride) {
+  const uint4 x = reinterpret_cast<const uint4*>(a)[i], y = reinterpret_cast<const uint4*>(b)[i];
+  const float2 x0 = unpack_bf16x2(x.x), x1 = unpack_bf16x2(x.y), x2 = unpack_bf16x2(x.z), x3 = unpack_bf16x2(x.w);
+  const float2 y0 = unpack_bf16x2(y.x), y1 = unpack_bf16x2(y.y), y2 = unpack_bf16x2(y.z), y3 = unpack_bf16x2(y.w);
+  uint4 o;
+  o.x = pack_bf16x2(x0.x * y0.x, x0.y * y0.y); o.y = pack_bf16x2(x1.x * y1.x, x1.y * y1.y);
+  o.z = pack_bf16x2(x2.x * y2.x, x2.y * y2.y); o.w = pack_bf16x2(x3.x * y3.x, x3.y * y3.y);
+  reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+extern "C" int omgsr_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+  if (n <= 0 || (n % 8)) return set_error(OMGSR_ERR_SHAPE, "mul: n=%lld (must be a positive multiple of 8)", n);
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return set_error(OMGSR_ERR_ALIGN, "mul: 16-byte alignment");
+  launch_pdl(mul_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const bf16*>(a), static_cast<const bf16*>(b), static_cast<bf16*>(out), n / 8);
+  return check_launch("mul_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -902,9 +957,9 @@ __global__ void embed_tokens_kernel(const int* __restrict__ ids, const bf16* __r
                                     bf16* __restrict__ out, long long rows, int T, int C, int vocab) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // one 8-channel granule each
   const int cg = C >> 3;
-  if (idx >= rows * cg) return;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;  // grid_for caps the grid: grid-stride loop
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < rows * cg; idx += stride) {
   const long long r = idx / cg;
   const int c = static_cast<int>(idx - r * cg) * 8;
   int id = ids[r];
@@ -919,6 +974,7 @@ __global__ void embed_tokens_kernel(const int* __restrict__ ids, const bf16* __r
     o.z = pack_bf16x2(a2.x + b2.x, a2.y + b2.y); o.w = pack_bf16x2(a3.x + b3.x, a3.y + b3.y);
   }
   *reinterpret_cast<uint4*>(out + r * C + c) = o;
+  }
 }
 
 extern "C" int omgsr_embed_tokens(const int* ids, const void* tok, const void* pos, void* out, long long rows, int T,

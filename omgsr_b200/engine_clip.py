@@ -120,7 +120,8 @@ def build_clip_text(spec, device):
         import omgsr_synth as syn
         name, _, query = spec[len("random://"):].partition("?")
         seed = int(dict(kv.split("=") for kv in query.split("&") if kv).get("seed", 0))
-        cfg = {"clip_h": syn.SD21_CLIP_H, "clip_l": syn.FLUX_CLIP_L, "clip_tiny": syn.TINY_CLIP}[name]
+        cfg = {"clip_h": syn.SD21_CLIP_H, "clip_l": syn.FLUX_CLIP_L, "clip_tiny": syn.TINY_CLIP,
+               "clip_tiny_flux": syn.TINY_FLUX_CLIP}[name]
         return B200CLIPText(syn.random_state_dict(syn.clip_text_shapes(cfg), seed=seed), cfg, device)
     if not os.path.isdir(spec):
         raise FileNotFoundError(spec)

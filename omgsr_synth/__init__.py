@@ -273,6 +273,9 @@ FLUX_CLIP_L = ClipTextConfig(hidden_size=768, intermediate_size=3072, num_layers
                              hidden_act="quick_gelu", pad_token_id=49407)
 TINY_CLIP = ClipTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2,
                            eos_token_id=999, pad_token_id=0)
+# sizes that match TINY_FLUX (pooled projection 64 wide, joint attention 256 wide)
+TINY_FLUX_CLIP = ClipTextConfig(vocab_size=1000, hidden_size=64, intermediate_size=128, num_layers=2, num_heads=2,
+                                hidden_act="quick_gelu", eos_token_id=999, pad_token_id=999)
 TINY_CLIP_QUICK = ClipTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2,
                                  hidden_act="quick_gelu", eos_token_id=999, pad_token_id=999)
 
@@ -292,6 +295,55 @@ def clip_text_shapes(cfg: ClipTextConfig) -> Dict[str, tuple]:
         _norm(sd, f"{b}.layer_norm2", C)
     _norm(sd, "text_model.final_layer_norm", C)
     return sd
+
+
+@dataclasses.dataclass
+class T5EncoderConfig:
+    """Encoder stack of T5 v1.1 as transformers' T5EncoderModel builds it (gated GELU-tanh feed-forward, RMS norms,
+    relative position bias shared by all layers, no biases)."""
+    vocab_size: int = 32128
+    d_model: int = 4096
+    d_kv: int = 64
+    d_ff: int = 10240
+    num_layers: int = 24
+    num_heads: int = 64
+    num_buckets: int = 32
+    max_distance: int = 128
+    layer_norm_eps: float = 1e-6
+    eos_token_id: int = 1
+    pad_token_id: int = 0
+
+
+# google/t5-v1_1-xxl encoder: `text_encoder_2` of FluxPipeline.encode_prompt (infer_omgsr_f.py:36-43), 512 tokens
+FLUX_T5_XXL = T5EncoderConfig()
+TINY_T5 = T5EncoderConfig(vocab_size=1000, d_model=128, d_kv=32, d_ff=256, num_layers=2, num_heads=4)
+TINY_FLUX_T5 = T5EncoderConfig(vocab_size=1000, d_model=256, d_kv=32, d_ff=512, num_layers=2, num_heads=4)
+SMALL_T5 = T5EncoderConfig(vocab_size=1000, d_model=512, d_kv=64, d_ff=1024, num_layers=3, num_heads=8)
+
+
+def t5_encoder_shapes(cfg: T5EncoderConfig) -> Dict[str, tuple]:
+    sd = {"shared.weight": (cfg.vocab_size, cfg.d_model)}
+    inner = cfg.num_heads * cfg.d_kv
+    for i in range(cfg.num_layers):
+        b = f"encoder.block.{i}.layer"
+        for n in ("q", "k", "v"):
+            sd[f"{b}.0.SelfAttention.{n}.weight"] = (inner, cfg.d_model)
+        sd[f"{b}.0.SelfAttention.o.weight"] = (cfg.d_model, inner)
+        if i == 0:
+            sd[f"{b}.0.SelfAttention.relative_attention_bias.weight"] = (cfg.num_buckets, cfg.num_heads)
+        sd[f"{b}.0.layer_norm.weight"] = (cfg.d_model,)
+        sd[f"{b}.1.DenseReluDense.wi_0.weight"] = (cfg.d_ff, cfg.d_model)
+        sd[f"{b}.1.DenseReluDense.wi_1.weight"] = (cfg.d_ff, cfg.d_model)
+        sd[f"{b}.1.DenseReluDense.wo.weight"] = (cfg.d_model, cfg.d_ff)
+        sd[f"{b}.1.layer_norm.weight"] = (cfg.d_model,)
+    sd["encoder.final_layer_norm.weight"] = (cfg.d_model,)
+    return sd
+
+
+def empty_prompt_ids_t5(cfg: T5EncoderConfig, length=512):
+    """T5 tokenisation of the empty prompt "" at max_length padding: [EOS, pad, pad, ...] (sentencepiece adds only the
+    end-of-sequence token)."""
+    return torch.tensor([[cfg.eos_token_id] + [cfg.pad_token_id] * (length - 1)], dtype=torch.int64)
 
 
 def empty_prompt_ids(cfg: ClipTextConfig):

@@ -301,3 +301,31 @@ def test_clip_text_oracle_matches_transformers(name):
     scale = float(ref.last_hidden_state.abs().max())
     assert float((h - ref.last_hidden_state).abs().max()) <= 2e-5 * scale
     assert float((pooled - ref.pooler_output).abs().max()) <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("name", ["TINY_T5", "SMALL_T5"])
+def test_t5_encoder_oracle_matches_transformers(name):
+    """oracle/t5_encoder.py == transformers.T5EncoderModel (v1.1: gated gelu_new feed-forward, RMS norms, shared
+    relative position bias) on the same random weights, 96 tokens (distances beyond max_exact and up to the logarithmic
+    buckets) incl. the empty prompt [EOS, pad...]."""
+    transformers = pytest.importorskip("transformers")
+    import omgsr_synth as syn
+    from oracle import t5_encoder
+    cfg = getattr(syn, name)
+    sd = syn.random_state_dict(syn.t5_encoder_shapes(cfg), seed=21)
+    hf_cfg = transformers.T5Config(
+        vocab_size=cfg.vocab_size, d_model=cfg.d_model, d_kv=cfg.d_kv, d_ff=cfg.d_ff, num_layers=cfg.num_layers,
+        num_heads=cfg.num_heads, relative_attention_num_buckets=cfg.num_buckets,
+        relative_attention_max_distance=cfg.max_distance, feed_forward_proj="gated-gelu",
+        layer_norm_epsilon=cfg.layer_norm_eps, dropout_rate=0.0)
+    model = transformers.T5EncoderModel(hf_cfg).eval()
+    sd_hf = dict(sd)
+    sd_hf["encoder.embed_tokens.weight"] = sd["shared.weight"]
+    missing, unexpected = model.load_state_dict(sd_hf, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    g = torch.Generator().manual_seed(6)
+    ids = torch.cat([syn.empty_prompt_ids_t5(cfg, 96), torch.randint(2, cfg.vocab_size, (1, 96), generator=g)])
+    with torch.no_grad():
+        ref = model(input_ids=ids).last_hidden_state
+        out = t5_encoder.t5_encoder_forward(sd, cfg, ids)
+    assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max())

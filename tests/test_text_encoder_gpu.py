@@ -69,3 +69,54 @@ def test_softmax_rows_causal_and_embed(capi):
     out = capi.embed_tokens(ids, tok, pos)
     ref = (tok.float()[ids.long()] + pos.float()[None]).bfloat16()
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("name,T", [("TINY_T5", 96), ("SMALL_T5", 512), ("FLUX_T5_XXL", 512)])
+def test_t5_encoder_engine_matches_oracle(name, T):
+    """T5EncoderModel(ids)[0] - OMGSR-F's prompt_embeds (FluxPipeline.encode_prompt, infer_omgsr_f.py:36-43) - through
+    the sm_100a engine against the fp32 oracle evaluated on the GPU in true fp32, same bf16-representable weights; the
+    full google/t5-v1_1-xxl encoder shape (24 x 4096, 64 heads, d_ff 10240, 4.7 B parameters) at 512 tokens. Bar: max-
+    relative error <= 2e-2."""
+    import omgsr_synth as syn
+    from omgsr_b200.engine_t5 import B200T5Encoder
+    from oracle import t5_encoder
+    cfg = getattr(syn, name)
+    # T5 has no 1/sqrt(d) in its attention: trained weights absorb it. N(0, 1/fan_in) weights would give logits of
+    # +-sqrt(d_kv) * 3 (one-hot softmaxes whose argmax flips under bf16 rounding of q / k): the q projection carries the
+    # factor instead, as in a trained model
+    sd = syn.random_state_dict(syn.t5_encoder_shapes(cfg), seed=21, dtype=torch.bfloat16, device="cuda",
+                               out_gain={"SelfAttention.q.weight": cfg.d_kv ** -0.5})
+    g = torch.Generator().manual_seed(6)
+    ids = torch.cat([syn.empty_prompt_ids_t5(cfg, T), torch.randint(2, cfg.vocab_size, (1, T), generator=g)])
+    eng = B200T5Encoder(sd, cfg, "cuda")
+    out = eng(ids)
+    torch.cuda.synchronize()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref = t5_encoder.t5_encoder_forward(sd, cfg, ids.cuda())
+    assert out.shape == (2, T, cfg.d_model) and torch.isfinite(out.float()).all()
+    e = _rel(out, ref)
+    print(f"\n[t5 encoder {name}] last_hidden_state max-rel {e:.3e} (rms-rel "
+          f"{float((out.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()):.3e})")
+    assert e <= 2e-2
+
+
+def test_rmsnorm_softmax_bias_mul(capi):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 50, 512, generator=g).cuda()
+    w = (torch.rand(512, generator=g) + 0.5).cuda()
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    for xin in (x, x.bfloat16()):
+        y = capi.rmsnorm(xin, w, 1e-6).float()
+        assert float((y - ref).abs().max()) <= (2e-2 if xin.dtype == torch.bfloat16 else 1.6e-2) * float(ref.abs().max())
+    s = torch.randn(2, 4, 96, 128, generator=g).cuda()
+    bias = torch.randn(4, 96, 96, generator=g).cuda()
+    p = capi.softmax_rows_bias(s, 96, 0.7, bias).float()
+    pref = torch.softmax(s[..., :96] * 0.7 + bias[None], -1)
+    assert float((p[..., :96] - pref).abs().max()) < 4e-3 and float(p[..., 96:].abs().max()) == 0.0
+    # sizes above the launch helpers' grid cap (148 x 8 blocks x 256 threads): grid-stride loops
+    a, b = torch.randn(5000, 1024, generator=g).bfloat16().cuda(), torch.randn(5000, 1024, generator=g).bfloat16().cuda()
+    assert torch.equal(capi.mul(a, b), (a.float() * b.float()).bfloat16())
+    tok = torch.randn(3000, 2048, generator=g).bfloat16().cuda()
+    ids = torch.randint(0, 3000, (4, 512), generator=g).to(torch.int32).cuda()
+    assert torch.equal(capi.embed_tokens(ids, tok, None), tok[ids.long()])
