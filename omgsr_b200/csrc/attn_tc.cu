@@ -582,11 +582,11 @@ constexpr float kAttnRebase = 1024.0f;
 // ================================================================================================================
 // v3 (round 2): 128 keys per block, single-buffered S and P, ping-pong order on the tensor pipe.
 //
-// scripts/mma_probe.cu (profiles/r02/mma_probe4_single_cta_tmemA.txt): a cta_group::1 tcgen05.mma costs ~154 cycles for
-// ANY N <= 128 (A from shared memory or from TMEM alike) and ~172 at N = 256. v2 issues S = Q K^T with N = 64 keys: per
-// 128 keys and 256 query rows its S instructions cost 2 x 2 x 8 x 154 = 4.9 k cycles for 2.5 k cycles of math, which is
-// why the FLUX attention sat at 34 % tensor-pipe activity whatever the softmax warps did. With 128 keys per block the
-// same S costs 2.5 k cycles (PV is unchanged: its N is the head dimension): 7.4 k -> 4.9 k cycles per 128 keys.
+// Design history: this kernel was motivated by a probe that showed ~154 cycles per tcgen05.mma for ANY N <= 128 (so v2's
+// N = 64 key blocks looked twice as expensive as N = 128 ones). That figure was the single-lane issue loop, not the
+// tensor pipe (with the warp-uniform issue loop below an N = 128 instruction costs its 64 pipe
+// cycles, an N = 64 one ~45). 128 keys per block still halve the number of instructions, barrier round trips and
+// softmax passes per key, and this is the fastest of the four kernels at both head sizes.
 //   * TMEM: S_a @0, S_b @128 (128 fp32 columns each, ONE buffer per group), O_a @256, O_b @384.
 //   * tensor-pipe order per block j:  PV_a(j), S_a(j+1), PV_b(j), S_b(j+1).  Group a exponentiates block j while
 //     the pipe runs PV_b(j-1) and S_b(j), group b while it runs PV_a(j) and S_a(j+1): each group has a window of two
@@ -911,11 +911,12 @@ static int launch_attn3(const void* q, const void* k, const void* v, void* out, 
 // ================================================================================================================
 // v4 (round 2, d = 128): v3 with the PV product TRANSPOSED so that it, too, is made of N = 256 instructions.
 //
-// In v3 every PV instruction is N = d = 128 at ~154 cycles for 128 query rows x 16 keys. Here the accumulator is
-// O^T [d = 128 lanes, 256 query columns (both groups)]: A = V^T (the V tile read as an MN-major A operand), B = P of
-// BOTH groups ([256 query rows, 16 keys], K-major: the two groups' P tiles are adjacent in shared memory), one N = 256
-// instruction at ~172 cycles per 16 keys serves 256 query rows. Per 128 keys and 256 query rows: S 2 x 8 x 154 +
-// PV^T 8 x 172 = 3.8 k cycles against v3's 4.9 k (mma_probe figures).
+// (Kept as OMGSR_ATTN_VARIANT=4, no longer the default: it was built on the wrong "154 cycles per N <= 128 instruction"
+// figure of the single-lane issue loop, DESIGN.md section 4. At the real costs - 64 cycles per N = 128, 128 per N = 256
+// instruction - the transposed product saves no tensor-pipe time and v3 is faster: 0.895 vs 0.977 ms on the FLUX shape.)
+// The accumulator is O^T [d = 128 lanes, 256 query columns (both groups)]: A = V^T (the V tile read as an MN-major A
+// operand), B = P of BOTH groups ([256 query rows, 16 keys], K-major: the two groups' P tiles are adjacent in shared
+// memory), one N = 256 instruction per 16 keys serves 256 query rows.
 //   * TMEM: S_a @0, S_b @128 (single buffers), O^T @256 (256 columns: group a's query rows are columns 0..127).
 //   * tensor-pipe order: S_a(j+1), S_b(j+1), PV^T(j). A group reads its S, exponentiates into REGISTERS (bf16-packed,
 //     64 registers), releases S at once (s_free) so that the next S can be issued, and stores P only when PV^T(j-1) has

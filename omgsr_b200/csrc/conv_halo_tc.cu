@@ -559,12 +559,14 @@ conv_halo_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row-shared CTA-pair kernel (round 2; the default for 16 < Cout <= 128).
+// Row-shared CTA-pair kernel (round 2).
 //
-// scripts/mma_probe.cu measured what bounds the kernel above: a tcgen05.mma of M = 128 rows per CTA costs ~127-141
-// cycles whatever N <= 128 is and ~174 cycles at N = 256, i.e. an N = 128 instruction stream cannot exceed ~62 % of the
-// N = 256 rate - exactly where conv_halo_tc2_kernel sat (profiles/r02/mma_probe*.txt). A 3x3 convolution with 128
-// output channels still has N = 256 instructions in it: for a fixed tap column s, output row t with tap row r reads
+// Design history: built when a probe showed ~130-170 cycles per tcgen05.mma whatever N <= 128 is, which made N = 256
+// instructions look twice as cheap per column. That figure was the single-lane issue loop (the
+// loops below are warp-uniform now and an N = 128 instruction costs its 64 pipe cycles). The pairing still halves the
+// instruction count of the shared rows; conv_halo_rr_kernel below supersedes this kernel wherever it applies (this one
+// remains for the 2x2 parity convolutions of the fused upsample and for short images). A 3x3 convolution with 128
+// output channels has N = 256 instructions in it: for a fixed tap column s, output row t with tap row r reads
 // input row rho = t + r, so (t, r) and (t + 1, r - 1) read the SAME A operand. With the two accumulators of a TM = 2
 // tile adjacent in TMEM, one instruction
 //     D[256 px pair, 256] (+)= A[row rho, shifted by s] x [ W(r = rho, s) | W(r = rho - 1, s) ]^T
