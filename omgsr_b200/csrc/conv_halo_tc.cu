@@ -14,6 +14,8 @@
 // conv_halo_tc2_kernel<2,true> (the same plus four transform warps that apply the INPUT's GroupNorm + SiLU to the halo
 // tile in shared memory, omgsr_conv2d_gn_nhwc_bf16) and the single-CTA conv_halo_tc_kernel<BN,2> (BN = 16 for thin
 // Cout such as the decoder's conv_out, BN = 128 for single-tile problems).
+#include <vector>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "../../include/omgsr_b200.h"
@@ -41,6 +43,7 @@ struct HaloParams {
   int gn_cpg, gn_groups, gn_slots;  // gn_sums: scratch [image][gn_slots][groups * 2], see gn_flush (epilogue.cuh)
   const float2* gn_in;        // optional [B][Cin] (scale, shift): GroupNorm + SiLU applied to the INPUT (pair kernel)
   int IH, IW;                 // input extents (validity of halo pixels for the input transform)
+  int res_tap;                // rolling-row kernel: the residual is accumulated as an identity-weight tap (see there)
 };
 
 template <int BN, int TM>
@@ -918,6 +921,11 @@ conv_halo_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //     8 KB: its 64-row half); one tcgen05.commit per B stage and one per unit (A slot).
 //   * work split: the B * ceil(tiles_x / 2) * H pair-rows are cut into one contiguous range per cluster (a range crosses
 //     at most a few strip boundaries; each segment costs two extra input rows), so all clusters finish together.
+//   * residual (Cout = 128): accumulated as an IDENTITY TAP - the residual row of output o is one more A row (TMA, full
+//     lines from DRAM instead of per-thread 32-byte loads), multiplied by the 128 x 128 identity (8 N = 128 instructions
+//     per output row, +11 % MMA time; exact: 1.0 x bf16 into the fp32 accumulator). The epilogue then has no residual
+//     loads, unpacks or adds: the heaviest variant (input GroupNorm + residual + statistics) went from 1.24 ms to the
+//     cost of the variant without residual plus the extra MMAs.
 //   * epilogue: warps 4..7 take columns 0..63 of every output row, warps 8..11 columns 64..127. A slot must be free
 //     again ONE row-step (~6.5 k cycles) after it completes, so a warp copies its 64 columns to registers, zeroes
 //     them and returns the slot before it does any arithmetic or stores.
@@ -970,7 +978,8 @@ __device__ __forceinline__ RrPlan rr_plan(int i, int L, uint32_t n0) {
 template <bool XF, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XF ? 512 : 384, 1)
 conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB128,
-                    const __grid_constant__ CUtensorMap tmB64, const HaloParams p) {
+                    const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmR,
+                    const __grid_constant__ CUtensorMap tmI64, const HaloParams p) {
   using C = HaloRrCfg;
   constexpr int BN = 128;
   extern __shared__ uint8_t smem_raw[];
@@ -997,6 +1006,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB128);
     tma_prefetch_desc(&tmB64);
+    if (p.res_tap) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmI64); }
     for (int i = 0; i < NA; ++i) {
       mbar_init(&a_full[i], XF ? 1 : 2);
       mbar_init(&a_ready[i], 8);
@@ -1074,6 +1084,22 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (++slot == NA) { slot = 0; ph ^= 1; }
           }
+          // residual as an identity tap: the residual row of output i - 1 follows the conv units of input row i
+          if (p.res_tap && i >= 1 && i <= L) {
+            for (int c = 0; c < 2; ++c) {
+              mbar_wait_relaxed(&a_empty[slot], ph ^ 1);
+              uint8_t* dst = sA + slot * C::kRowBytes;
+              if (XF) {
+                mbar_expect_tx(&a_full[slot], row_bytes);
+                tma_load_5d(dst, &tmR, &a_full[slot], c * 64, tx * 128 - p.pad_l, ya + i - 1, b, 0);
+              } else {
+                if (rank == 0) mbar_expect_tx(&a_full[slot], 2 * row_bytes);
+                else mbar_arrive_remote(&a_full[slot], 0);
+                tma2_load_5d(dst, &tmR, &a_full[slot], c * 64, tx * 128 - p.pad_l, ya + i - 1, b, 0);
+              }
+              if (++slot == NA) { slot = 0; ph ^= 1; }
+            }
+          }
         }
         g += L;
       }
@@ -1103,6 +1129,16 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (pl.pair[k]) tma2_load_4d(dst + pl.boff[k], &tmB128, &b_full[bs], kcol, 0, 0, 0);
                 else tma2_load_4d(dst + pl.boff[k], &tmB64, &b_full[bs], kcol, static_cast<int>(rank) * 64, 0, 0);
               }
+              if (++bs == NB) { bs = 0; bph ^= 1; }
+            }
+          }
+          if (p.res_tap && i >= 1 && i <= L) {  // identity weights of the residual tap: this CTA's 64 rows, one stage
+            for (int c = 0; c < 2; ++c) {
+              uint8_t* dst = sB + bs * C::kBSlotBytes;
+              mbar_wait_relaxed(&b_empty[bs], bph ^ 1);
+              if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * 8192);
+              else mbar_arrive_remote(&b_full[bs], 0);
+              tma2_load_4d(dst, &tmI64, &b_full[bs], c * 64, static_cast<int>(rank) * 64, 0, 0);
               if (++bs == NB) { bs = 0; bph ^= 1; }
             }
           }
@@ -1166,6 +1202,29 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (leader) tc_commit2_mc(&a_empty[as]);  // the row is free once everything issued so far retires
             if (++as == NA) { as = 0; aph ^= 1; }
+          }
+          if (p.res_tap && i >= 1 && i <= L) {
+            // residual of output i - 1 (its accumulator is live from step i - 1 to step i + 1): D += R[row, shifted by
+            // pad_l pixels] x I^T, N = 128, exact (1.0 x bf16 in an fp32 accumulator)
+            const uint32_t dr = tmem_base + ((n0 + i - 1) & 3u) * BN;
+            for (int c = 0; c < 2; ++c) {
+              if (XF) mbar_wait(&a_ready[as], aph);
+              else mbar_wait(&a_full[as], aph);
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t a_lo = desc_lo | ((smem_u32(sA + as * C::kRowBytes) + static_cast<uint32_t>(p.pad_l * 128)) >> 4);
+              const uint32_t b_lo = desc_lo | (smem_u32(sB + bs * C::kBSlotBytes) >> 4);
+              if (leader) {
+                if (!no_mma) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) tc_mma2_ss(dr, dsc(a_lo + 2 * k), dsc(b_lo + 2 * k), idesc128, 1u);
+                }
+                tc_commit2_mc(&b_empty[bs]);
+                tc_commit2_mc(&a_empty[as]);
+              }
+              if (++bs == NB) { bs = 0; bph ^= 1; }
+              if (++as == NA) { as = 0; aph ^= 1; }
+            }
           }
           if (i >= 2 && leader) tc_commit2_mc(&acc_full[(n0 + i - 2) & 3]);  // output i - 2 has received its three tap rows
         }
@@ -1265,6 +1324,16 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (++slot == NA) { slot = 0; ph ^= 1; }
         }
+        if (p.res_tap && i >= 1 && i <= L) {  // residual rows are not normalised: hand them on as they are
+          for (int c = 0; c < 2; ++c) {
+            mbar_wait_relaxed(&a_full[slot], ph, 32);
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(&a_ready[slot]); else mbar_arrive_remote_relaxed(&a_ready[slot], 0);
+            }
+            if (++slot == NA) { slot = 0; ph ^= 1; }
+          }
+        }
       }
       g += L;
     }
@@ -1302,7 +1371,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         e.gn_part = p.gn_sums ? gn_part : nullptr;
         const bool valid = !dummy && (x < p.W) && !(p.debug & 1);
         uint4 rr0[4] = {}, rr1[4] = {};
-        e.res_row = (p.res && !dummy) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
+        e.res_row = (p.res && !p.res_tap && !dummy) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
         if (e.res_row) {  // this thread's 64 residual channels are in flight before the accumulator wait
           load_res32(rr0, e, c_off, valid);
           load_res32(rr1, e, c_off + 32, valid);
@@ -1355,26 +1424,48 @@ static const int g_halo_rolling_default = getenv("OMGSR_HALO_ROLLING") ? atoi(ge
 int g_halo_rolling = g_halo_rolling_default;
 int halo_rolling_default() { return g_halo_rolling_default; }
 
+// 128 x 128 bf16 identity per device: the weight matrix of the residual tap
+static const void* identity128() {
+  static void* ptr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!ptr[dev]) {
+    std::vector<uint16_t> h(128 * 128, 0);
+    for (int i = 0; i < 128; ++i) h[i * 128 + i] = 0x3f80;  // bf16 1.0
+    void* d = nullptr;
+    if (cudaMalloc(&d, h.size() * 2) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    ptr[dev] = d;
+  }
+  return ptr[dev];
+}
+
 template <bool XF, int MODE>
 static int launch_halo_rr_m(const CUtensorMap& tmA, const CUtensorMap& tmB128, const CUtensorMap& tmB64,
-                            const HaloParams& p, int clusters, cudaStream_t st) {
+                            const CUtensorMap& tmR, const CUtensorMap& tmI64, const HaloParams& p, int clusters,
+                            cudaStream_t st) {
   using C = HaloRrCfg;
   static unsigned long long attr_done = 0;  // one bit per device
   if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_halo_rr_kernel<XF, MODE>), C::kSmemBytes, &attr_done,
                                 "conv_halo_rr")) return rc;
   g_trace_variant = XF ? "conv_halo_rr_kernel<1>" : "conv_halo_rr_kernel<0>";
-  launch_pdl(conv_halo_rr_kernel<XF, MODE>, dim3(2 * clusters), dim3(XF ? 512 : 384), C::kSmemBytes, st, tmA, tmB128, tmB64, p);
+  launch_pdl(conv_halo_rr_kernel<XF, MODE>, dim3(2 * clusters), dim3(XF ? 512 : 384), C::kSmemBytes, st, tmA, tmB128, tmB64,
+             tmR, tmI64, p);
   return check_launch("conv_halo_rr_kernel");
 }
 template <bool XF>
 static int launch_halo_rr(const CUtensorMap& tmA, const CUtensorMap& tmB128, const CUtensorMap& tmB64,
-                          const HaloParams& p, int clusters, cudaStream_t st) {
-  switch (epilogue_mode(p.act, false, p.res != nullptr, p.out_f32 != 0, p.gn_sums != nullptr)) {
-    case EPI_PLAIN: return launch_halo_rr_m<XF, EPI_PLAIN>(tmA, tmB128, tmB64, p, clusters, st);
-    case EPI_RES: return launch_halo_rr_m<XF, EPI_RES>(tmA, tmB128, tmB64, p, clusters, st);
-    case EPI_GN: return launch_halo_rr_m<XF, EPI_GN>(tmA, tmB128, tmB64, p, clusters, st);
-    case EPI_RES_GN: return launch_halo_rr_m<XF, EPI_RES_GN>(tmA, tmB128, tmB64, p, clusters, st);
-    default: return launch_halo_rr_m<XF, EPI_GENERIC>(tmA, tmB128, tmB64, p, clusters, st);
+                          const CUtensorMap& tmR, const CUtensorMap& tmI64, const HaloParams& p, int clusters,
+                          cudaStream_t st) {
+  // with the residual folded into the MMAs (p.res_tap) the epilogue is the one without residual
+  const bool epi_res = p.res != nullptr && !p.res_tap;
+  switch (epilogue_mode(p.act, false, epi_res, p.out_f32 != 0, p.gn_sums != nullptr)) {
+    case EPI_PLAIN: return launch_halo_rr_m<XF, EPI_PLAIN>(tmA, tmB128, tmB64, tmR, tmI64, p, clusters, st);
+    case EPI_RES: return launch_halo_rr_m<XF, EPI_RES>(tmA, tmB128, tmB64, tmR, tmI64, p, clusters, st);
+    case EPI_GN: return launch_halo_rr_m<XF, EPI_GN>(tmA, tmB128, tmB64, tmR, tmI64, p, clusters, st);
+    case EPI_RES_GN: return launch_halo_rr_m<XF, EPI_RES_GN>(tmA, tmB128, tmB64, tmR, tmI64, p, clusters, st);
+    default: return launch_halo_rr_m<XF, EPI_GENERIC>(tmA, tmB128, tmB64, tmR, tmI64, p, clusters, st);
   }
 }
 
@@ -1455,7 +1546,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   p.a_bytes = 128 * p.pw * (TM + R - 1);
   { static const int dbg = getenv("OMGSR_HALO_DEBUG") ? atoi(getenv("OMGSR_HALO_DEBUG")) : 0; p.debug = dbg; }
   p.gn_sums = nullptr; p.gn_cpg = 0; p.gn_groups = 0;
-  p.gn_in = reinterpret_cast<const float2*>(gn_in); p.IH = IH; p.IW = IW;
+  p.gn_in = reinterpret_cast<const float2*>(gn_in); p.IH = IH; p.IW = IW; p.res_tap = 0;
   if (gn_sums) {
     const int cpg = gn_groups > 0 ? Cout / gn_groups : 0;
     if (out_f32 || gn_groups <= 0 || gn_groups > 32 || Cout % gn_groups || !(cpg == 4 || cpg == 8 || cpg == 16)) return 1;
@@ -1505,8 +1596,30 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
                         Cin <= 256;  // (the input-GroupNorm coefficient table in shared memory holds 256 channels)
     const bool rr_on = g_halo_rolling >= 0 ? g_halo_rolling != 0 : gn_in != nullptr;
     if (rr_fit && rr_on) {
-      if (gn_in) return launch_halo_rr<true>(tmRow, tmB128, tmB64, p, max_clusters, st);
-      return launch_halo_rr<false>(tmRow, tmB128, tmB64, p, max_clusters, st);
+      // residual as an identity tap (Cout = 128, bf16 residual with TMA-compatible strides): OMGSR_HALO_RES_TAP=0 keeps
+      // the residual add in the epilogue (A/B timing)
+      static const bool tap_off = getenv("OMGSR_HALO_RES_TAP") && atoi(getenv("OMGSR_HALO_RES_TAP")) == 0;
+      CUtensorMap tmR = tmRow, tmI64 = tmB64;
+      HaloParams q = p;
+      q.res_tap = 0;
+      if (res && !tap_off && Cout == 128 && !out_f32 && r_sx >= 128 && (r_sx % 8) == 0 && (r_sy % 8) == 0 &&
+          (r_sb % 8) == 0 && (reinterpret_cast<uintptr_t>(res) % 16) == 0) {
+        const void* eye = identity128();
+        if (eye) {
+          uint64_t rdims[5] = {128, static_cast<uint64_t>(OW), static_cast<uint64_t>(OH), static_cast<uint64_t>(B), 1};
+          uint64_t rstr[4] = {static_cast<uint64_t>(r_sx) * eb, static_cast<uint64_t>(r_sy) * eb,
+                              static_cast<uint64_t>(r_sb) * eb, static_cast<uint64_t>(r_sb) * eb * B};
+          rc = make_tmap_bf16(&tmR, res, 5, rdims, rstr, rbox, CU_TENSOR_MAP_SWIZZLE_128B);
+          if (rc) return rc;
+          uint64_t id[4] = {128, 128, 1, 1};
+          uint64_t is[3] = {128 * eb, 128 * 128 * eb, 128 * 128 * eb};
+          rc = make_tmap_bf16(&tmI64, eye, 4, id, is, wb64, CU_TENSOR_MAP_SWIZZLE_128B);
+          if (rc) return rc;
+          q.res_tap = 1;
+        }
+      }
+      if (gn_in) return launch_halo_rr<true>(tmRow, tmB128, tmB64, tmR, tmI64, q, max_clusters, st);
+      return launch_halo_rr<false>(tmRow, tmB128, tmB64, tmR, tmI64, q, max_clusters, st);
     }
     if (gn_in) return launch_halo_rs<true>(tmRow, tmB128, tmB64, p, st);
     return launch_halo_rs<false>(tmRow, tmB128, tmB64, p, st);
