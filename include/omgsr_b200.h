@@ -86,6 +86,10 @@ int omgsr_set_gemm_2cta(int on);
  * rolling-row kernel, 1 the rolling-row kernel for every eligible convolution, -2 back to the start-up default
  * (OMGSR_HALO_ROLLING). Test / A-B timing only. */
 int omgsr_set_halo_rolling(int mode);
+/* 1 if omgsr_conv2d_gn_nhwc_bf16 can take a 3x3 / s1 / p1 convolution with 256 output channels on this device (two
+ * 128-channel passes of the rolling-row kernel): asked by the engines before they leave a GroupNorm + SiLU
+ * (diffusers ResnetBlock2D norm -> silu -> conv, task queue infer/vaehook.py:248-276) to the convolution after it. */
+int omgsr_conv_gn_wide_fusable(int B, int OH, int OW, int Cin, int Cout);
 
 /* Row-batched linear layer: D[b, m, :] = epi(A[b, m, :] * Wt^T) for b < batch, with independent batch strides
  * for A / D / res (tokens of one image may live inside a longer joint [text; image] sequence), a per-batch

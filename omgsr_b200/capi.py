@@ -25,7 +25,7 @@ SYMBOLS = [
     "omgsr_rmsnorm_rope", "omgsr_posterior_sample", "omgsr_latent_axpby", "omgsr_x0_unscale",
     "omgsr_pack_latents", "omgsr_unpack_latents", "omgsr_tile_blend",
     "omgsr_wavelet_fix", "omgsr_adain_fix", "omgsr_atrous_blur", "omgsr_nchw_to_nhwc", "omgsr_nhwc_to_nchw",
-    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta", "omgsr_set_halo_rolling", "omgsr_softmax_rows_causal", "omgsr_embed_tokens", "omgsr_softmax_rows_bias", "omgsr_rmsnorm", "omgsr_mul_bf16",
+    "omgsr_flash_attn_bf16", "omgsr_flash_attn_set_variant", "omgsr_set_gemm_2cta", "omgsr_set_halo_rolling", "omgsr_conv_gn_wide_fusable", "omgsr_softmax_rows_causal", "omgsr_embed_tokens", "omgsr_softmax_rows_bias", "omgsr_rmsnorm", "omgsr_mul_bf16",
     "omgsr_groupnorm_coef", "omgsr_conv2d_gn_nhwc_bf16",
     "omgsr_resample_coeffs", "omgsr_resize_u8_workspace", "omgsr_resize_u8", "omgsr_u8_to_input", "omgsr_output_to_u8",
 ]
@@ -300,8 +300,14 @@ def groupnorm_coef(stats, gamma, beta, B, HW, groups=32, eps=1e-6, shared_mod=0)
 
 def conv_gn_in_fusable(B, H, W, Cin, Cout):
     """can omgsr_conv2d_gn_nhwc_bf16 serve this 3x3/s1/p1 conv (CTA-pair input-halo path)?"""
+    if os.environ.get("OMGSR_NO_GN_IN_FUSION"):
+        return False
+    if Cout == 256:  # two 128-channel passes of the rolling-row kernel (large images only: the library decides)
+        if os.environ.get("OMGSR_NO_WIDE"):   # A/B timing
+            return False
+        return bool(_lib.omgsr_conv_gn_wide_fusable(_i(B), _i(H), _i(W), _i(Cin), _i(Cout)))
     tiles = ((W + 127) // 128) * ((H + 1) // 2) * B
-    return W >= 96 and Cin % 64 == 0 and 16 < Cout <= 128 and tiles >= 2 and not os.environ.get("OMGSR_NO_GN_IN_FUSION")
+    return W >= 96 and Cin % 64 == 0 and 16 < Cout <= 128 and tiles >= 2
 
 
 def conv2d_gn(x, coef, w, bias, res=None, out=None, gn_stats=None, gn_groups=32):

@@ -936,8 +936,8 @@ struct HaloRrCfg {
   static constexpr int kBSlotBytes = 24 * 1024; // weight units of ONE tap column of a unit: 16 KB pair + 8 KB single
   static constexpr int kBSlots = 4;
   static constexpr int kBarBytes = 512;
-  // + statistics partials (8 warps x 64 floats) + bias slices (8 x 128 floats) + input GroupNorm coefficient table (2 KB)
-  static constexpr int kSmemBytes = kASlots * kRowBytes + kBSlots * kBSlotBytes + 1024 + kBarBytes + 2048 + 32 * 128 + 2048;
+  // + statistics partials (8 warps x 64 floats) + bias slices (8 x 128 floats) + input GroupNorm coefficient table (4 KB: 512 channels)
+  static constexpr int kSmemBytes = kASlots * kRowBytes + kBSlots * kBSlotBytes + 1024 + kBarBytes + 2048 + 32 * 128 + 4096;
 };
 
 // the MMAs of one input row (step i of a segment of L output rows whose first output has running index n0): up to two
@@ -1043,17 +1043,23 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();  // nothing above touches global memory
 
   // this cluster's contiguous range of pair-rows: pair-strip q = (image, pair of 128-pixel strips), H rows each
+  // (Cout = 256: two passes of 128 output channels over the same pair-strip, back to back in the range, so the second
+  // pass finds the input rows in L2)
   const int xp = (p.tiles_x + 1) >> 1;
-  const long long G = static_cast<long long>(p.B) * xp * p.H;  // < 2^31 (host check)
+  const int nt = p.n_tiles;
+  const long long G = static_cast<long long>(p.B) * xp * p.H * nt;  // < 2^31 (host check)
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int g_begin = static_cast<int>(G * cluster_id / num_clusters), g_end = static_cast<int>(G * (cluster_id + 1) / num_clusters);
   const int row_bytes = p.pw * 128;
   constexpr int kBWarp = 2;
   // segment decode shared by all roles
+  int cur_n_tile = 0;  // output-channel tile (128 wide) of the current segment
   auto segment = [&](int g, int& b, int& tx, bool& dummy, int& ya, int& L) {
-    const int q = g / p.H;
-    ya = g - q * p.H;
+    const int q0 = g / p.H;
+    ya = g - q0 * p.H;
     L = min(p.H - ya, g_end - g);
+    cur_n_tile = q0 % nt;
+    const int q = q0 / nt;
     b = q / xp;
     tx = 2 * (q - b * xp) + static_cast<int>(rank);
     dummy = tx >= p.tiles_x;
@@ -1126,8 +1132,8 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int k = 0; k < pl.n_ops; ++k) {
                 const int r_mine = pl.pair[k] ? (rank == 0 ? pl.tap0[k] : pl.tap1[k]) : pl.tap0[k];
                 const int kcol = (r_mine * 3 + sx) * p.Cin + c * 64;
-                if (pl.pair[k]) tma2_load_4d(dst + pl.boff[k], &tmB128, &b_full[bs], kcol, 0, 0, 0);
-                else tma2_load_4d(dst + pl.boff[k], &tmB64, &b_full[bs], kcol, static_cast<int>(rank) * 64, 0, 0);
+                if (pl.pair[k]) tma2_load_4d(dst + pl.boff[k], &tmB128, &b_full[bs], kcol, cur_n_tile * 128, 0, 0);
+                else tma2_load_4d(dst + pl.boff[k], &tmB64, &b_full[bs], kcol, cur_n_tile * 128 + static_cast<int>(rank) * 64, 0, 0);
               }
               if (++bs == NB) { bs = 0; bph ^= 1; }
             }
@@ -1244,7 +1250,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int j = tid & 7;              // 16-byte unit (8 channels) of a 128-byte pixel row: fixed per thread
     const int p0 = tid >> 3;            // first pixel of this thread in a row; then every 16th (<= 9 per row)
     const uint32_t off0 = static_cast<uint32_t>(p0 * 128 + ((j ^ (p0 & 7)) << 4));
-    float* coef_tab = gn_acc + 8 * 64 + 8 * BN;  // scale / 2 [256] then shift / 2 [256] (separate arrays: the packed
+    float* coef_tab = gn_acc + 8 * 64 + 8 * BN;  // scale / 2 [512] then shift / 2 [512] (separate arrays: the packed
     const uint32_t coef_s = smem_u32(coef_tab);  // fp32 FMAs want (scale, scale) and (shift, shift) register pairs)
     int slot = 0;
     uint32_t ph = 0;
@@ -1265,7 +1271,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const float2 v = __ldg(p.gn_in + static_cast<long long>(b) * p.Cin + ch);
           // halved: silu(a x + b) = h + h tanh(h) with h = (a / 2) x + b / 2
           coef_tab[ch] = 0.5f * v.x;
-          coef_tab[256 + ch] = 0.5f * v.y;
+          coef_tab[512 + ch] = 0.5f * v.y;
         }
         named_bar_sync(3, 128);
         coef_b = b;
@@ -1279,7 +1285,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t ct = coef_s + static_cast<uint32_t>((c * 64 + j * 8) * 4);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const uint4 va = lds128(ct + q * 16), vb = lds128(ct + 1024 + q * 16);
+              const uint4 va = lds128(ct + q * 16), vb = lds128(ct + 2048 + q * 16);
               ca[4 * q] = __uint_as_float(va.x); ca[4 * q + 1] = __uint_as_float(va.y);
               ca[4 * q + 2] = __uint_as_float(va.z); ca[4 * q + 3] = __uint_as_float(va.w);
               cb[4 * q] = __uint_as_float(vb.x); cb[4 * q + 1] = __uint_as_float(vb.y);
@@ -1347,7 +1353,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int c_off = half * 64;
     float* my_gn = gn_acc + ew * 64;
     float* my_bias = gn_acc + 8 * 64 + ew * BN;
-    if (p.bias) stage_bias<BN>(my_bias, p.bias, 0, p.Cout, lane);
+    int bias_tile = -1;
     const int gn_n = p.gn_groups * 2;
     int gn_b = -1;
     if (p.gn_sums) { my_gn[lane] = 0.f; my_gn[lane + 32] = 0.f; __syncwarp(); }
@@ -1359,6 +1365,11 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.gn_sums && !dummy && b != gn_b) {
         if (gn_b >= 0) gn_flush(my_gn, gn_n, gn_slot(p.gn_sums, gn_b, gn_n, blockIdx.x * 8 + ew, p.gn_slots), lane);
         gn_b = b;
+      }
+      const int ch0 = cur_n_tile * BN + c_off;  // first output channel of this warp's 64 columns
+      if (p.bias && cur_n_tile != bias_tile) {
+        stage_bias<BN>(my_bias, p.bias, cur_n_tile * BN, p.Cout, lane);
+        bias_tile = cur_n_tile;
       }
       const int x = tx * 128 + row;
       for (int o = 0; o < L; ++o, ++n) {
@@ -1373,11 +1384,11 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint4 rr0[4] = {}, rr1[4] = {};
         e.res_row = (p.res && !p.res_tap && !dummy) ? p.res + (b * p.r_sb + y * p.r_sy + x * p.r_sx) : nullptr;
         if (e.res_row) {  // this thread's 64 residual channels are in flight before the accumulator wait
-          load_res32(rr0, e, c_off, valid);
-          load_res32(rr1, e, c_off + 32, valid);
+          load_res32(rr0, e, ch0, valid);
+          load_res32(rr1, e, ch0 + 32, valid);
           // the residual comes from DRAM: pull the NEXT row's 128-byte line of this thread into L2 now (the first use of
           // rr0 was the largest long-scoreboard stall of the epilogue, ncu profiles/r02/ncu_r02_halo_rr_gn_res_final.txt)
-          if (valid && o + 1 < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.res_row + p.r_sy + c_off));
+          if (valid && o + 1 < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.res_row + p.r_sy + ch0));
         }
         e.o_off = b * p.o_sb + y * p.o_sy + x * p.o_sx;
         const int slot = n & 3;
@@ -1400,7 +1411,7 @@ conv_halo_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else mbar_arrive_remote(&acc_empty[slot], 0);
         }
         if (!(p.debug & 2)) {  // (timing-only ablation: no epilogue)
-          epilogue_regs64<MODE>(v0, v1, c_off, c_off, valid, e, p.bias ? my_bias + c_off : nullptr, rr0, rr1, my_gn,
+          epilogue_regs64<MODE>(v0, v1, ch0, ch0, valid, e, p.bias ? my_bias + c_off : nullptr, rr0, rr1, my_gn,
                                 p.gn_cpg, lane);
         }
       }
@@ -1518,6 +1529,15 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
   return check_launch("conv_halo_tc_kernel");
 }
 
+// does the rolling-row kernel take this 3x3 problem? (a long enough share of pair-rows per cluster; the input GroupNorm
+// coefficient table in shared memory holds 512 channels; at most two 128-wide output-channel passes)
+static bool halo_rr_fits(int B, int OH, int OW, int Cin, int Cout) {
+  const int tiles_x = (OW + 127) / 128, nt = (Cout + 127) / 128;
+  const long long pair_rows = static_cast<long long>(B) * ((tiles_x + 1) / 2) * OH * nt;
+  return nt <= 2 && Cin <= 512 && Cin % 64 == 0 && pair_rows >= static_cast<long long>(sm_count() / 2) * 48 &&
+         pair_rows < 0x7fffffffLL;
+}
+
 // Returns 1 if this problem is not eligible (caller falls through to the generic kernel), 0 on success, <0 on error.
 int try_conv_halo(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int IH, int IW,
                   int OH, int OW, int Cin, int Cout, int R, int S, int pad_t, int pad_l, long long x_sx, long long x_sy,
@@ -1536,7 +1556,12 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   // bound by its L2->SMEM operand stream, i.e. Cout = 128 (128-wide tiles re-read A per 128 output channels):
   // 1150 vs 918 TFLOP/s at 128->128 @512^2. With 256-wide tiles (no room for a second TMEM accumulator set at
   // TM=2) the generic kernel is faster (1333 vs 1209 at 256->256 @256^2), so those stay on the generic path.
-  if (Cout % 256 == 0) return 1;
+  // Exception (round 2): with the GroupNorm + SiLU of the input fused in, Cout = 256 runs as TWO 128-channel passes of
+  // the rolling-row kernel over the same input rows (0.85 ms at 256->256 @256^2 x16 against 0.80 ms generic + 0.19 ms for
+  // the separate normalisation pass it replaces).
+  const bool wide_rr = Cout == 256 && gn_in != nullptr && R == 3 && S == 3 && OW >= 256 && g_halo_rolling != 0 &&
+                       halo_rr_fits(B, OH, OW, Cin, Cout);
+  if (Cout % 256 == 0 && !wide_rr) return 1;
   const int bn = 128;
   constexpr int TM = 2;
   HaloParams p;
@@ -1574,10 +1599,10 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
   rc = make_tmap_bf16(&tmB, w, 4, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (thin) return launch_halo<16, TM>(tmA, tmB, p, st);
-  if (gn_in && !pair)
-    return set_error(OMGSR_ERR_SHAPE, "conv_halo: the fused input GroupNorm needs the CTA-pair halo kernel (16 < Cout <= 128, >= 2 tiles)");
+  if (gn_in && !pair && !wide_rr)
+    return set_error(OMGSR_ERR_SHAPE, "conv_halo: the fused input GroupNorm needs the CTA-pair halo kernel (16 < Cout <= 128, >= 2 tiles; or Cout = 256 on the rolling-row kernel)");
   static const bool rs_off = getenv("OMGSR_HALO_ROW_SHARED") && atoi(getenv("OMGSR_HALO_ROW_SHARED")) == 0;  // A/B timing
-  if (pair && g_halo_row_shared && !rs_off && R >= 2) {
+  if ((pair || wide_rr) && g_halo_row_shared && !rs_off && R >= 2) {
     // row-shared schedule: one input ROW per A load, weight units of 128 rows (N = 256 instructions) or 64 rows
     CUtensorMap tmRow, tmB128, tmB64;
     uint32_t rbox[5] = {64, static_cast<uint32_t>(p.pw), 1, 1, 1};
@@ -1590,10 +1615,8 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
     if (rc) return rc;
     // rolling rows: every input row loaded / transformed once; worth it when a cluster's share of output rows is long
     // against the two extra input rows per segment
-    const long long pair_rows = static_cast<long long>(B) * ((p.tiles_x + 1) / 2) * OH;
     const int max_clusters = sm_count() / 2;
-    const bool rr_fit = R == 3 && S == 3 && pair_rows >= static_cast<long long>(max_clusters) * 48 && pair_rows < 0x7fffffffLL &&
-                        Cin <= 256;  // (the input-GroupNorm coefficient table in shared memory holds 256 channels)
+    const bool rr_fit = R == 3 && S == 3 && halo_rr_fits(B, OH, OW, Cin, Cout);
     const bool rr_on = g_halo_rolling >= 0 ? g_halo_rolling != 0 : gn_in != nullptr;
     if (rr_fit && rr_on) {
       // residual as an identity tap (Cout = 128, bf16 residual with TMA-compatible strides): OMGSR_HALO_RES_TAP=0 keeps
@@ -1621,6 +1644,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
       if (gn_in) return launch_halo_rr<true>(tmRow, tmB128, tmB64, tmR, tmI64, q, max_clusters, st);
       return launch_halo_rr<false>(tmRow, tmB128, tmB64, tmR, tmI64, q, max_clusters, st);
     }
+    if (wide_rr) return set_error(OMGSR_ERR_SHAPE, "conv_halo: Cout = 256 with a fused input GroupNorm needs the rolling-row kernel");
     if (gn_in) return launch_halo_rs<true>(tmRow, tmB128, tmB64, p, st);
     return launch_halo_rs<false>(tmRow, tmB128, tmB64, p, st);
   }
@@ -1634,4 +1658,11 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
 extern "C" int omgsr_set_halo_rolling(int mode) {
   omgsr::g_halo_rolling = mode < -1 ? omgsr::halo_rolling_default() : mode;  // < -1: back to the start-up default
   return OMGSR_OK;
+}
+
+/* can omgsr_conv2d_gn_nhwc_bf16 take a 3x3 / s1 / p1 convolution with 256 output channels (two passes of the rolling-row
+ * kernel)? The engines ask before they defer a GroupNorm to the convolution that follows it. */
+extern "C" int omgsr_conv_gn_wide_fusable(int B, int OH, int OW, int Cin, int Cout) {
+  return (Cout == 256 && OW >= 256 && omgsr::g_halo_rolling != 0 && omgsr::g_halo_row_shared != 0 &&
+          omgsr::halo_rr_fits(B, OH, OW, Cin, Cout)) ? 1 : 0;
 }

@@ -745,6 +745,46 @@ def test_conv_halo_rolling_rows(capi, B, H, W, Cin, Cout, variant):
         assert report(f"rolling rows {y0}..{y1} vs oracle [{variant}]", y_rr[:, y0:y1], band)[0]
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 256, 256, 256, 256), (4, 300, 384, 128, 256), (4, 512, 256, 512, 256)])
+@pytest.mark.parametrize("variant", ["gn_in", "gn_in_res_stats"])
+def test_conv_halo_rolling_rows_cout256(capi, B, H, W, Cin, Cout, variant):
+    """Cout = 256 with the input GroupNorm fused: two 128-channel passes of conv_halo_rr_kernel over the same rows (the
+    VAE's 256-channel level at 256^2 and above). Against the two-pass form (normalise, then the generic convolution) on
+    the whole tensor and against the fp32 oracle on row bands; odd strip count, Cin = 128 / 256 / 512."""
+    from oracle import ops
+    from omgsr_b200.pack import pack_conv_weight
+    assert capi.conv_gn_in_fusable(B, H, W, Cin, Cout)
+    g = _g(B * 17 + H + W + Cin + Cout)
+    x = bf16r(torch.randn(B, H, W, Cin, generator=g) * 1.5 + 0.3)
+    gamma, beta = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.2
+    w = bf16r(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9))
+    b = torch.randn(Cout, generator=g)
+    with_res = "res" in variant
+    r = bf16r(torch.randn(B, H, W, Cout, generator=g)) if with_res else None
+    xc, wc, bc = x.cuda().bfloat16(), pack_conv_weight(w).cuda(), b.cuda()
+    rc = r.cuda().bfloat16() if with_res else None
+    st = capi.groupnorm_stats(xc, 32)
+    coef = capi.groupnorm_coef(st, gamma.cuda(), beta.cuda(), B, H * W, 32, 1e-6)
+    so = torch.empty(B, 32, 2, device="cuda") if "stats" in variant else None
+    y = capi.conv2d_gn(xc, coef, wc, bc, res=rc, gn_stats=so)
+    torch.cuda.synchronize()
+    assert "conv_halo_rr_kernel<1>" in capi.last_conv_variant(), capi.last_conv_variant()
+    two_pass = capi.conv2d(capi.groupnorm_apply(xc, st, gamma.cuda(), beta.cuda(), 32, 1e-6, True), wc, bc, res=rc)
+    assert report(f"cout256 fused vs two-pass [{variant}]", y, two_pass.float().cpu(), 8e-3)[0]
+    if so is not None:
+        f32 = y.float()
+        s_ref = torch.stack([f32.reshape(B, H * W, 32, Cout // 32).sum((1, 3)),
+                             (f32 * f32).reshape(B, H * W, 32, Cout // 32).sum((1, 3))], -1)
+        assert report("cout256 output statistics", so, s_ref.cpu(), 1e-3)[0]
+    xin = bf16r(torch.nn.functional.silu(ops.groupnorm_nhwc(x, gamma, beta, 32, 1e-6)))
+    for y0, y1 in ((0, 4), (H - 4, H), (H // 2 - 2, H // 2 + 2)):
+        lo, hi = max(y0 - 1, 0), min(y1 + 1, H)
+        band = ops.conv2d_nhwc(xin[:, lo:hi], w, b)[:, y0 - lo:y0 - lo + (y1 - y0)]
+        if with_res:
+            band = band + r[:, y0:y1]
+        assert report(f"cout256 rows {y0}..{y1} vs oracle [{variant}]", y[:, y0:y1], band)[0]
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(2, 8, 128, 64, 128, False), (1, 33, 200, 128, 128, True),
                                                 (2, 40, 256, 256, 128, True), (1, 7, 130, 64, 64, False),
                                                 (3, 10, 300, 192, 128, False)])
