@@ -569,8 +569,8 @@ def bench_s512(ctx, args):
     return line
 
 
-PAIR256_TRAFFIC = 1.0394e9   # conv_gemm_tc2_kernel<256> (3x3 256->256 @256^2 x16): 0.5382 GB read + 0.5012 GB written,
-                             # profiles/r02/ncu_r02b_conv256.txt (algorithmic input + output = 2 x 0.5369 GB)
+PAIR256_TRAFFIC = 0.5127e9   # conv_gemm_tc2_kernel<256> (3x3 512->512 @128^2 x16): 0.2732 GB read + 0.2394 GB written,
+                             # profiles/r02/ncu_r02c_conv512.txt (algorithmic input + output = 2 x 0.2684 GB)
 
 
 def _time_launch(fn, n=10):
@@ -589,20 +589,20 @@ def _time_launch(fn, n=10):
 def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
     """Roofline of the step's dominant kernel, timed live on its launch stream.
 
-    By share of the step (ncu launch list, profiles/r02/launches_s512_b16_final_summary.txt) the dominant KERNEL is
-    conv_gemm_tc2_kernel<256> (CTA-pair implicit-GEMM conv / GEMM, N = 256 tiles: 40 % of the step, 82 launches), probed
-    on its largest recurring shape, the VAE's 3x3 256->256 convolution at 256x256 (0.62 TFLOP per launch at batch 16).
-    Second among the single layer shapes (18 %, 11 launches) and the kernel round 1's verdict asked to lift is the
-    128-channel input-halo convolution with the GroupNorm + SiLU of its input fused into the operand path (round 2:
-    conv_halo_rr_kernel<1>, rolling input rows; the largest single layer shape of the step: 1.24 TFLOP per launch):
-    reported next to it as `second`.
+    By share of the step (ncu launch list, profiles/r02/launches_s512_b16_final_summary.txt) the dominant KERNEL at the end
+    of round 2 is conv_halo_rr_kernel<1> - the rolling-row 3x3 convolution with the GroupNorm + SiLU of its input fused
+    into the operand path (32 % of the step in 21 launches since it also serves the 256-channel level) - probed on its
+    largest recurring shape, 128->128 channels at 512x512 (1.24 TFLOP per launch at batch 16; this is also the kernel
+    round 1 reported and its verdict asked to lift). Second: conv_gemm_tc2_kernel<256> (CTA-pair implicit-GEMM conv /
+    GEMM, N = 256 tiles: 28 % in 72 launches), probed on the VAE's 3x3 512->512 convolution at 128x128
+    (1.24 TFLOP per launch; its 256-channel layers moved to the rolling-row kernel), reported as `second`.
     Algorithmic FLOPs = 2*Cin*Cout*9*B*H*W in both cases."""
     from omgsr_b200.pack import pack_conv_weight
     # the burst peak is a cold-start figure: let the board leave the power-capped state of the timed steps first
     torch.cuda.synchronize()
     time.sleep(3.0)
     out = {}
-    for key, C, H in (("pair256", 256, 256), ("halo", 128, 512)):
+    for key, C, H in (("pair256", 512, 128), ("halo", 128, 512)):
         x = torch.randn(B, H, H, C, device=dev, dtype=torch.bfloat16)
         w = pack_conv_weight(torch.randn(C, C, 3, 3) / (3.0 * C ** 0.5)).to(dev)
         b = torch.zeros(C, device=dev)
@@ -615,8 +615,8 @@ def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
             traffic = HALO_GN_TRAFFIC if (B, C, H) == (16, 128, 512) else None
         else:
             ms = _time_launch(lambda: capi.conv2d(x, w, b, out=y))
-            label = "3x3, 256->256 ch, 256x256"
-            traffic = PAIR256_TRAFFIC if (B, C, H) == (16, 256, 256) else None
+            label = "3x3, 512->512 ch, 128x128"
+            traffic = PAIR256_TRAFFIC if (B, C, H) == (16, 512, 128) else None
         flops = 2.0 * C * C * 9 * B * H * H
         ach = flops / (ms * 1e-3) / 1e12
         out[key] = {"bound": "tensor", "kernel": f"{capi.last_conv_variant()} ({label}, batch {B})", "achieved": ach,
@@ -625,10 +625,11 @@ def dominant_kernel_roofline(capi, dev, B, peak_tflops, how):
                     "traffic": traffic, "traffic_unit": "bytes/launch",
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms}
         del x, y
-    roof = out["pair256"]
-    roof["share_of_step"] = "40 % (conv_gemm_tc2_kernel<256>, profiles/r02/launches_s512_b16_final_summary.txt)"
-    roof["second"] = out["halo"]
-    roof["second"]["share_of_step"] = "18 % (conv_halo_rr_kernel<1, *>: fused input GroupNorm, 11 launches)"
+    roof = out["halo"]
+    roof["share_of_step"] = ("32 % (conv_halo_rr_kernel<1, *>: fused input GroupNorm, 21 launches; "
+                             "profiles/r02/launches_s512_b16_final_summary.txt)")
+    roof["second"] = out["pair256"]
+    roof["second"]["share_of_step"] = "28 % (conv_gemm_tc2_kernel<256>, 72 launches)"
     return roof
 
 

@@ -1436,12 +1436,16 @@ int g_halo_rolling = g_halo_rolling_default;
 int halo_rolling_default() { return g_halo_rolling_default; }
 
 // 128 x 128 bf16 identity per device: the weight matrix of the residual tap
-static const void* identity128() {
+static const void* identity128(cudaStream_t st) {
   static void* ptr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
   if (!ptr[dev]) {
+    // first use on this device allocates and copies: not allowed while `st` is being captured into a CUDA graph (the
+    // caller then keeps the residual add in the epilogue; every later, un-captured call installs the buffer)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
     std::vector<uint16_t> h(128 * 128, 0);
     for (int i = 0; i < 128; ++i) h[i * 128 + i] = 0x3f80;  // bf16 1.0
     void* d = nullptr;
@@ -1627,7 +1631,7 @@ int try_conv_halo(const void* x, const void* w, const float* bias, const void* r
       q.res_tap = 0;
       if (res && !tap_off && Cout == 128 && !out_f32 && r_sx >= 128 && (r_sx % 8) == 0 && (r_sy % 8) == 0 &&
           (r_sb % 8) == 0 && (reinterpret_cast<uintptr_t>(res) % 16) == 0) {
-        const void* eye = identity128();
+        const void* eye = identity128(st);
         if (eye) {
           uint64_t rdims[5] = {128, static_cast<uint64_t>(OW), static_cast<uint64_t>(OH), static_cast<uint64_t>(B), 1};
           uint64_t rstr[4] = {static_cast<uint64_t>(r_sx) * eb, static_cast<uint64_t>(r_sy) * eb,
