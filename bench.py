@@ -484,7 +484,7 @@ def f_kernel_roofline(capi, dev, B, peak_tflops, how):
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
             "traffic": F_GEMM_TRAFFIC if B == 4 else None, "traffic_unit": "bytes/launch",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({how})", "ms_per_launch": ms,
-            "attention": {"kernel": "flash_attn3_kernel<128> (joint attention, 24 heads x 4608 tokens, d = 128, batch %d)" % B,
+            "attention": {"kernel": "flash_attn5_kernel<128> (joint attention, 24 heads x 4608 tokens, d = 128, batch %d)" % B,
                           "achieved": ach_a, "frac": ach_a / peak_tflops, "ms_per_launch": ms_a}}
 
 

@@ -125,8 +125,9 @@ int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out
                           long long o_head, long long o_batch, float scale, void* stream);
 
 /* A-B timing switch for the attention kernels: 0 = automatic, 1 = always the single-tile kernel, 2 = the 64-key
- * ping-pong kernel instead of the 128-key ones, 3 = the natural-layout 128-key kernel (the automatic choice), 4 = the
- * transposed-O 128-key kernel at d = 128. Test/bench only. */
+ * ping-pong kernel instead of the 128-key ones, 3 = the natural-layout 128-key kernel without the early S release,
+ * 4 = the transposed-O 128-key kernel at d = 128, 5 = the natural-layout kernel that releases S from registers (the
+ * automatic choice). Test/bench only. */
 int omgsr_flash_attn_set_variant(int variant);
 
 /* NHWC implicit-GEMM convolution, ksize in {1,3}, stride in {1,2}; `upsample2x` fuses a nearest 2x

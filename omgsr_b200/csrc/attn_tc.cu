@@ -575,6 +575,7 @@ __device__ __forceinline__ void exp2_poly2(float& t0, float& t1) {
   t1 = __int_as_float(__float_as_int(p1) + (__float_as_int(i1) << 23));
 }
 
+constexpr bool kAttnV5Default = true;   // v5 vs v3, same box: d = 128 0.881 -> 0.853 ms, d = 64 0.534 -> 0.461 ms (profiles/r02/attn_v5_ab.txt)
 constexpr int kAttnPolyDefault = 2;  // d = 64: 0.598 -> 0.538 ms, d = 128: 0.902 -> 0.888 ms (profiles/r02/attn_poly_exp2.txt)
 // one-pass softmax (v3 / v4): a block whose row sum exceeds this moves the row's reference exponent up by log2(sum)
 constexpr float kAttnRebase = 1024.0f;
@@ -865,6 +866,292 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ================================================================================================================
+// v5 (end of round 2): v3 with the S accumulator handed back as soon as a row is in REGISTERS.
+//
+// ncu on v3 (profiles/r02/ncu_r02_attn3_final.txt): the softmax warps wait for S 40 % of the time while the MMA issuer
+// waits ~900 cycles per block for P - each group is one serial chain S MMA -> softmax -> P -> PV MMA -> next S, and two
+// chains do not fill the tensor pipe (60.8 % active). Here a softmax thread first copies its whole row (128 fp32
+// scores) out of TMEM and arrives on s_free; the issuer then runs S_g(j+1) UNDER the softmax arithmetic of block j, so
+// the chain per block is softmax -> PV only. 128 score registers + the rest need ~200 registers per softmax thread:
+// the roles sit in whole warpgroups (producer + issuer + two idle warps | two softmax groups) and setmaxnreg moves the
+// first warpgroup's registers (40 each) to the softmax warps (232 each).
+// Tile order on the ring is the order of use: K0 | K1 V0 | K2 V1 | ...
+// ================================================================================================================
+template <int D, int PMASK>
+__global__ void __launch_bounds__(384, 1)
+flash_attn5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = Attn3Cfg<D>;
+  constexpr int BN = C::kBN, NS = C::kSlots;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                             // [group][d panel][128 rows x 128 B]
+  uint8_t* sKV = sQ + C::kQBytes;                 // [slot][d panel][128 keys x 128 B]
+  uint8_t* sP = sKV + NS * C::kTileBytes;         // [group][key panel][128 rows x 128 B]
+  uint8_t* sOnes = sP + 2 * C::kPBytes;           // [128 keys x 128 B] of bf16 1.0 (d = 64 only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::kOnesBytes);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* kv_full = q_full + 1;       // [NS]
+  uint64_t* kv_empty = kv_full + NS;    // [NS]
+  uint64_t* s_full = kv_empty + NS;     // [2 groups]
+  uint64_t* p_full = s_full + 2;        // [2]
+  uint64_t* pv_done = p_full + 2;       // [2]
+  uint64_t* s_free = pv_done + 2;       // [2] 128 arrivals: the group holds its scores in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform: see the MMA issuer
+  const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 128); mbar_init(&pv_done[g], 1); mbar_init(&s_free[g], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (C::kOnesCol) {
+    for (int i = threadIdx.x; i < C::kOnesBytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_launch_dependents();
+  pdl_wait();  // nothing above touches global memory
+
+  if (warp < 4) {
+  setmaxnreg_dec<40>();
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: Q (both groups) once, then K0 | K1 V0 | K2 V1 | ... through the ring ----
+      mbar_expect_tx(q_full, C::kQBytes);
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(sQ + (g * (D / 64) + pnl) * (128 * 128), &tmQ, q_full, pnl * 64, m0 + g * 128, h, b);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto load = [&](const CUtensorMap* tm, int blk) {
+        mbar_wait_relaxed(&kv_empty[slot], phase ^ 1);
+        uint8_t* dst = sKV + slot * C::kTileBytes;
+        mbar_expect_tx(&kv_full[slot], C::kTileBytes);
+#pragma unroll
+        for (int pnl = 0; pnl < D / 64; ++pnl)
+          tma_load_4d(dst + pnl * (BN * 128), tm, &kv_full[slot], pnl * 64, blk * BN, h, b);
+        if (++slot == NS) { slot = 0; phase ^= 1; }
+      };
+      load(&tmK, 0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) load(&tmK, j + 1);
+        load(&tmV, j);
+      }
+    }
+  } else if (warp == 1) {
+    {  // whole warp on warp-uniform values, one elected lane issues (gemm_conv_tc.cu has the argument)
+      const bool leader = elect_one();
+      // ---- MMA issuer ----
+      const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, C::kOnesCol ? D + 16 : D, 0, 1);
+      int slot = 0;     // ring position of the next tile to consume (same order as the producer)
+      uint32_t phase = 0;
+      auto next_tile = [&]() {
+        mbar_wait(&kv_full[slot], phase);
+        tc_fence_after();
+        const int s0 = slot;
+        if (++slot == NS) { slot = 0; phase ^= 1; }
+        return s0;
+      };
+      auto tile_addr = [&](int s0) { return smem_u32(sKV + s0 * C::kTileBytes); };
+      auto free_tile = [&](int s0) { if (leader) tc_commit(&kv_empty[s0]); };
+      auto issue_s = [&](int g, int t) {
+        const uint32_t aQ = smem_u32(sQ + g * (D / 64) * (128 * 128));
+        const uint32_t aK = tile_addr(t);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aQ + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc_sw128(aK + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
+          if (leader) tc_mma_ss(tmem_base + g * 128, da, db, idesc_s, kk != 0);
+        }
+        if (leader) tc_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, int t, int j) {
+        const uint32_t aP = smem_u32(sP + g * C::kPBytes);
+        const uint32_t aV = tile_addr(t);
+        // second 64-wide N atom: the next d panel (d = 128) or the all-ones panel (d = 64)
+        const uint32_t lbo = C::kOnesCol ? smem_u32(sOnes) - aV : BN * 128;
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(aP + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc_sw128(aV + kk * 2048, lbo, 1024);
+          if (leader) tc_mma_ss(tmem_base + 256 + g * 128, da, db, idesc_o, (j | kk) != 0);
+        }
+        if (leader) tc_commit(&pv_done[g]);
+      };
+      mbar_wait(q_full, 0);
+      {
+        const int s0 = next_tile();  // K(0)
+        issue_s(0, s0);
+        issue_s(1, s0);
+        free_tile(s0);
+      }
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {
+          const int sk = next_tile();  // K(j + 1)
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&s_free[g], j & 1);  // group g holds S_g(j) in registers: its TMEM columns may be overwritten
+            tc_fence_after();
+            issue_s(g, sk);
+          }
+          free_tile(sk);
+        }
+        const int sv = next_tile();    // V(j)
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g], j & 1);
+          tc_fence_after();
+          issue_pv(g, sv, j);
+        }
+        free_tile(sv);
+      }
+    }
+  }
+  } else {
+    setmaxnreg_inc<232>();
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + g * 128 + lane_off, tO = tmem_base + 256 + g * 128 + lane_off;
+    uint8_t* p_row = sP + g * C::kPBytes + row * 128;
+    float mb = 0.f, l_run = 0.f;  // mb: the row's reference exponent (log2 units), see flash_attn4_kernel
+    float pend_alpha = 1.0f;      // rescale decided at the end of the previous block
+    bool pend = false;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      const int n_valid = min(BN, p.N - j * BN);
+      // the whole row leaves TMEM first: S_g may then be overwritten by the next block's MMAs while we do the arithmetic
+      uint32_t sv[128];
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) tmem_ld32(tS + c0, *reinterpret_cast<uint32_t(*)[32]>(&sv[c0]));
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&s_free[g]);
+      if (n_valid < BN) {  // ragged last block only
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= n_valid) sv[i] = 0xff800000u;  // -inf
+      }
+      if (j == 0) {  // the first block fixes the reference at its maximum
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        mb = mx * p.scale_log2;
+      } else {
+        // P_g and O_g belong to PV_g(j - 1) until it has retired
+        mbar_wait(&pv_done[g], (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, pend)) {  // O rows are thread-local here: a warp rescales on its own
+#pragma unroll
+          for (int c0 = 0; c0 < (C::kOnesCol ? D + 32 : D); c0 += 32) {  // + the row-sum column(s) at D
+            uint32_t v[32];
+            tmem_ld32(tO + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * pend_alpha);
+            tmem_st32(tO + c0, v);
+          }
+          tmem_wait_st();
+          l_run *= pend_alpha;
+        }
+      }
+      // ONE pass over the row (flash_attn4_kernel has the argument): exponentials against the running reference; the
+      // block's row sum decides whether the NEXT block starts from a new one
+      const float nmb = -mb;
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {  // 16-byte chunk (8 keys) of the 256-byte P row: two 64-key panels
+        float pr[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float t0, t1;
+          ffma2(t0, t1, __uint_as_float(sv[ch * 8 + i]), __uint_as_float(sv[ch * 8 + i + 1]), p.scale_log2, nmb);
+          if ((PMASK >> (i >> 1)) & 1) {
+            exp2_poly2(t0, t1);  // (-inf -> 2^-125: negligible against the row sum, and its V row is zero)
+            pr[i] = t0; pr[i + 1] = t1;
+          } else {
+            pr[i] = exp2f(t0);  // exp2(-inf) = 0
+            pr[i + 1] = exp2f(t1);
+          }
+          fadd2(ls0, ls1, pr[i], pr[i + 1]);
+        }
+        uint4 u;
+        u.x = pack_bf16x2(pr[0], pr[1]); u.y = pack_bf16x2(pr[2], pr[3]);
+        u.z = pack_bf16x2(pr[4], pr[5]); u.w = pack_bf16x2(pr[6], pr[7]);
+        *reinterpret_cast<uint4*>(p_row + (ch >> 3) * (128 * 128) + (((ch & 7) ^ (row & 7)) << 4)) = u;
+      }
+      const float ls = ls0 + ls1;
+      l_run += ls;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[g]);
+      pend = ls > kAttnRebase;
+      const float lg = pend ? log2f(ls) : 0.f;
+      pend_alpha = exp2f(-lg);
+      mb += lg;
+    }
+    // epilogue: O / l
+    mbar_wait(&pv_done[g], (nblk - 1) & 1);
+    tc_fence_after();
+    const int m = m0 + g * 128 + row;
+    if (C::kOnesCol) {  // l = the ones column of O
+      uint32_t lv[16];
+      tmem_ld16(tO + D, lv);
+      tmem_wait_ld();
+      l_run = __uint_as_float(lv[0]);
+    }
+    const float inv = 1.0f / l_run;
+    bf16* o = p.out + static_cast<long long>(b) * p.o_batch + static_cast<long long>(m) * p.o_row +
+              static_cast<long long>(h) * p.o_head;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tO + c0, v);
+      tmem_wait_ld();
+      if (m < p.M) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv, __uint_as_float(v[q * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv, __uint_as_float(v[q * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv, __uint_as_float(v[q * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv, __uint_as_float(v[q * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + c0 + q * 8) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <int D>
 static int launch_attn3(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
                         const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
@@ -906,6 +1193,48 @@ static int launch_attn3(const void* q, const void* k, const void* v, void* out, 
   else if (poly == 1) launch_pdl(flash_attn3_kernel<D, 0x8>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
   else launch_pdl(flash_attn3_kernel<D, 0>, dim3(grid), dim3(320), C::kSmemBytes, st, tmQ, tmK, tmV, p);
   return check_launch("flash_attn3_kernel");
+}
+template <int D>
+static int launch_attn5(const void* q, const void* k, const void* v, void* out, int B, int H, int M, int N,
+                        const long long* qs, const long long* ks, const long long* vs, const long long* os, float scale,
+                        cudaStream_t st) {
+  using C = Attn3Cfg<D>;
+  // fraction of the exponentials on the FMA pipe: 0 none, 1 one pair in four, 2 every other pair (OMGSR_ATTN_POLY)
+  static const int poly = getenv("OMGSR_ATTN_POLY") ? atoi(getenv("OMGSR_ATTN_POLY")) : kAttnPolyDefault;
+  static unsigned long long attr_done[3] = {0, 0, 0};  // one bit per device
+  const void* kfn = poly == 2 ? reinterpret_cast<const void*>(&flash_attn5_kernel<D, 0xA>)
+                  : poly == 1 ? reinterpret_cast<const void*>(&flash_attn5_kernel<D, 0x8>)
+                              : reinterpret_cast<const void*>(&flash_attn5_kernel<D, 0>);
+  if (int rc = ensure_smem_attr(kfn, C::kSmemBytes, &attr_done[poly == 2 ? 2 : (poly == 1 ? 1 : 0)], "flash_attn5")) return rc;
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t eb = 2;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(M), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t str[3] = {qs[0] * eb, qs[1] * eb, qs[2] * eb};
+    uint32_t box[4] = {64, 128, 1, 1};
+    int rc = make_tmap_bf16(&tmQ, q, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint32_t box[4] = {64, static_cast<uint32_t>(C::kBN), 1, 1};
+    uint64_t strk[3] = {ks[0] * eb, ks[1] * eb, ks[2] * eb};
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, strk, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    uint64_t strv[3] = {vs[0] * eb, vs[1] * eb, vs[2] * eb};
+    rc = make_tmap_bf16(&tmV, v, 4, dims, strv, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.M = M; p.N = N; p.H = H; p.B = B;
+  p.o_row = os[0]; p.o_head = os[1]; p.o_batch = os[2];
+  p.out = static_cast<bf16*>(out);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((M + 255) / 256, H, B);
+  if (poly == 2) launch_pdl(flash_attn5_kernel<D, 0xA>, dim3(grid), dim3(384), C::kSmemBytes, st, tmQ, tmK, tmV, p);
+  else if (poly == 1) launch_pdl(flash_attn5_kernel<D, 0x8>, dim3(grid), dim3(384), C::kSmemBytes, st, tmQ, tmK, tmV, p);
+  else launch_pdl(flash_attn5_kernel<D, 0>, dim3(grid), dim3(384), C::kSmemBytes, st, tmQ, tmK, tmV, p);
+  return check_launch("flash_attn5_kernel");
 }
 
 // ================================================================================================================
@@ -1341,12 +1670,12 @@ using namespace omgsr;
 
 #include <cstdlib>
 static int g_attn_variant = getenv("OMGSR_ATTN_VARIANT") ? atoi(getenv("OMGSR_ATTN_VARIANT")) : 0;
-/* bring-up / A-B timing switch: 0 = automatic (v3: 128 keys, O in natural layout), 1 = always the single-tile kernel,
- * 2 = the 64-key ping-pong kernel (v2) wherever a 128-key kernel would be chosen, 3 = v3 explicitly, 4 = v4 (transposed
- * O, N = 256 PV instructions) at d = 128. v4 was the default while every kernel issued MMAs from a single-lane branch
- * (N = 128 instructions then cost 154 cycles, N = 256 172); with the warp-uniform issue loop an N = 128 instruction
- * costs its 64 tensor-pipe cycles and v3 is the faster one (0.895 vs 0.977 ms on the FLUX shape,
- * profiles/r02/attn_lean_issue.txt). */
+/* bring-up / A-B timing switch: 0 = automatic (v5: 128 keys, O in natural layout, S released from registers), 1 = always
+ * the single-tile kernel, 2 = the 64-key ping-pong kernel (v2) wherever a 128-key kernel would be chosen, 3 = v3 (v5
+ * without the early S release), 4 = v4 (transposed O, N = 256 PV instructions) at d = 128, 5 = v5 explicitly. v4 was the
+ * default while every kernel issued MMAs from a single-lane branch (N = 128 instructions then cost 154 cycles, N = 256
+ * 172); with the warp-uniform issue loop an N = 128 instruction costs its 64 tensor-pipe cycles and the natural layout
+ * is the faster one (profiles/r02/attn_lean_issue.txt, attn_v5_ab.txt). */
 extern "C" int omgsr_flash_attn_set_variant(int variant) { g_attn_variant = variant; return OMGSR_OK; }
 
 extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int M,
@@ -1370,6 +1699,10 @@ extern "C" int omgsr_flash_attn_bf16(const void* q, const void* k, const void* v
   const bool v2 = (M > 128) && g_attn_variant != 1;
   // long key sequences: 128 keys per block (v3: every S instruction is N = 128, half the instruction count of v2)
   if (v2 && N >= 128 && g_attn_variant != 2) {
+    if (g_attn_variant == 5 || (g_attn_variant == 0 && kAttnV5Default)) {
+      if (D == 64) return launch_attn5<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+      if (D == 128) return launch_attn5<128>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
+    }
     if (D == 64) return launch_attn3<64>(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);
     if (D == 128 && g_attn_variant == 4 && o_head == 128)  // (v4's coalesced row store assumes head-contiguous output)
       return launch_attn4(q, k, v, out, B, H, M, N, qs, ks, vs, os, scale, st);

@@ -20,7 +20,7 @@ for name, (B, H, M, N, D) in (("FLUX joint", (4, 24, 4608, 4608, 128)), ("UNet 6
     o = torch.empty_like(q)
     fl = 4.0 * B * H * M * N * D
     res = []
-    for variant, nm in ((2, "v2"), (3, "v3"), (4, "v4 (d=128 only)")):
+    for variant, nm in ((2, "v2"), (3, "v3"), (4, "v4 (d=128 only)"), (5, "v5")):
         capi.lib().omgsr_flash_attn_set_variant(variant)
         ms = timeit(lambda: capi.flash_attn(q, k, v, D ** -0.5, out=o))
         res.append(f"{nm} {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s")

@@ -337,7 +337,8 @@ def test_flash_attention_variants_agree(capi):
         capi.lib().omgsr_flash_attn_set_variant(0)
     assert report("flash v1 (single tile)", o1, ref, 2e-2)[0]
     assert report("flash auto (d=128: v3)", o2, ref, 2e-2)[0]
-    for variant, name in ((2, "v2 (64-key ping-pong)"), (3, "v3 (128 keys)"), (4, "v4 (128 keys, transposed O)")):
+    for variant, name in ((2, "v2 (64-key ping-pong)"), (3, "v3 (128 keys)"), (4, "v4 (128 keys, transposed O)"),
+                          (5, "v5 (128 keys, S released from registers)")):
         capi.lib().omgsr_flash_attn_set_variant(variant)
         try:
             ov = capi.flash_attn(qc, kc, vc, 0.25)
@@ -348,7 +349,7 @@ def test_flash_attention_variants_agree(capi):
     ramp = torch.linspace(0.0, 6.0, N)[None, :, None, None]
     k2 = bf16r(k * 0.2 + ramp * torch.sign(q.mean(dim=1, keepdim=True)))
     ref2 = ops.attention(q, k2, v, 0.25)
-    for variant in (0, 4):
+    for variant in (0, 4, 5):
         capi.lib().omgsr_flash_attn_set_variant(variant)
         try:
             o4 = capi.flash_attn(qc, k2.cuda().bfloat16(), vc, 0.25)
@@ -358,7 +359,7 @@ def test_flash_attention_variants_agree(capi):
 
 
 @pytest.mark.parametrize("D", [64, 128])
-@pytest.mark.parametrize("variant", [0, 4])
+@pytest.mark.parametrize("variant", [0, 4, 5])
 @pytest.mark.parametrize("shape", ["ramp", "spike"])
 def test_flash_attention_reference_rebase(capi, D, variant, shape):
     """One-pass softmax of v3 / v4: the row's reference exponent moves when a block's row sum exceeds 2^10.
