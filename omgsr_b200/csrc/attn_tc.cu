@@ -576,7 +576,8 @@ __device__ __forceinline__ void exp2_poly2(float& t0, float& t1) {
 }
 
 constexpr bool kAttnV5Default = true;   // v5 vs v3, same box: d = 128 0.881 -> 0.853 ms, d = 64 0.534 -> 0.461 ms (profiles/r02/attn_v5_ab.txt)
-constexpr int kAttnPolyDefault = 2;  // d = 64: 0.598 -> 0.538 ms, d = 128: 0.902 -> 0.888 ms (profiles/r02/attn_poly_exp2.txt)
+constexpr int kAttnPolyDefault = 2;  // d = 64 (MUFU-bound): half of the pairs, 0.561 -> 0.472 ms on v5; d = 128: a quarter
+                                     // (0.850 -> 0.833 ms; half: 0.861) (profiles/r02/attn_poly_exp2.txt, attn_v5_poly.txt)
 // one-pass softmax (v3 / v4): a block whose row sum exceeds this moves the row's reference exponent up by log2(sum)
 constexpr float kAttnRebase = 1024.0f;
 
@@ -1158,7 +1159,7 @@ static int launch_attn3(const void* q, const void* k, const void* v, void* out, 
                         cudaStream_t st) {
   using C = Attn3Cfg<D>;
   // fraction of the exponentials on the FMA pipe: 0 none, 1 one pair in four, 2 every other pair (OMGSR_ATTN_POLY)
-  static const int poly = getenv("OMGSR_ATTN_POLY") ? atoi(getenv("OMGSR_ATTN_POLY")) : kAttnPolyDefault;
+  static const int poly = getenv("OMGSR_ATTN_POLY") ? atoi(getenv("OMGSR_ATTN_POLY")) : (D == 64 ? kAttnPolyDefault : 1);
   static unsigned long long attr_done[3] = {0, 0, 0};  // one bit per device
   const void* kfn = poly == 2 ? reinterpret_cast<const void*>(&flash_attn3_kernel<D, 0xA>)
                   : poly == 1 ? reinterpret_cast<const void*>(&flash_attn3_kernel<D, 0x8>)
@@ -1200,7 +1201,7 @@ static int launch_attn5(const void* q, const void* k, const void* v, void* out, 
                         cudaStream_t st) {
   using C = Attn3Cfg<D>;
   // fraction of the exponentials on the FMA pipe: 0 none, 1 one pair in four, 2 every other pair (OMGSR_ATTN_POLY)
-  static const int poly = getenv("OMGSR_ATTN_POLY") ? atoi(getenv("OMGSR_ATTN_POLY")) : kAttnPolyDefault;
+  static const int poly = getenv("OMGSR_ATTN_POLY") ? atoi(getenv("OMGSR_ATTN_POLY")) : (D == 64 ? kAttnPolyDefault : 1);
   static unsigned long long attr_done[3] = {0, 0, 0};  // one bit per device
   const void* kfn = poly == 2 ? reinterpret_cast<const void*>(&flash_attn5_kernel<D, 0xA>)
                   : poly == 1 ? reinterpret_cast<const void*>(&flash_attn5_kernel<D, 0x8>)
