@@ -329,3 +329,26 @@ def test_t5_encoder_oracle_matches_transformers(name):
         ref = model(input_ids=ids).last_hidden_state
         out = t5_encoder.t5_encoder_forward(sd, cfg, ids)
     assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+def test_t5_relative_position_buckets_match_transformers():
+    """the bucket function of the product engine (omgsr_b200/engine_t5.py) and of the oracle == transformers'
+    T5Attention._relative_position_bucket (bidirectional, 32 buckets, max distance 128) for every offset that occurs
+    in a 512-token sequence; the empty-prompt ids of both tokenisers."""
+    transformers = pytest.importorskip("transformers")
+    from transformers.models.t5.modeling_t5 import T5Attention
+    import omgsr_synth as syn
+    from oracle import t5_encoder
+    rel = torch.arange(-511, 512)[None, :]
+    ref = T5Attention._relative_position_bucket(rel, bidirectional=True, num_buckets=32, max_distance=128)
+    assert torch.equal(t5_encoder.relative_position_bucket(rel, 32, 128), ref)
+    try:
+        from omgsr_b200.engine_t5 import _relative_position_bucket
+    except ImportError as e:  # the product package needs its CUDA library to import
+        pytest.skip(str(e))
+    assert torch.equal(_relative_position_bucket(rel, 32, 128), ref)
+    ids = syn.empty_prompt_ids(syn.SD21_CLIP_H)
+    assert ids.shape == (1, 77) and ids[0, :3].tolist() == [49406, 49407, 0]
+    assert syn.empty_prompt_ids(syn.FLUX_CLIP_L)[0, :3].tolist() == [49406, 49407, 49407]
+    t5 = syn.empty_prompt_ids_t5(syn.FLUX_T5_XXL)
+    assert t5.shape == (1, 512) and t5[0, :2].tolist() == [1, 0]
